@@ -1,0 +1,269 @@
+/*
+ * svin_b200.h — C ABI of the B200-native SVIn hot-path engine.
+ *
+ * Plain pointers and sizes only; no C++/torch types cross this boundary.  All
+ * functions return SVIN_OK (0) or a negative status; the message is available
+ * from svin_last_error().  Nothing throws across the ABI.  A context is not
+ * re-entrant: serialise calls per context (the reference serialises the
+ * back-end with estimator_mutex_, ThreadedKFVio.cpp:737,1083, and the front-end
+ * per camera with featureDetectorMutexes_[cam], Frontend.cpp:96).
+ *
+ * Reference seams each entry point replaces (paths relative to
+ * okvis_ros/okvis/ in AutonomousFieldRoboticsLab/SVIn):
+ *   svin_ba_*   : okvis::Estimator::optimize -> ceres::Map::solve()
+ *                 (okvis_ceres/src/Estimator.cpp:876-929,
+ *                  okvis_ceres/include/okvis/ceres/Map.hpp:347) and the
+ *                 ErrorInterface::EvaluateWithMinimalJacobians seam
+ *                 (okvis_ceres/include/okvis/ceres/ErrorInterface.hpp:93-96).
+ *   svin_fe_*   : okvis::Frame::detect / describe
+ *                 (okvis_cv/include/okvis/implementation/Frame.hpp:93-135),
+ *                 i.e. cv::FeatureDetector::detect + cv::DescriptorExtractor::compute
+ *                 as constructed at okvis_frontend/src/Frontend.cpp:997-1007.
+ *   svin_match_*: okvis::DenseMatcher::match<VioKeyframeWindowMatchingAlgorithm>
+ *                 (okvis_matcher/include/okvis/implementation/DenseMatcher.hpp:195-203,
+ *                  okvis_frontend/src/VioKeyframeWindowMatchingAlgorithm.cpp:124-323).
+ */
+#ifndef SVIN_B200_H_
+#define SVIN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status */
+#define SVIN_OK 0
+#define SVIN_ERR_INVALID_ARGUMENT (-1)
+#define SVIN_ERR_CUDA (-2)
+#define SVIN_ERR_NO_DEVICE (-3)
+#define SVIN_ERR_OUT_OF_MEMORY (-4)
+#define SVIN_ERR_STATE (-5)
+
+/* Thread-local message for the last failing call on this thread. */
+const char* svin_last_error(void);
+/* Library version string, e.g. "svin_b200 0.1 (sm_100a)". */
+const char* svin_version(void);
+
+/* =====================================================================
+ *  (B) sliding-window bundle adjustment
+ * ===================================================================== */
+
+/* Robust loss on reprojection terms. Estimator.cpp:61 uses CauchyLoss(1). */
+enum { SVIN_LOSS_NONE = 0, SVIN_LOSS_CAUCHY = 1, SVIN_LOSS_HUBER = 2 };
+
+/* Kinds of parameter block referenced by the marginalisation prior. */
+enum { SVIN_BLOCK_POSE = 0, SVIN_BLOCK_SPEEDBIAS = 1, SVIN_BLOCK_LANDMARK = 2 };
+
+/* Termination, mirroring ceres::TerminationType as used by Map::solve. */
+enum {
+  SVIN_TERM_NO_CONVERGENCE = 0, /* max_num_iterations reached */
+  SVIN_TERM_CONVERGENCE = 1,    /* function / gradient / parameter tolerance */
+  SVIN_TERM_FAILURE = 2,        /* too many invalid steps / radius underflow */
+  SVIN_TERM_USER_SUCCESS = 3    /* time limit hit after min_iterations (CeresIterationCallback.hpp:55-80) */
+};
+
+/* okvis::ImuParameters fields used by ImuError (Parameters.hpp; ImuError.cpp:76-263). */
+typedef struct SvinImuParams {
+  double sigma_g_c;  /* gyro noise density */
+  double sigma_a_c;  /* accelerometer noise density */
+  double sigma_gw_c; /* gyro drift noise density */
+  double sigma_aw_c; /* accelerometer drift noise density */
+  double g;          /* earth acceleration magnitude */
+  double g_max;      /* gyro saturation */
+  double a_max;      /* accelerometer saturation */
+} SvinImuParams;
+
+/*
+ * One sliding window = the contents of okvis::ceres::Map at the moment
+ * Estimator::optimize is called, flattened to SoA.  All pointers are HOST
+ * pointers owned by the caller.  pose_blocks/speedbias/landmarks are in/out
+ * (svin_ba_download / svin_ba_optimize write the solution back); everything
+ * else is read-only.
+ *
+ * Pose blocks hold every okvis::ceres::PoseParameterBlock of the window: the
+ * T_WS states AND the camera extrinsics T_SCi (Estimator.cpp:179-262), layout
+ * [x y z qx qy qz qw] (PoseParameterBlock.hpp:53).  Speed-and-bias blocks are
+ * [v(3) b_g(3) b_a(3)] (SpeedAndBiasParameterBlock.hpp:56).  Landmarks are
+ * homogeneous [x y z w] with Euclidean 3-dof update (HomogeneousPointManifold.cpp:57-66).
+ */
+typedef struct SvinBaWindow {
+  /* ---- parameter blocks ---- */
+  int32_t num_pose_blocks;
+  int32_t num_speedbias;
+  int32_t num_landmarks;
+  int32_t num_cameras;
+  double* pose_blocks;            /* [num_pose_blocks][7]  in/out */
+  double* speedbias;              /* [num_speedbias][9]    in/out */
+  double* landmarks;              /* [num_landmarks][4]    in/out */
+  const uint8_t* pose_fixed;      /* [num_pose_blocks]  Map::setParameterBlockConstant */
+  const uint8_t* speedbias_fixed; /* [num_speedbias] */
+  const uint8_t* landmark_fixed;  /* [num_landmarks] or NULL (none fixed) */
+  const double* intrinsics;       /* [num_cameras][8] fu fv cu cv k1 k2 p1 p2 (PinholeCamera<RadialTangentialDistortion>) */
+
+  /* ---- ReprojectionError terms (ReprojectionError.hpp impl:85-229) ---- */
+  int32_t num_obs;
+  int32_t loss_type;            /* SVIN_LOSS_* applied to every reprojection term */
+  double loss_scale;            /* 'a' of CauchyLoss(a)/HuberLoss(a) */
+  const int32_t* obs_pose;      /* [num_obs] pose block index of T_WS */
+  const int32_t* obs_landmark;  /* [num_obs] */
+  const int32_t* obs_extrinsics;/* [num_obs] pose block index of T_SC */
+  const int32_t* obs_camera;    /* [num_obs] intrinsics index */
+  const double* obs_measurement;/* [num_obs][2] keypoint */
+  const double* obs_information;/* [num_obs][4] row-major 2x2 (Estimator.hpp impl:64-67: 64/size^2 * I) */
+
+  /* ---- ImuError terms (ImuError.cpp) ---- */
+  int32_t num_imu;
+  SvinImuParams imu_params;
+  const int32_t* imu_pose0;       /* [num_imu] pose block of T_WS_0 */
+  const int32_t* imu_speedbias0;  /* [num_imu] */
+  const int32_t* imu_pose1;       /* [num_imu] */
+  const int32_t* imu_speedbias1;  /* [num_imu] */
+  const int64_t* imu_t0_ns;       /* [num_imu] okvis::Time t0_ as nanoseconds */
+  const int64_t* imu_t1_ns;       /* [num_imu] */
+  const int32_t* imu_meas_offset; /* [num_imu+1] into the measurement arrays */
+  const int64_t* imu_meas_t_ns;   /* [M] measurement stamps */
+  const double* imu_meas_gyro;    /* [M][3] */
+  const double* imu_meas_accel;   /* [M][3] */
+
+  /* ---- PoseError terms (PoseError.cpp:85-132) on any pose block ---- */
+  int32_t num_pose_priors;
+  const int32_t* pose_prior_block;      /* [n] */
+  const double* pose_prior_measurement; /* [n][7] */
+  const double* pose_prior_information; /* [n][36] row-major 6x6 (may be singular, Estimator.cpp:321-326) */
+
+  /* ---- SpeedAndBiasError terms (SpeedAndBiasError.cpp:84-111) ---- */
+  int32_t num_speedbias_priors;
+  const int32_t* speedbias_prior_block;      /* [n] */
+  const double* speedbias_prior_measurement; /* [n][9] */
+  const double* speedbias_prior_information; /* [n][81] */
+
+  /* ---- RelativePoseError terms (RelativePoseError.cpp:76-147) ---- */
+  int32_t num_relative_pose;
+  const int32_t* relative_pose_block0;      /* [n] */
+  const int32_t* relative_pose_block1;      /* [n] */
+  const double* relative_pose_information;  /* [n][36] */
+
+  /* ---- SonarError terms (SonarError.cpp:113-183) ---- */
+  int32_t num_sonar;
+  const int32_t* sonar_pose;         /* [n] */
+  const double* sonar_range;         /* [n] */
+  const double* sonar_heading;       /* [n] */
+  const double* sonar_information;   /* [n] scalar */
+  const double* sonar_landmark_mean; /* [n][3] mean of landmarkSubset_ (constant after construction) */
+  const double* sonar_T_SSo;         /* [7] sonar extrinsics (config sonar_params.T_SSo) */
+
+  /* ---- DepthError terms (DepthError.cpp:70-139) ---- */
+  int32_t num_depth;
+  const int32_t* depth_pose;        /* [n] */
+  const double* depth_measurement;  /* [n] */
+  const double* depth_first;        /* [n] first_depth_ */
+  const double* depth_information;  /* [n] scalar */
+
+  /* ---- MarginalizationError (MarginalizationError.cpp:798-844) ---- */
+  int32_t marg_num_blocks;                 /* 0 = no prior */
+  int32_t marg_dim;                        /* rows of e0 = cols of J = sum of minimal dims */
+  const int32_t* marg_block_kind;          /* [marg_num_blocks] SVIN_BLOCK_* */
+  const int32_t* marg_block_index;         /* [marg_num_blocks] index into the matching block array */
+  const double* marg_linearization_points; /* concatenated 7/9/4 doubles per block, in block order */
+  const double* marg_J;                    /* [marg_dim][marg_dim] row-major  (J_) */
+  const double* marg_e0;                   /* [marg_dim] */
+} SvinBaWindow;
+
+/* Solver options: the subset of ceres::Solver::Options Estimator::optimize sets
+ * (Estimator.cpp:878-899) plus the Ceres 2.2 defaults it leaves untouched. */
+typedef struct SvinBaOptions {
+  int32_t max_num_iterations;   /* numIter */
+  int32_t min_num_iterations;   /* CeresIterationCallback min iterations; only with time_limit >= 0 */
+  double time_limit_seconds;    /* < 0: none (Estimator.cpp:934-938) */
+  double initial_trust_region_radius; /* 1e4 */
+  double max_trust_region_radius;     /* 1e16 */
+  double min_trust_region_radius;     /* 1e-32 */
+  double min_relative_decrease;       /* 1e-3 */
+  double min_lm_diagonal;             /* 1e-6 */
+  double max_lm_diagonal;             /* 1e32 */
+  double function_tolerance;          /* 1e-6 */
+  double gradient_tolerance;          /* 1e-10 */
+  double parameter_tolerance;         /* 1e-8 */
+  int32_t max_num_consecutive_invalid_steps; /* 5 */
+  int32_t jacobi_scaling;             /* 1 */
+  int32_t compute_landmark_quality;   /* 1: Estimator.cpp:903-922 post-pass */
+} SvinBaOptions;
+
+void svin_ba_default_options(SvinBaOptions* opt);
+
+typedef struct SvinBaSummary {
+  int32_t iterations;           /* trust-region iterations performed (successful + unsuccessful) */
+  int32_t num_successful_steps;
+  int32_t termination;          /* SVIN_TERM_* */
+  int32_t imu_repropagations;   /* total redoPreintegration calls (ImuError.cpp:739-747) */
+  double initial_cost;
+  double final_cost;
+  double final_trust_region_radius;
+} SvinBaSummary;
+
+/* Residual/Jacobian dump of one window at its current estimate (the
+ * EvaluateWithMinimalJacobians seam).  Any pointer may be NULL to skip.
+ * Reprojection outputs are the *raw* (not loss-corrected) weighted residuals
+ * and minimal Jacobians exactly as ReprojectionError returns them. */
+typedef struct SvinBaEvaluation {
+  double* reproj_residuals;   /* [num_obs][2] */
+  double* reproj_J_pose;      /* [num_obs][2][6]  J0_minimal */
+  double* reproj_J_landmark;  /* [num_obs][2][3]  J1_minimal */
+  double* reproj_J_extrinsics;/* [num_obs][2][6]  J2_minimal */
+  double* imu_residuals;      /* [num_imu][15] */
+  double* imu_J_pose0;        /* [num_imu][15][6] */
+  double* imu_J_speedbias0;   /* [num_imu][15][9] */
+  double* imu_J_pose1;        /* [num_imu][15][6] */
+  double* imu_J_speedbias1;   /* [num_imu][15][9] */
+  double* cost;               /* [1] 0.5*sum rho(|r|^2) over all terms */
+} SvinBaEvaluation;
+
+typedef struct svin_ba_ctx svin_ba_ctx;
+
+int svin_ba_create(int device, svin_ba_ctx** out);
+void svin_ba_destroy(svin_ba_ctx* ctx);
+
+/* Copy `num_windows` independent windows to the device (replaces any previous
+ * batch).  Windows in one batch are solved concurrently by the same kernels. */
+int svin_ba_upload(svin_ba_ctx* ctx, const SvinBaWindow* windows, int32_t num_windows);
+
+/* Evaluate all terms of window `window_index` at the uploaded estimate. */
+int svin_ba_evaluate(svin_ba_ctx* ctx, int32_t window_index, SvinBaEvaluation* out);
+
+/* Run the trust-region (dogleg + Schur) solve on every uploaded window.
+ * `summaries` may be NULL, else [num_windows].  Synchronous on return. */
+int svin_ba_solve(svin_ba_ctx* ctx, const SvinBaOptions* opt, SvinBaSummary* summaries);
+
+/* Copy the solution of window `window_index` back into the caller's window
+ * (pose_blocks, speedbias, landmarks).  landmark_quality ([num_landmarks], may
+ * be NULL) receives sqrt(lambda_min/lambda_max) of the landmark Hessian block
+ * (Estimator.cpp:903-922). */
+int svin_ba_download(svin_ba_ctx* ctx, int32_t window_index, SvinBaWindow* window, double* landmark_quality);
+
+/* Reset the estimate on the device to the uploaded initial values (and the IMU
+ * pre-integration state) without a new host->device copy: lets a benchmark
+ * repeat a solve on HBM-resident inputs. */
+int svin_ba_reset(svin_ba_ctx* ctx);
+
+/* upload + solve + download in one call: the drop-in for Estimator::optimize.
+ * landmark_quality: NULL or array of num_windows pointers (each NULL or [num_landmarks]). */
+int svin_ba_optimize(svin_ba_ctx* ctx, SvinBaWindow* windows, int32_t num_windows, const SvinBaOptions* opt,
+                     SvinBaSummary* summaries, double* const* landmark_quality);
+
+/* Device time (ms, CUDA events on the engine's stream) of the last svin_ba_solve,
+ * and per-kernel-family launch counts / accumulated ms since the last upload. */
+typedef struct SvinBaTimings {
+  double solve_ms;
+  double h2d_ms;
+  double d2h_ms;
+  int64_t kernel_launches;
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+} SvinBaTimings;
+int svin_ba_timings(svin_ba_ctx* ctx, SvinBaTimings* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVIN_B200_H_ */

@@ -1,0 +1,144 @@
+"""ctypes view of ``include/svin_b200.h`` — the only way Python reaches the engine.
+
+The product library is ``svin_b200/lib/libsvin_b200.so`` (CUDA, sm_100a).  There is
+no CPU fallback: if the library is missing :func:`load` raises, and every engine
+call fails loudly when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsvin_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+c_uint8_p = C.POINTER(C.c_uint8)
+
+SVIN_LOSS_NONE, SVIN_LOSS_CAUCHY, SVIN_LOSS_HUBER = 0, 1, 2
+SVIN_BLOCK_POSE, SVIN_BLOCK_SPEEDBIAS, SVIN_BLOCK_LANDMARK = 0, 1, 2
+SVIN_TERM_NO_CONVERGENCE, SVIN_TERM_CONVERGENCE, SVIN_TERM_FAILURE, SVIN_TERM_USER_SUCCESS = 0, 1, 2, 3
+
+
+class SvinImuParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("sigma_g_c", "sigma_a_c", "sigma_gw_c", "sigma_aw_c", "g", "g_max", "a_max")]
+
+
+class SvinBaWindow(C.Structure):
+    _fields_ = [
+        ("num_pose_blocks", C.c_int32), ("num_speedbias", C.c_int32), ("num_landmarks", C.c_int32),
+        ("num_cameras", C.c_int32),
+        ("pose_blocks", c_double_p), ("speedbias", c_double_p), ("landmarks", c_double_p),
+        ("pose_fixed", c_uint8_p), ("speedbias_fixed", c_uint8_p), ("landmark_fixed", c_uint8_p),
+        ("intrinsics", c_double_p),
+        ("num_obs", C.c_int32), ("loss_type", C.c_int32), ("loss_scale", C.c_double),
+        ("obs_pose", c_int32_p), ("obs_landmark", c_int32_p), ("obs_extrinsics", c_int32_p),
+        ("obs_camera", c_int32_p), ("obs_measurement", c_double_p), ("obs_information", c_double_p),
+        ("num_imu", C.c_int32), ("imu_params", SvinImuParams),
+        ("imu_pose0", c_int32_p), ("imu_speedbias0", c_int32_p), ("imu_pose1", c_int32_p),
+        ("imu_speedbias1", c_int32_p), ("imu_t0_ns", c_int64_p), ("imu_t1_ns", c_int64_p),
+        ("imu_meas_offset", c_int32_p), ("imu_meas_t_ns", c_int64_p), ("imu_meas_gyro", c_double_p),
+        ("imu_meas_accel", c_double_p),
+        ("num_pose_priors", C.c_int32), ("pose_prior_block", c_int32_p), ("pose_prior_measurement", c_double_p),
+        ("pose_prior_information", c_double_p),
+        ("num_speedbias_priors", C.c_int32), ("speedbias_prior_block", c_int32_p),
+        ("speedbias_prior_measurement", c_double_p), ("speedbias_prior_information", c_double_p),
+        ("num_relative_pose", C.c_int32), ("relative_pose_block0", c_int32_p), ("relative_pose_block1", c_int32_p),
+        ("relative_pose_information", c_double_p),
+        ("num_sonar", C.c_int32), ("sonar_pose", c_int32_p), ("sonar_range", c_double_p),
+        ("sonar_heading", c_double_p), ("sonar_information", c_double_p), ("sonar_landmark_mean", c_double_p),
+        ("sonar_T_SSo", c_double_p),
+        ("num_depth", C.c_int32), ("depth_pose", c_int32_p), ("depth_measurement", c_double_p),
+        ("depth_first", c_double_p), ("depth_information", c_double_p),
+        ("marg_num_blocks", C.c_int32), ("marg_dim", C.c_int32), ("marg_block_kind", c_int32_p),
+        ("marg_block_index", c_int32_p), ("marg_linearization_points", c_double_p), ("marg_J", c_double_p),
+        ("marg_e0", c_double_p),
+    ]
+
+
+class SvinBaOptions(C.Structure):
+    _fields_ = [
+        ("max_num_iterations", C.c_int32), ("min_num_iterations", C.c_int32), ("time_limit_seconds", C.c_double),
+        ("initial_trust_region_radius", C.c_double), ("max_trust_region_radius", C.c_double),
+        ("min_trust_region_radius", C.c_double), ("min_relative_decrease", C.c_double),
+        ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double), ("function_tolerance", C.c_double),
+        ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+        ("max_num_consecutive_invalid_steps", C.c_int32), ("jacobi_scaling", C.c_int32),
+        ("compute_landmark_quality", C.c_int32),
+    ]
+
+
+class SvinBaSummary(C.Structure):
+    _fields_ = [
+        ("iterations", C.c_int32), ("num_successful_steps", C.c_int32), ("termination", C.c_int32),
+        ("imu_repropagations", C.c_int32), ("initial_cost", C.c_double), ("final_cost", C.c_double),
+        ("final_trust_region_radius", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class SvinBaEvaluation(C.Structure):
+    _fields_ = [(n, c_double_p) for n in (
+        "reproj_residuals", "reproj_J_pose", "reproj_J_landmark", "reproj_J_extrinsics", "imu_residuals",
+        "imu_J_pose0", "imu_J_speedbias0", "imu_J_pose1", "imu_J_speedbias1", "cost")]
+
+
+class SvinBaTimings(C.Structure):
+    _fields_ = [("solve_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+class SvinError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/svin_b200.h declares (tests check the .so exports each one)
+EXPORTED_SYMBOLS = [
+    "svin_last_error", "svin_version", "svin_ba_default_options", "svin_ba_create", "svin_ba_destroy",
+    "svin_ba_upload", "svin_ba_evaluate", "svin_ba_solve", "svin_ba_download", "svin_ba_reset", "svin_ba_optimize",
+    "svin_ba_timings",
+]
+
+
+def load(path: str | None = None) -> C.CDLL:
+    """Load the CUDA engine.  Raises if the shared library has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise SvinError(
+            f"{p} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+            "There is no CPU fallback.")
+    lib = C.CDLL(p)
+    lib.svin_last_error.restype = C.c_char_p
+    lib.svin_version.restype = C.c_char_p
+    lib.svin_ba_default_options.argtypes = [C.POINTER(SvinBaOptions)]
+    lib.svin_ba_default_options.restype = None
+    lib.svin_ba_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.svin_ba_destroy.argtypes = [C.c_void_p]
+    lib.svin_ba_destroy.restype = None
+    lib.svin_ba_upload.argtypes = [C.c_void_p, C.POINTER(SvinBaWindow), C.c_int32]
+    lib.svin_ba_evaluate.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SvinBaEvaluation)]
+    lib.svin_ba_solve.argtypes = [C.c_void_p, C.POINTER(SvinBaOptions), C.POINTER(SvinBaSummary)]
+    lib.svin_ba_download.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SvinBaWindow), c_double_p]
+    lib.svin_ba_reset.argtypes = [C.c_void_p]
+    lib.svin_ba_optimize.argtypes = [C.c_void_p, C.POINTER(SvinBaWindow), C.c_int32, C.POINTER(SvinBaOptions),
+                                     C.POINTER(SvinBaSummary), C.POINTER(c_double_p)]
+    lib.svin_ba_timings.argtypes = [C.c_void_p, C.POINTER(SvinBaTimings)]
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def check(status: int, lib: C.CDLL | None = None) -> None:
+    if status != 0:
+        lib = lib or load()
+        msg = lib.svin_last_error()
+        raise SvinError(f"svin_b200 error {status}: {msg.decode() if msg else '?'}")

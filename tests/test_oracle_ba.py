@@ -1,0 +1,239 @@
+"""CPU tests pinning the BA oracle against what the reference's own tests pin.
+
+The reference holds no golden vectors for this path; its tests assert
+numeric-differentiation agreement of the analytic Jacobians and convergence tolerances.
+Each test below names the reference test whose check it reproduces.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from oracle_lib import P
+from svin_b200 import capi
+from svin_b200.synthetic import EUROC_IMU, EUROC_INTRINSICS, make_window, pose_oplus, simulate_trajectory
+from svin_b200.window import default_options
+
+
+def _reproj(lib, pose, hp, extr, intr, z, info):
+    r, J0, J1, J2 = np.zeros(2), np.zeros((2, 6)), np.zeros((2, 3)), np.zeros((2, 6))
+    valid = C.c_int(0)
+    lib.svin_oracle_reprojection(P(pose), P(hp), P(extr), P(intr), P(z), P(info), P(r), P(J0), P(J1), P(J2),
+                                 C.byref(valid))
+    return r, J0, J1, J2, valid.value
+
+
+def test_reprojection_jacobians_match_numeric_differences():
+    # Map::isJacobianCorrect (Map.cpp:153-252) / TestReprojectionError.cpp: analytic minimal
+    # Jacobians vs central differences through the manifold plus().
+    lib = oracle_lib.load()
+    rng = np.random.default_rng(0)
+    intr = EUROC_INTRINSICS[0].copy()
+    for trial in range(20):
+        pose = pose_oplus(np.array([0, 0, 0, 0, 0, 0, 1.0]), rng.normal(0, 0.5, 6))
+        extr = pose_oplus(np.array([0, 0, 0, 0, 0, 0, 1.0]), rng.normal(0, 0.1, 6))
+        # point in front of the camera
+        hp = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(3, 8), 1.0])
+        # move it to world: p_W = T_WS T_SC p_C  -- use numdiff-independent construction
+        from svin_b200.synthetic import quat_to_rot
+        Rws, Rsc = quat_to_rot(pose[3:]), quat_to_rot(extr[3:])
+        pw = Rws @ (Rsc @ hp[:3] + extr[:3]) + pose[:3]
+        w_h = rng.uniform(0.5, 2.0)
+        hp_W = np.concatenate([pw * w_h, [w_h]])
+        z = rng.uniform(100, 300, 2)
+        info = np.array([2.0, 0.3, 0.3, 1.5])
+        r, J0, J1, J2, valid = _reproj(lib, pose, hp_W, extr, intr, z, info)
+        assert valid == 1
+        dx = 1e-6
+        for which, J, dim in ((0, J0, 6), (1, J1, 3), (2, J2, 6)):
+            Jn = np.zeros_like(J)
+            for k in range(dim):
+                d = np.zeros(dim)
+                d[k] = dx
+                if which == 0:
+                    rp = _reproj(lib, pose_oplus(pose, d), hp_W, extr, intr, z, info)[0]
+                    rm = _reproj(lib, pose_oplus(pose, -d), hp_W, extr, intr, z, info)[0]
+                elif which == 1:
+                    rp = _reproj(lib, pose, hp_W + np.append(d, 0), extr, intr, z, info)[0]
+                    rm = _reproj(lib, pose, hp_W - np.append(d, 0), extr, intr, z, info)[0]
+                else:
+                    rp = _reproj(lib, pose, hp_W, pose_oplus(extr, d), intr, z, info)[0]
+                    rm = _reproj(lib, pose, hp_W, pose_oplus(extr, -d), intr, z, info)[0]
+                Jn[:, k] = (rp - rm) / (2 * dx)
+            assert np.abs(J - Jn).max() < 1e-4 * max(1.0, np.abs(J).max()), (which, J, Jn)
+
+
+def test_reprojection_invalid_point_zeroes_jacobians():
+    # ReprojectionError.hpp impl:139-147,162,185,208: z/w < 0.2 m -> Jacobians set to zero, residual kept.
+    lib = oracle_lib.load()
+    pose = np.array([0, 0, 0, 0, 0, 0, 1.0])
+    extr = np.array([0, 0, 0, 0, 0, 0, 1.0])
+    hp = np.array([0.01, 0.02, 0.1, 1.0])
+    r, J0, J1, J2, valid = _reproj(lib, pose, hp, extr, EUROC_INTRINSICS[0].copy(), np.array([300.0, 200.0]),
+                                   np.array([1.0, 0, 0, 1.0]))
+    assert valid == 0
+    assert np.all(J0 == 0) and np.all(J1 == 0) and np.all(J2 == 0)
+    assert np.all(np.isfinite(r)) and np.abs(r).max() > 0
+
+
+def test_project_backproject_roundtrip():
+    # TestPinholeCamera.cpp:78: project(backProject(ip)) within 0.01 px
+    lib = oracle_lib.load()
+    rng = np.random.default_rng(1)
+    for c in range(2):
+        intr = EUROC_INTRINSICS[c].copy()
+        for _ in range(200):
+            ip = np.array([rng.uniform(0, 751), rng.uniform(0, 479)])
+            d, ip2 = np.zeros(3), np.zeros(2)
+            assert lib.svin_oracle_backproject(P(intr), P(ip), P(d)) == 1
+            st = lib.svin_oracle_project(P(intr), P(d), P(ip2), capi.c_double_p(), 752, 480)
+            assert st == 0
+            assert np.abs(ip - ip2).max() < 0.01
+
+
+def _imu_eval(lib, traj, params, t0, t1, pose0, sb0, pose1, sb1):
+    r = np.zeros(15)
+    J0, J1, J2, J3 = np.zeros((15, 6)), np.zeros((15, 9)), np.zeros((15, 6)), np.zeros((15, 9))
+    p = capi.SvinImuParams(**params)
+    t = np.ascontiguousarray(traj["t_imu"])
+    g, a = np.ascontiguousarray(traj["gyr"]), np.ascontiguousarray(traj["acc"])
+    lib.svin_oracle_imu(len(t), t.ctypes.data_as(capi.c_int64_p), P(g), P(a), C.byref(p), int(t0), int(t1), P(pose0),
+                        P(sb0), P(pose1), P(sb1), P(r), P(J0), P(J1), P(J2), P(J3))
+    return r, J0, J1, J2, J3
+
+
+def test_imu_error_jacobians_match_numeric_differences():
+    # TestImuError.cpp:286-371: analytic minimal Jacobians J0..J3 vs central differences (dx = 1e-6).
+    # The reference asserts an absolute ||dJ|| < 1e-3 on its own scene; entries here reach 1e5
+    # (sqrt information), so the same check is applied relative to ||J||.
+    lib = oracle_lib.load()
+    rng = np.random.default_rng(5)
+    params = dict(EUROC_IMU)
+    traj = simulate_trajectory(rng, 1.0, params)
+    i0, i1 = 102, 352  # 1 kHz grid, off the IMU sample grid
+    t0, t1 = i0 * 1000000, i1 * 1000000
+    pose0 = np.concatenate([traj["r"][i0], traj["q"][i0]])
+    pose1 = np.concatenate([traj["r"][i1], traj["q"][i1]])
+    sb0 = np.concatenate([traj["v"][i0], np.zeros(6)])
+    sb1 = np.concatenate([traj["v"][i1], np.zeros(6)])
+    pose1 = pose_oplus(pose1, np.concatenate([rng.normal(0, 0.01, 3), rng.normal(0, 0.01, 3)]))
+    r, J0, J1, J2, J3 = _imu_eval(lib, traj, params, t0, t1, pose0, sb0, pose1, sb1)
+    # at ground truth the (weighted) error is a few sigma, not thousands
+    rt = _imu_eval(lib, traj, params, t0, t1, pose0, sb0, np.concatenate([traj["r"][i1], traj["q"][i1]]), sb1)[0]
+    assert np.linalg.norm(rt) < 10.0
+    dx = 1e-6
+    for which, J, dim in ((0, J0, 6), (1, J1, 9), (2, J2, 6), (3, J3, 9)):
+        Jn = np.zeros_like(J)
+        for k in range(dim):
+            d = np.zeros(dim)
+            d[k] = dx
+            args_p = [pose0, sb0, pose1, sb1]
+            args_m = [pose0, sb0, pose1, sb1]
+            if which in (0, 2):
+                args_p[which] = pose_oplus(args_p[which], d)
+                args_m[which] = pose_oplus(args_m[which], -d)
+            else:
+                args_p[which] = args_p[which] + d
+                args_m[which] = args_m[which] - d
+            rp = _imu_eval(lib, traj, params, t0, t1, *args_p)[0]
+            rm = _imu_eval(lib, traj, params, t0, t1, *args_m)[0]
+            Jn[:, k] = (rp - rm) / (2 * dx)
+        assert np.linalg.norm(J - Jn) < 1e-3 * np.linalg.norm(J), (which, np.linalg.norm(J - Jn), np.linalg.norm(J))
+
+
+def test_singular_pose_prior_information_follows_eigen_llt_early_exit():
+    # Estimator.cpp:321-326 builds diag(1e8,1e8,1e8,0,0,1e8); PoseError.cpp:70-76 runs Eigen::LLT on it.
+    # Eigen's unblocked LLT stops at the first non-positive pivot and leaves the rest of the matrix
+    # untouched, so matrixL().transpose() is diag(1e4,1e4,1e4,0,0,1e8).
+    lib = oracle_lib.load()
+    info = np.zeros((6, 6))
+    info[0, 0] = info[1, 1] = info[2, 2] = info[5, 5] = 1e8
+    U = np.zeros((6, 6))
+    lib.svin_oracle_sqrt_information(P(info), P(U), 6)
+    assert np.allclose(np.diag(U), [1e4, 1e4, 1e4, 0, 0, 1e8])
+    assert np.count_nonzero(U - np.diag(np.diag(U))) == 0
+    # regular SPD case equals numpy's Cholesky
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((9, 9))
+    S = A @ A.T + 9 * np.eye(9)
+    U9 = np.zeros((9, 9))
+    lib.svin_oracle_sqrt_information(P(S), P(U9), 9)
+    assert np.allclose(U9, np.linalg.cholesky(S).T, atol=1e-12)
+
+
+def test_pose_manifold_plus_minus_roundtrip():
+    # TestTransformation / PoseManifold::verify: minus(plus(x, d), x) == d to first order
+    lib = oracle_lib.load()
+    rng = np.random.default_rng(3)
+    x = pose_oplus(np.array([0, 0, 0, 0, 0, 0, 1.0]), rng.normal(0, 1, 6))
+    d = rng.normal(0, 1e-3, 6)
+    xp, d2 = np.zeros(7), np.zeros(6)
+    lib.svin_oracle_pose_plus(P(x), P(d), P(xp))
+    lib.svin_oracle_pose_minus(P(xp), P(x), P(d2))
+    assert np.allclose(d, d2, atol=1e-8)
+    assert abs(np.linalg.norm(xp[3:]) - 1) < 1e-15
+
+
+def _angle(q_a, q_b):
+    from svin_b200.synthetic import quat_mul
+    qi = q_b * np.array([-1, -1, -1, 1.0])
+    d = quat_mul(q_a[None], qi[None])[0]
+    return 2 * np.linalg.norm(d[:3])
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_solver_converges_like_TestEstimator(seed):
+    # TestEstimator.cpp:187-212: optimize(10, ...) on a synthetic stereo+IMU window, then
+    # rotation error < 1e-2 rad, translation error < 1e-1 m, speed/bias error < 0.04.
+    w, truth = make_window(seed=seed, num_keyframes=4, num_imu_frames=3, num_landmarks=400, mode="initial")
+    summary, q = oracle_lib.solve(w, default_options(max_num_iterations=10))
+    assert summary["final_cost"] < 1e-3 * summary["initial_cost"]
+    P_ = 7
+    for f in range(P_):
+        assert np.linalg.norm(w.pose_blocks[f, :3] - truth["pose_blocks"][f, :3]) < 1e-1
+        assert _angle(w.pose_blocks[f, 3:], truth["pose_blocks"][f, 3:]) < 1e-2
+    assert np.abs(w.speedbias[:, :3] - truth["speedbias"][:, :3]).max() < 0.04
+    assert np.all((q >= 0) & (q <= 1))
+
+
+def test_solution_is_a_stationary_point_of_the_robust_cost():
+    # independent of the Schur/dogleg internals: after many iterations the directional derivative of the
+    # total cost (evaluated by the oracle's term code) along random manifold directions vanishes.
+    w, _ = make_window(seed=21, num_keyframes=3, num_imu_frames=2, num_landmarks=60, mode="initial")
+    c0 = oracle_lib.evaluate(w)["cost"][0]
+    opts = default_options(max_num_iterations=60, function_tolerance=1e-16, parameter_tolerance=1e-16,
+                           gradient_tolerance=1e-16)
+    oracle_lib.solve(w, opts, quality=False)
+    c1 = oracle_lib.evaluate(w)["cost"][0]
+    assert c1 < c0
+    rng = np.random.default_rng(0)
+
+    def cost_at(dp, dl, eps):
+        w2 = w.copy()
+        for i in range(len(w.pose_blocks)):
+            if not w.pose_fixed[i]:
+                w2.pose_blocks[i] = pose_oplus(w.pose_blocks[i], eps * dp[i])
+        w2.landmarks[:, :3] += eps * dl
+        return oracle_lib.evaluate(w2)["cost"][0]
+
+    for _ in range(3):
+        dp = rng.standard_normal((len(w.pose_blocks), 6)) * np.array([1, 1, 1, 0.2, 0.2, 0.2])
+        dl = rng.standard_normal((w.num_landmarks, 3))
+        eps = 1e-5
+        deriv = (cost_at(dp, dl, eps) - cost_at(dp, dl, -eps)) / (2 * eps)
+        curv = (cost_at(dp, dl, eps) - 2 * c1 + cost_at(dp, dl, -eps)) / eps ** 2
+        # |directional derivative| tiny compared with curvature * unit step
+        assert abs(deriv) < 1e-5 * abs(curv), (deriv, curv)
+
+
+def test_window_variants_solve(tmp_path):
+    # steady-state window with a marginalisation prior; Cave-shape terms (sonar, depth, extrinsics random walk)
+    w, _ = make_window(seed=31, num_keyframes=4, num_imu_frames=3, num_landmarks=200, mode="steady")
+    s, _ = oracle_lib.solve(w)
+    assert s["final_cost"] < s["initial_cost"] and np.isfinite(s["final_cost"])
+    w, _ = make_window(seed=32, num_keyframes=3, num_imu_frames=3, num_landmarks=200, mode="steady",
+                       extrinsics="random_walk", sonar=True, depth=True)
+    assert w.dense_dim() == 6 * (6 + 12) + 9 * 3
+    s, _ = oracle_lib.solve(w)
+    assert s["final_cost"] < s["initial_cost"] and np.isfinite(s["final_cost"])
