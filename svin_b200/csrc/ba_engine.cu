@@ -1,0 +1,924 @@
+// Host side of the BA engine: flattens SvinBaWindow batches into one device arena, drives the
+// trust-region slots on a CUDA stream and implements the svin_ba_* C ABI (include/svin_b200.h).
+//
+// Reference seam: okvis::Estimator::optimize -> okvis::ceres::Map::solve()
+// (okvis_ros/okvis/okvis_ceres/src/Estimator.cpp:876-929, include/okvis/ceres/Map.hpp:347).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "ba_kernels.cuh"
+#include "common.hpp"
+
+namespace svin {
+void launch_gather_state(const Batch& b, const int* pose_win, const int* sb_win, double* pose_out, double* sb_out,
+                         double* lm_out, cudaStream_t st);
+// x <- uploaded initial values (both state buffers)
+static void launch_reset_state(const Batch& b, cudaStream_t st) {
+  for (int k = 0; k < 2; ++k) {
+    if (b.NPB) cudaMemcpyAsync(b.pose[k], b.pose_init, 56 * (size_t)b.NPB, cudaMemcpyDeviceToDevice, st);
+    if (b.NSB) cudaMemcpyAsync(b.sb[k], b.sb_init, 72 * (size_t)b.NSB, cudaMemcpyDeviceToDevice, st);
+    if (b.NL) cudaMemcpyAsync(b.lm[k], b.lm_init, 32 * (size_t)b.NL, cudaMemcpyDeviceToDevice, st);
+  }
+}
+}  // namespace svin
+
+using namespace svin;
+
+namespace {
+
+// Eigen::LLT (unblocked, lower) incl. its early exit on a non-positive pivot, then U = L^T.
+// (ReprojectionError.hpp impl:66-72, PoseError.cpp:70-76, ...)
+void llt_sqrt_information(const double* info, double* U, int n) {
+  std::vector<double> L(info, info + (size_t)n * n);
+  for (int k = 0; k < n; ++k) {
+    double x = L[(size_t)k * n + k];
+    for (int j = 0; j < k; ++j) x -= L[(size_t)k * n + j] * L[(size_t)k * n + j];
+    if (x <= 0.0) break;
+    x = std::sqrt(x);
+    L[(size_t)k * n + k] = x;
+    for (int i = k + 1; i < n; ++i) {
+      double s = L[(size_t)i * n + k];
+      for (int j = 0; j < k; ++j) s -= L[(size_t)i * n + j] * L[(size_t)k * n + j];
+      L[(size_t)i * n + k] = s / x;
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) U[(size_t)i * n + j] = (j >= i) ? L[(size_t)j * n + i] : 0.0;
+}
+
+struct Region {
+  size_t bytes = 0;
+  size_t add(size_t b) {
+    const size_t off = bytes;
+    bytes += (b + 255) & ~(size_t)255;
+    return off;
+  }
+};
+
+}  // namespace
+
+struct svin_ba_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  Batch b{};
+  bool uploaded = false;
+  // arenas
+  void* d_in = nullptr;       // uploaded inputs
+  size_t d_in_cap = 0;
+  void* h_in = nullptr;       // pinned staging mirror of d_in
+  size_t h_in_cap = 0;
+  void* d_work = nullptr;     // scratch
+  size_t d_work_cap = 0;
+  void* d_out = nullptr;      // results gathered for download
+  size_t d_out_cap = 0;
+  void* h_out = nullptr;      // pinned
+  size_t h_out_cap = 0;
+  size_t in_bytes = 0, out_bytes = 0;
+  // host metadata
+  std::vector<WinDesc> h_win;
+  std::vector<int> obs_perm;  // sorted obs position -> caller's obs index (window-local)
+  int n_max = 0, smem_bytes = 0;
+  int* d_active = nullptr;
+  int* h_active = nullptr;
+  // pointers into arenas kept for reset/download
+  WinState* d_ws_init = nullptr;
+  ImuCache* d_imu_cache_init = nullptr;
+  int *d_pose_win = nullptr, *d_sb_win = nullptr;
+  double *d_pose_out = nullptr, *d_sb_out = nullptr, *d_lm_out = nullptr;
+  size_t out_off_pose = 0, out_off_sb = 0, out_off_lm = 0, out_off_q = 0, out_off_ws = 0;
+  size_t clear_bytes = 0;
+  void* d_clear = nullptr;
+  bool quality_valid = false;
+  bool solved = false;
+  SvinBaTimings tm{};
+};
+
+namespace {
+
+int ensure(void** p, size_t* cap, size_t need, bool pinned) {
+  if (*cap >= need && *p) return SVIN_OK;
+  if (*p) {
+    if (pinned)
+      cudaFreeHost(*p);
+    else
+      cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+  }
+  const size_t want = need + need / 4 + 4096;
+  cudaError_t e = pinned ? cudaMallocHost(p, want) : cudaMalloc(p, want);
+  if (e != cudaSuccess) {
+    set_error(std::string("allocation of ") + std::to_string(want) + " bytes failed: " + cudaGetErrorString(e));
+    cudaGetLastError();
+    return SVIN_ERR_OUT_OF_MEMORY;
+  }
+  *cap = want;
+  return SVIN_OK;
+}
+
+int validate(const SvinBaWindow& w, int idx) {
+  auto bad = [&](const char* what) {
+    set_error("window " + std::to_string(idx) + ": " + what);
+    return SVIN_ERR_INVALID_ARGUMENT;
+  };
+  if (w.num_pose_blocks < 0 || w.num_speedbias < 0 || w.num_landmarks < 0 || w.num_obs < 0) return bad("negative count");
+  if (w.num_pose_blocks && (!w.pose_blocks || !w.pose_fixed)) return bad("pose_blocks/pose_fixed is NULL");
+  if (w.num_speedbias && (!w.speedbias || !w.speedbias_fixed)) return bad("speedbias/speedbias_fixed is NULL");
+  if (w.num_landmarks && !w.landmarks) return bad("landmarks is NULL");
+  if (w.num_obs && (!w.obs_pose || !w.obs_landmark || !w.obs_extrinsics || !w.obs_camera || !w.obs_measurement ||
+                    !w.obs_information || !w.intrinsics))
+    return bad("observation arrays / intrinsics are NULL");
+  for (int i = 0; i < w.num_obs; ++i) {
+    if (w.obs_pose[i] < 0 || w.obs_pose[i] >= w.num_pose_blocks) return bad("obs_pose out of range");
+    if (w.obs_extrinsics[i] < 0 || w.obs_extrinsics[i] >= w.num_pose_blocks) return bad("obs_extrinsics out of range");
+    if (w.obs_landmark[i] < 0 || w.obs_landmark[i] >= w.num_landmarks) return bad("obs_landmark out of range");
+    if (w.obs_camera[i] < 0 || w.obs_camera[i] >= w.num_cameras) return bad("obs_camera out of range");
+  }
+  for (int i = 0; i < w.num_imu; ++i) {
+    if (w.imu_pose0[i] < 0 || w.imu_pose0[i] >= w.num_pose_blocks || w.imu_pose1[i] < 0 ||
+        w.imu_pose1[i] >= w.num_pose_blocks || w.imu_speedbias0[i] < 0 || w.imu_speedbias0[i] >= w.num_speedbias ||
+        w.imu_speedbias1[i] < 0 || w.imu_speedbias1[i] >= w.num_speedbias)
+      return bad("IMU term block index out of range");
+    const int a = w.imu_meas_offset[i], e = w.imu_meas_offset[i + 1];
+    if (e - a < 2) return bad("IMU term needs at least two measurements");
+    if (w.imu_meas_t_ns[a] > w.imu_t0_ns[i] || w.imu_meas_t_ns[e - 1] < w.imu_t1_ns[i])
+      return bad("IMU measurements do not cover [t0, t1] (ImuError.cpp:66-73)");
+  }
+  for (int i = 0; i < w.num_pose_priors; ++i)
+    if (w.pose_prior_block[i] < 0 || w.pose_prior_block[i] >= w.num_pose_blocks) return bad("pose prior block");
+  for (int i = 0; i < w.num_speedbias_priors; ++i)
+    if (w.speedbias_prior_block[i] < 0 || w.speedbias_prior_block[i] >= w.num_speedbias) return bad("speedbias prior block");
+  for (int i = 0; i < w.num_relative_pose; ++i)
+    if (w.relative_pose_block0[i] < 0 || w.relative_pose_block0[i] >= w.num_pose_blocks ||
+        w.relative_pose_block1[i] < 0 || w.relative_pose_block1[i] >= w.num_pose_blocks)
+      return bad("relative pose block");
+  for (int i = 0; i < w.num_sonar; ++i)
+    if (w.sonar_pose[i] < 0 || w.sonar_pose[i] >= w.num_pose_blocks) return bad("sonar pose");
+  for (int i = 0; i < w.num_depth; ++i)
+    if (w.depth_pose[i] < 0 || w.depth_pose[i] >= w.num_pose_blocks) return bad("depth pose");
+  if (w.marg_num_blocks > 64) return bad("marginalisation prior with more than 64 blocks is not supported");
+  if (w.marg_dim > 512) return bad("marginalisation prior dimension > 512 is not supported");
+  int md = 0;
+  for (int i = 0; i < w.marg_num_blocks; ++i) {
+    const int k = w.marg_block_kind[i], x = w.marg_block_index[i];
+    if (k == SVIN_BLOCK_LANDMARK)
+      return bad("landmark blocks inside the marginalisation prior are not supported (OKVIS marginalises them out, "
+                 "Estimator.cpp:731-741)");
+    if (k == SVIN_BLOCK_POSE) {
+      if (x < 0 || x >= w.num_pose_blocks) return bad("marg pose block index");
+      if (!w.pose_fixed[x]) md += 6;
+    } else if (k == SVIN_BLOCK_SPEEDBIAS) {
+      if (x < 0 || x >= w.num_speedbias) return bad("marg speedbias block index");
+      if (!w.speedbias_fixed[x]) md += 9;
+    } else {
+      return bad("unknown marg block kind");
+    }
+  }
+  if (md != w.marg_dim) return bad("marg_dim does not equal the sum of the minimal dimensions of its free blocks");
+  return SVIN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void svin_ba_default_options(SvinBaOptions* o) {
+  if (!o) return;
+  o->max_num_iterations = 10;
+  o->min_num_iterations = 3;
+  o->time_limit_seconds = -1.0;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->jacobi_scaling = 1;
+  o->compute_landmark_quality = 1;
+}
+
+int svin_ba_create(int device, svin_ba_ctx** out) {
+  if (!out) {
+    set_error("svin_ba_create: out is NULL");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: the svin_b200 engine has no CPU fallback");
+    return SVIN_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) {
+    set_error("device index out of range");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  SVIN_CUDA(cudaSetDevice(device));
+  svin_ba_ctx* c = new svin_ba_ctx();
+  c->device = device;
+  SVIN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto& ev : c->ev) SVIN_CUDA(cudaEventCreate(&ev));
+  SVIN_CUDA(cudaMalloc(&c->d_active, sizeof(int)));
+  SVIN_CUDA(cudaMallocHost(&c->h_active, sizeof(int)));
+  *out = c;
+  return SVIN_OK;
+}
+
+void svin_ba_destroy(svin_ba_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_in);
+  cudaFree(c->d_work);
+  cudaFree(c->d_out);
+  cudaFreeHost(c->h_in);
+  cudaFreeHost(c->h_out);
+  cudaFree(c->d_active);
+  cudaFreeHost(c->h_active);
+  for (auto& ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
+  if (!c || !wins || B <= 0) {
+    set_error("svin_ba_upload: invalid arguments");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  SVIN_CUDA(cudaSetDevice(c->device));
+  for (int i = 0; i < B; ++i) {
+    const int rc = validate(wins[i], i);
+    if (rc != SVIN_OK) return rc;
+  }
+  c->uploaded = false;
+  c->solved = false;
+  // ---------------- totals
+  long long NPB = 0, NSB = 0, NL = 0, NC = 0, NOBS = 0, NIMU = 0, NMEAS = 0, NPP = 0, NSP = 0, NRP = 0, NSO = 0, NDE = 0;
+  long long NMB = 0, NMJ = 0, NME = 0, NMLIN = 0, ND = 0, NROWS = 0, NH = 0, NJD = 0;
+  int n_obs_tiles = 0, n_lm_tiles = 0;
+  c->h_win.assign(B, WinDesc{});
+  c->n_max = 0;
+  int has_ext = 0;
+  for (int i = 0; i < B; ++i) {
+    const SvinBaWindow& w = wins[i];
+    WinDesc& d = c->h_win[i];
+    d.pose_begin = (int)NPB; NPB += w.num_pose_blocks; d.pose_end = (int)NPB;
+    d.sb_begin = (int)NSB; NSB += w.num_speedbias; d.sb_end = (int)NSB;
+    d.lm_begin = (int)NL; NL += w.num_landmarks; d.lm_end = (int)NL;
+    d.obs_begin = (int)NOBS; NOBS += w.num_obs; d.obs_end = (int)NOBS;
+    NC += w.num_cameras;
+    int n = 0;
+    for (int k = 0; k < w.num_pose_blocks; ++k) n += w.pose_fixed[k] ? 0 : 6;
+    for (int k = 0; k < w.num_speedbias; ++k) n += w.speedbias_fixed[k] ? 0 : 9;
+    d.n_dense = n;
+    c->n_max = std::max(c->n_max, n);
+    d.imu_begin = (int)NIMU; NIMU += w.num_imu; d.imu_end = (int)NIMU;
+    if (w.num_imu) NMEAS += w.imu_meas_offset[w.num_imu];
+    d.pp_begin = (int)NPP; NPP += w.num_pose_priors; d.pp_end = (int)NPP;
+    d.sp_begin = (int)NSP; NSP += w.num_speedbias_priors; d.sp_end = (int)NSP;
+    d.rp_begin = (int)NRP; NRP += w.num_relative_pose; d.rp_end = (int)NRP;
+    d.so_begin = (int)NSO; NSO += w.num_sonar; d.so_end = (int)NSO;
+    d.de_begin = (int)NDE; NDE += w.num_depth; d.de_end = (int)NDE;
+    d.marg_blk_begin = (int)NMB; NMB += w.marg_num_blocks; d.marg_blk_end = (int)NMB;
+    d.marg_dim = w.marg_dim;
+    d.margJ_off = NMJ; NMJ += (long long)w.marg_dim * w.marg_dim;
+    d.marg_e0_off = (int)NME; NME += w.marg_dim;
+    d.marg_lin_off = (int)NMLIN;
+    for (int k = 0; k < w.marg_num_blocks; ++k) NMLIN += (w.marg_block_kind[k] == SVIN_BLOCK_POSE) ? 7 : 9;
+    const int rows = 15 * w.num_imu + 6 * w.num_pose_priors + 9 * w.num_speedbias_priors + 6 * w.num_relative_pose +
+                     w.num_sonar + w.num_depth + w.marg_dim;
+    d.n_rows = rows;
+    d.d_off = (int)ND; ND += n;
+    d.rd_off = (int)NROWS; NROWS += rows;
+    d.H_off = NH; NH += (long long)n * n;
+    d.Jd_off = NJD; NJD += (long long)rows * n;
+    d.loss_type = w.loss_type;
+    d.loss_scale = w.loss_scale;
+    d.imu = ImuP{w.imu_params.sigma_g_c, w.imu_params.sigma_a_c, w.imu_params.sigma_gw_c, w.imu_params.sigma_aw_c,
+                 w.imu_params.g, w.imu_params.g_max, w.imu_params.a_max};
+    for (int k = 0; k < 7; ++k) d.T_SSo[k] = (w.num_sonar && w.sonar_T_SSo) ? w.sonar_T_SSo[k] : (k == 6 ? 1.0 : 0.0);
+    n_obs_tiles += (w.num_obs + kObsTile - 1) / kObsTile;
+    n_lm_tiles += (w.num_landmarks + kLmTile - 1) / kLmTile;
+    for (int o = 0; o < w.num_obs && !has_ext; ++o)
+      if (!w.pose_fixed[w.obs_extrinsics[o]]) has_ext = 1;
+  }
+  if (NOBS >= (1ll << 31) || NH >= (1ll << 40)) {
+    set_error("batch too large");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  // ---------------- input arena layout
+  Region in;
+  const size_t o_win = in.add(sizeof(WinDesc) * B), o_ws = in.add(sizeof(WinState) * B);
+  const size_t o_pose = in.add(8 * 7 * NPB), o_sb = in.add(8 * 9 * NSB), o_lm = in.add(8 * 4 * NL);
+  const size_t o_poff = in.add(4 * NPB), o_sboff = in.add(4 * NSB), o_lmfix = in.add(NL), o_lmwin = in.add(4 * NL);
+  const size_t o_pwin = in.add(4 * NPB), o_sbwin = in.add(4 * NSB);
+  const size_t o_intr = in.add(8 * 8 * NC);
+  const size_t o_opose = in.add(4 * NOBS), o_olm = in.add(4 * NOBS), o_oext = in.add(4 * NOBS), o_ocam = in.add(4 * NOBS);
+  const size_t o_zx = in.add(8 * NOBS), o_zy = in.add(8 * NOBS), o_u00 = in.add(8 * NOBS), o_u01 = in.add(8 * NOBS),
+               o_u11 = in.add(8 * NOBS);
+  const size_t o_lmob = in.add(4 * (NL + 1));
+  const size_t o_otw = in.add(4 * (size_t)n_obs_tiles), o_otb = in.add(4 * (size_t)n_obs_tiles);
+  const size_t o_ltw = in.add(4 * (size_t)n_lm_tiles), o_ltb = in.add(4 * (size_t)n_lm_tiles);
+  const size_t o_imu = in.add(sizeof(ImuTerm) * NIMU), o_imuc = in.add(sizeof(ImuCache) * NIMU);
+  const size_t o_mt = in.add(8 * NMEAS), o_mg = in.add(24 * NMEAS), o_ma = in.add(24 * NMEAS);
+  const size_t o_pp = in.add(sizeof(PosePrior) * NPP), o_sp = in.add(sizeof(SbPrior) * NSP);
+  const size_t o_rp = in.add(sizeof(RelPose) * NRP), o_so = in.add(sizeof(SonarTerm) * NSO);
+  const size_t o_de = in.add(sizeof(DepthTerm) * NDE), o_mb = in.add(sizeof(MargBlock) * NMB);
+  const size_t o_mJ = in.add(8 * NMJ), o_me = in.add(8 * NME), o_ml = in.add(8 * NMLIN);
+  int rc;
+  if ((rc = ensure(&c->h_in, &c->h_in_cap, in.bytes, true)) != SVIN_OK) return rc;
+  if ((rc = ensure(&c->d_in, &c->d_in_cap, in.bytes, false)) != SVIN_OK) return rc;
+  char* H = (char*)c->h_in;
+  auto hp = [&](size_t off) { return H + off; };
+  // ---------------- fill staging
+  WinDesc* hw = (WinDesc*)hp(o_win);
+  WinState* hs = (WinState*)hp(o_ws);
+  double *h_pose = (double*)hp(o_pose), *h_sb = (double*)hp(o_sb), *h_lm = (double*)hp(o_lm);
+  int *h_poff = (int*)hp(o_poff), *h_sboff = (int*)hp(o_sboff), *h_lmwin = (int*)hp(o_lmwin);
+  int *h_pwin = (int*)hp(o_pwin), *h_sbwin = (int*)hp(o_sbwin);
+  uint8_t* h_lmfix = (uint8_t*)hp(o_lmfix);
+  double* h_intr = (double*)hp(o_intr);
+  int *h_opose = (int*)hp(o_opose), *h_olm = (int*)hp(o_olm), *h_oext = (int*)hp(o_oext), *h_ocam = (int*)hp(o_ocam);
+  double *h_zx = (double*)hp(o_zx), *h_zy = (double*)hp(o_zy), *h_u00 = (double*)hp(o_u00), *h_u01 = (double*)hp(o_u01),
+         *h_u11 = (double*)hp(o_u11);
+  int* h_lmob = (int*)hp(o_lmob);
+  int *h_otw = (int*)hp(o_otw), *h_otb = (int*)hp(o_otb), *h_ltw = (int*)hp(o_ltw), *h_ltb = (int*)hp(o_ltb);
+  ImuTerm* h_imu = (ImuTerm*)hp(o_imu);
+  ImuCache* h_imuc = (ImuCache*)hp(o_imuc);
+  long long* h_mt = (long long*)hp(o_mt);
+  double *h_mg = (double*)hp(o_mg), *h_ma = (double*)hp(o_ma);
+  PosePrior* h_pp = (PosePrior*)hp(o_pp);
+  SbPrior* h_sp = (SbPrior*)hp(o_sp);
+  RelPose* h_rp = (RelPose*)hp(o_rp);
+  SonarTerm* h_so = (SonarTerm*)hp(o_so);
+  DepthTerm* h_de = (DepthTerm*)hp(o_de);
+  MargBlock* h_mb = (MargBlock*)hp(o_mb);
+  double *h_mJ = (double*)hp(o_mJ), *h_me = (double*)hp(o_me), *h_ml = (double*)hp(o_ml);
+
+  c->obs_perm.resize((size_t)NOBS);
+  int cam_base = 0, ot = 0, lt = 0;
+  long long meas_base = 0;
+  std::vector<int> order, cnt;
+  for (int i = 0; i < B; ++i) {
+    const SvinBaWindow& w = wins[i];
+    WinDesc& d = c->h_win[i];
+    std::memcpy(h_pose + 7 * (size_t)d.pose_begin, w.pose_blocks, 56 * (size_t)w.num_pose_blocks);
+    std::memcpy(h_sb + 9 * (size_t)d.sb_begin, w.speedbias, 72 * (size_t)w.num_speedbias);
+    std::memcpy(h_lm + 4 * (size_t)d.lm_begin, w.landmarks, 32 * (size_t)w.num_landmarks);
+    int off = 0;
+    for (int k = 0; k < w.num_pose_blocks; ++k) {
+      h_poff[d.pose_begin + k] = w.pose_fixed[k] ? -1 : off;
+      if (!w.pose_fixed[k]) off += 6;
+      h_pwin[d.pose_begin + k] = i;
+    }
+    for (int k = 0; k < w.num_speedbias; ++k) {
+      h_sboff[d.sb_begin + k] = w.speedbias_fixed[k] ? -1 : off;
+      if (!w.speedbias_fixed[k]) off += 9;
+      h_sbwin[d.sb_begin + k] = i;
+    }
+    for (int k = 0; k < w.num_landmarks; ++k) {
+      h_lmfix[d.lm_begin + k] = (w.landmark_fixed && w.landmark_fixed[k]) ? 1 : 0;
+      h_lmwin[d.lm_begin + k] = i;
+    }
+    std::memcpy(h_intr + 8 * (size_t)cam_base, w.intrinsics, 64 * (size_t)w.num_cameras);
+    // observations sorted by (landmark, pose, camera); identity when the caller already sorted them
+    const int N = w.num_obs;
+    order.resize(N);
+    std::iota(order.begin(), order.end(), 0);
+    bool sorted = true;
+    for (int o = 1; o < N && sorted; ++o) {
+      const int a = o - 1;
+      if (w.obs_landmark[a] > w.obs_landmark[o] ||
+          (w.obs_landmark[a] == w.obs_landmark[o] &&
+           (w.obs_pose[a] > w.obs_pose[o] || (w.obs_pose[a] == w.obs_pose[o] && w.obs_camera[a] > w.obs_camera[o]))))
+        sorted = false;
+    }
+    if (!sorted)
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b2) {
+        if (w.obs_landmark[a] != w.obs_landmark[b2]) return w.obs_landmark[a] < w.obs_landmark[b2];
+        if (w.obs_pose[a] != w.obs_pose[b2]) return w.obs_pose[a] < w.obs_pose[b2];
+        return w.obs_camera[a] < w.obs_camera[b2];
+      });
+    cnt.assign(w.num_landmarks + 1, 0);
+    for (int k = 0; k < N; ++k) {
+      const int o = order[k];
+      const size_t g = (size_t)d.obs_begin + k;
+      c->obs_perm[g] = o;
+      h_opose[g] = d.pose_begin + w.obs_pose[o];
+      h_olm[g] = d.lm_begin + w.obs_landmark[o];
+      h_oext[g] = d.pose_begin + w.obs_extrinsics[o];
+      h_ocam[g] = cam_base + w.obs_camera[o];
+      h_zx[g] = w.obs_measurement[2 * o];
+      h_zy[g] = w.obs_measurement[2 * o + 1];
+      double U[4];
+      llt_sqrt_information(w.obs_information + 4 * (size_t)o, U, 2);
+      h_u00[g] = U[0];
+      h_u01[g] = U[1];
+      h_u11[g] = U[3];
+      cnt[w.obs_landmark[o] + 1]++;
+    }
+    int run = d.obs_begin;
+    for (int k = 0; k < w.num_landmarks; ++k) {
+      h_lmob[d.lm_begin + k] = run;
+      run += cnt[k + 1];
+    }
+    for (int t0 = 0; t0 < N; t0 += kObsTile) {
+      h_otw[ot] = i;
+      h_otb[ot] = d.obs_begin + t0;
+      ++ot;
+    }
+    for (int t0 = 0; t0 < w.num_landmarks; t0 += kLmTile) {
+      h_ltw[lt] = i;
+      h_ltb[lt] = d.lm_begin + t0;
+      ++lt;
+    }
+    // dense terms, rows laid out IMU | pose priors | speedbias priors | relative pose | sonar | depth | marg
+    int row = 0;
+    for (int k = 0; k < w.num_imu; ++k) {
+      ImuTerm& t = h_imu[d.imu_begin + k];
+      t.pose0 = d.pose_begin + w.imu_pose0[k];
+      t.pose1 = d.pose_begin + w.imu_pose1[k];
+      t.sb0 = d.sb_begin + w.imu_speedbias0[k];
+      t.sb1 = d.sb_begin + w.imu_speedbias1[k];
+      t.meas_begin = (int)(meas_base + w.imu_meas_offset[k]);
+      t.meas_end = (int)(meas_base + w.imu_meas_offset[k + 1]);
+      t.row0 = row;
+      t.win = i;
+      t.t0 = w.imu_t0_ns[k];
+      t.t1 = w.imu_t1_ns[k];
+      row += 15;
+      ImuCache& ic = h_imuc[d.imu_begin + k];
+      std::memset(&ic, 0, sizeof ic);
+      ic.Delta_q[3] = 1.0;
+      ic.redo = 1;
+    }
+    if (w.num_imu) {
+      const int nm = w.imu_meas_offset[w.num_imu];
+      std::memcpy(h_mt + meas_base, w.imu_meas_t_ns, 8 * (size_t)nm);
+      std::memcpy(h_mg + 3 * meas_base, w.imu_meas_gyro, 24 * (size_t)nm);
+      std::memcpy(h_ma + 3 * meas_base, w.imu_meas_accel, 24 * (size_t)nm);
+      meas_base += nm;
+    }
+    for (int k = 0; k < w.num_pose_priors; ++k) {
+      PosePrior& t = h_pp[d.pp_begin + k];
+      t.block = d.pose_begin + w.pose_prior_block[k];
+      t.row0 = row;
+      t.win = i;
+      t.pad = 0;
+      std::memcpy(t.meas, w.pose_prior_measurement + 7 * (size_t)k, 56);
+      llt_sqrt_information(w.pose_prior_information + 36 * (size_t)k, t.U, 6);
+      row += 6;
+    }
+    for (int k = 0; k < w.num_speedbias_priors; ++k) {
+      SbPrior& t = h_sp[d.sp_begin + k];
+      t.block = d.sb_begin + w.speedbias_prior_block[k];
+      t.row0 = row;
+      t.win = i;
+      t.pad = 0;
+      std::memcpy(t.meas, w.speedbias_prior_measurement + 9 * (size_t)k, 72);
+      llt_sqrt_information(w.speedbias_prior_information + 81 * (size_t)k, t.U, 9);
+      row += 9;
+    }
+    for (int k = 0; k < w.num_relative_pose; ++k) {
+      RelPose& t = h_rp[d.rp_begin + k];
+      t.block0 = d.pose_begin + w.relative_pose_block0[k];
+      t.block1 = d.pose_begin + w.relative_pose_block1[k];
+      t.row0 = row;
+      t.win = i;
+      llt_sqrt_information(w.relative_pose_information + 36 * (size_t)k, t.U, 6);
+      row += 6;
+    }
+    for (int k = 0; k < w.num_sonar; ++k) {
+      SonarTerm& t = h_so[d.so_begin + k];
+      t.pose = d.pose_begin + w.sonar_pose[k];
+      t.row0 = row;
+      t.win = i;
+      t.pad = 0;
+      t.range = w.sonar_range[k];
+      t.heading = w.sonar_heading[k];
+      t.sqrt_info = std::sqrt(w.sonar_information[k]);  // SonarError.cpp:97-104
+      for (int x = 0; x < 3; ++x) t.mean[x] = w.sonar_landmark_mean[3 * (size_t)k + x];
+      row += 1;
+    }
+    for (int k = 0; k < w.num_depth; ++k) {
+      DepthTerm& t = h_de[d.de_begin + k];
+      t.pose = d.pose_begin + w.depth_pose[k];
+      t.row0 = row;
+      t.win = i;
+      t.pad = 0;
+      t.depth = w.depth_measurement[k];
+      t.first = w.depth_first[k];
+      t.sqrt_info = std::sqrt(w.depth_information[k]);  // DepthError.cpp:55-62
+      row += 1;
+    }
+    d.marg_row0 = row;
+    int col = 0, lin = 0;
+    for (int k = 0; k < w.marg_num_blocks; ++k) {
+      MargBlock& mb = h_mb[d.marg_blk_begin + k];
+      mb.kind = w.marg_block_kind[k];
+      const int x = w.marg_block_index[k];
+      const bool is_pose = mb.kind == SVIN_BLOCK_POSE;
+      const bool fixed = is_pose ? w.pose_fixed[x] : w.speedbias_fixed[x];
+      mb.index = (is_pose ? d.pose_begin : d.sb_begin) + x;
+      mb.col0 = fixed ? -1 : col;
+      mb.lin_off = lin;
+      if (!fixed) col += is_pose ? 6 : 9;
+      lin += is_pose ? 7 : 9;
+    }
+    if (w.marg_dim) {
+      std::memcpy(h_mJ + d.margJ_off, w.marg_J, 8 * (size_t)w.marg_dim * w.marg_dim);
+      std::memcpy(h_me + d.marg_e0_off, w.marg_e0, 8 * (size_t)w.marg_dim);
+      std::memcpy(h_ml + d.marg_lin_off, w.marg_linearization_points, 8 * (size_t)lin);
+    }
+    hw[i] = d;
+    WinState& s = hs[i];
+    std::memset(&s, 0, sizeof s);
+    s.radius = 1e4;  // overwritten by svin_ba_solve with the options' initial radius
+    s.mu = 1e-8;
+    s.last_successful = 1;
+    cam_base += w.num_cameras;
+  }
+  h_lmob[NL] = (int)NOBS;
+
+  // ---------------- work arena
+  const size_t S = ((size_t)NOBS + 31) & ~(size_t)31;
+  Region wk;
+  size_t o_poseb[2], o_sbb[2], o_lmb[2], o_r[2], o_Jp[2], o_Jl[2], o_Je[2], o_Jd[2], o_rd[2];
+  for (int k = 0; k < 2; ++k) {
+    o_poseb[k] = wk.add(56 * NPB);
+    o_sbb[k] = wk.add(72 * NSB);
+    o_lmb[k] = wk.add(32 * NL);
+    o_r[k] = wk.add(8 * 2 * S);
+    o_Jp[k] = wk.add(8 * 12 * S);
+    o_Jl[k] = wk.add(8 * 6 * S);
+    o_Je[k] = has_ext ? wk.add(8 * 12 * S) : 0;
+    o_Jd[k] = wk.add(8 * NJD);
+    o_rd[k] = wk.add(8 * NROWS);
+  }
+  const size_t o_wsw = wk.add(sizeof(WinState) * B), o_imucw = wk.add(sizeof(ImuCache) * NIMU);
+  const size_t o_lms = wk.add(24 * NL), o_lmV = wk.add(48 * NL), o_lmb2 = wk.add(24 * NL), o_lmd = wk.add(24 * NL),
+               o_lmg = wk.add(24 * NL), o_lmgn = wk.add(24 * NL);
+  // cleared every slot: H, g_red, g_raw, Hdiag (kept contiguous)
+  const size_t o_clear = wk.bytes;
+  const size_t o_H = wk.add(8 * NH), o_gred = wk.add(8 * ND), o_graw = wk.add(8 * ND), o_hd = wk.add(8 * ND);
+  const size_t clear_bytes = wk.bytes - o_clear;
+  const size_t o_sc = wk.add(8 * ND), o_dg = wk.add(8 * ND), o_gr = wk.add(8 * ND), o_gn = wk.add(8 * ND),
+               o_u = wk.add(8 * ND), o_c = wk.add(8 * ND), o_dl = wk.add(8 * ND);
+  if ((rc = ensure(&c->d_work, &c->d_work_cap, wk.bytes, false)) != SVIN_OK) return rc;
+  // ---------------- output arena
+  Region out;
+  c->out_off_pose = out.add(56 * NPB);
+  c->out_off_sb = out.add(72 * NSB);
+  c->out_off_lm = out.add(32 * NL);
+  c->out_off_q = out.add(8 * NL);
+  c->out_off_ws = out.add(sizeof(WinState) * B);
+  c->out_bytes = out.bytes;
+  if ((rc = ensure(&c->d_out, &c->d_out_cap, out.bytes, false)) != SVIN_OK) return rc;
+  if ((rc = ensure(&c->h_out, &c->h_out_cap, out.bytes, true)) != SVIN_OK) return rc;
+
+  // ---------------- device pointers
+  char* D = (char*)c->d_in;
+  char* Wk = (char*)c->d_work;
+  char* O = (char*)c->d_out;
+  Batch& b = c->b;
+  b = Batch{};
+  b.B = B; b.NPB = (int)NPB; b.NSB = (int)NSB; b.NL = (int)NL; b.NC = (int)NC; b.NOBS = (int)NOBS;
+  b.NIMU = (int)NIMU; b.NMEAS = (int)NMEAS;
+  b.n_obs_tiles = n_obs_tiles; b.n_lm_tiles = n_lm_tiles; b.has_ext = has_ext; b.obs_stride = S;
+  b.win = (WinDesc*)(D + o_win);
+  c->d_ws_init = (WinState*)(D + o_ws);
+  b.ws = (WinState*)(Wk + o_wsw);
+  b.pose_init = (double*)(D + o_pose); b.sb_init = (double*)(D + o_sb); b.lm_init = (double*)(D + o_lm);
+  b.pose_off = (int*)(D + o_poff); b.sb_off = (int*)(D + o_sboff);
+  b.lm_fixed = (uint8_t*)(D + o_lmfix); b.lm_win = (int*)(D + o_lmwin);
+  c->d_pose_win = (int*)(D + o_pwin); c->d_sb_win = (int*)(D + o_sbwin);
+  b.intr = (double*)(D + o_intr);
+  b.obs_pose = (int*)(D + o_opose); b.obs_lm = (int*)(D + o_olm); b.obs_ext = (int*)(D + o_oext);
+  b.obs_cam = (int*)(D + o_ocam);
+  b.obs_zx = (double*)(D + o_zx); b.obs_zy = (double*)(D + o_zy);
+  b.obs_u00 = (double*)(D + o_u00); b.obs_u01 = (double*)(D + o_u01); b.obs_u11 = (double*)(D + o_u11);
+  b.lm_obs_begin = (int*)(D + o_lmob);
+  b.obs_tile_win = (int*)(D + o_otw); b.obs_tile_begin = (int*)(D + o_otb);
+  b.lm_tile_win = (int*)(D + o_ltw); b.lm_tile_begin = (int*)(D + o_ltb);
+  b.imu = (ImuTerm*)(D + o_imu);
+  c->d_imu_cache_init = (ImuCache*)(D + o_imuc);
+  b.imu_cache = (ImuCache*)(Wk + o_imucw);
+  b.imu_meas_t = (long long*)(D + o_mt); b.imu_meas_gyro = (double*)(D + o_mg); b.imu_meas_accel = (double*)(D + o_ma);
+  b.pp = (PosePrior*)(D + o_pp); b.sp = (SbPrior*)(D + o_sp); b.rp = (RelPose*)(D + o_rp);
+  b.so = (SonarTerm*)(D + o_so); b.de = (DepthTerm*)(D + o_de); b.marg_blk = (MargBlock*)(D + o_mb);
+  b.marg_J = (double*)(D + o_mJ); b.marg_e0 = (double*)(D + o_me); b.marg_lin = (double*)(D + o_ml);
+  for (int k = 0; k < 2; ++k) {
+    b.pose[k] = (double*)(Wk + o_poseb[k]); b.sb[k] = (double*)(Wk + o_sbb[k]); b.lm[k] = (double*)(Wk + o_lmb[k]);
+    b.lin_r[k] = (double*)(Wk + o_r[k]); b.lin_Jp[k] = (double*)(Wk + o_Jp[k]); b.lin_Jl[k] = (double*)(Wk + o_Jl[k]);
+    b.lin_Je[k] = has_ext ? (double*)(Wk + o_Je[k]) : nullptr;
+    b.Jd[k] = (double*)(Wk + o_Jd[k]); b.rd[k] = (double*)(Wk + o_rd[k]);
+  }
+  b.lm_scale = (double*)(Wk + o_lms); b.lm_Vinv = (double*)(Wk + o_lmV); b.lm_bs = (double*)(Wk + o_lmb2);
+  b.lm_diag = (double*)(Wk + o_lmd); b.lm_grad = (double*)(Wk + o_lmg); b.lm_gn = (double*)(Wk + o_lmgn);
+  b.H = (double*)(Wk + o_H); b.g_red = (double*)(Wk + o_gred); b.g_raw = (double*)(Wk + o_graw);
+  b.Hdiag = (double*)(Wk + o_hd);
+  b.scale_d = (double*)(Wk + o_sc); b.diag_d = (double*)(Wk + o_dg); b.grad_d = (double*)(Wk + o_gr);
+  b.gn_d = (double*)(Wk + o_gn); b.u_d = (double*)(Wk + o_u); b.c_d = (double*)(Wk + o_c);
+  b.delta_d = (double*)(Wk + o_dl);
+  c->d_pose_out = (double*)(O + c->out_off_pose); c->d_sb_out = (double*)(O + c->out_off_sb);
+  c->d_lm_out = (double*)(O + c->out_off_lm);
+  b.lm_quality = (double*)(O + c->out_off_q);
+  c->d_clear = Wk + o_clear;
+  c->clear_bytes = clear_bytes;
+  c->in_bytes = in.bytes;
+
+  // ---------------- copy + initialise
+  SVIN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  SVIN_CUDA(cudaMemcpyAsync(c->d_in, c->h_in, in.bytes, cudaMemcpyHostToDevice, c->stream));
+  SVIN_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  // Jd must be zero outside the blocks the terms write (structure is static)
+  for (int k = 0; k < 2; ++k) SVIN_CUDA(cudaMemsetAsync(b.Jd[k], 0, 8 * (size_t)NJD + 8, c->stream));
+  SVIN_CUDA(cudaMemsetAsync(b.lm_quality, 0, 8 * (size_t)NL + 8, c->stream));
+  launch_reset_state(b, c->stream);
+  SVIN_CUDA(cudaMemcpyAsync(b.ws, c->d_ws_init, sizeof(WinState) * B, cudaMemcpyDeviceToDevice, c->stream));
+  if (NIMU)
+    SVIN_CUDA(cudaMemcpyAsync(b.imu_cache, c->d_imu_cache_init, sizeof(ImuCache) * NIMU, cudaMemcpyDeviceToDevice,
+                              c->stream));
+  SVIN_CUDA(cudaGetLastError());
+  // the reduced system lives in shared memory when it fits
+  c->smem_bytes = dense_solve_smem_bytes(c->n_max);
+  if (c->smem_bytes > 200 * 1024) c->smem_bytes = 0;
+  if (c->smem_bytes > 0) SVIN_CUDA(configure_dense_solve(c->smem_bytes));
+  SVIN_CUDA(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  c->tm = SvinBaTimings{};
+  c->tm.h2d_ms = ms;
+  c->tm.h2d_bytes = (int64_t)in.bytes;
+  c->uploaded = true;
+  c->quality_valid = false;
+  return SVIN_OK;
+}
+
+int svin_ba_reset(svin_ba_ctx* c) {
+  if (!c || !c->uploaded) {
+    set_error("svin_ba_reset: nothing uploaded");
+    return SVIN_ERR_STATE;
+  }
+  SVIN_CUDA(cudaSetDevice(c->device));
+  Batch& b = c->b;
+  launch_reset_state(b, c->stream);
+  SVIN_CUDA(cudaMemcpyAsync(b.ws, c->d_ws_init, sizeof(WinState) * b.B, cudaMemcpyDeviceToDevice, c->stream));
+  if (b.NIMU)
+    SVIN_CUDA(cudaMemcpyAsync(b.imu_cache, c->d_imu_cache_init, sizeof(ImuCache) * b.NIMU, cudaMemcpyDeviceToDevice,
+                              c->stream));
+  SVIN_CUDA(cudaGetLastError());
+  c->solved = false;
+  c->quality_valid = false;
+  return SVIN_OK;
+}
+
+static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
+  Batch& b = c->b;
+  SVIN_CUDA(cudaMemsetAsync(c->d_clear, 0, c->clear_bytes, c->stream));
+  launch_schur(b, opt, c->stream);
+  launch_dense_solve(b, opt, c->smem_bytes, c->stream);
+  launch_backsub(b, c->stream);
+  launch_step_dense(b, opt, c->stream);
+  launch_step_lm(b, c->stream);
+  launch_linearize(b, 1, 0, c->stream);
+  launch_dense_eval(b, 1, 0, nullptr, c->stream);
+  launch_decide(b, opt, c->stream);
+  c->tm.kernel_launches += 8;
+  return SVIN_OK;
+}
+
+int svin_ba_solve(svin_ba_ctx* c, const SvinBaOptions* opt_in, SvinBaSummary* summaries) {
+  if (!c || !c->uploaded) {
+    set_error("svin_ba_solve: nothing uploaded");
+    return SVIN_ERR_STATE;
+  }
+  SVIN_CUDA(cudaSetDevice(c->device));
+  SvinBaOptions opt;
+  if (opt_in)
+    opt = *opt_in;
+  else
+    svin_ba_default_options(&opt);
+  Batch& b = c->b;
+  if (c->solved) {
+    const int rc = svin_ba_reset(c);
+    if (rc != SVIN_OK) return rc;
+  }
+  SVIN_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  // initial evaluation (IterationZero)
+  {
+    // radius from the options
+    std::vector<WinState> tmp;  // only radius differs from the uploaded init; patch on device via memcpy2D
+    const double r0 = opt.initial_trust_region_radius;
+    SVIN_CUDA(cudaMemcpy2DAsync(&b.ws[0].radius, sizeof(WinState), &r0, 0, sizeof(double), b.B, cudaMemcpyHostToDevice,
+                                c->stream));
+  }
+  launch_linearize(b, 0, 0, c->stream);
+  launch_dense_eval(b, 0, 0, nullptr, c->stream);
+  launch_init(b, opt, c->stream);
+  c->tm.kernel_launches += 3;
+  int slots_done = 0;
+  const int chunk = std::max(1, opt.max_num_iterations);
+  const int hard_cap = opt.max_num_iterations * 10 + 16;
+  while (true) {
+    for (int s = 0; s < chunk; ++s) {
+      const int rc = enqueue_slot(c, opt);
+      if (rc != SVIN_OK) return rc;
+    }
+    slots_done += chunk;
+    SVIN_CUDA(cudaMemsetAsync(c->d_active, 0, sizeof(int), c->stream));
+    launch_count_active(b, c->d_active, c->stream);
+    c->tm.kernel_launches += 1;
+    SVIN_CUDA(cudaMemcpyAsync(c->h_active, c->d_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SVIN_CUDA(cudaStreamSynchronize(c->stream));
+    SVIN_CUDA(cudaGetLastError());
+    if (*c->h_active == 0) break;
+    if (slots_done >= hard_cap) {
+      set_error("svin_ba_solve: windows still active after the slot cap (solver did not terminate)");
+      return SVIN_ERR_STATE;
+    }
+  }
+  if (opt.compute_landmark_quality) {
+    launch_quality(b, c->stream);
+    c->tm.kernel_launches += 1;
+    c->quality_valid = true;
+  }
+  SVIN_CUDA(cudaEventRecord(c->ev[3], c->stream));
+  SVIN_CUDA(cudaMemcpyAsync((char*)c->h_out + c->out_off_ws, b.ws, sizeof(WinState) * b.B, cudaMemcpyDeviceToHost,
+                            c->stream));
+  SVIN_CUDA(cudaStreamSynchronize(c->stream));
+  SVIN_CUDA(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+  c->tm.solve_ms = ms;
+  c->solved = true;
+  if (summaries) {
+    const WinState* ws = (const WinState*)((char*)c->h_out + c->out_off_ws);
+    for (int i = 0; i < b.B; ++i) {
+      SvinBaSummary& s = summaries[i];
+      s.iterations = ws[i].iter;
+      s.num_successful_steps = ws[i].num_successful;
+      s.termination = ws[i].termination;
+      s.imu_repropagations = ws[i].imu_redo;
+      s.initial_cost = ws[i].initial_cost;
+      s.final_cost = ws[i].cost_x;
+      s.final_trust_region_radius = ws[i].radius;
+    }
+  }
+  return SVIN_OK;
+}
+
+static int fetch_results(svin_ba_ctx* c) {
+  Batch& b = c->b;
+  launch_gather_state(b, c->d_pose_win, c->d_sb_win, c->d_pose_out, c->d_sb_out, c->d_lm_out, c->stream);
+  SVIN_CUDA(cudaEventRecord(c->ev[4], c->stream));
+  SVIN_CUDA(cudaMemcpyAsync(c->h_out, c->d_out, c->out_off_ws, cudaMemcpyDeviceToHost, c->stream));
+  SVIN_CUDA(cudaEventRecord(c->ev[5], c->stream));
+  SVIN_CUDA(cudaStreamSynchronize(c->stream));
+  SVIN_CUDA(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+  c->tm.d2h_ms = ms;
+  c->tm.d2h_bytes = (int64_t)c->out_off_ws;
+  return SVIN_OK;
+}
+
+static void scatter_window(svin_ba_ctx* c, int i, SvinBaWindow* w, double* quality) {
+  const WinDesc& d = c->h_win[i];
+  const char* Hh = (const char*)c->h_out;
+  std::memcpy(w->pose_blocks, (const double*)(Hh + c->out_off_pose) + 7 * (size_t)d.pose_begin,
+              56 * (size_t)(d.pose_end - d.pose_begin));
+  std::memcpy(w->speedbias, (const double*)(Hh + c->out_off_sb) + 9 * (size_t)d.sb_begin,
+              72 * (size_t)(d.sb_end - d.sb_begin));
+  std::memcpy(w->landmarks, (const double*)(Hh + c->out_off_lm) + 4 * (size_t)d.lm_begin,
+              32 * (size_t)(d.lm_end - d.lm_begin));
+  if (quality)
+    std::memcpy(quality, (const double*)(Hh + c->out_off_q) + d.lm_begin, 8 * (size_t)(d.lm_end - d.lm_begin));
+}
+
+int svin_ba_download(svin_ba_ctx* c, int32_t i, SvinBaWindow* w, double* quality) {
+  if (!c || !c->uploaded || !w || i < 0 || i >= c->b.B) {
+    set_error("svin_ba_download: invalid arguments");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  const WinDesc& d = c->h_win[i];
+  if (w->num_pose_blocks != d.pose_end - d.pose_begin || w->num_speedbias != d.sb_end - d.sb_begin ||
+      w->num_landmarks != d.lm_end - d.lm_begin) {
+    set_error("svin_ba_download: window shape differs from the uploaded one");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  SVIN_CUDA(cudaSetDevice(c->device));
+  const int rc = fetch_results(c);
+  if (rc != SVIN_OK) return rc;
+  scatter_window(c, i, w, quality);
+  return SVIN_OK;
+}
+
+int svin_ba_optimize(svin_ba_ctx* c, SvinBaWindow* wins, int32_t B, const SvinBaOptions* opt, SvinBaSummary* summaries,
+                     double* const* quality) {
+  int rc = svin_ba_upload(c, wins, B);
+  if (rc != SVIN_OK) return rc;
+  rc = svin_ba_solve(c, opt, summaries);
+  if (rc != SVIN_OK) return rc;
+  rc = fetch_results(c);
+  if (rc != SVIN_OK) return rc;
+  for (int i = 0; i < B; ++i) scatter_window(c, i, &wins[i], quality ? quality[i] : nullptr);
+  return SVIN_OK;
+}
+
+int svin_ba_evaluate(svin_ba_ctx* c, int32_t wi, SvinBaEvaluation* out) {
+  if (!c || !c->uploaded || !out || wi < 0 || wi >= c->b.B) {
+    set_error("svin_ba_evaluate: invalid arguments");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  SVIN_CUDA(cudaSetDevice(c->device));
+  Batch& b = c->b;
+  const WinDesc& d = c->h_win[wi];
+  const int N = d.obs_end - d.obs_begin, NI = d.imu_end - d.imu_begin;
+  // total cost at the current estimate: regular evaluation, then restore the state
+  int rc = svin_ba_reset(c);
+  if (rc != SVIN_OK) return rc;
+  launch_linearize(b, 0, 0, c->stream);
+  launch_dense_eval(b, 0, 0, nullptr, c->stream);
+  double cost = 0;
+  SVIN_CUDA(cudaMemcpyAsync(&cost, &b.ws[wi].cost_cand, 8, cudaMemcpyDeviceToHost, c->stream));
+  SVIN_CUDA(cudaStreamSynchronize(c->stream));
+  if (out->cost) out->cost[0] = cost;
+  rc = svin_ba_reset(c);
+  if (rc != SVIN_OK) return rc;
+  // raw dump into the inactive buffers
+  double* imu_dump = nullptr;
+  const size_t imu_per = 15 + 90 + 135 + 90 + 135;
+  if (b.NIMU) SVIN_CUDA(cudaMalloc(&imu_dump, 8 * imu_per * (size_t)b.NIMU));
+  const double* dump[5] = {imu_dump, imu_dump ? imu_dump + 15 * (size_t)b.NIMU : nullptr,
+                           imu_dump ? imu_dump + (15 + 90) * (size_t)b.NIMU : nullptr,
+                           imu_dump ? imu_dump + (15 + 90 + 135) * (size_t)b.NIMU : nullptr,
+                           imu_dump ? imu_dump + (15 + 90 + 135 + 90) * (size_t)b.NIMU : nullptr};
+  // the solver only materialises the extrinsics Jacobian when some extrinsics block is estimated;
+  // for the dump it is always produced, into a temporary plane set
+  const size_t S = b.obs_stride;
+  double* je_tmp = nullptr;
+  Batch braw = b;
+  if (!b.has_ext) {
+    SVIN_CUDA(cudaMalloc(&je_tmp, 8 * 12 * S + 8));
+    braw.lin_Je[1] = je_tmp;
+  }
+  launch_linearize(braw, 1, 1, c->stream);
+  launch_dense_eval(b, 1, 1, dump, c->stream);
+  SVIN_CUDA(cudaStreamSynchronize(c->stream));
+  SVIN_CUDA(cudaGetLastError());
+  std::vector<double> plane(N ? (size_t)N : 1);
+  auto pull = [&](const double* base, int planes, double* dst, int stride) -> int {
+    if (!dst) return SVIN_OK;
+    for (int k = 0; k < planes; ++k) {
+      SVIN_CUDA(cudaMemcpy(plane.data(), base + k * S + d.obs_begin, 8 * (size_t)N, cudaMemcpyDeviceToHost));
+      for (int o = 0; o < N; ++o) dst[(size_t)c->obs_perm[(size_t)d.obs_begin + o] * stride + k] = plane[o];
+    }
+    return SVIN_OK;
+  };
+  // inactive buffer index of this window: state was reset so cur == 0 -> inactive == 1
+  if ((rc = pull(b.lin_r[1], 2, out->reproj_residuals, 2)) != SVIN_OK) return rc;
+  if ((rc = pull(b.lin_Jp[1], 12, out->reproj_J_pose, 12)) != SVIN_OK) return rc;
+  if ((rc = pull(b.lin_Jl[1], 6, out->reproj_J_landmark, 6)) != SVIN_OK) return rc;
+  if ((rc = pull(braw.lin_Je[1], 12, out->reproj_J_extrinsics, 12)) != SVIN_OK) return rc;
+  if (je_tmp) cudaFree(je_tmp);
+  if (NI) {
+    auto pull_imu = [&](const double* src, int per, double* dst) -> int {
+      if (!dst) return SVIN_OK;
+      SVIN_CUDA(cudaMemcpy(dst, src + (size_t)per * d.imu_begin, 8 * (size_t)per * NI, cudaMemcpyDeviceToHost));
+      return SVIN_OK;
+    };
+    if ((rc = pull_imu(dump[0], 15, out->imu_residuals)) != SVIN_OK) return rc;
+    if ((rc = pull_imu(dump[1], 90, out->imu_J_pose0)) != SVIN_OK) return rc;
+    if ((rc = pull_imu(dump[2], 135, out->imu_J_speedbias0)) != SVIN_OK) return rc;
+    if ((rc = pull_imu(dump[3], 90, out->imu_J_pose1)) != SVIN_OK) return rc;
+    if ((rc = pull_imu(dump[4], 135, out->imu_J_speedbias1)) != SVIN_OK) return rc;
+  }
+  if (imu_dump) cudaFree(imu_dump);
+  return svin_ba_reset(c);
+}
+
+int svin_ba_timings(svin_ba_ctx* c, SvinBaTimings* out) {
+  if (!c || !out) {
+    set_error("svin_ba_timings: invalid arguments");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  *out = c->tm;
+  return SVIN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1939 @@
+// CUDA kernels of the sliding-window BA engine (sm_100a, fp64).
+//
+// One batch = many independent windows solved concurrently by the same launches; every
+// kernel is keyed by tiles that never straddle a window, and consults the window's
+// trust-region state (WinState) to decide whether it has work in this slot.
+//
+// Kernel family           work item          reference arithmetic it carries
+//   k_linearize           observation        ReprojectionError::EvaluateWithMinimalJacobians
+//                                            (okvis_ceres/.../implementation/ReprojectionError.hpp:85-229)
+//                                            + Ceres loss corrector (restated in-tree at
+//                                            okvis_ceres/src/MarginalizationError.cpp:283-330)
+//   k_dense_eval          window (CTA)       ImuError (ImuError.cpp:76-263,706-866), PoseError, SpeedAndBiasError,
+//                                            RelativePoseError, SonarError, DepthError, MarginalizationError::Evaluate
+//   k_schur               landmark           landmark-block elimination (Ceres SchurEliminator; the in-tree
+//                                            analogue is MarginalizationError.cpp:556-619)
+//   k_dense_solve         window (CTA)       reduced camera system: Jacobi scaling, LM diagonal, Cholesky, solve
+//   k_backsub             landmark           landmark back-substitution + Cauchy-point accumulation
+//   k_step_dense/k_step_lm                   dogleg interpolation (Ceres DoglegStrategy), candidate x (+) delta
+//                                            (PoseManifold.cpp:59-82, HomogeneousPointManifold.cpp:57-66), model cost
+//   k_decide              window             Ceres TrustRegionMinimizer accept/reject + termination tests
+//   k_quality             landmark           Estimator.cpp:903-922 landmark quality
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "ba_kernels.cuh"
+#include "ba_math.cuh"
+
+namespace svin {
+
+// ------------------------------------------------------------------------------------------ utilities
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Sum K per-thread values over the CTA and atomically add them to K targets.
+template <int K, int THREADS>
+__device__ __forceinline__ void block_atomic_add(double (&v)[K], double* const (&dst)[K]) {
+  __shared__ double red[K][THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double s = warp_sum(v[k]);
+    if (lane == 0) red[k][wid] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) s += red[threadIdx.x][i];
+    if (s != 0.0) atomicAdd(dst[threadIdx.x], s);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void atomic_max_nonneg(unsigned long long* addr, double v) {
+  atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ceres::CauchyLoss / HuberLoss + Corrector
+__device__ __forceinline__ void loss_eval(int type, double a, double s, double& rho0, double& rho1, double& rho2) {
+  if (type == SVIN_LOSS_CAUCHY) {
+    const double bb = a * a, c = 1.0 / bb;
+    const double sum = 1.0 + s * c;
+    const double inv = 1.0 / sum;
+    rho0 = bb * log(sum);
+    rho1 = fmax(inv, 2.2250738585072014e-308);
+    rho2 = -c * (inv * inv);
+  } else if (type == SVIN_LOSS_HUBER) {
+    const double bb = a * a;
+    if (s > bb) {
+      const double r = sqrt(s);
+      rho0 = 2.0 * a * r - bb;
+      rho1 = fmax(a / r, 2.2250738585072014e-308);
+      rho2 = -rho1 / (2.0 * s);
+    } else {
+      rho0 = s;
+      rho1 = 1.0;
+      rho2 = 0.0;
+    }
+  } else {
+    rho0 = s;
+    rho1 = 1.0;
+    rho2 = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ reprojection
+struct Reproj {
+  double r0, r1;
+  double Jp[12], Jl[6], Je[12];
+  double cost;
+};
+
+// ReprojectionError::EvaluateWithMinimalJacobians for PinholeCamera<RadialTangentialDistortion>.
+// raw=true returns the weighted residual and minimal Jacobians before loss correction.
+template <bool WANT_J, bool WANT_E>
+__device__ __forceinline__ void reproj_eval(const double* __restrict__ pose, const double* __restrict__ lm,
+                                            const double* __restrict__ ext, const double* __restrict__ intr, double zx,
+                                            double zy, double u00, double u01, double u11, int loss_type,
+                                            double loss_a, bool raw, Reproj& o) {
+  const V3 t_WS{pose[0], pose[1], pose[2]};
+  const M3 C_SW = m3t(qrot(Q4{pose[3], pose[4], pose[5], pose[6]}));
+  const V3 t_SC{ext[0], ext[1], ext[2]};
+  const M3 C_CS = m3t(qrot(Q4{ext[3], ext[4], ext[5], ext[6]}));
+  const V3 hw{lm[0], lm[1], lm[2]};
+  const double w = lm[3];
+  const V3 cst = m3v(C_SW, t_WS);
+  V3 hS = m3v(C_SW, hw);
+  hS.x -= cst.x * w;
+  hS.y -= cst.y * w;
+  hS.z -= cst.z * w;
+  const V3 cct = m3v(C_CS, t_SC);
+  V3 hC = m3v(C_CS, hS);
+  hC.x -= cct.x * w;
+  hC.y -= cct.y * w;
+  hC.z -= cct.z * w;
+  // projectHomogeneous: flip the head when w < 0 (the Jacobian is NOT flipped back in the reference)
+  V3 hd = hC;
+  if (w < 0) {
+    hd.x = -hd.x;
+    hd.y = -hd.y;
+    hd.z = -hd.z;
+  }
+  double kx = 0.0, ky = 0.0;
+  double Jh[6] = {0, 0, 0, 0, 0, 0};
+  if (!(fabs(hd.z) < 1.0e-12)) {
+    const double fu = intr[0], fv = intr[1], cu = intr[2], cv = intr[3];
+    const double rz = 1.0 / hd.z, rz2 = rz * rz;
+    double d0, d1, D00, D01, D10, D11;
+    radtan_distort(intr, hd.x * rz, hd.y * rz, d0, d1, D00, D01, D10, D11);
+    kx = fu * d0 + cu;
+    ky = fv * d1 + cv;
+    if (WANT_J) {
+      Jh[0] = fu * D00 * rz;
+      Jh[1] = fu * D01 * rz;
+      Jh[2] = -fu * (hd.x * D00 + hd.y * D01) * rz2;
+      Jh[3] = fv * D10 * rz;
+      Jh[4] = fv * D11 * rz;
+      Jh[5] = -fv * (hd.x * D10 + hd.y * D11) * rz2;
+    }
+  }
+  const double e0 = zx - kx, e1 = zy - ky;
+  double r0 = u00 * e0 + u01 * e1;
+  double r1 = u11 * e1;
+  bool valid = true;
+  if (fabs(w) > 1.0e-8) {
+    if (hC.z / w < 0.2) valid = false;
+  }
+  const double sq = r0 * r0 + r1 * r1;
+  double rho0, rho1, rho2;
+  loss_eval(loss_type, loss_a, sq, rho0, rho1, rho2);
+  o.cost = 0.5 * rho0;
+  if (WANT_J) {
+    // Jhw = U * Jh
+    double Jw[6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      Jw[c] = u00 * Jh[c] + u01 * Jh[3 + c];
+      Jw[3 + c] = u11 * Jh[3 + c];
+    }
+    double A[6], Bm[6];  // A = Jw * C_CS ; Bm = A * C_SW
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        A[i * 3 + j] = Jw[i * 3] * C_CS.m[j] + Jw[i * 3 + 1] * C_CS.m[3 + j] + Jw[i * 3 + 2] * C_CS.m[6 + j];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        Bm[i * 3 + j] = A[i * 3] * C_SW.m[j] + A[i * 3 + 1] * C_SW.m[3 + j] + A[i * 3 + 2] * C_SW.m[6 + j];
+    const double vz = valid ? 1.0 : 0.0;
+    const V3 p{hw.x - t_WS.x * w, hw.y - t_WS.y * w, hw.z - t_WS.z * w};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const double b0 = Bm[i * 3], b1 = Bm[i * 3 + 1], b2 = Bm[i * 3 + 2];
+      o.Jp[i * 6 + 0] = vz * b0 * w;
+      o.Jp[i * 6 + 1] = vz * b1 * w;
+      o.Jp[i * 6 + 2] = vz * b2 * w;
+      o.Jp[i * 6 + 3] = -vz * (b1 * p.z - b2 * p.y);
+      o.Jp[i * 6 + 4] = -vz * (-b0 * p.z + b2 * p.x);
+      o.Jp[i * 6 + 5] = -vz * (b0 * p.y - b1 * p.x);
+      o.Jl[i * 3 + 0] = -vz * b0;
+      o.Jl[i * 3 + 1] = -vz * b1;
+      o.Jl[i * 3 + 2] = -vz * b2;
+    }
+    if (WANT_E) {
+      const V3 pS{hS.x - t_SC.x * w, hS.y - t_SC.y * w, hS.z - t_SC.z * w};
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double a0 = A[i * 3], a1 = A[i * 3 + 1], a2 = A[i * 3 + 2];
+        o.Je[i * 6 + 0] = vz * a0 * w;
+        o.Je[i * 6 + 1] = vz * a1 * w;
+        o.Je[i * 6 + 2] = vz * a2 * w;
+        o.Je[i * 6 + 3] = -vz * (a1 * pS.z - a2 * pS.y);
+        o.Je[i * 6 + 4] = -vz * (-a0 * pS.z + a2 * pS.x);
+        o.Je[i * 6 + 5] = -vz * (a0 * pS.y - a1 * pS.x);
+      }
+    }
+    if (!raw && loss_type != SVIN_LOSS_NONE) {
+      // Corrector (corrector.cc): uses the uncorrected residuals for the Jacobian
+      const double sqrt_rho1 = sqrt(rho1);
+      double residual_scaling = sqrt_rho1, alpha_sq_norm = 0.0;
+      if (!(sq == 0.0 || rho2 <= 0.0)) {
+        const double D = 1.0 + 2.0 * sq * rho2 / rho1;
+        const double alpha = 1.0 - sqrt(D);
+        residual_scaling = sqrt_rho1 / (1 - alpha);
+        alpha_sq_norm = alpha / sq;
+      }
+      if (alpha_sq_norm == 0.0) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) o.Jp[i] *= sqrt_rho1;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) o.Jl[i] *= sqrt_rho1;
+        if (WANT_E) {
+#pragma unroll
+          for (int i = 0; i < 12; ++i) o.Je[i] *= sqrt_rho1;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const double rtj = o.Jp[c] * r0 + o.Jp[6 + c] * r1;
+          o.Jp[c] = sqrt_rho1 * (o.Jp[c] - alpha_sq_norm * r0 * rtj);
+          o.Jp[6 + c] = sqrt_rho1 * (o.Jp[6 + c] - alpha_sq_norm * r1 * rtj);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double rtj = o.Jl[c] * r0 + o.Jl[3 + c] * r1;
+          o.Jl[c] = sqrt_rho1 * (o.Jl[c] - alpha_sq_norm * r0 * rtj);
+          o.Jl[3 + c] = sqrt_rho1 * (o.Jl[3 + c] - alpha_sq_norm * r1 * rtj);
+        }
+        if (WANT_E) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            const double rtj = o.Je[c] * r0 + o.Je[6 + c] * r1;
+            o.Je[c] = sqrt_rho1 * (o.Je[c] - alpha_sq_norm * r0 * rtj);
+            o.Je[6 + c] = sqrt_rho1 * (o.Je[6 + c] - alpha_sq_norm * r1 * rtj);
+          }
+        }
+      }
+      r0 *= residual_scaling;
+      r1 *= residual_scaling;
+    }
+  }
+  o.r0 = r0;
+  o.r1 = r1;
+}
+
+__device__ __forceinline__ bool step_is_invalid(const WinState& ws) { return ws.gn_failed || !(-ws.acc_mc > 0.0); }
+
+// which: 0 = linearise the current estimate (initialisation), 1 = the candidate.  raw: evaluation dump.
+template <bool HAS_EXT>
+__global__ void __launch_bounds__(kObsTile) k_linearize(Batch b, int which, int raw) {
+  const int tile = blockIdx.x;
+  const int w = b.obs_tile_win[tile];
+  WinState& ws = b.ws[w];
+  if (!raw) {
+    if (ws.done) return;
+    if (which == 1 && (ws.skip_slot || step_is_invalid(ws))) return;
+  }
+  const WinDesc& wd = b.win[w];
+  const int buf = (which == 0) ? ws.cur : 1 - ws.cur;
+  const int sbuf = raw ? ws.cur : buf;  // state to read
+  const int o = b.obs_tile_begin[tile] + threadIdx.x;
+  double cost[1] = {0.0};
+  if (o < wd.obs_end) {
+    Reproj R;
+    const int ip = b.obs_pose[o], il = b.obs_lm[o], ie = b.obs_ext[o], ic = b.obs_cam[o];
+    reproj_eval<true, HAS_EXT>(b.pose[sbuf] + 7 * (size_t)ip, b.lm[sbuf] + 4 * (size_t)il,
+                               b.pose[sbuf] + 7 * (size_t)ie, b.intr + 8 * (size_t)ic, b.obs_zx[o], b.obs_zy[o],
+                               b.obs_u00[o], b.obs_u01[o], b.obs_u11[o], wd.loss_type, wd.loss_scale, raw != 0, R);
+    cost[0] = R.cost;
+    const size_t S = b.obs_stride;
+    double* r = b.lin_r[buf];
+    r[o] = R.r0;
+    r[S + o] = R.r1;
+    double* Jp = b.lin_Jp[buf];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) Jp[k * S + o] = R.Jp[k];
+    double* Jl = b.lin_Jl[buf];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Jl[k * S + o] = R.Jl[k];
+    if (HAS_EXT) {
+      double* Je = b.lin_Je[buf];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) Je[k * S + o] = R.Je[k];
+    }
+  }
+  double* const dst[1] = {&ws.cost_cand};
+  block_atomic_add<1, kObsTile>(cost, dst);
+}
+
+// ------------------------------------------------------------------------------------------ Schur
+// 3x3 SPD inverse through Cholesky (Ceres InvertPSDMatrix, assume_full_rank); NaN on failure.
+__device__ __forceinline__ void spd3_inverse(const double* V /*6: 00 01 02 11 12 22*/, double* Vi /*6*/) {
+  const double l00 = sqrt(V[0]);
+  const double l10 = V[1] / l00, l20 = V[2] / l00;
+  const double l11 = sqrt(V[3] - l10 * l10);
+  const double l21 = (V[4] - l20 * l10) / l11;
+  const double l22 = sqrt(V[5] - l20 * l20 - l21 * l21);
+  const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+  const double i10 = -l10 * i00 * i11;
+  const double i21 = -l21 * i11 * i22;
+  const double i20 = -(l20 * i00 + l21 * i10) * i22;
+  // Vinv = Li^T Li
+  Vi[0] = i00 * i00 + i10 * i10 + i20 * i20;
+  Vi[1] = i10 * i11 + i20 * i21;
+  Vi[2] = i20 * i22;
+  Vi[3] = i11 * i11 + i21 * i21;
+  Vi[4] = i21 * i22;
+  Vi[5] = i22 * i22;
+}
+
+struct ObsJ {
+  double r0, r1;
+  double Jp[12], Jl[6];
+};
+__device__ __forceinline__ void load_obs(const Batch& b, int buf, int o, ObsJ& J) {
+  const size_t S = b.obs_stride;
+  const double* r = b.lin_r[buf];
+  J.r0 = r[o];
+  J.r1 = r[S + o];
+  const double* Jp = b.lin_Jp[buf];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) J.Jp[k] = Jp[k * S + o];
+  const double* Jl = b.lin_Jl[buf];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) J.Jl[k] = Jl[k * S + o];
+}
+__device__ __forceinline__ void load_Je(const Batch& b, int buf, int o, double* Je) {
+  const size_t S = b.obs_stride;
+  const double* p = b.lin_Je[buf];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) Je[k] = p[k * S + o];
+}
+
+// W(6x3) += Jd^T (2x6)^T * Jls (2x3)
+__device__ __forceinline__ void acc_W(const double* Jd, const double* Jls, double* W) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) W[i * 3 + j] += Jd[i] * Jls[j] + Jd[6 + i] * Jls[3 + j];
+}
+// add block -Z * Wq^T at (offp, offq) of the window's upper-triangular reduced matrix
+__device__ __forceinline__ void sub_block(double* H, int n, int offp, int offq, const double* Z, const double* Wq) {
+  if (offp == offq) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        if (j < i) continue;
+        // symmetric sum of both orderings is handled by the caller (it visits each unordered pair once)
+        const double v = Z[i * 3] * Wq[j * 3] + Z[i * 3 + 1] * Wq[j * 3 + 1] + Z[i * 3 + 2] * Wq[j * 3 + 2];
+        atomicAdd(&H[(size_t)(offp + i) * n + offq + j], -v);
+      }
+  } else if (offp < offq) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const double v = Z[i * 3] * Wq[j * 3] + Z[i * 3 + 1] * Wq[j * 3 + 1] + Z[i * 3 + 2] * Wq[j * 3 + 2];
+        atomicAdd(&H[(size_t)(offp + i) * n + offq + j], -v);
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const double v = Z[i * 3] * Wq[j * 3] + Z[i * 3 + 1] * Wq[j * 3 + 1] + Z[i * 3 + 2] * Wq[j * 3 + 2];
+        atomicAdd(&H[(size_t)(offq + j) * n + offp + i], -v);
+      }
+  }
+}
+
+template <bool HAS_EXT>
+__global__ void __launch_bounds__(kLmTile) k_schur(Batch b, SvinBaOptions opt) {
+  const int tile = blockIdx.x;
+  const int w = b.lm_tile_win[tile];
+  WinState& ws = b.ws[w];
+  if (ws.done || ws.reuse) return;
+  const WinDesc& wd = b.win[w];
+  const int l = b.lm_tile_begin[tile] + threadIdx.x;
+  if (l >= wd.lm_end) return;
+  const int buf = ws.cur;
+  const int n = wd.n_dense;
+  double* H = b.H + wd.H_off;
+  double* g_red = b.g_red + wd.d_off;
+  double* g_raw = b.g_raw + wd.d_off;
+  double* Hdiag = b.Hdiag + wd.d_off;
+  const int ob = b.lm_obs_begin[l], oe = b.lm_obs_begin[l + 1];
+  const bool lfix = b.lm_fixed[l] != 0;
+  const double mu = ws.mu;
+
+  // ---- pass 1: V = sum Jl^T Jl, bl = sum Jl^T r (unscaled)
+  double V[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+  {
+    const size_t S = b.obs_stride;
+    const double* r = b.lin_r[buf];
+    const double* Jl = b.lin_Jl[buf];
+    for (int o = ob; o < oe; ++o) {
+      const double r0 = r[o], r1 = r[S + o];
+      double a[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a[k] = Jl[k * S + o];
+      V[0] += a[0] * a[0] + a[3] * a[3];
+      V[1] += a[0] * a[1] + a[3] * a[4];
+      V[2] += a[0] * a[2] + a[3] * a[5];
+      V[3] += a[1] * a[1] + a[4] * a[4];
+      V[4] += a[1] * a[2] + a[4] * a[5];
+      V[5] += a[2] * a[2] + a[5] * a[5];
+      bl[0] += a[0] * r0 + a[3] * r1;
+      bl[1] += a[1] * r0 + a[4] * r1;
+      bl[2] += a[2] * r0 + a[5] * r1;
+    }
+  }
+  double s[3] = {1.0, 1.0, 1.0}, Vi[6] = {0, 0, 0, 0, 0, 0}, bs[3] = {0, 0, 0};
+  if (!lfix) {
+    if (ws.iter == 0 && ws.num_successful == 0 && !ws.invalid) {
+      // Jacobi scaling from the first Jacobian: 1 / (1 + ||column||)
+      if (opt.jacobi_scaling) {
+        s[0] = 1.0 / (1.0 + sqrt(V[0]));
+        s[1] = 1.0 / (1.0 + sqrt(V[3]));
+        s[2] = 1.0 / (1.0 + sqrt(V[5]));
+      }
+      b.lm_scale[3 * (size_t)l] = s[0];
+      b.lm_scale[3 * (size_t)l + 1] = s[1];
+      b.lm_scale[3 * (size_t)l + 2] = s[2];
+    } else {
+      s[0] = b.lm_scale[3 * (size_t)l];
+      s[1] = b.lm_scale[3 * (size_t)l + 1];
+      s[2] = b.lm_scale[3 * (size_t)l + 2];
+    }
+    atomic_max_nonneg(&ws.gmax_bits, fmax(fabs(bl[0]), fmax(fabs(bl[1]), fabs(bl[2]))));
+    double Vs[6] = {V[0] * s[0] * s[0], V[1] * s[0] * s[1], V[2] * s[0] * s[2],
+                    V[3] * s[1] * s[1], V[4] * s[1] * s[2], V[5] * s[2] * s[2]};
+    const double d0 = sqrt(fmin(fmax(Vs[0], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    const double d1 = sqrt(fmin(fmax(Vs[3], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    const double d2 = sqrt(fmin(fmax(Vs[5], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    Vs[0] += mu * d0 * d0;
+    Vs[3] += mu * d1 * d1;
+    Vs[5] += mu * d2 * d2;
+    spd3_inverse(Vs, Vi);
+    bs[0] = s[0] * bl[0];
+    bs[1] = s[1] * bl[1];
+    bs[2] = s[2] * bl[2];
+    double* p;
+    p = b.lm_Vinv + 6 * (size_t)l;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) p[k] = Vi[k];
+    p = b.lm_bs + 3 * (size_t)l;
+    p[0] = bs[0]; p[1] = bs[1]; p[2] = bs[2];
+    p = b.lm_diag + 3 * (size_t)l;
+    p[0] = d0; p[1] = d1; p[2] = d2;
+    p = b.lm_grad + 3 * (size_t)l;
+    p[0] = bs[0] / d0; p[1] = bs[1] / d1; p[2] = bs[2] / d2;
+  }
+
+  // ---- pass 2: dense blocks and the rank-3 update of the reduced system
+  if (!HAS_EXT) {
+    int i = ob;
+    while (i < oe) {
+      const int p = b.obs_pose[i];
+      int j = i + 1;
+      while (j < oe && b.obs_pose[j] == p) ++j;
+      const int offp = b.pose_off[p];
+      if (offp >= 0) {
+        double Hpp[21], gp[6], W[18];
+#pragma unroll
+        for (int k = 0; k < 21; ++k) Hpp[k] = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gp[k] = 0;
+#pragma unroll
+        for (int k = 0; k < 18; ++k) W[k] = 0;
+        for (int o = i; o < j; ++o) {
+          ObsJ J;
+          load_obs(b, buf, o, J);
+          int idx = 0;
+#pragma unroll
+          for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int c = a; c < 6; ++c) Hpp[idx++] += J.Jp[a] * J.Jp[c] + J.Jp[6 + a] * J.Jp[6 + c];
+#pragma unroll
+          for (int a = 0; a < 6; ++a) gp[a] += J.Jp[a] * J.r0 + J.Jp[6 + a] * J.r1;
+          double Jls[6] = {J.Jl[0] * s[0], J.Jl[1] * s[1], J.Jl[2] * s[2], J.Jl[3] * s[0], J.Jl[4] * s[1], J.Jl[5] * s[2]};
+          acc_W(J.Jp, Jls, W);
+        }
+        {
+          int idx = 0;
+#pragma unroll
+          for (int a = 0; a < 6; ++a) {
+            atomicAdd(&Hdiag[offp + a], Hpp[idx]);
+            idx += 6 - a;
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) atomicAdd(&g_raw[offp + a], gp[a]);
+        double Z[18];
+        if (!lfix) {
+          // Z = W * Vinv
+#pragma unroll
+          for (int a = 0; a < 6; ++a) {
+            const double w0 = W[a * 3], w1 = W[a * 3 + 1], w2 = W[a * 3 + 2];
+            Z[a * 3 + 0] = w0 * Vi[0] + w1 * Vi[1] + w2 * Vi[2];
+            Z[a * 3 + 1] = w0 * Vi[1] + w1 * Vi[3] + w2 * Vi[4];
+            Z[a * 3 + 2] = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
+          }
+          int idx = 0;
+#pragma unroll
+          for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int c = a; c < 6; ++c)
+              Hpp[idx++] -= Z[a * 3] * W[c * 3] + Z[a * 3 + 1] * W[c * 3 + 1] + Z[a * 3 + 2] * W[c * 3 + 2];
+#pragma unroll
+          for (int a = 0; a < 6; ++a) gp[a] -= Z[a * 3] * bs[0] + Z[a * 3 + 1] * bs[1] + Z[a * 3 + 2] * bs[2];
+        }
+        {
+          int idx = 0;
+#pragma unroll
+          for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int c = a; c < 6; ++c) atomicAdd(&H[(size_t)(offp + a) * n + offp + c], Hpp[idx++]);
+        }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) atomicAdd(&g_red[offp + a], gp[a]);
+        if (!lfix) {
+          // cross blocks with every later pose run of this landmark
+          int i2 = j;
+          while (i2 < oe) {
+            const int q = b.obs_pose[i2];
+            int j2 = i2 + 1;
+            while (j2 < oe && b.obs_pose[j2] == q) ++j2;
+            const int offq = b.pose_off[q];
+            if (offq >= 0) {
+              double Wq[18];
+#pragma unroll
+              for (int k = 0; k < 18; ++k) Wq[k] = 0;
+              const size_t S = b.obs_stride;
+              const double* Jpp = b.lin_Jp[buf];
+              const double* Jlp = b.lin_Jl[buf];
+              for (int o = i2; o < j2; ++o) {
+                double Jp[12], Jls[6];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) Jp[k] = Jpp[k * S + o];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) Jls[k] = Jlp[k * S + o] * s[k % 3];
+                acc_W(Jp, Jls, Wq);
+              }
+              sub_block(H, n, offp, offq, Z, Wq);
+            }
+            i2 = j2;
+          }
+        }
+      }
+      i = j;
+    }
+  } else {
+    // general path: every observation carries a pose block and an extrinsics block
+    for (int o = ob; o < oe; ++o) {
+      ObsJ J;
+      load_obs(b, buf, o, J);
+      double Je[12];
+      load_Je(b, buf, o, Je);
+      const int offs[2] = {b.pose_off[b.obs_pose[o]], b.pose_off[b.obs_ext[o]]};
+      const double* Jd[2] = {J.Jp, Je};
+      double Jls[6] = {J.Jl[0] * s[0], J.Jl[1] * s[1], J.Jl[2] * s[2], J.Jl[3] * s[0], J.Jl[4] * s[1], J.Jl[5] * s[2]};
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        if (offs[a] < 0) continue;
+        const double* Ja = Jd[a];
+        // unreduced diagonal blocks, cross block pose-extrinsics, gradient
+        for (int x = 0; x < 6; ++x) {
+          atomicAdd(&Hdiag[offs[a] + x], Ja[x] * Ja[x] + Ja[6 + x] * Ja[6 + x]);
+          const double gv = Ja[x] * J.r0 + Ja[6 + x] * J.r1;
+          atomicAdd(&g_raw[offs[a] + x], gv);
+          atomicAdd(&g_red[offs[a] + x], gv);
+          for (int y = x; y < 6; ++y)
+            atomicAdd(&H[(size_t)(offs[a] + x) * n + offs[a] + y], Ja[x] * Ja[y] + Ja[6 + x] * Ja[6 + y]);
+        }
+        if (a == 0 && offs[1] >= 0) {
+          for (int x = 0; x < 6; ++x)
+            for (int y = 0; y < 6; ++y) {
+              const double v = J.Jp[x] * Je[y] + J.Jp[6 + x] * Je[6 + y];
+              if (offs[0] < offs[1])
+                atomicAdd(&H[(size_t)(offs[0] + x) * n + offs[1] + y], v);
+              else
+                atomicAdd(&H[(size_t)(offs[1] + y) * n + offs[0] + x], v);
+            }
+        }
+        if (lfix) continue;
+        double W[18], Z[18];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) W[k] = 0;
+        acc_W(Ja, Jls, W);
+#pragma unroll
+        for (int x = 0; x < 6; ++x) {
+          const double w0 = W[x * 3], w1 = W[x * 3 + 1], w2 = W[x * 3 + 2];
+          Z[x * 3 + 0] = w0 * Vi[0] + w1 * Vi[1] + w2 * Vi[2];
+          Z[x * 3 + 1] = w0 * Vi[1] + w1 * Vi[3] + w2 * Vi[4];
+          Z[x * 3 + 2] = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
+        }
+        for (int x = 0; x < 6; ++x)
+          atomicAdd(&g_red[offs[a] + x], -(Z[x * 3] * bs[0] + Z[x * 3 + 1] * bs[1] + Z[x * 3 + 2] * bs[2]));
+        // pair with every (observation, block) of this landmark, each unordered pair of distinct
+        // entries once and the self pair once; same-offset pairs of distinct entries need both orderings
+        for (int o2 = ob; o2 < oe; ++o2) {
+          double Jp2[12], Je2[12], Jl2[6];
+          {
+            const size_t S = b.obs_stride;
+            const double* pp = b.lin_Jp[buf];
+            const double* pl = b.lin_Jl[buf];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) Jp2[k] = pp[k * S + o2];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) Jl2[k] = pl[k * S + o2] * s[k % 3];
+            load_Je(b, buf, o2, Je2);
+          }
+          const int offs2[2] = {b.pose_off[b.obs_pose[o2]], b.pose_off[b.obs_ext[o2]]};
+          for (int a2 = 0; a2 < 2; ++a2) {
+            if (offs2[a2] < 0) continue;
+            const bool same_entry = (o2 == o && a2 == a);
+            // visit ordered pairs (entry, entry2) with entry <= entry2 in (o, a) lexicographic order
+            if (o2 < o || (o2 == o && a2 < a)) continue;
+            double W2[18];
+#pragma unroll
+            for (int k = 0; k < 18; ++k) W2[k] = 0;
+            acc_W(a2 == 0 ? Jp2 : Je2, Jl2, W2);
+            if (same_entry) {
+              sub_block(H, n, offs[a], offs2[a2], Z, W2);
+            } else if (offs[a] == offs2[a2]) {
+              // two distinct entries on the same dense block: Z W2^T + (Z W2^T)^T on the upper triangle
+              for (int x = 0; x < 6; ++x)
+                for (int y = x; y < 6; ++y) {
+                  const double v1 = Z[x * 3] * W2[y * 3] + Z[x * 3 + 1] * W2[y * 3 + 1] + Z[x * 3 + 2] * W2[y * 3 + 2];
+                  const double v2 = Z[y * 3] * W2[x * 3] + Z[y * 3 + 1] * W2[x * 3 + 1] + Z[y * 3 + 2] * W2[x * 3 + 2];
+                  atomicAdd(&H[(size_t)(offs[a] + x) * n + offs[a] + y], -(v1 + v2));
+                }
+            } else {
+              sub_block(H, n, offs[a], offs2[a2], Z, W2);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ dense terms
+// Warp-cooperative 15x15 helpers on shared memory (row-major).
+__device__ __forceinline__ void warp_mm15(const double* A, const double* Bm, double* C, bool transB, int lane) {
+  for (int e = lane; e < 225; e += 32) {
+    const int i = e / 15, j = e % 15;
+    double s = 0;
+    if (!transB) {
+#pragma unroll
+      for (int k = 0; k < 15; ++k) s += A[i * 15 + k] * Bm[k * 15 + j];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 15; ++k) s += A[i * 15 + k] * Bm[j * 15 + k];
+    }
+    C[e] = s;
+  }
+}
+__device__ __forceinline__ void set_blk(double* F, int r0, int c0, const M3& Bm, double sc) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) F[(r0 + a) * 15 + c0 + c] = sc * Bm.m[a * 3 + c];
+}
+
+// ImuError::redoPreintegration (ImuError.cpp:76-263) by one warp; sm = 3*225 doubles scratch (P, F, T).
+__device__ void imu_redo_warp(const Batch& b, const ImuTerm& t, ImuCache* c, const ImuP& P, const double* sb0,
+                              double* sm, int lane) {
+  double* Pm = sm;
+  double* F = sm + 225;
+  double* T = sm + 450;
+  for (int e = lane; e < 225; e += 32) Pm[e] = 0.0;
+  __syncwarp();
+  // running quantities live in lane 0's registers
+  Q4 Delta_q{0, 0, 0, 1};
+  M3 C_integral, C_doubleintegral, cross, dalpha_db_g, dv_db_g, dp_db_g;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    C_integral.m[k] = 0; C_doubleintegral.m[k] = 0; cross.m[k] = 0;
+    dalpha_db_g.m[k] = 0; dv_db_g.m[k] = 0; dp_db_g.m[k] = 0;
+  }
+  V3 acc_integral{0, 0, 0}, acc_doubleintegral{0, 0, 0};
+  long long time = t.t0;
+  const long long end = t.t1;
+  const int n = t.meas_end - t.meas_begin;
+  const long long* mt = b.imu_meas_t + t.meas_begin;
+  const double* mg = b.imu_meas_gyro + 3 * (size_t)t.meas_begin;
+  const double* ma = b.imu_meas_accel + 3 * (size_t)t.meas_begin;
+  bool hasStarted = false;
+  if (!(mt[n - 1] >= end)) return;
+  for (int it = 0; it < n; ++it) {
+    const int nx = (it + 1 < n) ? it + 1 : it;
+    V3 w0{mg[3 * it], mg[3 * it + 1], mg[3 * it + 2]}, a0{ma[3 * it], ma[3 * it + 1], ma[3 * it + 2]};
+    V3 w1{mg[3 * nx], mg[3 * nx + 1], mg[3 * nx + 2]}, a1{ma[3 * nx], ma[3 * nx + 1], ma[3 * nx + 2]};
+    long long nexttime = (it + 1 == n) ? t.t1 : mt[it + 1];
+    double dt = ns_to_sec(nexttime - time);
+    if (end < nexttime) {
+      const double interval = ns_to_sec(nexttime - mt[it]);
+      nexttime = t.t1;
+      dt = ns_to_sec(nexttime - time);
+      const double r = dt / interval;
+      w1 = V3{(1.0 - r) * w0.x + r * w1.x, (1.0 - r) * w0.y + r * w1.y, (1.0 - r) * w0.z + r * w1.z};
+      a1 = V3{(1.0 - r) * a0.x + r * a1.x, (1.0 - r) * a0.y + r * a1.y, (1.0 - r) * a0.z + r * a1.z};
+    }
+    if (dt <= 0.0) continue;  // warp-uniform
+    if (!hasStarted) {
+      hasStarted = true;
+      const double r = dt / ns_to_sec(nexttime - mt[it]);
+      w0 = V3{r * w0.x + (1.0 - r) * w1.x, r * w0.y + (1.0 - r) * w1.y, r * w0.z + (1.0 - r) * w1.z};
+      a0 = V3{r * a0.x + (1.0 - r) * a1.x, r * a0.y + (1.0 - r) * a1.y, r * a0.z + (1.0 - r) * a1.z};
+    }
+    double sigma_g_c = P.sigma_g_c, sigma_a_c = P.sigma_a_c;
+    if (fabs(w0.x) > P.g_max || fabs(w0.y) > P.g_max || fabs(w0.z) > P.g_max || fabs(w1.x) > P.g_max ||
+        fabs(w1.y) > P.g_max || fabs(w1.z) > P.g_max)
+      sigma_g_c *= 100;
+    if (fabs(a0.x) > P.a_max || fabs(a0.y) > P.a_max || fabs(a0.z) > P.a_max || fabs(a1.x) > P.a_max ||
+        fabs(a1.y) > P.a_max || fabs(a1.z) > P.a_max)
+      sigma_a_c *= 100;
+    if (lane == 0) {
+      const V3 wt{0.5 * (w0.x + w1.x) - sb0[3], 0.5 * (w0.y + w1.y) - sb0[4], 0.5 * (w0.z + w1.z) - sb0[5]};
+      const V3 at{0.5 * (a0.x + a1.x) - sb0[6], 0.5 * (a0.y + a1.y) - sb0[7], 0.5 * (a0.z + a1.z) - sb0[8]};
+      const double theta_half = sqrt(wt.x * wt.x + wt.y * wt.y + wt.z * wt.z) * 0.5 * dt;
+      const double sth = sinc_okvis(theta_half), cth = cos(theta_half);
+      const Q4 dq{sth * wt.x * 0.5 * dt, sth * wt.y * 0.5 * dt, sth * wt.z * 0.5 * dt, cth};
+      const Q4 Delta_q_1 = qmul(Delta_q, dq);
+      const M3 C = qrot(Delta_q), C_1 = qrot(Delta_q_1);
+      M3 CC;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) CC.m[k] = C.m[k] + C_1.m[k];
+      const V3 CCa = m3v(CC, at);
+      M3 C_integral_1;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) C_integral_1.m[k] = C_integral.m[k] + 0.5 * CC.m[k] * dt;
+      const V3 acc_integral_1{acc_integral.x + 0.5 * CCa.x * dt, acc_integral.y + 0.5 * CCa.y * dt,
+                              acc_integral.z + 0.5 * CCa.z * dt};
+#pragma unroll
+      for (int k = 0; k < 9; ++k) C_doubleintegral.m[k] += C_integral.m[k] * dt + 0.25 * CC.m[k] * dt * dt;
+      acc_doubleintegral.x += acc_integral.x * dt + 0.25 * CCa.x * dt * dt;
+      acc_doubleintegral.y += acc_integral.y * dt + 0.25 * CCa.y * dt * dt;
+      acc_doubleintegral.z += acc_integral.z * dt + 0.25 * CCa.z * dt * dt;
+      const M3 Jr = right_jacobian(V3{wt.x * dt, wt.y * dt, wt.z * dt});
+      const M3 C1Jr = m3mul(C_1, Jr);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) dalpha_db_g.m[k] += C1Jr.m[k] * dt;
+      const M3 t9 = m3mul(qrot(qinverse(dq)), cross);
+      M3 cross_1;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) cross_1.m[k] = t9.m[k] + Jr.m[k] * dt;
+      const M3 ax = crossmx(at);
+      const M3 B0 = m3mul(m3mul(C, ax), cross);
+      const M3 B1 = m3mul(m3mul(C_1, ax), cross_1);
+      M3 G;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) G.m[k] = B0.m[k] + B1.m[k];
+      M3 dv_db_g_1, F09, F012;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        dv_db_g_1.m[k] = dv_db_g.m[k] + 0.5 * dt * G.m[k];
+        F09.m[k] = dt * dv_db_g.m[k] + 0.25 * dt * dt * G.m[k];
+        dp_db_g.m[k] += F09.m[k];
+        F012.m[k] = -C_integral.m[k] * dt + 0.25 * CC.m[k] * dt * dt;
+      }
+      // F_delta
+      for (int k = 0; k < 225; ++k) F[k] = 0.0;
+      for (int k = 0; k < 15; ++k) F[k * 15 + k] = 1.0;
+      set_blk(F, 0, 3,
+              crossmx(V3{acc_integral.x * dt + 0.25 * CCa.x * dt * dt, acc_integral.y * dt + 0.25 * CCa.y * dt * dt,
+                         acc_integral.z * dt + 0.25 * CCa.z * dt * dt}),
+              -1.0);
+      M3 I3;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) I3.m[k] = 0;
+      I3.m[0] = I3.m[4] = I3.m[8] = 1.0;
+      set_blk(F, 0, 6, I3, dt);
+      set_blk(F, 0, 9, F09, 1.0);
+      set_blk(F, 0, 12, F012, 1.0);
+      set_blk(F, 3, 9, C_1, -dt);
+      set_blk(F, 6, 3, crossmx(V3{0.5 * CCa.x * dt, 0.5 * CCa.y * dt, 0.5 * CCa.z * dt}), -1.0);
+      set_blk(F, 6, 9, G, 0.5 * dt);
+      set_blk(F, 6, 12, CC, -0.5 * dt);
+      Delta_q = Delta_q_1;
+      C_integral = C_integral_1;
+      acc_integral = acc_integral_1;
+      cross = cross_1;
+      dv_db_g = dv_db_g_1;
+    }
+    __syncwarp();
+    warp_mm15(F, Pm, T, false, lane);
+    __syncwarp();
+    warp_mm15(T, F, Pm, true, lane);
+    __syncwarp();
+    if (lane == 0) {
+      const double sigma2_dalpha = dt * sigma_g_c * sigma_g_c;
+      const double sigma2_v = dt * sigma_a_c * sigma_a_c;
+      const double sigma2_p = 0.5 * dt * dt * sigma2_v;
+      const double sigma2_b_g = dt * P.sigma_gw_c * P.sigma_gw_c;
+      const double sigma2_b_a = dt * P.sigma_aw_c * P.sigma_aw_c;
+      for (int k = 0; k < 3; ++k) {
+        Pm[(3 + k) * 15 + 3 + k] += sigma2_dalpha;
+        Pm[(6 + k) * 15 + 6 + k] += sigma2_v;
+        Pm[(0 + k) * 15 + 0 + k] += sigma2_p;
+        Pm[(9 + k) * 15 + 9 + k] += sigma2_b_g;
+        Pm[(12 + k) * 15 + 12 + k] += sigma2_b_a;
+      }
+    }
+    __syncwarp();
+    time = nexttime;
+    if (nexttime == t.t1) break;
+  }
+  if (lane == 0) {
+    c->Delta_q[0] = Delta_q.x; c->Delta_q[1] = Delta_q.y; c->Delta_q[2] = Delta_q.z; c->Delta_q[3] = Delta_q.w;
+    for (int k = 0; k < 9; ++k) {
+      c->C_integral[k] = C_integral.m[k];
+      c->C_doubleintegral[k] = C_doubleintegral.m[k];
+      c->dalpha_db_g[k] = dalpha_db_g.m[k];
+      c->dv_db_g[k] = dv_db_g.m[k];
+      c->dp_db_g[k] = dp_db_g.m[k];
+      c->sb_ref[k] = sb0[k];
+    }
+    c->acc_integral[0] = acc_integral.x; c->acc_integral[1] = acc_integral.y; c->acc_integral[2] = acc_integral.z;
+    c->acc_doubleintegral[0] = acc_doubleintegral.x;
+    c->acc_doubleintegral[1] = acc_doubleintegral.y;
+    c->acc_doubleintegral[2] = acc_doubleintegral.z;
+  }
+  // symmetrise P -> F ; invert (LU, partial pivoting) ; symmetrise ; LLT
+  for (int e = lane; e < 225; e += 32) {
+    const int i = e / 15, j = e % 15;
+    F[e] = 0.5 * Pm[i * 15 + j] + 0.5 * Pm[j * 15 + i];
+  }
+  __syncwarp();
+  // LU in F (in place), pivots tracked by lane 0 in T[0..15) as doubles
+  for (int k = 0; k < 15; ++k) {
+    int p = k;
+    if (lane == 0) {
+      double best = fabs(F[k * 15 + k]);
+      for (int i = k + 1; i < 15; ++i)
+        if (fabs(F[i * 15 + k]) > best) {
+          best = fabs(F[i * 15 + k]);
+          p = i;
+        }
+    }
+    p = __shfl_sync(0xffffffffu, p, 0);
+    if (k == 0 && lane < 15) T[lane] = (double)lane;
+    __syncwarp();
+    if (p != k) {
+      if (lane < 15) {
+        const double tmp = F[k * 15 + lane];
+        F[k * 15 + lane] = F[p * 15 + lane];
+        F[p * 15 + lane] = tmp;
+      }
+      if (lane == 0) {
+        const double tp = T[k];
+        T[k] = T[p];
+        T[p] = tp;
+      }
+    }
+    __syncwarp();
+    const double piv = F[k * 15 + k];
+    if (lane > k && lane < 15) F[lane * 15 + k] /= piv;
+    __syncwarp();
+    // trailing update: element (i, j), i,j > k
+    for (int e = lane; e < 225; e += 32) {
+      const int i = e / 15, j = e % 15;
+      if (i > k && j > k) F[e] -= F[i * 15 + k] * F[k * 15 + j];
+    }
+    __syncwarp();
+  }
+  // columns of the inverse: lane c solves A x = e_c  (result into Pm, row-major)
+  if (lane < 15) {
+    double y[15];
+    for (int i = 0; i < 15; ++i) {
+      double s = ((int)T[i] == lane) ? 1.0 : 0.0;
+      for (int j = 0; j < i; ++j) s -= F[i * 15 + j] * y[j];
+      y[i] = s;
+    }
+    for (int i = 14; i >= 0; --i) {
+      double s = y[i];
+      for (int j = i + 1; j < 15; ++j) s -= F[i * 15 + j] * y[j];
+      y[i] = s / F[i * 15 + i];
+    }
+    for (int i = 0; i < 15; ++i) Pm[i * 15 + lane] = y[i];
+  }
+  __syncwarp();
+  for (int e = lane; e < 225; e += 32) {
+    const int i = e / 15, j = e % 15;
+    F[e] = 0.5 * Pm[i * 15 + j] + 0.5 * Pm[j * 15 + i];  // information_
+  }
+  __syncwarp();
+  // Eigen LLT (lower, left-looking), in F; early exit on a non-positive pivot like Eigen
+  for (int k = 0; k < 15; ++k) {
+    double x = F[k * 15 + k];
+    for (int j = 0; j < k; ++j) x -= F[k * 15 + j] * F[k * 15 + j];
+    if (x <= 0.0) break;
+    x = sqrt(x);
+    __syncwarp();
+    if (lane == 0) F[k * 15 + k] = x;
+    if (lane > k && lane < 15) {
+      double s = F[lane * 15 + k];
+      for (int j = 0; j < k; ++j) s -= F[lane * 15 + j] * F[k * 15 + j];
+      F[lane * 15 + k] = s / x;
+    }
+    __syncwarp();
+  }
+  // squareRootInformation_ = L^T
+  for (int e = lane; e < 225; e += 32) {
+    const int i = e / 15, j = e % 15;
+    c->sqrt_info[e] = (j >= i) ? F[j * 15 + i] : 0.0;
+  }
+  __syncwarp();
+}
+
+struct ImuEvalOut {  // optional raw dump (svin_ba_evaluate)
+  double *r, *J0, *J1, *J2, *J3;
+};
+
+// ImuError::EvaluateWithMinimalJacobians (ImuError.cpp:706-866) by one warp.
+__device__ void imu_eval_warp(const Batch& b, int ti, int sbuf, double* Jd, double* rd, int n, bool want_jac,
+                              double* sm, int lane, double* cost_out, ImuEvalOut* dump) {
+  const ImuTerm& t = b.imu[ti];
+  ImuCache* c = b.imu_cache + ti;
+  const WinDesc& wd = b.win[t.win];
+  const double* pose0 = b.pose[sbuf] + 7 * (size_t)t.pose0;
+  const double* pose1 = b.pose[sbuf] + 7 * (size_t)t.pose1;
+  const double* sb0 = b.sb[sbuf] + 9 * (size_t)t.sb0;
+  const double* sb1 = b.sb[sbuf] + 9 * (size_t)t.sb1;
+  const double Delta_t = ns_to_sec(t.t1 - t.t0);
+  double Delta_b[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) Delta_b[k] = sb0[3 + k] - c->sb_ref[3 + k];
+  const double nb = sqrt(Delta_b[0] * Delta_b[0] + Delta_b[1] * Delta_b[1] + Delta_b[2] * Delta_b[2]);
+  const bool redo = (c->redo != 0) || (nb * Delta_t > 0.0001);
+  __syncwarp();
+  if (redo) {
+    imu_redo_warp(b, t, c, wd.imu, sb0, sm, lane);
+    if (lane == 0) {
+      c->redo_counter++;
+      c->redo = 0;
+      atomicAdd(&b.ws[t.win].imu_redo, 1);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Delta_b[k] = 0.0;
+    __syncwarp();
+  }
+  double* F0 = sm;          // 225
+  double* F1 = sm + 225;    // 225
+  double* err = sm + 450;   // 15
+  if (lane == 0) {
+    const Tf T0 = tf_load(pose0), T1 = tf_load(pose1);
+    const M3 C_S0_W = m3t(T0.C);
+    const V3 g_W{0.0, 0.0, wd.imu.g};
+    for (int k = 0; k < 225; ++k) {
+      F0[k] = 0.0;
+      F1[k] = 0.0;
+    }
+    for (int k = 0; k < 15; ++k) {
+      F0[k * 15 + k] = 1.0;
+      F1[k * 15 + k] = -1.0;
+    }
+    const V3 dp{T0.r.x - T1.r.x + sb0[0] * Delta_t - 0.5 * g_W.x * Delta_t * Delta_t,
+                T0.r.y - T1.r.y + sb0[1] * Delta_t - 0.5 * g_W.y * Delta_t * Delta_t,
+                T0.r.z - T1.r.z + sb0[2] * Delta_t - 0.5 * g_W.z * Delta_t * Delta_t};
+    const V3 dv{sb0[0] - sb1[0] - g_W.x * Delta_t, sb0[1] - sb1[1] - g_W.y * Delta_t,
+                sb0[2] - sb1[2] - g_W.z * Delta_t};
+    M3 dalpha, dvg, dpg, Cint, Cdint;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      dalpha.m[k] = c->dalpha_db_g[k];
+      dvg.m[k] = c->dv_db_g[k];
+      dpg.m[k] = c->dp_db_g[k];
+      Cint.m[k] = c->C_integral[k];
+      Cdint.m[k] = c->C_doubleintegral[k];
+    }
+    const V3 adb = m3v(dalpha, V3{Delta_b[0], Delta_b[1], Delta_b[2]});
+    const Q4 Dq = qmul(delta_q(V3{-adb.x, -adb.y, -adb.z}),
+                       Q4{c->Delta_q[0], c->Delta_q[1], c->Delta_q[2], c->Delta_q[3]});
+    set_blk(F0, 0, 0, C_S0_W, 1.0);
+    set_blk(F0, 0, 3, m3mul(C_S0_W, crossmx(dp)), 1.0);
+    set_blk(F0, 0, 6, C_S0_W, Delta_t);
+    set_blk(F0, 0, 9, dpg, 1.0);
+    set_blk(F0, 0, 12, Cdint, -1.0);
+    const Q4 q1inv = qinverse(T1.q);
+    double Qa[16], Qb[16], Qc[16], Qd[16];
+    qplus44(qmul(Dq, q1inv), Qa);
+    qoplus44(T0.q, Qb);
+    mat44mul(Qa, Qb, Qc);
+    M3 B33;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) B33.m[a * 3 + cc] = Qc[a * 4 + cc];
+    set_blk(F0, 3, 3, B33, 1.0);
+    qoplus44(qmul(q1inv, T0.q), Qa);
+    qoplus44(Dq, Qb);
+    mat44mul(Qa, Qb, Qc);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) B33.m[a * 3 + cc] = Qc[a * 4 + cc];
+    M3 nd;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) nd.m[k] = -dalpha.m[k];
+    set_blk(F0, 3, 9, m3mul(B33, nd), 1.0);
+    set_blk(F0, 6, 3, m3mul(C_S0_W, crossmx(dv)), 1.0);
+    set_blk(F0, 6, 6, C_S0_W, 1.0);
+    set_blk(F0, 6, 9, dvg, 1.0);
+    set_blk(F0, 6, 12, Cint, -1.0);
+    set_blk(F1, 0, 0, C_S0_W, -1.0);
+    qplus44(Dq, Qa);
+    qoplus44(T0.q, Qb);
+    qplus44(q1inv, Qd);
+    mat44mul(Qa, Qb, Qc);
+    mat44mul(Qc, Qd, Qa);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) B33.m[a * 3 + cc] = Qa[a * 4 + cc];
+    set_blk(F1, 3, 3, B33, -1.0);
+    set_blk(F1, 6, 6, C_S0_W, -1.0);
+    const V3 a3 = m3v(C_S0_W, dp);
+    const double a3v[3] = {a3.x, a3.y, a3.z};
+    for (int k = 0; k < 3; ++k) {
+      double s = 0;
+      for (int cc = 0; cc < 6; ++cc) s += F0[(0 + k) * 15 + 9 + cc] * Delta_b[cc];
+      err[k] = a3v[k] + c->acc_doubleintegral[k] + s;
+    }
+    const Q4 qe = qmul(Dq, qmul(q1inv, T0.q));
+    err[3] = 2 * qe.x;
+    err[4] = 2 * qe.y;
+    err[5] = 2 * qe.z;
+    const V3 b3 = m3v(C_S0_W, dv);
+    const double b3v[3] = {b3.x, b3.y, b3.z};
+    for (int k = 0; k < 3; ++k) {
+      double s = 0;
+      for (int cc = 0; cc < 6; ++cc) s += F0[(6 + k) * 15 + 9 + cc] * Delta_b[cc];
+      err[6 + k] = b3v[k] + c->acc_integral[k] + s;
+    }
+    for (int k = 0; k < 6; ++k) err[9 + k] = sb0[3 + k] - sb1[3 + k];
+  }
+  __syncwarp();
+  const double* U = c->sqrt_info;
+  double cst = 0.0;
+  if (lane < 15) {
+    double s = 0;
+    for (int k = lane; k < 15; ++k) s += U[lane * 15 + k] * err[k];
+    if (rd) rd[t.row0 + lane] = s;
+    if (dump && dump->r) dump->r[15 * (size_t)ti + lane] = s;
+    cst = 0.5 * s * s;
+  }
+  cst = warp_sum(cst);
+  if (lane == 0 && cost_out) atomicAdd(cost_out, cst);
+  if (want_jac) {
+    const int offs[4] = {b.pose_off[t.pose0], b.sb_off[t.sb0], b.pose_off[t.pose1], b.sb_off[t.sb1]};
+    // 15 x 30 outputs: columns 0..5 F0[:,0:6], 6..14 F0[:,6:15], 15..20 F1[:,0:6], 21..29 F1[:,6:15]
+    for (int e = lane; e < 450; e += 32) {
+      const int a = e / 30, col = e % 30;
+      const double* F = (col < 15) ? F0 : F1;
+      const int fc = (col < 15) ? col : col - 15;
+      double s = 0;
+      for (int k = a; k < 15; ++k) s += U[a * 15 + k] * F[k * 15 + fc];
+      const int blk = (col < 6) ? 0 : (col < 15) ? 1 : (col < 21) ? 2 : 3;
+      const int cc = (blk == 0) ? col : (blk == 1) ? col - 6 : (blk == 2) ? col - 15 : col - 21;
+      if (Jd && offs[blk] >= 0) Jd[(size_t)(t.row0 + a) * n + offs[blk] + cc] = s;
+      if (dump) {
+        if (blk == 0 && dump->J0) dump->J0[90 * (size_t)ti + a * 6 + cc] = s;
+        if (blk == 1 && dump->J1) dump->J1[135 * (size_t)ti + a * 9 + cc] = s;
+        if (blk == 2 && dump->J2) dump->J2[90 * (size_t)ti + a * 6 + cc] = s;
+        if (blk == 3 && dump->J3) dump->J3[135 * (size_t)ti + a * 9 + cc] = s;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// pose-type error  r = U * [t_m - t ; 2 vec(q_m * q^-1)]   (PoseError.cpp:85-132)
+__device__ void pose_error_eval(const double* meas, const double* U, const double* pose, double* r, double* J) {
+  const Tf Tm = tf_load(meas), T = tf_load(pose);
+  const Tf dp = tf_mul(Tm, tf_inverse(T));
+  const double e[6] = {Tm.r.x - T.r.x, Tm.r.y - T.r.y, Tm.r.z - T.r.z, 2 * dp.q.x, 2 * dp.q.y, 2 * dp.q.z};
+  for (int i = 0; i < 6; ++i) {
+    double s = 0;
+    for (int k = 0; k < 6; ++k) s += U[i * 6 + k] * e[k];
+    r[i] = s;
+  }
+  if (J) {
+    double Jm[36];
+    for (int k = 0; k < 36; ++k) Jm[k] = 0;
+    for (int k = 0; k < 6; ++k) Jm[k * 6 + k] = -1.0;
+    const M3 Qp = qplus33(dp.q);
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c) Jm[(3 + a) * 6 + 3 + c] = -Qp.m[a * 3 + c];
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) {
+        double s = 0;
+        for (int k = 0; k < 6; ++k) s += U[i * 6 + k] * Jm[k * 6 + j];
+        J[i * 6 + j] = s;
+      }
+  }
+}
+
+// One CTA per window evaluates every non-reprojection term at state buffer (which: 0 cur, 1 candidate),
+// writing residuals into rd[buf] and local Jacobians into Jd[buf] (dense rows x n_dense).
+__global__ void __launch_bounds__(128) k_dense_eval(Batch b, int which, int raw, ImuEvalOut dump) {
+  const int w = blockIdx.x;
+  WinState& ws = b.ws[w];
+  if (!raw) {
+    if (ws.done) return;
+    if (which == 1 && (ws.skip_slot || step_is_invalid(ws))) return;
+  }
+  const WinDesc& wd = b.win[w];
+  const int buf = (which == 0) ? ws.cur : 1 - ws.cur;
+  const int sbuf = raw ? ws.cur : buf;
+  const int n = wd.n_dense;
+  double* Jd = b.Jd[buf] + wd.Jd_off;
+  double* rd = b.rd[buf] + wd.rd_off;
+  __shared__ double sm[4][3 * 225];
+  __shared__ double cost_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) cost_s = 0.0;
+  __syncthreads();
+  ImuEvalOut* dp = raw ? &dump : nullptr;
+  for (int ti = wd.imu_begin + wid; ti < wd.imu_end; ti += 4)
+    imu_eval_warp(b, ti, sbuf, raw ? nullptr : Jd, raw ? nullptr : rd, n, true, sm[wid], lane, &cost_s, dp);
+  // small single-thread terms, spread over threads
+  const int n_pp = wd.pp_end - wd.pp_begin, n_sp = wd.sp_end - wd.sp_begin, n_rp = wd.rp_end - wd.rp_begin;
+  const int n_so = wd.so_end - wd.so_begin, n_de = wd.de_end - wd.de_begin;
+  const int n_small = raw ? 0 : n_pp + n_sp + n_rp + n_so + n_de;
+  for (int k = threadIdx.x; k < n_small; k += blockDim.x) {
+    double cst = 0;
+    if (k < n_pp) {
+      const PosePrior& t = b.pp[wd.pp_begin + k];
+      double r[6], J[36];
+      pose_error_eval(t.meas, t.U, b.pose[sbuf] + 7 * (size_t)t.block, r, J);
+      const int off = b.pose_off[t.block];
+      for (int i = 0; i < 6; ++i) {
+        rd[t.row0 + i] = r[i];
+        cst += 0.5 * r[i] * r[i];
+        if (off >= 0)
+          for (int j = 0; j < 6; ++j) Jd[(size_t)(t.row0 + i) * n + off + j] = J[i * 6 + j];
+      }
+    } else if (k < n_pp + n_sp) {
+      const SbPrior& t = b.sp[wd.sp_begin + k - n_pp];
+      const double* x = b.sb[sbuf] + 9 * (size_t)t.block;
+      const int off = b.sb_off[t.block];
+      for (int i = 0; i < 9; ++i) {
+        double s = 0;
+        for (int c = 0; c < 9; ++c) s += t.U[i * 9 + c] * (t.meas[c] - x[c]);
+        rd[t.row0 + i] = s;
+        cst += 0.5 * s * s;
+        if (off >= 0)
+          for (int j = 0; j < 9; ++j) Jd[(size_t)(t.row0 + i) * n + off + j] = -t.U[i * 9 + j];
+      }
+    } else if (k < n_pp + n_sp + n_rp) {
+      // RelativePoseError.cpp:76-147
+      const RelPose& t = b.rp[wd.rp_begin + k - n_pp - n_sp];
+      const Tf T0 = tf_load(b.pose[sbuf] + 7 * (size_t)t.block0), T1 = tf_load(b.pose[sbuf] + 7 * (size_t)t.block1);
+      const Tf dpq = tf_mul(T1, tf_inverse(T0));
+      const double e[6] = {T1.r.x - T0.r.x, T1.r.y - T0.r.y, T1.r.z - T0.r.z, 2 * dpq.q.x, 2 * dpq.q.y, 2 * dpq.q.z};
+      const M3 Qp = qplus33(dpq.q), Qo = qoplus33(dpq.q);
+      const int off0 = b.pose_off[t.block0], off1 = b.pose_off[t.block1];
+      for (int i = 0; i < 6; ++i) {
+        double s = 0;
+        for (int c = 0; c < 6; ++c) s += t.U[i * 6 + c] * e[c];
+        rd[t.row0 + i] = s;
+        cst += 0.5 * s * s;
+        for (int j = 0; j < 6; ++j) {
+          // J0 = U * [-I 0; 0 -plus33], J1 = U * [I 0; 0 oplus33]
+          double j0 = 0, j1 = 0;
+          if (j < 3) {
+            j0 = -t.U[i * 6 + j];
+            j1 = t.U[i * 6 + j];
+          } else {
+            for (int c = 0; c < 3; ++c) {
+              j0 -= t.U[i * 6 + 3 + c] * Qp.m[c * 3 + (j - 3)];
+              j1 += t.U[i * 6 + 3 + c] * Qo.m[c * 3 + (j - 3)];
+            }
+          }
+          if (off0 >= 0) Jd[(size_t)(t.row0 + i) * n + off0 + j] = j0;
+          if (off1 >= 0) Jd[(size_t)(t.row0 + i) * n + off1 + j] = j1;
+        }
+      }
+    } else if (k < n_pp + n_sp + n_rp + n_so) {
+      // SonarError.cpp:113-183 (Jacobian reproduced as written in the reference)
+      const SonarTerm& t = b.so[wd.so_begin + k - n_pp - n_sp - n_rp];
+      const Tf T = tf_load(b.pose[sbuf] + 7 * (size_t)t.pose);
+      const double dx = T.r.x - t.mean[0], dy = T.r.y - t.mean[1], dz = T.r.z - t.mean[2];
+      const double r = t.sqrt_info * (t.range - sqrt(dx * dx + dy * dy + dz * dz));
+      rd[t.row0] = r;
+      cst += 0.5 * r * r;
+      const int off = b.pose_off[t.pose];
+      if (off >= 0) {
+        const Tf T_SSo = tf_load(wd.T_SSo);
+        const Tf T_WSo = tf_mul(T, T_SSo);
+        const Tf sp = tf_make(V3{t.range * cos(t.heading), t.range * sin(t.heading), 0.0}, Q4{0, 0, 0, 1});
+        const Tf Tp = tf_mul(T_WSo, sp);
+        double* Jr = Jd + (size_t)t.row0 * n + off;
+        Jr[0] = t.sqrt_info * ((T.r.x - Tp.r.x) / t.range);
+        Jr[1] = t.sqrt_info * ((T.r.y - Tp.r.y) / t.range);
+        Jr[2] = t.sqrt_info * ((T.r.z - Tp.r.z) / t.range);
+        Jr[3] = 0; Jr[4] = 0; Jr[5] = 0;
+      }
+    } else {
+      // DepthError.cpp:70-139
+      const DepthTerm& t = b.de[wd.de_begin + k - n_pp - n_sp - n_rp - n_so];
+      const double* x = b.pose[sbuf] + 7 * (size_t)t.pose;
+      const double r = t.sqrt_info * (x[2] - (-1 * t.depth + t.first));
+      rd[t.row0] = r;
+      cst += 0.5 * r * r;
+      const int off = b.pose_off[t.pose];
+      if (off >= 0) {
+        double* Jr = Jd + (size_t)t.row0 * n + off;
+        Jr[0] = 0; Jr[1] = 0; Jr[2] = t.sqrt_info; Jr[3] = 0; Jr[4] = 0; Jr[5] = 0;
+      }
+    }
+    if (!raw) atomicAdd(&cost_s, cst);
+  }
+  // marginalisation prior (MarginalizationError.cpp:798-844): e = e0 + J dchi ; local J per block
+  if (wd.marg_dim > 0 && !raw) {
+    const int m = wd.marg_dim;
+    __shared__ double dchi[512];
+    __shared__ double Mrot[64][9];
+    const int nb = wd.marg_blk_end - wd.marg_blk_begin;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+      const MargBlock& mb = b.marg_blk[wd.marg_blk_begin + k];
+      if (mb.col0 < 0) continue;
+      const double* lp = b.marg_lin + wd.marg_lin_off + mb.lin_off;
+      if (mb.kind == SVIN_BLOCK_POSE) {
+        const double* x = b.pose[sbuf] + 7 * (size_t)mb.index;
+        // PoseManifold::minus (PoseManifold.cpp:92-102)
+        const Q4 d = qmul(Q4{x[3], x[4], x[5], x[6]}, qinverse(Q4{lp[3], lp[4], lp[5], lp[6]}));
+        dchi[mb.col0 + 0] = x[0] - lp[0];
+        dchi[mb.col0 + 1] = x[1] - lp[1];
+        dchi[mb.col0 + 2] = x[2] - lp[2];
+        dchi[mb.col0 + 3] = 2 * d.x;
+        dchi[mb.col0 + 4] = 2 * d.y;
+        dchi[mb.col0 + 5] = 2 * d.z;
+        // J_lift(x_lin) * J_plus(x): top-left 3x3 of oplus(conj(q_lin)) * oplus(normalized(q))
+        double A[16], Bq[16], Cq[16];
+        qoplus44(Q4{-lp[3], -lp[4], -lp[5], lp[6]}, A);
+        qoplus44(qnormalized(Q4{x[3], x[4], x[5], x[6]}), Bq);
+        mat44mul(A, Bq, Cq);
+        for (int a = 0; a < 3; ++a)
+          for (int c = 0; c < 3; ++c) Mrot[k][a * 3 + c] = Cq[a * 4 + c];
+      } else {
+        const double* x = b.sb[sbuf] + 9 * (size_t)mb.index;
+        for (int c = 0; c < 9; ++c) dchi[mb.col0 + c] = x[c] - lp[c];
+      }
+    }
+    __syncthreads();
+    const double* MJ = b.marg_J + wd.margJ_off;
+    const double* e0 = b.marg_e0 + wd.marg_e0_off;
+    double cst = 0;
+    for (int r = threadIdx.x; r < m; r += blockDim.x) {
+      double s = e0[r];
+      for (int c = 0; c < m; ++c) s += MJ[(size_t)r * m + c] * dchi[c];
+      rd[wd.marg_row0 + r] = s;
+      cst += 0.5 * s * s;
+    }
+    atomicAdd(&cost_s, cst);
+    // Jacobian rows
+    for (int e = threadIdx.x; e < m * nb; e += blockDim.x) {
+      const int r = e / nb, k = e % nb;
+      const MargBlock& mb = b.marg_blk[wd.marg_blk_begin + k];
+      if (mb.col0 < 0) continue;
+      const double* Jrow = MJ + (size_t)r * m + mb.col0;
+      if (mb.kind == SVIN_BLOCK_POSE) {
+        const int off = b.pose_off[mb.index];
+        double* out = Jd + (size_t)(wd.marg_row0 + r) * n + off;
+        out[0] = Jrow[0];
+        out[1] = Jrow[1];
+        out[2] = Jrow[2];
+        for (int c = 0; c < 3; ++c)
+          out[3 + c] = Jrow[3] * Mrot[k][0 * 3 + c] + Jrow[4] * Mrot[k][1 * 3 + c] + Jrow[5] * Mrot[k][2 * 3 + c];
+      } else {
+        const int off = b.sb_off[mb.index];
+        double* out = Jd + (size_t)(wd.marg_row0 + r) * n + off;
+        for (int c = 0; c < 9; ++c) out[c] = Jrow[c];
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && !raw) atomicAdd(&ws.cost_cand, cost_s);
+}
+
+// ------------------------------------------------------------------------------------------ reduced system
+// One CTA per window.  Adds the dense-term normal equations, applies Jacobi scaling and the LM
+// diagonal, factorises (Cholesky) and solves; prepares the vectors the landmark kernels need.
+__global__ void __launch_bounds__(kDenseThreads) k_dense_solve(Batch b, SvinBaOptions opt, int use_smem) {
+  extern __shared__ double smem[];
+  const int w = blockIdx.x;
+  WinState& ws = b.ws[w];
+  if (ws.done || ws.reuse) return;
+  const WinDesc& wd = b.win[w];
+  const int n = wd.n_dense, M = wd.n_rows, buf = ws.cur;
+  const int tid = threadIdx.x, T = blockDim.x;
+  double* Hg = b.H + wd.H_off;
+  double* A = use_smem ? smem : Hg;  // (n+1) x n when in smem; in global the rhs row lives in g_red
+  const double* Jd = b.Jd[buf] + wd.Jd_off;
+  const double* rd = b.rd[buf] + wd.rd_off;
+  double* g_red = b.g_red + wd.d_off;
+  double* g_raw = b.g_raw + wd.d_off;
+  double* Hdiag = b.Hdiag + wd.d_off;
+  double* scale = b.scale_d + wd.d_off;
+  double* diag = b.diag_d + wd.d_off;
+  double* grad = b.grad_d + wd.d_off;
+  double* gn = b.gn_d + wd.d_off;
+  double* u = b.u_d + wd.d_off;
+  double* cvec = b.c_d + wd.d_off;
+  __shared__ int fail_s;
+  // 1. A(upper) = H~ + Jd^T Jd
+  for (int e = tid; e < n * n; e += T) {
+    const int i = e / n, j = e % n;
+    if (j < i) continue;
+    double s = Hg[(size_t)i * n + j];
+    for (int r = 0; r < M; ++r) s += Jd[(size_t)r * n + i] * Jd[(size_t)r * n + j];
+    A[(size_t)i * n + j] = s;
+  }
+  // 2. vectors
+  double gmax_l = 0.0;
+  for (int i = tid; i < n; i += T) {
+    double hd = Hdiag[i], gr = 0.0;
+    for (int r = 0; r < M; ++r) {
+      const double jv = Jd[(size_t)r * n + i];
+      hd += jv * jv;
+      gr += jv * rd[r];
+    }
+    Hdiag[i] = hd;
+    g_raw[i] += gr;
+    g_red[i] += gr;
+    gmax_l = fmax(gmax_l, fabs(g_raw[i]));
+  }
+  if (tid == 0) fail_s = 0;
+  atomic_max_nonneg(&ws.gmax_bits, gmax_l);
+  __syncthreads();
+  // 3. gradient tolerance (FinalizeIterationAndCheckIfMinimizerCanContinue order: after max-iterations)
+  __shared__ unsigned long long gmax_s;
+  if (tid == 0) gmax_s = atomicMax(&ws.gmax_bits, 0ull);  // atomic read: L1 may hold a stale WinState line
+  __syncthreads();
+  const double gmax = __longlong_as_double((long long)gmax_s);
+  if (ws.last_successful && gmax <= opt.gradient_tolerance) {
+    __syncthreads();
+    if (tid == 0) {
+      ws.done = 1;
+      ws.termination = SVIN_TERM_CONVERGENCE;
+    }
+    return;
+  }
+  const bool first = (ws.iter == 0 && ws.num_successful == 0 && !ws.invalid);
+  const double mu = ws.mu;
+  for (int i = tid; i < n; i += T) {
+    double s;
+    if (first) {
+      s = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(Hdiag[i])) : 1.0;
+      scale[i] = s;
+    } else {
+      s = scale[i];
+    }
+    const double d = sqrt(fmin(fmax(Hdiag[i] * s * s, opt.min_lm_diagonal), opt.max_lm_diagonal));
+    diag[i] = d;
+    grad[i] = s * g_raw[i] / d;
+  }
+  __syncthreads();
+  // 4. scaled system, full symmetric, + LM diagonal; rhs in row n (smem) or g_red (global)
+  for (int e = tid; e < n * n; e += T) {
+    const int i = e / n, j = e % n;
+    if (j < i) continue;
+    double v = A[(size_t)i * n + j] * scale[i] * scale[j];
+    if (i == j) v += mu * diag[i] * diag[i];
+    A[(size_t)i * n + j] = v;
+  }
+  __syncthreads();
+  for (int e = tid; e < n * n; e += T) {
+    const int i = e / n, j = e % n;
+    if (j < i) A[(size_t)i * n + j] = A[(size_t)j * n + i];
+  }
+  double* rhs = use_smem ? (A + (size_t)n * n) : g_red;
+  for (int i = tid; i < n; i += T) rhs[i] = scale[i] * g_red[i];
+  __syncthreads();
+  // 5. right-looking Cholesky (lower) with the rhs carried as an extra row -> forward solve for free
+  for (int k = 0; k < n; ++k) {
+    const double akk = A[(size_t)k * n + k];
+    if (!(akk > 0.0) || !isfinite(akk)) {
+      if (tid == 0) fail_s = 1;
+      break;
+    }
+    const double d = sqrt(akk);
+    __syncthreads();
+    for (int i = k + 1 + tid; i <= n; i += T) {
+      if (i < n)
+        A[(size_t)i * n + k] /= d;
+      else
+        rhs[k] /= d;
+    }
+    if (tid == 0) A[(size_t)k * n + k] = d;
+    __syncthreads();
+    const int mrem = n - k - 1;
+    for (int e = tid; e < (mrem + 1) * mrem; e += T) {
+      const int ii = e / mrem, jj = e % mrem;  // ii in [0, mrem], row mrem is the rhs row
+      const int j = k + 1 + jj;
+      if (ii < mrem) {
+        const int i = k + 1 + ii;
+        if (j <= i) A[(size_t)i * n + j] -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+      } else {
+        rhs[j] -= rhs[k] * A[(size_t)j * n + k];
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (fail_s) {
+    if (tid == 0) {
+      // DoglegStrategy::ComputeGaussNewtonStep retry: mu *= 10 while mu < max_mu (1.0)
+      ws.mu *= 10.0;
+      if (ws.mu < 1.0) {
+        ws.skip_slot = 1;  // redo the elimination in the next slot; no iteration consumed
+      } else {
+        ws.gn_failed = 1;  // linear solver FAILURE -> invalid step
+      }
+    }
+    return;
+  }
+  // 6. backward solve L^T y = z by warp 0
+  if (tid < 32) {
+    for (int k = n - 1; k >= 0; --k) {
+      const double yk = rhs[k] / A[(size_t)k * n + k];
+      __syncwarp();
+      if (tid == 0) rhs[k] = yk;
+      for (int i = tid; i < k; i += 32) rhs[i] -= A[(size_t)k * n + i] * yk;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  bool bad = false;
+  double g2 = 0, n2 = 0, gd = 0;
+  for (int i = tid; i < n; i += T) {
+    const double y = rhs[i];
+    if (!isfinite(y)) bad = true;
+    const double gni = -y * diag[i];
+    gn[i] = gni;
+    u[i] = scale[i] * y;
+    cvec[i] = scale[i] * grad[i] / diag[i];
+    g2 += grad[i] * grad[i];
+    n2 += gni * gni;
+    gd += grad[i] * gni;
+  }
+  if (__syncthreads_or(bad)) {
+    if (tid == 0) {
+      ws.mu *= 10.0;
+      if (ws.mu < 1.0)
+        ws.skip_slot = 1;
+      else
+        ws.gn_failed = 1;
+    }
+    return;
+  }
+  // Cauchy-point accumulation over the dense rows: |Jd c|^2
+  double jg2 = 0;
+  for (int r = tid; r < M; r += T) {
+    double s = 0;
+    for (int i = 0; i < n; ++i) s += Jd[(size_t)r * n + i] * cvec[i];
+    jg2 += s * s;
+  }
+  double v[4] = {g2, n2, gd, jg2};
+  double* const dst[4] = {&ws.acc_g2, &ws.acc_n2, &ws.acc_gdot, &ws.acc_Jg2};
+  block_atomic_add<4, kDenseThreads>(v, dst);
+}
+
+// ------------------------------------------------------------------------------------------ back-substitution
+template <bool HAS_EXT>
+__global__ void __launch_bounds__(kLmTile) k_backsub(Batch b) {
+  const int tile = blockIdx.x;
+  const int w = b.lm_tile_win[tile];
+  WinState& ws = b.ws[w];
+  if (ws.done || ws.reuse || ws.skip_slot || ws.gn_failed) return;
+  const WinDesc& wd = b.win[w];
+  const int l = b.lm_tile_begin[tile] + threadIdx.x;
+  const int buf = ws.cur;
+  double acc[4] = {0, 0, 0, 0};  // g2, n2, gdot, Jg2
+  if (l < wd.lm_end) {
+    const double* u = b.u_d + wd.d_off;
+    const double* cv = b.c_d + wd.d_off;
+    const bool lfix = b.lm_fixed[l] != 0;
+    double s[3] = {1, 1, 1}, cl[3] = {0, 0, 0}, gr[3] = {0, 0, 0}, dg[3] = {1, 1, 1};
+    if (!lfix) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        s[k] = b.lm_scale[3 * (size_t)l + k];
+        gr[k] = b.lm_grad[3 * (size_t)l + k];
+        dg[k] = b.lm_diag[3 * (size_t)l + k];
+        cl[k] = s[k] * gr[k] / dg[k];
+      }
+    }
+    double a3[3] = {0, 0, 0};
+    const int ob = b.lm_obs_begin[l], oe = b.lm_obs_begin[l + 1];
+    for (int o = ob; o < oe; ++o) {
+      ObsJ J;
+      load_obs(b, buf, o, J);
+      const int offp = b.pose_off[b.obs_pose[o]];
+      double t0 = 0, t1 = 0, m0 = 0, m1 = 0;
+      if (offp >= 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          t0 += J.Jp[k] * u[offp + k];
+          t1 += J.Jp[6 + k] * u[offp + k];
+          m0 += J.Jp[k] * cv[offp + k];
+          m1 += J.Jp[6 + k] * cv[offp + k];
+        }
+      }
+      if (HAS_EXT) {
+        const int offe = b.pose_off[b.obs_ext[o]];
+        if (offe >= 0) {
+          double Je[12];
+          load_Je(b, buf, o, Je);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            t0 += Je[k] * u[offe + k];
+            t1 += Je[6 + k] * u[offe + k];
+            m0 += Je[k] * cv[offe + k];
+            m1 += Je[6 + k] * cv[offe + k];
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        a3[k] += J.Jl[k] * t0 + J.Jl[3 + k] * t1;
+        m0 += J.Jl[k] * cl[k];
+        m1 += J.Jl[3 + k] * cl[k];
+      }
+      acc[3] += m0 * m0 + m1 * m1;
+    }
+    if (!lfix) {
+      const double* Vi = b.lm_Vinv + 6 * (size_t)l;
+      const double* bs = b.lm_bs + 3 * (size_t)l;
+      const double r0 = bs[0] - s[0] * a3[0], r1 = bs[1] - s[1] * a3[1], r2 = bs[2] - s[2] * a3[2];
+      const double y0 = Vi[0] * r0 + Vi[1] * r1 + Vi[2] * r2;
+      const double y1 = Vi[1] * r0 + Vi[3] * r1 + Vi[4] * r2;
+      const double y2 = Vi[2] * r0 + Vi[4] * r1 + Vi[5] * r2;
+      const double g0 = -y0 * dg[0], g1 = -y1 * dg[1], g2 = -y2 * dg[2];
+      double* gn = b.lm_gn + 3 * (size_t)l;
+      gn[0] = g0;
+      gn[1] = g1;
+      gn[2] = g2;
+      acc[0] = gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2];
+      acc[1] = g0 * g0 + g1 * g1 + g2 * g2;
+      acc[2] = gr[0] * g0 + gr[1] * g1 + gr[2] * g2;
+      if (!isfinite(y0) || !isfinite(y1) || !isfinite(y2)) acc[1] = nan("");
+    }
+  }
+  double* const dst[4] = {&ws.acc_g2, &ws.acc_n2, &ws.acc_gdot, &ws.acc_Jg2};
+  block_atomic_add<4, kLmTile>(acc, dst);
+}
+
+// ------------------------------------------------------------------------------------------ dogleg step
+// One CTA per window: iteration accounting, dogleg interpolation coefficients, dense part of the step,
+// candidate poses / speed-biases, dense rows of the model cost change.
+__global__ void __launch_bounds__(128) k_step_dense(Batch b, SvinBaOptions opt) {
+  const int w = blockIdx.x;
+  WinState& ws = b.ws[w];
+  if (ws.done || ws.skip_slot) return;
+  const WinDesc& wd = b.win[w];
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int n = wd.n_dense, M = wd.n_rows, buf = ws.cur;
+  __shared__ double cg_s, cn_s;
+  __shared__ int failed_s;
+  __syncthreads();
+  if (tid == 0) {
+    ws.iter += 1;
+    ws.last_successful = 0;
+    ws.t_iter_start_ns = globaltimer_ns();
+    if (!ws.gn_failed) {
+      if (!ws.reuse) {
+        ws.alpha = ws.acc_g2 / ws.acc_Jg2;
+        if (!isfinite(ws.acc_n2)) ws.gn_failed = 1;  // IsArrayValid(gauss_newton_step_) failed
+      }
+    }
+    double cg = 0, cn = 0;
+    if (!ws.gn_failed) {
+      // DoglegStrategy::ComputeTraditionalDoglegStep
+      const double g2 = ws.acc_g2, n2 = ws.acc_n2, gdot = ws.acc_gdot, radius = ws.radius, alpha = ws.alpha;
+      const double gradient_norm = sqrt(g2), gauss_newton_norm = sqrt(n2);
+      if (gauss_newton_norm <= radius) {
+        cg = 0.0;
+        cn = 1.0;
+        ws.dogleg_step_norm = gauss_newton_norm;
+      } else if (gradient_norm * alpha >= radius) {
+        cg = -(radius / gradient_norm);
+        cn = 0.0;
+        ws.dogleg_step_norm = radius;
+      } else {
+        const double b_dot_a = -alpha * gdot;
+        const double a_squared_norm = (alpha * gradient_norm) * (alpha * gradient_norm);
+        const double b_minus_a_squared_norm = a_squared_norm - 2 * b_dot_a + gauss_newton_norm * gauss_newton_norm;
+        const double c = b_dot_a - a_squared_norm;
+        const double d = sqrt(c * c + b_minus_a_squared_norm * (radius * radius - a_squared_norm));
+        const double beta = (c <= 0) ? (d - c) / b_minus_a_squared_norm : (radius * radius - a_squared_norm) / (d + c);
+        cg = -alpha * (1.0 - beta);
+        cn = beta;
+        ws.dogleg_step_norm = sqrt(fmax(0.0, cg * cg * g2 + 2.0 * cg * cn * gdot + cn * cn * n2));
+      }
+    }
+    ws.cg = cg;
+    ws.cn = cn;
+    ws.reuse = 1;
+    cg_s = cg;
+    cn_s = cn;
+    failed_s = ws.gn_failed;
+  }
+  __syncthreads();
+  if (failed_s) return;
+  const double cg = cg_s, cn = cn_s;
+  const double* scale = b.scale_d + wd.d_off;
+  const double* diag = b.diag_d + wd.d_off;
+  const double* grad = b.grad_d + wd.d_off;
+  const double* gn = b.gn_d + wd.d_off;
+  double* delta = b.delta_d + wd.d_off;
+  for (int i = tid; i < n; i += T) delta[i] = scale[i] * (cg * grad[i] + cn * gn[i]) / diag[i];
+  __syncthreads();
+  double acc[3] = {0, 0, 0};  // mc, step2, xnorm2
+  // candidate dense state (x (+) delta) into the other buffer; fixed blocks are copied
+  const int np = wd.pose_end - wd.pose_begin, ns = wd.sb_end - wd.sb_begin;
+  for (int k = tid; k < np + ns; k += T) {
+    if (k < np) {
+      const int p = wd.pose_begin + k;
+      const double* x = b.pose[buf] + 7 * (size_t)p;
+      double* y = b.pose[1 - buf] + 7 * (size_t)p;
+      const int off = b.pose_off[p];
+      if (off >= 0) {
+        pose_plus(x, delta + off, y);
+        for (int c = 0; c < 7; ++c) {
+          acc[1] += (x[c] - y[c]) * (x[c] - y[c]);
+          acc[2] += x[c] * x[c];
+        }
+      } else {
+        for (int c = 0; c < 7; ++c) y[c] = x[c];
+      }
+    } else {
+      const int s = wd.sb_begin + k - np;
+      const double* x = b.sb[buf] + 9 * (size_t)s;
+      double* y = b.sb[1 - buf] + 9 * (size_t)s;
+      const int off = b.sb_off[s];
+      for (int c = 0; c < 9; ++c) {
+        y[c] = (off >= 0) ? x[c] + delta[off + c] : x[c];
+        if (off >= 0) {
+          acc[1] += (x[c] - y[c]) * (x[c] - y[c]);
+          acc[2] += x[c] * x[c];
+        }
+      }
+    }
+  }
+  // dense rows of the model: m = Jd * delta
+  const double* Jd = b.Jd[buf] + wd.Jd_off;
+  const double* rd = b.rd[buf] + wd.rd_off;
+  for (int r = tid; r < M; r += T) {
+    double m = 0;
+    for (int i = 0; i < n; ++i) m += Jd[(size_t)r * n + i] * delta[i];
+    acc[0] += m * (rd[r] + m / 2.0);
+  }
+  double* const dst[3] = {&ws.acc_mc, &ws.acc_step2, &ws.acc_xnorm2};
+  block_atomic_add<3, 128>(acc, dst);
+}
+
+template <bool HAS_EXT>
+__global__ void __launch_bounds__(kLmTile) k_step_lm(Batch b) {
+  const int tile = blockIdx.x;
+  const int w = b.lm_tile_win[tile];
+  WinState& ws = b.ws[w];
+  if (ws.done || ws.skip_slot || ws.gn_failed) return;
+  const WinDesc& wd = b.win[w];
+  const int l = b.lm_tile_begin[tile] + threadIdx.x;
+  const int buf = ws.cur;
+  double acc[3] = {0, 0, 0};
+  if (l < wd.lm_end) {
+    const double cg = ws.cg, cn = ws.cn;
+    const double* delta = b.delta_d + wd.d_off;
+    const bool lfix = b.lm_fixed[l] != 0;
+    const double* x = b.lm[buf] + 4 * (size_t)l;
+    double* y = b.lm[1 - buf] + 4 * (size_t)l;
+    double dl[3] = {0, 0, 0};
+    const double x0 = x[0], x1 = x[1], x2 = x[2], x3 = x[3];
+    if (!lfix) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        dl[k] = b.lm_scale[3 * (size_t)l + k] *
+                (cg * b.lm_grad[3 * (size_t)l + k] + cn * b.lm_gn[3 * (size_t)l + k]) / b.lm_diag[3 * (size_t)l + k];
+      acc[1] = dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2];
+      acc[2] = x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
+    }
+    y[0] = x0 + dl[0];
+    y[1] = x1 + dl[1];
+    y[2] = x2 + dl[2];
+    y[3] = x3;
+    const int ob = b.lm_obs_begin[l], oe = b.lm_obs_begin[l + 1];
+    for (int o = ob; o < oe; ++o) {
+      ObsJ J;
+      load_obs(b, buf, o, J);
+      double m0 = J.Jl[0] * dl[0] + J.Jl[1] * dl[1] + J.Jl[2] * dl[2];
+      double m1 = J.Jl[3] * dl[0] + J.Jl[4] * dl[1] + J.Jl[5] * dl[2];
+      const int offp = b.pose_off[b.obs_pose[o]];
+      if (offp >= 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          m0 += J.Jp[k] * delta[offp + k];
+          m1 += J.Jp[6 + k] * delta[offp + k];
+        }
+      }
+      if (HAS_EXT) {
+        const int offe = b.pose_off[b.obs_ext[o]];
+        if (offe >= 0) {
+          double Je[12];
+          load_Je(b, buf, o, Je);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            m0 += Je[k] * delta[offe + k];
+            m1 += Je[6 + k] * delta[offe + k];
+          }
+        }
+      }
+      acc[0] += m0 * (J.r0 + m0 / 2.0) + m1 * (J.r1 + m1 / 2.0);
+    }
+  }
+  double* const dst[3] = {&ws.acc_mc, &ws.acc_step2, &ws.acc_xnorm2};
+  block_atomic_add<3, kLmTile>(acc, dst);
+}
+
+// ------------------------------------------------------------------------------------------ accept / reject
+__device__ __forceinline__ void clear_accumulators(WinState& ws) {
+  ws.acc_g2 = ws.acc_n2 = ws.acc_gdot = ws.acc_Jg2 = 0.0;
+}
+__global__ void k_decide(Batch b, SvinBaOptions opt) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= b.B) return;
+  WinState& ws = b.ws[w];
+  if (ws.done) return;
+  if (ws.skip_slot) {
+    ws.skip_slot = 0;
+    clear_accumulators(ws);
+    ws.gmax_bits = 0ull;
+    return;
+  }
+  const double model_cost_change = -ws.acc_mc;
+  if (ws.gn_failed || !(model_cost_change > 0.0)) {
+    // HandleInvalidStep + DoglegStrategy::StepIsInvalid
+    ws.invalid += 1;
+    if (ws.invalid >= opt.max_num_consecutive_invalid_steps) {
+      ws.done = 1;
+      ws.termination = SVIN_TERM_FAILURE;
+    }
+    ws.mu *= 10.0;
+    ws.reuse = 0;
+    ws.gn_failed = 0;
+  } else {
+    ws.invalid = 0;
+    const double step_norm = sqrt(ws.acc_step2), x_norm = sqrt(ws.acc_xnorm2);
+    const double cost_change = ws.cost_x - ws.cost_cand;
+    if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
+      ws.done = 1;
+      ws.termination = SVIN_TERM_CONVERGENCE;
+    } else if (fabs(cost_change) <= opt.function_tolerance * ws.cost_x) {
+      ws.done = 1;
+      ws.termination = SVIN_TERM_CONVERGENCE;
+    } else {
+      const double relative_decrease = cost_change / model_cost_change;
+      if (relative_decrease > opt.min_relative_decrease) {
+        // HandleSuccessfulStep + DoglegStrategy::StepAccepted
+        ws.cur ^= 1;
+        ws.cost_x = ws.cost_cand;
+        ws.last_successful = 1;
+        ws.num_successful += 1;
+        if (relative_decrease < 0.25) ws.radius *= 0.5;
+        if (relative_decrease > 0.75) ws.radius = fmax(ws.radius, 3.0 * ws.dogleg_step_norm);
+        ws.mu = fmax(1e-8, 2.0 * ws.mu / 10.0);
+        ws.reuse = 0;
+      } else {
+        ws.radius *= 0.5;  // StepRejected; reuse stays set
+      }
+    }
+  }
+  ws.cost_cand = 0.0;
+  ws.acc_mc = ws.acc_step2 = ws.acc_xnorm2 = 0.0;
+  if (!ws.reuse) {
+    clear_accumulators(ws);
+    ws.gmax_bits = 0ull;
+  }
+  if (!ws.done) {
+    const unsigned long long now = globaltimer_ns();
+    const double iter_time = (double)(now - ws.t_iter_start_ns) * 1e-9;
+    const double cumulative = (double)(now - ws.t_start_ns) * 1e-9;
+    if (opt.time_limit_seconds >= 0.0 && ws.iter >= opt.min_num_iterations &&
+        cumulative + iter_time > opt.time_limit_seconds) {
+      ws.done = 1;
+      ws.termination = SVIN_TERM_USER_SUCCESS;
+    } else if (ws.iter >= opt.max_num_iterations) {
+      ws.done = 1;
+      ws.termination = SVIN_TERM_NO_CONVERGENCE;
+    } else if (ws.radius < opt.min_trust_region_radius) {
+      ws.done = 1;
+      ws.termination = SVIN_TERM_CONVERGENCE;
+    }
+  }
+}
+
+// after the initial linearisation
+__global__ void k_init(Batch b, SvinBaOptions opt) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= b.B) return;
+  WinState& ws = b.ws[w];
+  ws.cost_x = ws.cost_cand;
+  ws.initial_cost = ws.cost_cand;
+  ws.cost_cand = 0.0;
+  ws.t_start_ns = globaltimer_ns();
+  if (opt.max_num_iterations <= 0) {
+    ws.done = 1;
+    ws.termination = SVIN_TERM_NO_CONVERGENCE;
+  }
+}
+
+__global__ void k_count_active(Batch b, int* out) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= b.B) return;
+  if (!b.ws[w].done) atomicAdd(out, 1);
+}
+
+// Estimator.cpp:903-922: H = sum J1min^T J1min over the landmark's residuals (no loss), quality = sqrt(lmin/lmax)
+__global__ void __launch_bounds__(kLmTile) k_quality(Batch b) {
+  const int tile = blockIdx.x;
+  const int w = b.lm_tile_win[tile];
+  const WinDesc& wd = b.win[w];
+  const WinState& ws = b.ws[w];
+  const int l = b.lm_tile_begin[tile] + threadIdx.x;
+  if (l >= wd.lm_end) return;
+  const int buf = ws.cur;
+  double Hm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const int ob = b.lm_obs_begin[l], oe = b.lm_obs_begin[l + 1];
+  for (int o = ob; o < oe; ++o) {
+    Reproj R;
+    reproj_eval<true, false>(b.pose[buf] + 7 * (size_t)b.obs_pose[o], b.lm[buf] + 4 * (size_t)l,
+                             b.pose[buf] + 7 * (size_t)b.obs_ext[o], b.intr + 8 * (size_t)b.obs_cam[o], b.obs_zx[o],
+                             b.obs_zy[o], b.obs_u00[o], b.obs_u01[o], b.obs_u11[o], wd.loss_type, wd.loss_scale, true,
+                             R);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Hm[i * 3 + j] += R.Jl[i] * R.Jl[j] + R.Jl[3 + i] * R.Jl[3 + j];
+  }
+  double ev[3];
+  sym3_eigenvalues(Hm, ev);
+  b.lm_quality[l] = (ev[0] < 1.0e-12) ? 0.0 : sqrt(ev[0]) / sqrt(ev[2]);
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+void launch_linearize(const Batch& b, int which, int raw, cudaStream_t st) {
+  if (b.n_obs_tiles == 0) return;
+  if (b.has_ext || (raw && b.lin_Je[1] != nullptr))
+    k_linearize<true><<<b.n_obs_tiles, kObsTile, 0, st>>>(b, which, raw);
+  else
+    k_linearize<false><<<b.n_obs_tiles, kObsTile, 0, st>>>(b, which, raw);
+}
+void launch_dense_eval(const Batch& b, int which, int raw, const double* const* dump, cudaStream_t st) {
+  ImuEvalOut d{nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (dump) {
+    d.r = const_cast<double*>(dump[0]);
+    d.J0 = const_cast<double*>(dump[1]);
+    d.J1 = const_cast<double*>(dump[2]);
+    d.J2 = const_cast<double*>(dump[3]);
+    d.J3 = const_cast<double*>(dump[4]);
+  }
+  k_dense_eval<<<b.B, 128, 0, st>>>(b, which, raw, d);
+}
+void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {
+  if (b.n_lm_tiles == 0) return;
+  if (b.has_ext)
+    k_schur<true><<<b.n_lm_tiles, kLmTile, 0, st>>>(b, opt);
+  else
+    k_schur<false><<<b.n_lm_tiles, kLmTile, 0, st>>>(b, opt);
+}
+int dense_solve_smem_bytes(int n_max) { return (int)(((size_t)n_max + 1) * n_max * sizeof(double)); }
+cudaError_t configure_dense_solve(int smem_bytes) {
+  return cudaFuncSetAttribute(k_dense_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+}
+void launch_dense_solve(const Batch& b, const SvinBaOptions& opt, int smem_bytes, cudaStream_t st) {
+  k_dense_solve<<<b.B, kDenseThreads, smem_bytes, st>>>(b, opt, smem_bytes > 0 ? 1 : 0);
+}
+void launch_backsub(const Batch& b, cudaStream_t st) {
+  if (b.n_lm_tiles == 0) return;
+  if (b.has_ext)
+    k_backsub<true><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
+  else
+    k_backsub<false><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
+}
+void launch_step_dense(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {
+  k_step_dense<<<b.B, 128, 0, st>>>(b, opt);
+}
+void launch_step_lm(const Batch& b, cudaStream_t st) {
+  if (b.n_lm_tiles == 0) return;
+  if (b.has_ext)
+    k_step_lm<true><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
+  else
+    k_step_lm<false><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
+}
+void launch_decide(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {
+  k_decide<<<div_up(b.B, 64), 64, 0, st>>>(b, opt);
+}
+void launch_init(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {
+  k_init<<<div_up(b.B, 64), 64, 0, st>>>(b, opt);
+}
+void launch_count_active(const Batch& b, int* out, cudaStream_t st) {
+  k_count_active<<<div_up(b.B, 64), 64, 0, st>>>(b, out);
+}
+// copy the accepted estimate (buffer ws.cur of each window) into contiguous output arrays
+__global__ void k_gather_state(Batch b, const int* pose_win, const int* sb_win, double* pose_out, double* sb_out,
+                               double* lm_out) {
+  const int stride = gridDim.x * blockDim.x;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = t0; i < b.NPB * 7; i += stride) pose_out[i] = b.pose[b.ws[pose_win[i / 7]].cur][i];
+  for (int i = t0; i < b.NSB * 9; i += stride) sb_out[i] = b.sb[b.ws[sb_win[i / 9]].cur][i];
+  for (int i = t0; i < b.NL * 4; i += stride) lm_out[i] = b.lm[b.ws[b.lm_win[i / 4]].cur][i];
+}
+void launch_gather_state(const Batch& b, const int* pose_win, const int* sb_win, double* pose_out, double* sb_out,
+                         double* lm_out, cudaStream_t st) {
+  const int n = max(b.NPB * 7, max(b.NSB * 9, b.NL * 4));
+  k_gather_state<<<max(1u, min(div_up(n, 256), 1184u)), 256, 0, st>>>(b, pose_win, sb_win, pose_out, sb_out, lm_out);
+}
+
+void launch_quality(const Batch& b, cudaStream_t st) {
+  if (b.n_lm_tiles == 0) return;
+  k_quality<<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
+}
+
+}  // namespace svin

@@ -1,0 +1,97 @@
+"""Thin Python handle on the CUDA BA engine (ctypes over include/svin_b200.h).
+
+Mirrors the call sequence of okvis::Estimator::optimize (Estimator.cpp:876-929): the window is
+flattened, solved on the device and the solution plus the per-landmark quality is written back.
+There is no CPU path here: every method raises SvinError if the CUDA library or device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .window import BaWindow, default_options
+
+
+class BaEngine:
+    def __init__(self, device: int = 0):
+        self._lib = capi.load()
+        self._ctx = C.c_void_p()
+        capi.check(self._lib.svin_ba_create(device, C.byref(self._ctx)), self._lib)
+        self._windows = None
+
+    def close(self):
+        if self._ctx:
+            self._lib.svin_ba_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- staged API -----------------------------------------------------------------------
+    def upload(self, windows: list[BaWindow]):
+        arr = (capi.SvinBaWindow * len(windows))(*[w.c_struct() for w in windows])
+        capi.check(self._lib.svin_ba_upload(self._ctx, arr, len(windows)), self._lib)
+        self._windows = windows
+        self._arr = arr
+
+    def reset(self):
+        capi.check(self._lib.svin_ba_reset(self._ctx), self._lib)
+
+    def solve(self, options: capi.SvinBaOptions | None = None) -> list[dict]:
+        opt = options or default_options()
+        n = len(self._windows)
+        summ = (capi.SvinBaSummary * n)()
+        capi.check(self._lib.svin_ba_solve(self._ctx, C.byref(opt), summ), self._lib)
+        return [s.as_dict() for s in summ]
+
+    def download(self, index: int, into: BaWindow | None = None):
+        w = into or self._windows[index]
+        q = np.zeros(w.num_landmarks)
+        s = w.c_struct()
+        capi.check(self._lib.svin_ba_download(self._ctx, index, C.byref(s), q.ctypes.data_as(capi.c_double_p)),
+                   self._lib)
+        return w, q
+
+    def evaluate(self, index: int = 0) -> dict:
+        w = self._windows[index]
+        n, m = w.num_obs, len(w.imu_pose0)
+        out = dict(reproj_residuals=np.zeros((n, 2)), reproj_J_pose=np.zeros((n, 2, 6)),
+                   reproj_J_landmark=np.zeros((n, 2, 3)), reproj_J_extrinsics=np.zeros((n, 2, 6)),
+                   imu_residuals=np.zeros((m, 15)), imu_J_pose0=np.zeros((m, 15, 6)),
+                   imu_J_speedbias0=np.zeros((m, 15, 9)), imu_J_pose1=np.zeros((m, 15, 6)),
+                   imu_J_speedbias1=np.zeros((m, 15, 9)), cost=np.zeros(1))
+        ev = capi.SvinBaEvaluation()
+        for k, v in out.items():
+            setattr(ev, k, v.ctypes.data_as(capi.c_double_p))
+        capi.check(self._lib.svin_ba_evaluate(self._ctx, index, C.byref(ev)), self._lib)
+        return out
+
+    def timings(self) -> dict:
+        t = capi.SvinBaTimings()
+        capi.check(self._lib.svin_ba_timings(self._ctx, C.byref(t)), self._lib)
+        return {n: getattr(t, n) for n, _ in t._fields_}
+
+    # ---- one-shot API: the drop-in for Estimator::optimize ---------------------------------------
+    def optimize(self, windows: list[BaWindow], options: capi.SvinBaOptions | None = None):
+        """upload + solve + download (host buffers in, host buffers out).  Returns (summaries, qualities)."""
+        opt = options or default_options()
+        n = len(windows)
+        arr = (capi.SvinBaWindow * n)(*[w.c_struct() for w in windows])
+        summ = (capi.SvinBaSummary * n)()
+        quals = [np.zeros(w.num_landmarks) for w in windows]
+        qptr = (capi.c_double_p * n)(*[q.ctypes.data_as(capi.c_double_p) for q in quals])
+        capi.check(self._lib.svin_ba_optimize(self._ctx, arr, n, C.byref(opt), summ, qptr), self._lib)
+        self._windows = windows
+        self._arr = arr
+        return [s.as_dict() for s in summ], quals

@@ -1,0 +1,121 @@
+"""GPU parity tests for hot path (B): CUDA engine (through the C ABI) vs the CPU oracle on the
+same seeded windows.  fp64 throughout; tolerances are written next to each assertion."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from svin_b200.synthetic import make_window
+from svin_b200.window import default_options
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from svin_b200.engine import BaEngine
+    e = BaEngine(0)
+    yield e
+    e.close()
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(1e-300, np.abs(b).max())
+
+
+@pytest.mark.parametrize("kw", [
+    dict(seed=101, num_keyframes=4, num_imu_frames=3, num_landmarks=300, mode="initial"),
+    dict(seed=102, num_keyframes=5, num_imu_frames=3, num_landmarks=500, mode="steady"),
+    dict(seed=103, num_keyframes=3, num_imu_frames=3, num_landmarks=200, mode="steady", extrinsics="random_walk",
+         sonar=True, depth=True),
+])
+def test_term_evaluation_matches_oracle(engine, kw):
+    # EvaluateWithMinimalJacobians seam: residuals and minimal Jacobians of every reprojection and IMU
+    # term.  Reprojection: <= 1e-12 relative.  IMU: the 15x15 covariance inverse has condition ~1e8,
+    # so fused-multiply-add rounding shows up at ~1e-8 relative in the square-root information.
+    w, _ = make_window(**kw)
+    ref = oracle_lib.evaluate(w)
+    engine.upload([w])
+    got = engine.evaluate(0)
+    for k in ("reproj_residuals", "reproj_J_pose", "reproj_J_landmark", "reproj_J_extrinsics"):
+        assert _rel(got[k], ref[k]) < 1e-12, k
+    for k in ("imu_residuals", "imu_J_pose0", "imu_J_speedbias0", "imu_J_pose1", "imu_J_speedbias1"):
+        assert _rel(got[k], ref[k]) < 1e-6, (k, _rel(got[k], ref[k]))
+    assert abs(got["cost"][0] - ref["cost"][0]) < 1e-7 * abs(ref["cost"][0])
+
+
+@pytest.mark.parametrize("kw", [
+    dict(seed=201, num_keyframes=4, num_imu_frames=3, num_landmarks=300, mode="initial"),
+    dict(seed=202, num_keyframes=5, num_imu_frames=3, num_landmarks=600, mode="steady"),
+    dict(seed=203, num_keyframes=10, num_imu_frames=3, num_landmarks=2000, mode="steady"),
+    dict(seed=204, num_keyframes=3, num_imu_frames=3, num_landmarks=200, mode="steady", extrinsics="random_walk",
+         sonar=True, depth=True),
+])
+def test_solve_matches_oracle_after_same_iteration_count(engine, kw):
+    # north_star: pose/landmark solutions within 1e-6 relative after the same iteration count.
+    w_gpu, _ = make_window(**kw)
+    w_ref = w_gpu.copy()
+    opt = default_options(max_num_iterations=10)
+    s_ref, q_ref = oracle_lib.solve(w_ref, opt)
+    s_gpu, q_gpu = engine.optimize([w_gpu], opt)
+    s_gpu, q_gpu = s_gpu[0], q_gpu[0]
+    assert s_gpu["iterations"] == s_ref["iterations"]
+    assert s_gpu["num_successful_steps"] == s_ref["num_successful_steps"]
+    assert s_gpu["termination"] == s_ref["termination"]
+    assert abs(s_gpu["initial_cost"] - s_ref["initial_cost"]) < 1e-9 * s_ref["initial_cost"]
+    assert abs(s_gpu["final_cost"] - s_ref["final_cost"]) < 1e-6 * s_ref["final_cost"]
+    assert _rel(w_gpu.pose_blocks, w_ref.pose_blocks) < 1e-6
+    assert _rel(w_gpu.speedbias, w_ref.speedbias) < 1e-6
+    assert _rel(w_gpu.landmarks, w_ref.landmarks) < 1e-6
+    assert np.abs(q_gpu - q_ref).max() < 1e-6
+
+
+def test_batch_of_windows_is_solved_independently(engine):
+    # ragged batch: different sizes, one window without IMU/prior terms, one empty of observations
+    ws = [make_window(seed=300 + i, num_keyframes=3 + i, num_imu_frames=3, num_landmarks=150 + 70 * i,
+                      mode="steady" if i % 2 else "initial")[0] for i in range(5)]
+    refs = [w.copy() for w in ws]
+    opt = default_options(max_num_iterations=6)
+    s_gpu, _ = engine.optimize(ws, opt)
+    for w, r, s in zip(ws, refs, s_gpu):
+        s_ref, _ = oracle_lib.solve(r, opt)
+        assert s["iterations"] == s_ref["iterations"]
+        assert _rel(w.pose_blocks, r.pose_blocks) < 1e-6
+        assert _rel(w.landmarks, r.landmarks) < 1e-6
+
+
+def test_unsorted_observations_and_fixed_blocks(engine):
+    w, _ = make_window(seed=401, num_keyframes=4, num_imu_frames=3, num_landmarks=250, mode="initial")
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(w.num_obs)
+    for name in ("obs_pose", "obs_landmark", "obs_extrinsics", "obs_camera", "obs_measurement", "obs_information"):
+        setattr(w, name, getattr(w, name)[perm].copy())
+    w.pose_fixed[2] = 1
+    w.landmark_fixed = np.zeros(w.num_landmarks, dtype=np.uint8)
+    w.landmark_fixed[::7] = 1
+    w.finalize()
+    r = w.copy()
+    opt = default_options(max_num_iterations=8)
+    s_ref, _ = oracle_lib.solve(r, opt)
+    s_gpu, _ = engine.optimize([w], opt)
+    assert s_gpu[0]["iterations"] == s_ref["iterations"]
+    assert _rel(w.pose_blocks, r.pose_blocks) < 1e-6
+    assert _rel(w.landmarks, r.landmarks) < 1e-6
+    assert np.array_equal(w.pose_blocks[2], r.pose_blocks[2])
+
+
+def test_reset_and_resolve_is_repeatable(engine):
+    w, _ = make_window(seed=501, num_keyframes=5, num_imu_frames=3, num_landmarks=400, mode="steady")
+    engine.upload([w])
+    a = engine.solve(default_options())
+    engine.reset()
+    b = engine.solve(default_options())
+    assert a[0]["iterations"] == b[0]["iterations"]
+    assert abs(a[0]["final_cost"] - b[0]["final_cost"]) < 1e-9 * abs(a[0]["final_cost"])
+
+
+def test_invalid_window_is_rejected_with_message(engine):
+    from svin_b200.capi import SvinError
+    w, _ = make_window(seed=601, num_keyframes=3, num_imu_frames=3, num_landmarks=50, mode="initial")
+    w.obs_landmark[3] = 10 ** 6
+    with pytest.raises(SvinError, match="obs_landmark"):
+        engine.upload([w])
