@@ -263,6 +263,28 @@ typedef struct SvinBaTimings {
 } SvinBaTimings;
 int svin_ba_timings(svin_ba_ctx* ctx, SvinBaTimings* out);
 
+/* Per-kernel-family device time of the last svin_ba_solve, measured with CUDA events on the engine's
+ * stream around every launch.  Only filled when profiling is enabled (it adds an event pair per launch,
+ * so throughput numbers are taken with it off). */
+enum {
+  SVIN_BA_K_LINEARIZE = 0, /* reprojection residual + Jacobian, one thread per observation */
+  SVIN_BA_K_DENSE_EVAL,    /* IMU / prior / sonar / depth / marginalisation terms */
+  SVIN_BA_K_SCHUR,         /* landmark-block elimination into the reduced system */
+  SVIN_BA_K_DENSE_SOLVE,   /* reduced-system Cholesky + solve */
+  SVIN_BA_K_BACKSUB,       /* landmark back-substitution + Cauchy point */
+  SVIN_BA_K_STEP_DENSE,    /* dogleg step, candidate poses */
+  SVIN_BA_K_STEP_LM,       /* candidate landmarks + model cost */
+  SVIN_BA_K_DECIDE,        /* accept / reject */
+  SVIN_BA_K_CLEAR,         /* per-slot memset of the reduced-system accumulators */
+  SVIN_BA_K_COUNT
+};
+typedef struct SvinBaKernelTimes {
+  double ms[SVIN_BA_K_COUNT];
+  int64_t launches[SVIN_BA_K_COUNT];
+} SvinBaKernelTimes;
+int svin_ba_set_profiling(svin_ba_ctx* ctx, int enable);
+int svin_ba_kernel_times(svin_ba_ctx* ctx, SvinBaKernelTimes* out);
+
 #ifdef __cplusplus
 }
 #endif

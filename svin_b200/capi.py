@@ -92,6 +92,14 @@ class SvinBaTimings(C.Structure):
                 ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
+BA_KERNEL_NAMES = ["linearize", "dense_eval", "schur", "dense_solve", "backsub", "step_dense", "step_lm", "decide",
+                   "clear"]
+
+
+class SvinBaKernelTimes(C.Structure):
+    _fields_ = [("ms", C.c_double * 9), ("launches", C.c_int64 * 9)]
+
+
 class SvinError(RuntimeError):
     pass
 
@@ -102,7 +110,7 @@ _lib = None
 EXPORTED_SYMBOLS = [
     "svin_last_error", "svin_version", "svin_ba_default_options", "svin_ba_create", "svin_ba_destroy",
     "svin_ba_upload", "svin_ba_evaluate", "svin_ba_solve", "svin_ba_download", "svin_ba_reset", "svin_ba_optimize",
-    "svin_ba_timings",
+    "svin_ba_timings", "svin_ba_set_profiling", "svin_ba_kernel_times",
 ]
 
 
@@ -132,6 +140,8 @@ def load(path: str | None = None) -> C.CDLL:
     lib.svin_ba_optimize.argtypes = [C.c_void_p, C.POINTER(SvinBaWindow), C.c_int32, C.POINTER(SvinBaOptions),
                                      C.POINTER(SvinBaSummary), C.POINTER(c_double_p)]
     lib.svin_ba_timings.argtypes = [C.c_void_p, C.POINTER(SvinBaTimings)]
+    lib.svin_ba_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    lib.svin_ba_kernel_times.argtypes = [C.c_void_p, C.POINTER(SvinBaKernelTimes)]
     if path is None:
         _lib = lib
     return lib

@@ -99,6 +99,11 @@ struct svin_ba_ctx {
   bool quality_valid = false;
   bool solved = false;
   SvinBaTimings tm{};
+  // optional per-kernel profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<int> prof_family;  // family of the launch bracketed by events (2i, 2i+1)
+  SvinBaKernelTimes ktimes{};
 };
 
 namespace {
@@ -250,6 +255,7 @@ void svin_ba_destroy(svin_ba_ctx* c) {
   cudaFreeHost(c->h_active);
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->prof_events) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -687,17 +693,40 @@ int svin_ba_reset(svin_ba_ctx* c) {
   return SVIN_OK;
 }
 
+// bracket one launch with an event pair when profiling
+struct ProfScope {
+  svin_ba_ctx* c;
+  ProfScope(svin_ba_ctx* c_, int family) : c(c_) {
+    if (!c->profiling) return;
+    const size_t i = c->prof_family.size();
+    while (c->prof_events.size() < 2 * (i + 1)) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      c->prof_events.push_back(e);
+    }
+    c->prof_family.push_back(family);
+    cudaEventRecord(c->prof_events[2 * i], c->stream);
+  }
+  ~ProfScope() {
+    if (!c->profiling) return;
+    cudaEventRecord(c->prof_events[2 * (c->prof_family.size() - 1) + 1], c->stream);
+  }
+};
+
 static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
   Batch& b = c->b;
-  SVIN_CUDA(cudaMemsetAsync(c->d_clear, 0, c->clear_bytes, c->stream));
-  launch_schur(b, opt, c->stream);
-  launch_dense_solve(b, opt, c->smem_bytes, c->stream);
-  launch_backsub(b, c->stream);
-  launch_step_dense(b, opt, c->stream);
-  launch_step_lm(b, c->stream);
-  launch_linearize(b, 1, 0, c->stream);
-  launch_dense_eval(b, 1, 0, nullptr, c->stream);
-  launch_decide(b, opt, c->stream);
+  {
+    ProfScope p(c, SVIN_BA_K_CLEAR);
+    SVIN_CUDA(cudaMemsetAsync(c->d_clear, 0, c->clear_bytes, c->stream));
+  }
+  { ProfScope p(c, SVIN_BA_K_SCHUR); launch_schur(b, opt, c->stream); }
+  { ProfScope p(c, SVIN_BA_K_DENSE_SOLVE); launch_dense_solve(b, opt, c->smem_bytes, c->stream); }
+  { ProfScope p(c, SVIN_BA_K_BACKSUB); launch_backsub(b, c->stream); }
+  { ProfScope p(c, SVIN_BA_K_STEP_DENSE); launch_step_dense(b, opt, c->stream); }
+  { ProfScope p(c, SVIN_BA_K_STEP_LM); launch_step_lm(b, c->stream); }
+  { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 1, 0, c->stream); }
+  { ProfScope p(c, SVIN_BA_K_DENSE_EVAL); launch_dense_eval(b, 1, 0, nullptr, c->stream); }
+  { ProfScope p(c, SVIN_BA_K_DECIDE); launch_decide(b, opt, c->stream); }
   c->tm.kernel_launches += 8;
   return SVIN_OK;
 }
@@ -719,16 +748,10 @@ int svin_ba_solve(svin_ba_ctx* c, const SvinBaOptions* opt_in, SvinBaSummary* su
     if (rc != SVIN_OK) return rc;
   }
   SVIN_CUDA(cudaEventRecord(c->ev[2], c->stream));
-  // initial evaluation (IterationZero)
-  {
-    // radius from the options
-    std::vector<WinState> tmp;  // only radius differs from the uploaded init; patch on device via memcpy2D
-    const double r0 = opt.initial_trust_region_radius;
-    SVIN_CUDA(cudaMemcpy2DAsync(&b.ws[0].radius, sizeof(WinState), &r0, 0, sizeof(double), b.B, cudaMemcpyHostToDevice,
-                                c->stream));
-  }
-  launch_linearize(b, 0, 0, c->stream);
-  launch_dense_eval(b, 0, 0, nullptr, c->stream);
+  // initial evaluation (IterationZero); k_init also installs the options' initial trust-region radius
+  c->prof_family.clear();
+  { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 0, 0, c->stream); }
+  { ProfScope p(c, SVIN_BA_K_DENSE_EVAL); launch_dense_eval(b, 0, 0, nullptr, c->stream); }
   launch_init(b, opt, c->stream);
   c->tm.kernel_launches += 3;
   int slots_done = 0;
@@ -766,6 +789,15 @@ int svin_ba_solve(svin_ba_ctx* c, const SvinBaOptions* opt_in, SvinBaSummary* su
   cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
   c->tm.solve_ms = ms;
   c->solved = true;
+  if (c->profiling) {
+    c->ktimes = SvinBaKernelTimes{};
+    for (size_t i = 0; i < c->prof_family.size(); ++i) {
+      float t = 0;
+      cudaEventElapsedTime(&t, c->prof_events[2 * i], c->prof_events[2 * i + 1]);
+      c->ktimes.ms[c->prof_family[i]] += t;
+      c->ktimes.launches[c->prof_family[i]] += 1;
+    }
+  }
   if (summaries) {
     const WinState* ws = (const WinState*)((char*)c->h_out + c->out_off_ws);
     for (int i = 0; i < b.B; ++i) {
@@ -910,6 +942,24 @@ int svin_ba_evaluate(svin_ba_ctx* c, int32_t wi, SvinBaEvaluation* out) {
   }
   if (imu_dump) cudaFree(imu_dump);
   return svin_ba_reset(c);
+}
+
+int svin_ba_set_profiling(svin_ba_ctx* c, int enable) {
+  if (!c) {
+    set_error("svin_ba_set_profiling: ctx is NULL");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  c->profiling = enable != 0;
+  return SVIN_OK;
+}
+
+int svin_ba_kernel_times(svin_ba_ctx* c, SvinBaKernelTimes* out) {
+  if (!c || !out) {
+    set_error("svin_ba_kernel_times: invalid arguments");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  *out = c->ktimes;
+  return SVIN_OK;
 }
 
 int svin_ba_timings(svin_ba_ctx* c, SvinBaTimings* out) {

@@ -1815,6 +1815,7 @@ __global__ void k_init(Batch b, SvinBaOptions opt) {
   ws.cost_x = ws.cost_cand;
   ws.initial_cost = ws.cost_cand;
   ws.cost_cand = 0.0;
+  ws.radius = opt.initial_trust_region_radius;
   ws.t_start_ns = globaltimer_ns();
   if (opt.max_num_iterations <= 0) {
     ws.done = 1;

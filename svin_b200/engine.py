@@ -82,6 +82,14 @@ class BaEngine:
         capi.check(self._lib.svin_ba_timings(self._ctx, C.byref(t)), self._lib)
         return {n: getattr(t, n) for n, _ in t._fields_}
 
+    def set_profiling(self, enable: bool):
+        capi.check(self._lib.svin_ba_set_profiling(self._ctx, int(enable)), self._lib)
+
+    def kernel_times(self) -> dict:
+        t = capi.SvinBaKernelTimes()
+        capi.check(self._lib.svin_ba_kernel_times(self._ctx, C.byref(t)), self._lib)
+        return {n: dict(ms=t.ms[i], launches=t.launches[i]) for i, n in enumerate(capi.BA_KERNEL_NAMES)}
+
     # ---- one-shot API: the drop-in for Estimator::optimize ---------------------------------------
     def optimize(self, windows: list[BaWindow], options: capi.SvinBaOptions | None = None):
         """upload + solve + download (host buffers in, host buffers out).  Returns (summaries, qualities)."""
