@@ -1,0 +1,262 @@
+// Reduced camera system, fast path: one CTA per window with the whole system in shared memory.
+//
+//   A   = H~ (landmark-eliminated pose blocks, from k_schur) + Jd^T Jd   (dense-term rows)
+//   solve (S A S + mu * diag^2) y = S g~   with Jacobi scaling S and the dogleg's LM diagonal
+//
+// which is what Ceres' SchurComplementSolver hands to its Cholesky after SchurEliminator::Eliminate
+// (the per-iteration linear solve inside Map::solve(), okvis_ceres/include/okvis/ceres/Map.hpp:347).
+// Storage is packed lower-triangular with the right-hand side carried as an extra row, so the
+// factorisation performs the forward substitution for free.  Threads are laid out 16x16 so the
+// trailing update needs no integer division.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "ba_device_utils.cuh"
+#include "ba_kernels.cuh"
+
+namespace svin {
+
+namespace {
+constexpr int kTS = 16;              // thread layout kTS x kTS
+constexpr int kNT = 7;               // accumulators per thread per dimension in one panel
+constexpr int kPanel = kTS * kNT;    // 112 columns per panel
+constexpr int kRT = 8;               // dense-term rows staged per tile
+
+__device__ __forceinline__ int tri(int i, int j) { return (i * (i + 1) >> 1) + j; }  // j <= i
+}  // namespace
+
+size_t dense_solve_smem_bytes(int n) {
+  const size_t a = (size_t)(n + 1) * (n + 2) / 2;
+  return sizeof(double) * (a + (size_t)kRT * n + kRT + 8 * (size_t)n + 16);
+}
+
+__global__ void __launch_bounds__(kTS* kTS, 2) k_dense_solve_smem(Batch b, SvinBaOptions opt) {
+  extern __shared__ double smem[];
+  const int w = blockIdx.x;
+  WinState& ws = b.ws[w];
+  if (ws.done || ws.reuse) return;
+  const WinDesc& wd = b.win[w];
+  const int n = wd.n_dense, M = wd.n_rows, buf = ws.cur;
+  const int tid = threadIdx.x, tx = tid & (kTS - 1), ty = tid >> 4;
+  const int lane = tid & 31, wid = tid >> 5;
+  double* A = smem;
+  double* Js = A + (size_t)(n + 1) * (n + 2) / 2;
+  double* rds = Js + (size_t)kRT * n;
+  double* v_hd = rds + kRT;     // column square norms
+  double* v_graw = v_hd + n;    // unreduced gradient
+  double* v_gred = v_graw + n;  // reduced rhs
+  double* v_sc = v_gred + n;    // Jacobi scale
+  double* v_dg = v_sc + n;      // dogleg diagonal
+  double* v_c = v_dg + n;       // scale * gradient_ / diag (Cauchy direction, unscaled space)
+  double* v_tmp = v_c + n;
+  const double* Hg = b.H + wd.H_off;
+  const double* Jd = b.Jd[buf] + wd.Jd_off;
+  const double* rd = b.rd[buf] + wd.rd_off;
+  __shared__ unsigned long long gmax_s;
+
+  // ---- 1. A(lower) = H~ + Jd^T Jd, panel by panel; vectors on the first pass
+  double hd_acc = 0.0, gr_acc = 0.0;  // thread tid < n owns column tid
+  const int n_panels = (n + kPanel - 1) / kPanel;
+  for (int ip = 0; ip < n_panels; ++ip)
+    for (int jp = 0; jp <= ip; ++jp) {
+      double acc[kNT][kNT];
+#pragma unroll
+      for (int x = 0; x < kNT; ++x)
+#pragma unroll
+        for (int y = 0; y < kNT; ++y) acc[x][y] = 0.0;
+      const bool first = (ip == 0 && jp == 0);
+      for (int r0 = 0; r0 < M; r0 += kRT) {
+        const int rows = min(kRT, M - r0);
+        __syncthreads();
+        for (int e = tid; e < rows * n; e += kTS * kTS) Js[e] = Jd[(size_t)r0 * n + e];
+        if (tid < rows) rds[tid] = rd[r0 + tid];
+        __syncthreads();
+        for (int r = 0; r < rows; ++r) {
+          const double* row = Js + r * n;
+          double a[kNT], c[kNT];
+#pragma unroll
+          for (int x = 0; x < kNT; ++x) {
+            const int i = ip * kPanel + ty + kTS * x;
+            a[x] = (i < n) ? row[i] : 0.0;
+            const int j = jp * kPanel + tx + kTS * x;
+            c[x] = (j < n) ? row[j] : 0.0;
+          }
+#pragma unroll
+          for (int x = 0; x < kNT; ++x)
+#pragma unroll
+            for (int y = 0; y < kNT; ++y) acc[x][y] += a[x] * c[y];
+          if (first && tid < n) {
+            const double jv = row[tid];
+            hd_acc += jv * jv;
+            gr_acc += jv * rds[r];
+          }
+        }
+      }
+#pragma unroll
+      for (int x = 0; x < kNT; ++x)
+#pragma unroll
+        for (int y = 0; y < kNT; ++y) {
+          const int i = ip * kPanel + ty + kTS * x, j = jp * kPanel + tx + kTS * y;
+          if (i < n && j <= i) A[tri(i, j)] = acc[x][y] + Hg[(size_t)j * n + i];  // H~ keeps the upper triangle
+        }
+    }
+  // ---- 2. vectors
+  double gmax_l = 0.0;
+  if (tid < n) {
+    const double hd = b.Hdiag[wd.d_off + tid] + hd_acc;
+    const double gr = b.g_raw[wd.d_off + tid] + gr_acc;
+    v_hd[tid] = hd;
+    v_graw[tid] = gr;
+    v_gred[tid] = b.g_red[wd.d_off + tid] + gr_acc;
+    gmax_l = fabs(gr);
+  }
+
+  atomic_max_nonneg(&ws.gmax_bits, gmax_l);
+  __syncthreads();
+  if (tid == 0) gmax_s = atomicMax(&ws.gmax_bits, 0ull);  // atomic read (L1 may hold a stale WinState line)
+  __syncthreads();
+  // ---- 3. gradient tolerance (checked after the max-iteration test of the previous slot)
+  if (ws.last_successful && __longlong_as_double((long long)gmax_s) <= opt.gradient_tolerance) {
+    if (tid == 0) {
+      ws.done = 1;
+      ws.termination = SVIN_TERM_CONVERGENCE;
+    }
+    return;
+  }
+  // ---- 4. Jacobi scaling (first Jacobian only), dogleg diagonal, scaled gradient
+  const bool first_jac = (ws.iter == 0 && ws.num_successful == 0 && !ws.invalid);
+  const double mu = ws.mu;
+  if (tid < n) {
+    double s;
+    if (first_jac) {
+      s = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(v_hd[tid])) : 1.0;
+      b.scale_d[wd.d_off + tid] = s;
+    } else {
+      s = b.scale_d[wd.d_off + tid];
+    }
+    const double d = sqrt(fmin(fmax(v_hd[tid] * s * s, opt.min_lm_diagonal), opt.max_lm_diagonal));
+    const double g = s * v_graw[tid] / d;
+    v_sc[tid] = s;
+    v_dg[tid] = d;
+    v_tmp[tid] = g;  // gradient_
+    b.diag_d[wd.d_off + tid] = d;
+    b.grad_d[wd.d_off + tid] = g;
+  }
+  __syncthreads();
+  // ---- 5. scaled system + LM diagonal; rhs row n
+  for (int i = ty; i <= n; i += kTS) {
+    if (i < n) {
+      const double si = v_sc[i];
+      for (int j = tx; j <= i; j += kTS) {
+        double v = A[tri(i, j)] * si * v_sc[j];
+        if (i == j) v += mu * v_dg[i] * v_dg[i];
+        A[tri(i, j)] = v;
+      }
+    } else {
+      for (int j = tx; j < n; j += kTS) A[tri(n, j)] = v_sc[j] * v_gred[j];
+    }
+  }
+  // ---- 6. right-looking Cholesky, rhs row included (forward substitution)
+  bool fail = false;
+  for (int k = 0; k < n; ++k) {
+    __syncthreads();
+    const double akk = A[tri(k, k)];
+    if (!(akk > 0.0) || !isfinite(akk)) {
+      fail = true;
+      break;
+    }
+    const double d = sqrt(akk);
+    for (int i = k + 1 + tid; i <= n; i += kTS * kTS) A[tri(i, k)] /= d;
+    __syncthreads();
+    if (tid == 0) A[tri(k, k)] = d;
+    for (int i = k + 1 + ty; i <= n; i += kTS) {
+      const double aik = A[tri(i, k)];
+      const int jmax = min(i, n - 1);
+      double* Ai = A + tri(i, 0);
+      for (int j = k + 1 + tx; j <= jmax; j += kTS) Ai[j] -= aik * A[tri(j, k)];
+    }
+  }
+  __syncthreads();
+  if (fail) {
+    if (tid == 0) {
+      // DoglegStrategy::ComputeGaussNewtonStep: mu *= 10 and retry while mu < max_mu (1.0)
+      ws.mu *= 10.0;
+      if (ws.mu < 1.0)
+        ws.skip_slot = 1;  // re-eliminate next slot, no iteration consumed
+      else
+        ws.gn_failed = 1;  // linear solver FAILURE -> invalid step
+    }
+    return;
+  }
+  // ---- 7. backward solve L^T y = z (row n) by warp 0
+  double* z = A + tri(n, 0);
+  if (wid == 0) {
+    for (int k = n - 1; k >= 0; --k) {
+      const double yk = z[k] / A[tri(k, k)];
+      __syncwarp();
+      if (lane == 0) z[k] = yk;
+      const double* Lk = A + tri(k, 0);
+      for (int i = lane; i < k; i += 32) z[i] -= Lk[i] * yk;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // ---- 8. outputs
+  bool bad = false;
+  double g2 = 0, n2 = 0, gd = 0;
+  if (tid < n) {
+    const double y = z[tid];
+    if (!isfinite(y)) bad = true;
+    const double g = v_tmp[tid];
+    const double gni = -y * v_dg[tid];
+    b.gn_d[wd.d_off + tid] = gni;
+    b.u_d[wd.d_off + tid] = v_sc[tid] * y;
+    const double cv = v_sc[tid] * g / v_dg[tid];
+    b.c_d[wd.d_off + tid] = cv;
+    v_c[tid] = cv;
+    g2 = g * g;
+    n2 = gni * gni;
+    gd = g * gni;
+  }
+  if (__syncthreads_or(bad)) {
+    if (tid == 0) {
+      ws.mu *= 10.0;
+      if (ws.mu < 1.0)
+        ws.skip_slot = 1;
+      else
+        ws.gn_failed = 1;
+    }
+    return;
+  }
+  // Cauchy point over the dense rows: sum_r (Jd[r,:] . c)^2, one warp per row of each tile
+  double jg2 = 0.0;
+  for (int r0 = 0; r0 < M; r0 += kRT) {
+    const int rows = min(kRT, M - r0);
+    __syncthreads();
+    for (int e = tid; e < rows * n; e += kTS * kTS) Js[e] = Jd[(size_t)r0 * n + e];
+    __syncthreads();
+    if (wid < rows) {
+      const double* row = Js + wid * n;
+      double s = 0.0;
+      for (int i = lane; i < n; i += 32) s += row[i] * v_c[i];
+      s = warp_sum(s);
+      if (lane == 0) jg2 += s * s;
+    }
+  }
+  double v[4] = {g2, n2, gd, jg2};
+  double* const dst[4] = {&ws.acc_g2, &ws.acc_n2, &ws.acc_gdot, &ws.acc_Jg2};
+  block_atomic_add<4, kTS * kTS>(v, dst);
+}
+
+cudaError_t configure_dense_solve(int smem_bytes) {
+  return cudaFuncSetAttribute(k_dense_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+}
+void launch_dense_solve_generic(const Batch& b, const SvinBaOptions& opt, cudaStream_t st);
+void launch_dense_solve(const Batch& b, const SvinBaOptions& opt, int smem_bytes, cudaStream_t st) {
+  if (smem_bytes > 0)
+    k_dense_solve_smem<<<b.B, kTS * kTS, smem_bytes, st>>>(b, opt);
+  else
+    launch_dense_solve_generic(b, opt, st);
+}
+
+}  // namespace svin

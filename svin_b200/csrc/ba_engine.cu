@@ -53,6 +53,87 @@ void llt_sqrt_information(const double* info, double* U, int n) {
     for (int j = 0; j < n; ++j) U[(size_t)i * n + j] = (j >= i) ? L[(size_t)j * n + i] : 0.0;
 }
 
+// Internal ordering of one window's landmarks and observations.
+//  * observations sorted by (landmark, pose block, camera)
+//  * when `group` is set, landmarks are additionally grouped by their exact (pose, camera) observation
+//    pattern so that k_schur_warp can hand each warp <= 32 landmarks with identical pose runs.
+struct WindowOrder {
+  std::vector<int> lm_perm;   // internal landmark k -> caller landmark
+  std::vector<int> obs_order; // internal observation k -> caller observation
+  std::vector<int> lm_count;  // observations of internal landmark k
+  std::vector<int> chunk_begin, chunk_count;  // Schur warp chunks (window-local internal landmark indices)
+};
+
+void order_window(const SvinBaWindow& w, bool group, WindowOrder& out) {
+  const int N = w.num_obs, L = w.num_landmarks;
+  std::vector<int> ord(N);
+  std::iota(ord.begin(), ord.end(), 0);
+  bool sorted = true;
+  for (int o = 1; o < N && sorted; ++o) {
+    const int a = o - 1;
+    if (w.obs_landmark[a] > w.obs_landmark[o] ||
+        (w.obs_landmark[a] == w.obs_landmark[o] &&
+         (w.obs_pose[a] > w.obs_pose[o] || (w.obs_pose[a] == w.obs_pose[o] && w.obs_camera[a] > w.obs_camera[o]))))
+      sorted = false;
+  }
+  if (!sorted)
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) {
+      if (w.obs_landmark[a] != w.obs_landmark[b2]) return w.obs_landmark[a] < w.obs_landmark[b2];
+      if (w.obs_pose[a] != w.obs_pose[b2]) return w.obs_pose[a] < w.obs_pose[b2];
+      return w.obs_camera[a] < w.obs_camera[b2];
+    });
+  std::vector<int> start(L + 1, 0);
+  for (int o = 0; o < N; ++o) start[w.obs_landmark[o] + 1]++;
+  for (int k = 0; k < L; ++k) start[k + 1] += start[k];
+  out.lm_perm.resize(L);
+  std::iota(out.lm_perm.begin(), out.lm_perm.end(), 0);
+  auto fixed = [&](int l) { return (w.landmark_fixed && w.landmark_fixed[l]) ? 1 : 0; };
+  auto same_pattern = [&](int la, int lb) {
+    const int na = start[la + 1] - start[la];
+    if (na != start[lb + 1] - start[lb] || fixed(la) != fixed(lb)) return false;
+    for (int k = 0; k < na; ++k) {
+      const int oa = ord[start[la] + k], ob = ord[start[lb] + k];
+      if (w.obs_pose[oa] != w.obs_pose[ob] || w.obs_camera[oa] != w.obs_camera[ob]) return false;
+    }
+    return true;
+  };
+  if (group) {
+    std::vector<uint64_t> key(L);
+    for (int l = 0; l < L; ++l) {
+      uint64_t h = 1469598103934665603ull ^ (uint64_t)fixed(l);
+      for (int k = start[l]; k < start[l + 1]; ++k) {
+        const int o = ord[k];
+        h = (h ^ (uint64_t)(w.obs_pose[o] * 4 + w.obs_camera[o] + 1)) * 1099511628211ull;
+      }
+      // primary: number of observations, then first pose (locality), then the pattern hash
+      const uint64_t nobs = (uint64_t)(start[l + 1] - start[l]);
+      const uint64_t first = nobs ? (uint64_t)w.obs_pose[ord[start[l]]] : 0;
+      key[l] = (nobs << 54) | ((first & 0x3ff) << 44) | (h >> 20);
+    }
+    std::stable_sort(out.lm_perm.begin(), out.lm_perm.end(), [&](int a, int b2) { return key[a] < key[b2]; });
+  }
+  out.obs_order.resize(N);
+  out.lm_count.resize(L);
+  int pos = 0;
+  for (int k = 0; k < L; ++k) {
+    const int l = out.lm_perm[k];
+    out.lm_count[k] = start[l + 1] - start[l];
+    for (int q = start[l]; q < start[l + 1]; ++q) out.obs_order[pos++] = ord[q];
+  }
+  out.chunk_begin.clear();
+  out.chunk_count.clear();
+  if (group) {
+    int k = 0;
+    while (k < L) {
+      int e = k + 1;
+      while (e < L && e - k < 32 && same_pattern(out.lm_perm[k], out.lm_perm[e])) ++e;
+      out.chunk_begin.push_back(k);
+      out.chunk_count.push_back(e - k);
+      k = e;
+    }
+  }
+}
+
 struct Region {
   size_t bytes = 0;
   size_t add(size_t b) {
@@ -85,6 +166,7 @@ struct svin_ba_ctx {
   // host metadata
   std::vector<WinDesc> h_win;
   std::vector<int> obs_perm;  // sorted obs position -> caller's obs index (window-local)
+  std::vector<int> lm_perm;   // internal landmark position (global) -> caller's landmark index (window-local)
   int n_max = 0, smem_bytes = 0;
   int* d_active = nullptr;
   int* h_active = nullptr;
@@ -279,6 +361,15 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   c->h_win.assign(B, WinDesc{});
   c->n_max = 0;
   int has_ext = 0;
+  for (int i = 0; i < B && !has_ext; ++i)
+    for (int o = 0; o < wins[i].num_obs && !has_ext; ++o)
+      if (!wins[i].pose_fixed[wins[i].obs_extrinsics[o]]) has_ext = 1;
+  std::vector<WindowOrder> orders(B);
+  long long NSW = 0;
+  for (int i = 0; i < B; ++i) {
+    order_window(wins[i], !has_ext, orders[i]);
+    NSW += (long long)orders[i].chunk_begin.size();
+  }
   for (int i = 0; i < B; ++i) {
     const SvinBaWindow& w = wins[i];
     WinDesc& d = c->h_win[i];
@@ -319,8 +410,6 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     for (int k = 0; k < 7; ++k) d.T_SSo[k] = (w.num_sonar && w.sonar_T_SSo) ? w.sonar_T_SSo[k] : (k == 6 ? 1.0 : 0.0);
     n_obs_tiles += (w.num_obs + kObsTile - 1) / kObsTile;
     n_lm_tiles += (w.num_landmarks + kLmTile - 1) / kLmTile;
-    for (int o = 0; o < w.num_obs && !has_ext; ++o)
-      if (!w.pose_fixed[w.obs_extrinsics[o]]) has_ext = 1;
   }
   if (NOBS >= (1ll << 31) || NH >= (1ll << 40)) {
     set_error("batch too large");
@@ -339,6 +428,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   const size_t o_lmob = in.add(4 * (NL + 1));
   const size_t o_otw = in.add(4 * (size_t)n_obs_tiles), o_otb = in.add(4 * (size_t)n_obs_tiles);
   const size_t o_ltw = in.add(4 * (size_t)n_lm_tiles), o_ltb = in.add(4 * (size_t)n_lm_tiles);
+  const size_t o_sww = in.add(4 * (size_t)NSW), o_swb = in.add(4 * (size_t)NSW), o_swc = in.add(4 * (size_t)NSW);
   const size_t o_imu = in.add(sizeof(ImuTerm) * NIMU), o_imuc = in.add(sizeof(ImuCache) * NIMU);
   const size_t o_mt = in.add(8 * NMEAS), o_mg = in.add(24 * NMEAS), o_ma = in.add(24 * NMEAS);
   const size_t o_pp = in.add(sizeof(PosePrior) * NPP), o_sp = in.add(sizeof(SbPrior) * NSP);
@@ -363,6 +453,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
          *h_u11 = (double*)hp(o_u11);
   int* h_lmob = (int*)hp(o_lmob);
   int *h_otw = (int*)hp(o_otw), *h_otb = (int*)hp(o_otb), *h_ltw = (int*)hp(o_ltw), *h_ltb = (int*)hp(o_ltb);
+  int *h_sww = (int*)hp(o_sww), *h_swb = (int*)hp(o_swb), *h_swc = (int*)hp(o_swc);
   ImuTerm* h_imu = (ImuTerm*)hp(o_imu);
   ImuCache* h_imuc = (ImuCache*)hp(o_imuc);
   long long* h_mt = (long long*)hp(o_mt);
@@ -376,15 +467,15 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   double *h_mJ = (double*)hp(o_mJ), *h_me = (double*)hp(o_me), *h_ml = (double*)hp(o_ml);
 
   c->obs_perm.resize((size_t)NOBS);
-  int cam_base = 0, ot = 0, lt = 0;
+  c->lm_perm.resize((size_t)NL);
+  int cam_base = 0, ot = 0, lt = 0, sw = 0;
   long long meas_base = 0;
-  std::vector<int> order, cnt;
+  std::vector<int> cnt;
   for (int i = 0; i < B; ++i) {
     const SvinBaWindow& w = wins[i];
     WinDesc& d = c->h_win[i];
     std::memcpy(h_pose + 7 * (size_t)d.pose_begin, w.pose_blocks, 56 * (size_t)w.num_pose_blocks);
     std::memcpy(h_sb + 9 * (size_t)d.sb_begin, w.speedbias, 72 * (size_t)w.num_speedbias);
-    std::memcpy(h_lm + 4 * (size_t)d.lm_begin, w.landmarks, 32 * (size_t)w.num_landmarks);
     int off = 0;
     for (int k = 0; k < w.num_pose_blocks; ++k) {
       h_poff[d.pose_begin + k] = w.pose_fixed[k] ? -1 : off;
@@ -396,36 +487,26 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
       if (!w.speedbias_fixed[k]) off += 9;
       h_sbwin[d.sb_begin + k] = i;
     }
+    const WindowOrder& wo = orders[i];
+    std::vector<int>& inv = cnt;  // caller landmark -> internal landmark (reuses the scratch vector)
+    inv.assign(w.num_landmarks, 0);
     for (int k = 0; k < w.num_landmarks; ++k) {
-      h_lmfix[d.lm_begin + k] = (w.landmark_fixed && w.landmark_fixed[k]) ? 1 : 0;
+      const int lc = wo.lm_perm[k];
+      inv[lc] = k;
+      c->lm_perm[(size_t)d.lm_begin + k] = lc;
+      std::memcpy(h_lm + 4 * ((size_t)d.lm_begin + k), w.landmarks + 4 * (size_t)lc, 32);
+      h_lmfix[d.lm_begin + k] = (w.landmark_fixed && w.landmark_fixed[lc]) ? 1 : 0;
       h_lmwin[d.lm_begin + k] = i;
     }
     std::memcpy(h_intr + 8 * (size_t)cam_base, w.intrinsics, 64 * (size_t)w.num_cameras);
-    // observations sorted by (landmark, pose, camera); identity when the caller already sorted them
+    // observations in internal order (landmark-major, then pose, then camera)
     const int N = w.num_obs;
-    order.resize(N);
-    std::iota(order.begin(), order.end(), 0);
-    bool sorted = true;
-    for (int o = 1; o < N && sorted; ++o) {
-      const int a = o - 1;
-      if (w.obs_landmark[a] > w.obs_landmark[o] ||
-          (w.obs_landmark[a] == w.obs_landmark[o] &&
-           (w.obs_pose[a] > w.obs_pose[o] || (w.obs_pose[a] == w.obs_pose[o] && w.obs_camera[a] > w.obs_camera[o]))))
-        sorted = false;
-    }
-    if (!sorted)
-      std::stable_sort(order.begin(), order.end(), [&](int a, int b2) {
-        if (w.obs_landmark[a] != w.obs_landmark[b2]) return w.obs_landmark[a] < w.obs_landmark[b2];
-        if (w.obs_pose[a] != w.obs_pose[b2]) return w.obs_pose[a] < w.obs_pose[b2];
-        return w.obs_camera[a] < w.obs_camera[b2];
-      });
-    cnt.assign(w.num_landmarks + 1, 0);
     for (int k = 0; k < N; ++k) {
-      const int o = order[k];
+      const int o = wo.obs_order[k];
       const size_t g = (size_t)d.obs_begin + k;
       c->obs_perm[g] = o;
       h_opose[g] = d.pose_begin + w.obs_pose[o];
-      h_olm[g] = d.lm_begin + w.obs_landmark[o];
+      h_olm[g] = d.lm_begin + inv[w.obs_landmark[o]];
       h_oext[g] = d.pose_begin + w.obs_extrinsics[o];
       h_ocam[g] = cam_base + w.obs_camera[o];
       h_zx[g] = w.obs_measurement[2 * o];
@@ -435,12 +516,17 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
       h_u00[g] = U[0];
       h_u01[g] = U[1];
       h_u11[g] = U[3];
-      cnt[w.obs_landmark[o] + 1]++;
     }
     int run = d.obs_begin;
     for (int k = 0; k < w.num_landmarks; ++k) {
       h_lmob[d.lm_begin + k] = run;
-      run += cnt[k + 1];
+      run += wo.lm_count[k];
+    }
+    for (size_t k = 0; k < wo.chunk_begin.size(); ++k) {
+      h_sww[sw] = i;
+      h_swb[sw] = d.lm_begin + wo.chunk_begin[k];
+      h_swc[sw] = wo.chunk_count[k];
+      ++sw;
     }
     for (int t0 = 0; t0 < N; t0 += kObsTile) {
       h_otw[ot] = i;
@@ -620,6 +706,8 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   b.lm_obs_begin = (int*)(D + o_lmob);
   b.obs_tile_win = (int*)(D + o_otw); b.obs_tile_begin = (int*)(D + o_otb);
   b.lm_tile_win = (int*)(D + o_ltw); b.lm_tile_begin = (int*)(D + o_ltb);
+  b.n_schur_warps = (int)NSW;
+  b.sw_win = (int*)(D + o_sww); b.sw_lm_begin = (int*)(D + o_swb); b.sw_count = (int*)(D + o_swc);
   b.imu = (ImuTerm*)(D + o_imu);
   c->d_imu_cache_init = (ImuCache*)(D + o_imuc);
   b.imu_cache = (ImuCache*)(Wk + o_imucw);
@@ -661,9 +749,11 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
                               c->stream));
   SVIN_CUDA(cudaGetLastError());
   // the reduced system lives in shared memory when it fits
-  c->smem_bytes = dense_solve_smem_bytes(c->n_max);
-  if (c->smem_bytes > 200 * 1024) c->smem_bytes = 0;
-  if (c->smem_bytes > 0) SVIN_CUDA(configure_dense_solve(c->smem_bytes));
+  {
+    const size_t need = dense_solve_smem_bytes(c->n_max);
+    c->smem_bytes = (need <= 227 * 1024 && c->n_max <= 256 && c->n_max > 0) ? (int)need : 0;
+    if (c->smem_bytes > 0) SVIN_CUDA(configure_dense_solve(c->smem_bytes));
+  }
   SVIN_CUDA(cudaStreamSynchronize(c->stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
@@ -836,10 +926,13 @@ static void scatter_window(svin_ba_ctx* c, int i, SvinBaWindow* w, double* quali
               56 * (size_t)(d.pose_end - d.pose_begin));
   std::memcpy(w->speedbias, (const double*)(Hh + c->out_off_sb) + 9 * (size_t)d.sb_begin,
               72 * (size_t)(d.sb_end - d.sb_begin));
-  std::memcpy(w->landmarks, (const double*)(Hh + c->out_off_lm) + 4 * (size_t)d.lm_begin,
-              32 * (size_t)(d.lm_end - d.lm_begin));
-  if (quality)
-    std::memcpy(quality, (const double*)(Hh + c->out_off_q) + d.lm_begin, 8 * (size_t)(d.lm_end - d.lm_begin));
+  const double* lm_out = (const double*)(Hh + c->out_off_lm) + 4 * (size_t)d.lm_begin;
+  const double* q_out = (const double*)(Hh + c->out_off_q) + d.lm_begin;
+  const int* perm = c->lm_perm.data() + d.lm_begin;
+  for (int k = 0; k < d.lm_end - d.lm_begin; ++k) {
+    std::memcpy(w->landmarks + 4 * (size_t)perm[k], lm_out + 4 * (size_t)k, 32);
+    if (quality) quality[perm[k]] = q_out[k];
+  }
 }
 
 int svin_ba_download(svin_ba_ctx* c, int32_t i, SvinBaWindow* w, double* quality) {

@@ -22,72 +22,11 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include "ba_device_utils.cuh"
 #include "ba_kernels.cuh"
 #include "ba_math.cuh"
 
 namespace svin {
-
-// ------------------------------------------------------------------------------------------ utilities
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-// Sum K per-thread values over the CTA and atomically add them to K targets.
-template <int K, int THREADS>
-__device__ __forceinline__ void block_atomic_add(double (&v)[K], double* const (&dst)[K]) {
-  __shared__ double red[K][THREADS / 32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const double s = warp_sum(v[k]);
-    if (lane == 0) red[k][wid] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < K) {
-    double s = 0;
-#pragma unroll
-    for (int i = 0; i < THREADS / 32; ++i) s += red[threadIdx.x][i];
-    if (s != 0.0) atomicAdd(dst[threadIdx.x], s);
-  }
-  __syncthreads();
-}
-__device__ __forceinline__ void atomic_max_nonneg(unsigned long long* addr, double v) {
-  atomicMax(addr, (unsigned long long)__double_as_longlong(v));
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-
-// ceres::CauchyLoss / HuberLoss + Corrector
-__device__ __forceinline__ void loss_eval(int type, double a, double s, double& rho0, double& rho1, double& rho2) {
-  if (type == SVIN_LOSS_CAUCHY) {
-    const double bb = a * a, c = 1.0 / bb;
-    const double sum = 1.0 + s * c;
-    const double inv = 1.0 / sum;
-    rho0 = bb * log(sum);
-    rho1 = fmax(inv, 2.2250738585072014e-308);
-    rho2 = -c * (inv * inv);
-  } else if (type == SVIN_LOSS_HUBER) {
-    const double bb = a * a;
-    if (s > bb) {
-      const double r = sqrt(s);
-      rho0 = 2.0 * a * r - bb;
-      rho1 = fmax(a / r, 2.2250738585072014e-308);
-      rho2 = -rho1 / (2.0 * s);
-    } else {
-      rho0 = s;
-      rho1 = 1.0;
-      rho2 = 0.0;
-    }
-  } else {
-    rho0 = s;
-    rho1 = 1.0;
-    rho2 = 0.0;
-  }
-}
 
 // ------------------------------------------------------------------------------------------ reprojection
 struct Reproj {
@@ -646,6 +585,243 @@ __global__ void __launch_bounds__(kLmTile) k_schur(Batch b, SvinBaOptions opt) {
         }
       }
     }
+  }
+}
+
+// Warp-aggregated variant for batches whose extrinsics are fixed.  The host groups landmarks of a
+// window by their exact (pose, camera) observation pattern and hands every warp a chunk of <= 32
+// landmarks sharing one pattern, so all lanes walk identical pose runs.  Each lane eliminates its
+// own landmark in registers; the per-run 6x6 / 6-vector contributions are then summed across the
+// warp with a recursive-halving reduce-scatter and only ONE lane per matrix entry issues the
+// fp64 RED to the reduced system (32x fewer atomics than the per-thread kernel above).
+__global__ void __launch_bounds__(128) k_schur_warp(Batch b, SvinBaOptions opt) {
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (chunk >= b.n_schur_warps) return;
+  const int w = b.sw_win[chunk];
+  WinState& ws = b.ws[w];
+  if (ws.done || ws.reuse) return;
+  const WinDesc& wd = b.win[w];
+  const int cnt = b.sw_count[chunk];
+  const bool active = lane < cnt;
+  const int l = b.sw_lm_begin[chunk] + (active ? lane : 0);
+  const double wgt = active ? 1.0 : 0.0;
+  const int buf = ws.cur;
+  const int n = wd.n_dense;
+  double* H = b.H + wd.H_off;
+  double* g_red = b.g_red + wd.d_off;
+  double* g_raw = b.g_raw + wd.d_off;
+  double* Hdiag = b.Hdiag + wd.d_off;
+  const int ob = b.lm_obs_begin[l];
+  const int nobs = b.lm_obs_begin[l + 1] - ob;  // identical on every lane of the chunk
+  const bool lfix = b.lm_fixed[l] != 0;         // part of the pattern, hence warp-uniform
+  const double mu = ws.mu;
+  const size_t S = b.obs_stride;
+  const double* rP = b.lin_r[buf];
+  const double* JpP = b.lin_Jp[buf];
+  const double* JlP = b.lin_Jl[buf];
+
+  // ---- pass 1: V = sum Jl^T Jl, bl = sum Jl^T r (unscaled)
+  double V[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+  for (int k = 0; k < nobs; ++k) {
+    const int o = ob + k;
+    const double r0 = rP[o], r1 = rP[S + o];
+    double a[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) a[q] = JlP[q * S + o];
+    V[0] += a[0] * a[0] + a[3] * a[3];
+    V[1] += a[0] * a[1] + a[3] * a[4];
+    V[2] += a[0] * a[2] + a[3] * a[5];
+    V[3] += a[1] * a[1] + a[4] * a[4];
+    V[4] += a[1] * a[2] + a[4] * a[5];
+    V[5] += a[2] * a[2] + a[5] * a[5];
+    bl[0] += a[0] * r0 + a[3] * r1;
+    bl[1] += a[1] * r0 + a[4] * r1;
+    bl[2] += a[2] * r0 + a[5] * r1;
+  }
+  double s[3] = {1.0, 1.0, 1.0}, Vi[6] = {0, 0, 0, 0, 0, 0}, bs[3] = {0, 0, 0};
+  if (!lfix) {
+    if (ws.iter == 0 && ws.num_successful == 0 && !ws.invalid) {
+      if (opt.jacobi_scaling) {
+        s[0] = 1.0 / (1.0 + sqrt(V[0]));
+        s[1] = 1.0 / (1.0 + sqrt(V[3]));
+        s[2] = 1.0 / (1.0 + sqrt(V[5]));
+      }
+      if (active) {
+        b.lm_scale[3 * (size_t)l] = s[0];
+        b.lm_scale[3 * (size_t)l + 1] = s[1];
+        b.lm_scale[3 * (size_t)l + 2] = s[2];
+      }
+    } else {
+      s[0] = b.lm_scale[3 * (size_t)l];
+      s[1] = b.lm_scale[3 * (size_t)l + 1];
+      s[2] = b.lm_scale[3 * (size_t)l + 2];
+    }
+    double gm = active ? fmax(fabs(bl[0]), fmax(fabs(bl[1]), fabs(bl[2]))) : 0.0;
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o2));
+    if (lane == 0) atomic_max_nonneg(&ws.gmax_bits, gm);
+    double Vs[6] = {V[0] * s[0] * s[0], V[1] * s[0] * s[1], V[2] * s[0] * s[2],
+                    V[3] * s[1] * s[1], V[4] * s[1] * s[2], V[5] * s[2] * s[2]};
+    const double d0 = sqrt(fmin(fmax(Vs[0], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    const double d1 = sqrt(fmin(fmax(Vs[3], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    const double d2 = sqrt(fmin(fmax(Vs[5], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    Vs[0] += mu * d0 * d0;
+    Vs[3] += mu * d1 * d1;
+    Vs[5] += mu * d2 * d2;
+    spd3_inverse(Vs, Vi);
+    bs[0] = s[0] * bl[0];
+    bs[1] = s[1] * bl[1];
+    bs[2] = s[2] * bl[2];
+    if (active) {
+      double* p = b.lm_Vinv + 6 * (size_t)l;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) p[k] = Vi[k];
+      p = b.lm_bs + 3 * (size_t)l;
+      p[0] = bs[0]; p[1] = bs[1]; p[2] = bs[2];
+      p = b.lm_diag + 3 * (size_t)l;
+      p[0] = d0; p[1] = d1; p[2] = d2;
+      p = b.lm_grad + 3 * (size_t)l;
+      p[0] = bs[0] / d0; p[1] = bs[1] / d1; p[2] = bs[2] / d2;
+    }
+  }
+
+  // ---- pass 2: pose runs (identical structure on every lane)
+  int i = 0;
+  while (i < nobs) {
+    const int p = b.obs_pose[ob + i];
+    int j = i + 1;
+    while (j < nobs && b.obs_pose[ob + j] == p) ++j;
+    const int offp = b.pose_off[p];
+    if (offp >= 0) {
+      double v[32];  // [0,21) H block upper, [21,27) reduced gradient, [27,32) Hdiag 0..4
+      double ex[7];  // Hdiag 5, raw gradient 0..5
+      double W[18];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = 0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) ex[k] = 0;
+#pragma unroll
+      for (int k = 0; k < 18; ++k) W[k] = 0;
+      for (int k = i; k < j; ++k) {
+        const int o = ob + k;
+        double Jp[12], Jls[6];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) Jp[q] = JpP[q * S + o];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) Jls[q] = JlP[q * S + o] * s[q % 3];
+        const double r0 = rP[o], r1 = rP[S + o];
+        int idx = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int c = a; c < 6; ++c) v[idx++] += Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) ex[1 + a] += Jp[a] * r0 + Jp[6 + a] * r1;
+        acc_W(Jp, Jls, W);
+      }
+      // column square norms = diagonal of the unreduced block
+      v[27] = v[0]; v[28] = v[6]; v[29] = v[11]; v[30] = v[15]; v[31] = v[18];
+      ex[0] = v[20];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) v[21 + a] = ex[1 + a];
+      double Z[18];
+      if (!lfix) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          const double w0 = W[a * 3], w1 = W[a * 3 + 1], w2 = W[a * 3 + 2];
+          Z[a * 3 + 0] = w0 * Vi[0] + w1 * Vi[1] + w2 * Vi[2];
+          Z[a * 3 + 1] = w0 * Vi[1] + w1 * Vi[3] + w2 * Vi[4];
+          Z[a * 3 + 2] = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
+        }
+        int idx = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int c = a; c < 6; ++c)
+            v[idx++] -= Z[a * 3] * W[c * 3] + Z[a * 3 + 1] * W[c * 3 + 1] + Z[a * 3 + 2] * W[c * 3 + 2];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) v[21 + a] -= Z[a * 3] * bs[0] + Z[a * 3 + 1] * bs[1] + Z[a * 3 + 2] * bs[2];
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] *= wgt;
+      warp_reduce_scatter32(v, lane);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) ex[k] = warp_sum(ex[k] * wgt);
+      {
+        // lane -> destination of the value it now owns
+        double* dst;
+        if (lane < 21) {
+          const int a = (lane >= 6) + (lane >= 11) + (lane >= 15) + (lane >= 18) + (lane >= 20);
+          const int c = lane - (a * 6 - (a * (a - 1) >> 1)) + a;
+          dst = &H[(size_t)(offp + a) * n + offp + c];
+        } else if (lane < 27) {
+          dst = &g_red[offp + lane - 21];
+        } else {
+          dst = &Hdiag[offp + lane - 27];
+        }
+        atomicAdd(dst, v[0]);
+        if (lane < 7) {
+          double e = ex[0];
+#pragma unroll
+          for (int k = 1; k < 7; ++k) e = (lane == k) ? ex[k] : e;
+          atomicAdd(lane == 0 ? &Hdiag[offp + 5] : &g_raw[offp + lane - 1], e);
+        }
+      }
+      if (!lfix) {
+        int i2 = j;
+        while (i2 < nobs) {
+          const int q = b.obs_pose[ob + i2];
+          int j2 = i2 + 1;
+          while (j2 < nobs && b.obs_pose[ob + j2] == q) ++j2;
+          const int offq = b.pose_off[q];
+          if (offq >= 0) {
+            double Wq[18];
+#pragma unroll
+            for (int k = 0; k < 18; ++k) Wq[k] = 0;
+            for (int k = i2; k < j2; ++k) {
+              const int o = ob + k;
+              double Jp[12], Jls[6];
+#pragma unroll
+              for (int t = 0; t < 12; ++t) Jp[t] = JpP[t * S + o];
+#pragma unroll
+              for (int t = 0; t < 6; ++t) Jls[t] = JlP[t * S + o] * s[t % 3];
+              acc_W(Jp, Jls, Wq);
+            }
+            double blk[32], e4[4];
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+              for (int c = 0; c < 6; ++c) {
+                const double val =
+                    -(Z[a * 3] * Wq[c * 3] + Z[a * 3 + 1] * Wq[c * 3 + 1] + Z[a * 3 + 2] * Wq[c * 3 + 2]) * wgt;
+                if (a * 6 + c < 32)
+                  blk[a * 6 + c] = val;
+                else
+                  e4[a * 6 + c - 32] = val;
+              }
+            warp_reduce_scatter32(blk, lane);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e4[k] = warp_sum(e4[k]);
+            {
+              const int a = lane / 6, c = lane - a * 6;
+              double* dst = (offp < offq) ? &H[(size_t)(offp + a) * n + offq + c] : &H[(size_t)(offq + c) * n + offp + a];
+              atomicAdd(dst, blk[0]);
+              if (lane < 4) {
+                double e = e4[0];
+#pragma unroll
+                for (int k = 1; k < 4; ++k) e = (lane == k) ? e4[k] : e;
+                const int c2 = 2 + lane;  // entries (5,2)..(5,5)
+                double* d2 = (offp < offq) ? &H[(size_t)(offp + 5) * n + offq + c2] : &H[(size_t)(offq + c2) * n + offp + 5];
+                atomicAdd(d2, e);
+              }
+            }
+          }
+          i2 = j2;
+        }
+      }
+    }
+    i = j;
   }
 }
 
@@ -1881,15 +2057,14 @@ void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {
   if (b.n_lm_tiles == 0) return;
   if (b.has_ext)
     k_schur<true><<<b.n_lm_tiles, kLmTile, 0, st>>>(b, opt);
+  else if (b.n_schur_warps > 0)
+    k_schur_warp<<<div_up(b.n_schur_warps, 4), 128, 0, st>>>(b, opt);
   else
     k_schur<false><<<b.n_lm_tiles, kLmTile, 0, st>>>(b, opt);
 }
-int dense_solve_smem_bytes(int n_max) { return (int)(((size_t)n_max + 1) * n_max * sizeof(double)); }
-cudaError_t configure_dense_solve(int smem_bytes) {
-  return cudaFuncSetAttribute(k_dense_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-}
-void launch_dense_solve(const Batch& b, const SvinBaOptions& opt, int smem_bytes, cudaStream_t st) {
-  k_dense_solve<<<b.B, kDenseThreads, smem_bytes, st>>>(b, opt, smem_bytes > 0 ? 1 : 0);
+// generic fallback (reduced system stays in global memory); the fast path is in ba_dense_solve.cu
+void launch_dense_solve_generic(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {
+  k_dense_solve<<<b.B, kDenseThreads, 0, st>>>(b, opt, 0);
 }
 void launch_backsub(const Batch& b, cudaStream_t st) {
   if (b.n_lm_tiles == 0) return;

@@ -8,7 +8,7 @@ namespace svin {
 void launch_linearize(const Batch& b, int which, int raw, cudaStream_t st);
 void launch_dense_eval(const Batch& b, int which, int raw, const double* const* dump, cudaStream_t st);
 void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st);
-int dense_solve_smem_bytes(int n_max);
+size_t dense_solve_smem_bytes(int n_max);
 cudaError_t configure_dense_solve(int smem_bytes);
 void launch_dense_solve(const Batch& b, const SvinBaOptions& opt, int smem_bytes, cudaStream_t st);
 void launch_backsub(const Batch& b, cudaStream_t st);

@@ -133,6 +133,9 @@ struct Batch {
   int* lm_obs_begin;  // [NL+1]
   int *obs_tile_win, *obs_tile_begin;
   int *lm_tile_win, *lm_tile_begin;
+  // Schur warp chunks: <= 32 consecutive landmarks with an identical (pose, camera) observation pattern
+  int n_schur_warps;
+  int *sw_win, *sw_lm_begin, *sw_count;
   // linearisation, two buffers: planes [k][obs_stride]
   double* lin_r[2];   // 2 planes
   double* lin_Jp[2];  // 12 planes
