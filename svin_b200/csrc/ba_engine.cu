@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -61,6 +63,7 @@ struct WindowOrder {
   std::vector<int> lm_perm;   // internal landmark k -> caller landmark
   std::vector<int> obs_order; // internal observation k -> caller observation
   std::vector<int> lm_count;  // observations of internal landmark k
+  std::vector<int> lm_first, lm_stride;  // window-local position of its first observation, stride between them
   std::vector<int> chunk_begin, chunk_count;  // Schur warp chunks (window-local internal landmark indices)
 };
 
@@ -112,14 +115,8 @@ void order_window(const SvinBaWindow& w, bool group, WindowOrder& out) {
     }
     std::stable_sort(out.lm_perm.begin(), out.lm_perm.end(), [&](int a, int b2) { return key[a] < key[b2]; });
   }
-  out.obs_order.resize(N);
   out.lm_count.resize(L);
-  int pos = 0;
-  for (int k = 0; k < L; ++k) {
-    const int l = out.lm_perm[k];
-    out.lm_count[k] = start[l + 1] - start[l];
-    for (int q = start[l]; q < start[l + 1]; ++q) out.obs_order[pos++] = ord[q];
-  }
+  for (int k = 0; k < L; ++k) out.lm_count[k] = start[out.lm_perm[k] + 1] - start[out.lm_perm[k]];
   out.chunk_begin.clear();
   out.chunk_count.clear();
   if (group) {
@@ -130,6 +127,30 @@ void order_window(const SvinBaWindow& w, bool group, WindowOrder& out) {
       out.chunk_begin.push_back(k);
       out.chunk_count.push_back(e - k);
       k = e;
+    }
+  }
+  out.obs_order.resize(N);
+  out.lm_first.resize(L);
+  out.lm_stride.resize(L);
+  int pos = 0;
+  if (group) {
+    // pattern-major inside a chunk: position (k, lane) -> pos + k * count + lane
+    for (size_t ch = 0; ch < out.chunk_begin.size(); ++ch) {
+      const int k0 = out.chunk_begin[ch], cntc = out.chunk_count[ch], m = out.lm_count[k0];
+      for (int lane = 0; lane < cntc; ++lane) {
+        const int l = out.lm_perm[k0 + lane];
+        out.lm_first[k0 + lane] = pos + lane;
+        out.lm_stride[k0 + lane] = cntc;
+        for (int q = 0; q < m; ++q) out.obs_order[pos + q * cntc + lane] = ord[start[l] + q];
+      }
+      pos += m * cntc;
+    }
+  } else {
+    for (int k = 0; k < L; ++k) {
+      const int l = out.lm_perm[k];
+      out.lm_first[k] = pos;
+      out.lm_stride[k] = 1;
+      for (int q = start[l]; q < start[l + 1]; ++q) out.obs_order[pos++] = ord[q];
     }
   }
 }
@@ -366,10 +387,19 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
       if (!wins[i].pose_fixed[wins[i].obs_extrinsics[o]]) has_ext = 1;
   std::vector<WindowOrder> orders(B);
   long long NSW = 0;
-  for (int i = 0; i < B; ++i) {
-    order_window(wins[i], !has_ext, orders[i]);
-    NSW += (long long)orders[i].chunk_begin.size();
+  {
+    // independent per window: spread over host threads (this is on the end-to-end path)
+    const int nt = std::max(1, std::min<int>(B, (int)std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    std::atomic<int> next{0};
+    auto work = [&]() {
+      for (int i = next.fetch_add(1); i < B; i = next.fetch_add(1)) order_window(wins[i], !has_ext, orders[i]);
+    };
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
   }
+  for (int i = 0; i < B; ++i) NSW += (long long)orders[i].chunk_begin.size();
   for (int i = 0; i < B; ++i) {
     const SvinBaWindow& w = wins[i];
     WinDesc& d = c->h_win[i];
@@ -425,7 +455,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   const size_t o_opose = in.add(4 * NOBS), o_olm = in.add(4 * NOBS), o_oext = in.add(4 * NOBS), o_ocam = in.add(4 * NOBS);
   const size_t o_zx = in.add(8 * NOBS), o_zy = in.add(8 * NOBS), o_u00 = in.add(8 * NOBS), o_u01 = in.add(8 * NOBS),
                o_u11 = in.add(8 * NOBS);
-  const size_t o_lmob = in.add(4 * (NL + 1));
+  const size_t o_lmof = in.add(4 * NL), o_lmos = in.add(4 * NL), o_lmoc = in.add(4 * NL);
   const size_t o_otw = in.add(4 * (size_t)n_obs_tiles), o_otb = in.add(4 * (size_t)n_obs_tiles);
   const size_t o_ltw = in.add(4 * (size_t)n_lm_tiles), o_ltb = in.add(4 * (size_t)n_lm_tiles);
   const size_t o_sww = in.add(4 * (size_t)NSW), o_swb = in.add(4 * (size_t)NSW), o_swc = in.add(4 * (size_t)NSW);
@@ -451,7 +481,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   int *h_opose = (int*)hp(o_opose), *h_olm = (int*)hp(o_olm), *h_oext = (int*)hp(o_oext), *h_ocam = (int*)hp(o_ocam);
   double *h_zx = (double*)hp(o_zx), *h_zy = (double*)hp(o_zy), *h_u00 = (double*)hp(o_u00), *h_u01 = (double*)hp(o_u01),
          *h_u11 = (double*)hp(o_u11);
-  int* h_lmob = (int*)hp(o_lmob);
+  int *h_lmof = (int*)hp(o_lmof), *h_lmos = (int*)hp(o_lmos), *h_lmoc = (int*)hp(o_lmoc);
   int *h_otw = (int*)hp(o_otw), *h_otb = (int*)hp(o_otb), *h_ltw = (int*)hp(o_ltw), *h_ltb = (int*)hp(o_ltb);
   int *h_sww = (int*)hp(o_sww), *h_swb = (int*)hp(o_swb), *h_swc = (int*)hp(o_swc);
   ImuTerm* h_imu = (ImuTerm*)hp(o_imu);
@@ -517,10 +547,10 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
       h_u01[g] = U[1];
       h_u11[g] = U[3];
     }
-    int run = d.obs_begin;
     for (int k = 0; k < w.num_landmarks; ++k) {
-      h_lmob[d.lm_begin + k] = run;
-      run += wo.lm_count[k];
+      h_lmof[d.lm_begin + k] = d.obs_begin + wo.lm_first[k];
+      h_lmos[d.lm_begin + k] = wo.lm_stride[k];
+      h_lmoc[d.lm_begin + k] = wo.lm_count[k];
     }
     for (size_t k = 0; k < wo.chunk_begin.size(); ++k) {
       h_sww[sw] = i;
@@ -644,7 +674,6 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     s.last_successful = 1;
     cam_base += w.num_cameras;
   }
-  h_lmob[NL] = (int)NOBS;
 
   // ---------------- work arena
   const size_t S = ((size_t)NOBS + 31) & ~(size_t)31;
@@ -703,7 +732,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   b.obs_cam = (int*)(D + o_ocam);
   b.obs_zx = (double*)(D + o_zx); b.obs_zy = (double*)(D + o_zy);
   b.obs_u00 = (double*)(D + o_u00); b.obs_u01 = (double*)(D + o_u01); b.obs_u11 = (double*)(D + o_u11);
-  b.lm_obs_begin = (int*)(D + o_lmob);
+  b.lm_obs_first = (int*)(D + o_lmof); b.lm_obs_stride = (int*)(D + o_lmos); b.lm_obs_cnt = (int*)(D + o_lmoc);
   b.obs_tile_win = (int*)(D + o_otw); b.obs_tile_begin = (int*)(D + o_otb);
   b.lm_tile_win = (int*)(D + o_ltw); b.lm_tile_begin = (int*)(D + o_ltb);
   b.n_schur_warps = (int)NSW;

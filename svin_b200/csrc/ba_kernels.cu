@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(kLmTile) k_schur(Batch b, SvinBaOptions opt) {
   double* g_red = b.g_red + wd.d_off;
   double* g_raw = b.g_raw + wd.d_off;
   double* Hdiag = b.Hdiag + wd.d_off;
-  const int ob = b.lm_obs_begin[l], oe = b.lm_obs_begin[l + 1];
+  const int ob = b.lm_obs_first[l], oe = ob + b.lm_obs_cnt[l];  // this kernel is only used with stride-1 layouts
   const bool lfix = b.lm_fixed[l] != 0;
   const double mu = ws.mu;
 
@@ -612,8 +612,9 @@ __global__ void __launch_bounds__(128) k_schur_warp(Batch b, SvinBaOptions opt) 
   double* g_red = b.g_red + wd.d_off;
   double* g_raw = b.g_raw + wd.d_off;
   double* Hdiag = b.Hdiag + wd.d_off;
-  const int ob = b.lm_obs_begin[l];
-  const int nobs = b.lm_obs_begin[l + 1] - ob;  // identical on every lane of the chunk
+  const int ob = b.lm_obs_first[l];
+  const int ost = b.lm_obs_stride[l];
+  const int nobs = b.lm_obs_cnt[l];  // identical on every lane of the chunk
   const bool lfix = b.lm_fixed[l] != 0;         // part of the pattern, hence warp-uniform
   const double mu = ws.mu;
   const size_t S = b.obs_stride;
@@ -624,7 +625,7 @@ __global__ void __launch_bounds__(128) k_schur_warp(Batch b, SvinBaOptions opt) 
   // ---- pass 1: V = sum Jl^T Jl, bl = sum Jl^T r (unscaled)
   double V[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
   for (int k = 0; k < nobs; ++k) {
-    const int o = ob + k;
+    const int o = ob + k * ost;
     const double r0 = rP[o], r1 = rP[S + o];
     double a[6];
 #pragma unroll
@@ -689,9 +690,9 @@ __global__ void __launch_bounds__(128) k_schur_warp(Batch b, SvinBaOptions opt) 
   // ---- pass 2: pose runs (identical structure on every lane)
   int i = 0;
   while (i < nobs) {
-    const int p = b.obs_pose[ob + i];
+    const int p = b.obs_pose[ob + i * ost];
     int j = i + 1;
-    while (j < nobs && b.obs_pose[ob + j] == p) ++j;
+    while (j < nobs && b.obs_pose[ob + j * ost] == p) ++j;
     const int offp = b.pose_off[p];
     if (offp >= 0) {
       double v[32];  // [0,21) H block upper, [21,27) reduced gradient, [27,32) Hdiag 0..4
@@ -704,7 +705,7 @@ __global__ void __launch_bounds__(128) k_schur_warp(Batch b, SvinBaOptions opt) 
 #pragma unroll
       for (int k = 0; k < 18; ++k) W[k] = 0;
       for (int k = i; k < j; ++k) {
-        const int o = ob + k;
+        const int o = ob + k * ost;
         double Jp[12], Jls[6];
 #pragma unroll
         for (int q = 0; q < 12; ++q) Jp[q] = JpP[q * S + o];
@@ -771,16 +772,16 @@ __global__ void __launch_bounds__(128) k_schur_warp(Batch b, SvinBaOptions opt) 
       if (!lfix) {
         int i2 = j;
         while (i2 < nobs) {
-          const int q = b.obs_pose[ob + i2];
+          const int q = b.obs_pose[ob + i2 * ost];
           int j2 = i2 + 1;
-          while (j2 < nobs && b.obs_pose[ob + j2] == q) ++j2;
+          while (j2 < nobs && b.obs_pose[ob + j2 * ost] == q) ++j2;
           const int offq = b.pose_off[q];
           if (offq >= 0) {
             double Wq[18];
 #pragma unroll
             for (int k = 0; k < 18; ++k) Wq[k] = 0;
             for (int k = i2; k < j2; ++k) {
-              const int o = ob + k;
+              const int o = ob + k * ost;
               double Jp[12], Jls[6];
 #pragma unroll
               for (int t = 0; t < 12; ++t) Jp[t] = JpP[t * S + o];
@@ -1675,8 +1676,9 @@ __global__ void __launch_bounds__(kLmTile) k_backsub(Batch b) {
       }
     }
     double a3[3] = {0, 0, 0};
-    const int ob = b.lm_obs_begin[l], oe = b.lm_obs_begin[l + 1];
-    for (int o = ob; o < oe; ++o) {
+    const int ob = b.lm_obs_first[l], ost = b.lm_obs_stride[l], nobs = b.lm_obs_cnt[l];
+    for (int k = 0; k < nobs; ++k) {
+      const int o = ob + k * ost;
       ObsJ J;
       load_obs(b, buf, o, J);
       const int offp = b.pose_off[b.obs_pose[o]];
@@ -1873,8 +1875,9 @@ __global__ void __launch_bounds__(kLmTile) k_step_lm(Batch b) {
     y[1] = x1 + dl[1];
     y[2] = x2 + dl[2];
     y[3] = x3;
-    const int ob = b.lm_obs_begin[l], oe = b.lm_obs_begin[l + 1];
-    for (int o = ob; o < oe; ++o) {
+    const int ob = b.lm_obs_first[l], ost = b.lm_obs_stride[l], nobs = b.lm_obs_cnt[l];
+    for (int k = 0; k < nobs; ++k) {
+      const int o = ob + k * ost;
       ObsJ J;
       load_obs(b, buf, o, J);
       double m0 = J.Jl[0] * dl[0] + J.Jl[1] * dl[1] + J.Jl[2] * dl[2];
@@ -2015,8 +2018,9 @@ __global__ void __launch_bounds__(kLmTile) k_quality(Batch b) {
   if (l >= wd.lm_end) return;
   const int buf = ws.cur;
   double Hm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  const int ob = b.lm_obs_begin[l], oe = b.lm_obs_begin[l + 1];
-  for (int o = ob; o < oe; ++o) {
+  const int ob = b.lm_obs_first[l], ost = b.lm_obs_stride[l], nobs = b.lm_obs_cnt[l];
+  for (int k = 0; k < nobs; ++k) {
+    const int o = ob + k * ost;
     Reproj R;
     reproj_eval<true, false>(b.pose[buf] + 7 * (size_t)b.obs_pose[o], b.lm[buf] + 4 * (size_t)l,
                              b.pose[buf] + 7 * (size_t)b.obs_ext[o], b.intr + 8 * (size_t)b.obs_cam[o], b.obs_zx[o],

@@ -130,7 +130,10 @@ struct Batch {
   // observations (sorted by landmark, pose, camera)
   int *obs_pose, *obs_lm, *obs_ext, *obs_cam;
   double *obs_zx, *obs_zy, *obs_u00, *obs_u01, *obs_u11;
-  int* lm_obs_begin;  // [NL+1]
+  // observations of landmark l are  lm_obs_first[l] + k * lm_obs_stride[l],  k < lm_obs_cnt[l].
+  // Inside a Schur chunk (landmarks sharing one observation pattern) they are stored pattern-major
+  // (stride = chunk size) so lane-consecutive landmarks read consecutive addresses; otherwise stride = 1.
+  int *lm_obs_first, *lm_obs_stride, *lm_obs_cnt;  // [NL]
   int *obs_tile_win, *obs_tile_begin;
   int *lm_tile_win, *lm_tile_begin;
   // Schur warp chunks: <= 32 consecutive landmarks with an identical (pose, camera) observation pattern
