@@ -285,6 +285,97 @@ typedef struct SvinBaKernelTimes {
 int svin_ba_set_profiling(svin_ba_ctx* ctx, int enable);
 int svin_ba_kernel_times(svin_ba_ctx* ctx, SvinBaKernelTimes* out);
 
+/* =====================================================================
+ *  (A) BRISK-2 front-end: detect / describe / match
+ * ===================================================================== */
+
+/* cv::KeyPoint memory layout (28 bytes), as filled by Frame::detect / Frame::describe. */
+typedef struct SvinKeypoint {
+  float x, y;     /* pt */
+  float size;     /* 12 at octave 0 */
+  float angle;    /* degrees, gravity-aligned (Frame.hpp impl:113-129) */
+  float response; /* Harris score */
+  int32_t octave;
+  int32_t class_id;
+} SvinKeypoint;
+
+#define SVIN_DESCRIPTOR_BYTES 48 /* 384 bit, Hamming over 3 x 128 bit (VioKeyframeWindowMatchingAlgorithm.hpp:263) */
+
+/* The arguments of brisk::ScaleSpaceFeatureDetector<HarrisScoreCalculator>(threshold, octaves, absoluteThreshold,
+ * maxNoKeypoints) and brisk::BriskDescriptorExtractor(rotationInvariance, scaleInvariance) as constructed at
+ * okvis_frontend/src/Frontend.cpp:997-1007 from detection_options.* (config_fpga_p2_euroc.yaml:65-68). */
+typedef struct SvinFeOptions {
+  int32_t image_width, image_height;
+  double detection_threshold; /* uniformity radius in pixels (40) */
+  int32_t detection_octaves;  /* only 0 (single scale) is implemented, as in both shipped configs */
+  double absolute_threshold;  /* 800 (Frontend.cpp:75) */
+  int32_t max_keypoints;      /* 400 */
+  int32_t rotation_invariance;/* 1: use the supplied keypoint angle */
+  int32_t scale_invariance;   /* must be 0 */
+  int32_t max_images;         /* capacity of one batched call */
+} SvinFeOptions;
+
+void svin_fe_default_options(SvinFeOptions* opt);
+
+typedef struct svin_fe_ctx svin_fe_ctx;
+int svin_fe_create(int device, const SvinFeOptions* opt, svin_fe_ctx** out);
+void svin_fe_destroy(svin_fe_ctx* ctx);
+
+/* Frame::detect + Frame::describe for `num_images` images of the configured size in one launch sequence.
+ * images[i] points to 8-bit grey rows with `stride` bytes between rows; intrinsics [n][8] (fu fv cu cv k1 k2 p1 p2);
+ * extraction_direction [n][3] is gravity in the camera frame (Frontend.cpp:107-108).  Outputs, all host buffers:
+ * keypoints [n][max_keypoints], descriptors [n][max_keypoints][48], counts [n]. */
+int svin_fe_detect_describe(svin_fe_ctx* ctx, int32_t num_images, const uint8_t* const* images, int32_t stride,
+                            const double* intrinsics, const double* extraction_direction, SvinKeypoint* keypoints,
+                            uint8_t* descriptors, int32_t* counts);
+/* Split form for device-resident benchmarking: upload once, run many times, download. */
+int svin_fe_upload(svin_fe_ctx* ctx, int32_t num_images, const uint8_t* const* images, int32_t stride,
+                   const double* intrinsics, const double* extraction_direction);
+int svin_fe_run(svin_fe_ctx* ctx);
+int svin_fe_download(svin_fe_ctx* ctx, SvinKeypoint* keypoints, uint8_t* descriptors, int32_t* counts);
+/* Harris score image of uploaded image `index` (int32 [H][W]); test hook. */
+int svin_fe_scores(svin_fe_ctx* ctx, int32_t index, int32_t* out);
+
+/* One DenseMatcher::match<VioKeyframeWindowMatchingAlgorithm> call (3.2 in SURVEY.md). */
+enum { SVIN_MATCH_3D2D = 0, SVIN_MATCH_2D2D = 1 };
+typedef struct SvinMatchProblem {
+  int32_t type;                 /* SVIN_MATCH_* (matchingType_) */
+  int32_t nA, nB;
+  const uint8_t* descA;         /* [nA][48] */
+  const uint8_t* descB;         /* [nB][48] */
+  const uint8_t* skipA;         /* [nA] graph-state skips decided by the host (landmark not added/initialised...), or NULL */
+  const uint8_t* skipB;         /* [nB] or NULL */
+  const SvinKeypoint* kpA;      /* [nA] */
+  const SvinKeypoint* kpB;      /* [nB] */
+  float distance_threshold;     /* 60 (Frontend.cpp:79) */
+  const double* landmarksA;     /* 3D-2D: [nA][4] hp_W of the landmark each A keypoint observes */
+  const double* T_CbW;          /* 3D-2D: [7] */
+  double pose_uncertainty;      /* 3D-2D: UOplus translation variance (VKWMA.cpp:132-144) */
+  const double* intrA;          /* [8] */
+  const double* intrB;          /* [8] */
+  const double* T_CaCb;         /* 2D-2D: [7] */
+  int32_t image_width, image_height;
+} SvinMatchProblem;
+typedef struct SvinMatchResult {
+  int32_t* best_index;     /* [nA][4] best-4 list per A keypoint (index in B, -1 = empty) */
+  float* best_distance;    /* [nA][4] */
+  int32_t* match_of_B;     /* [nB] final pairing per B keypoint (index in A or -1), B-index order like matchBody */
+  float* match_distance;   /* [nB] */
+  uint8_t* skipA_effective;/* [nA] skipA after doSetup (projection failures added), or NULL */
+} SvinMatchResult;
+/* Solves `num_problems` independent match problems; assignment order is the declared deterministic one
+ * (A ascending, single worker).  Host buffers in and out. */
+int svin_match(svin_fe_ctx* ctx, int32_t num_problems, const SvinMatchProblem* problems, SvinMatchResult* results);
+
+typedef struct SvinFeTimings {
+  double run_ms;   /* device time of the last svin_fe_run / svin_match (CUDA events) */
+  double h2d_ms, d2h_ms;
+  int64_t kernel_launches;
+  int64_t h2d_bytes, d2h_bytes;
+  double kernel_ms[8]; /* harris, nms-compact, sort, uniformity, orient-describe, match, assign, (unused) */
+} SvinFeTimings;
+int svin_fe_timings(svin_fe_ctx* ctx, SvinFeTimings* out);
+
 #ifdef __cplusplus
 }
 #endif

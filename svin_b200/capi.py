@@ -92,6 +92,42 @@ class SvinBaTimings(C.Structure):
                 ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
+class SvinKeypoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32), ("class_id", C.c_int32)]
+
+
+class SvinFeOptions(C.Structure):
+    _fields_ = [("image_width", C.c_int32), ("image_height", C.c_int32), ("detection_threshold", C.c_double),
+                ("detection_octaves", C.c_int32), ("absolute_threshold", C.c_double), ("max_keypoints", C.c_int32),
+                ("rotation_invariance", C.c_int32), ("scale_invariance", C.c_int32), ("max_images", C.c_int32)]
+
+
+SVIN_MATCH_3D2D, SVIN_MATCH_2D2D = 0, 1
+c_float_p = C.POINTER(C.c_float)
+
+
+class SvinMatchProblem(C.Structure):
+    _fields_ = [("type", C.c_int32), ("nA", C.c_int32), ("nB", C.c_int32), ("descA", c_uint8_p), ("descB", c_uint8_p),
+                ("skipA", c_uint8_p), ("skipB", c_uint8_p), ("kpA", C.POINTER(SvinKeypoint)),
+                ("kpB", C.POINTER(SvinKeypoint)), ("distance_threshold", C.c_float), ("landmarksA", c_double_p),
+                ("T_CbW", c_double_p), ("pose_uncertainty", C.c_double), ("intrA", c_double_p), ("intrB", c_double_p),
+                ("T_CaCb", c_double_p), ("image_width", C.c_int32), ("image_height", C.c_int32)]
+
+
+class SvinMatchResult(C.Structure):
+    _fields_ = [("best_index", c_int32_p), ("best_distance", c_float_p), ("match_of_B", c_int32_p),
+                ("match_distance", c_float_p), ("skipA_effective", c_uint8_p)]
+
+
+class SvinFeTimings(C.Structure):
+    _fields_ = [("run_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("kernel_ms", C.c_double * 8)]
+
+
+FE_KERNEL_NAMES = ["harris", "nms_compact", "sort", "uniformity", "orient_describe", "match", "assign", "unused"]
+
 BA_KERNEL_NAMES = ["linearize", "dense_eval", "schur", "dense_solve", "backsub", "step_dense", "step_lm", "decide",
                    "clear"]
 
@@ -111,6 +147,8 @@ EXPORTED_SYMBOLS = [
     "svin_last_error", "svin_version", "svin_ba_default_options", "svin_ba_create", "svin_ba_destroy",
     "svin_ba_upload", "svin_ba_evaluate", "svin_ba_solve", "svin_ba_download", "svin_ba_reset", "svin_ba_optimize",
     "svin_ba_timings", "svin_ba_set_profiling", "svin_ba_kernel_times",
+    "svin_fe_default_options", "svin_fe_create", "svin_fe_destroy", "svin_fe_detect_describe", "svin_fe_upload",
+    "svin_fe_run", "svin_fe_download", "svin_fe_scores", "svin_match", "svin_fe_timings",
 ]
 
 
@@ -142,6 +180,20 @@ def load(path: str | None = None) -> C.CDLL:
     lib.svin_ba_timings.argtypes = [C.c_void_p, C.POINTER(SvinBaTimings)]
     lib.svin_ba_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.svin_ba_kernel_times.argtypes = [C.c_void_p, C.POINTER(SvinBaKernelTimes)]
+    lib.svin_fe_default_options.argtypes = [C.POINTER(SvinFeOptions)]
+    lib.svin_fe_default_options.restype = None
+    lib.svin_fe_create.argtypes = [C.c_int, C.POINTER(SvinFeOptions), C.POINTER(C.c_void_p)]
+    lib.svin_fe_destroy.argtypes = [C.c_void_p]
+    lib.svin_fe_destroy.restype = None
+    pp_u8 = C.POINTER(c_uint8_p)
+    lib.svin_fe_detect_describe.argtypes = [C.c_void_p, C.c_int32, pp_u8, C.c_int32, c_double_p, c_double_p,
+                                            C.POINTER(SvinKeypoint), c_uint8_p, c_int32_p]
+    lib.svin_fe_upload.argtypes = [C.c_void_p, C.c_int32, pp_u8, C.c_int32, c_double_p, c_double_p]
+    lib.svin_fe_run.argtypes = [C.c_void_p]
+    lib.svin_fe_download.argtypes = [C.c_void_p, C.POINTER(SvinKeypoint), c_uint8_p, c_int32_p]
+    lib.svin_fe_scores.argtypes = [C.c_void_p, C.c_int32, c_int32_p]
+    lib.svin_match.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SvinMatchProblem), C.POINTER(SvinMatchResult)]
+    lib.svin_fe_timings.argtypes = [C.c_void_p, C.POINTER(SvinFeTimings)]
     if path is None:
         _lib = lib
     return lib

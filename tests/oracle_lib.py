@@ -86,3 +86,136 @@ def solve(window, options=None, quality=True):
     rc = lib.svin_oracle_ba_solve(C.byref(s), C.byref(opt), C.byref(summ), P(q))
     assert rc == 0, rc
     return summ.as_dict(), q
+
+
+# ------------------------------------------------------------------------------ front-end oracle
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libref_matcher.so")
+_ref = None
+
+
+def load_fe():
+    lib = load()
+    if getattr(lib, "_fe_ready", False):
+        return lib
+    u8p, i32p, fp, dp = capi.c_uint8_p, capi.c_int32_p, capi.c_float_p, capi.c_double_p
+    lib.svin_oracle_fe_detect_describe.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, dp,
+                                                   dp, C.POINTER(capi.SvinKeypoint), u8p]
+    lib.svin_oracle_fe_harris.argtypes = [u8p, C.c_int, C.c_int, C.c_int, i32p]
+    lib.svin_oracle_hamming48.argtypes = [u8p, u8p]
+    lib.svin_oracle_hamming48.restype = C.c_uint32
+    lib.svin_oracle_match.argtypes = [C.POINTER(capi.SvinMatchProblem), i32p, fp, i32p, fp, u8p]
+    lib.svin_oracle_match_matrix.argtypes = [C.c_int, C.c_int, fp, u8p, u8p, C.c_float, i32p, fp, i32p, fp]
+    lib._fe_ready = True
+    return lib
+
+
+def load_ref_matcher():
+    """The reference's own DenseMatcher (oracle/_ref, built from /root/reference when present); None if absent."""
+    global _ref
+    if _ref is not None:
+        return _ref
+    if not os.path.exists(REF_SO):
+        try:
+            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref"])
+        except Exception:
+            pass
+    if not os.path.exists(REF_SO):
+        return None
+    lib = C.CDLL(REF_SO)
+    lib.svin_ref_dense_match.argtypes = [C.c_int, C.c_int, capi.c_float_p, capi.c_uint8_p, capi.c_uint8_p, C.c_float,
+                                         C.c_float, C.c_int, C.c_int, capi.c_int32_p, capi.c_float_p]
+    _ref = lib
+    return lib
+
+
+def _u8(a):
+    return a.ctypes.data_as(capi.c_uint8_p) if a is not None else capi.c_uint8_p()
+
+
+def fe_detect_describe(img, intr, edir, radius=40.0, abs_thr=800.0, max_kp=400):
+    lib = load_fe()
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    H, W = img.shape
+    kps = (capi.SvinKeypoint * max_kp)()
+    desc = np.zeros((max_kp, 48), dtype=np.uint8)
+    intr = np.ascontiguousarray(intr, dtype=np.float64)
+    edir = np.ascontiguousarray(edir, dtype=np.float64)
+    n = lib.svin_oracle_fe_detect_describe(_u8(img), W, W, H, radius, abs_thr, max_kp, P(intr), P(edir), kps, _u8(desc))
+    arr = np.frombuffer(kps, dtype=KP_DTYPE)[:n].copy()
+    return arr, desc[:n].copy()
+
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+
+
+def fe_harris(img):
+    lib = load_fe()
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    H, W = img.shape
+    out = np.zeros((H, W), dtype=np.int32)
+    lib.svin_oracle_fe_harris(_u8(img), W, W, H, out.ctypes.data_as(capi.c_int32_p))
+    return out
+
+
+def match_matrix(D, skipA=None, skipB=None, thr=60.0):
+    lib = load_fe()
+    D = np.ascontiguousarray(D, dtype=np.float32)
+    nA, nB = D.shape
+    bi, bd = np.zeros((nA, 4), np.int32), np.zeros((nA, 4), np.float32)
+    mb, md = np.zeros(nB, np.int32), np.zeros(nB, np.float32)
+    lib.svin_oracle_match_matrix(nA, nB, D.ctypes.data_as(capi.c_float_p), _u8(skipA), _u8(skipB), thr,
+                                 bi.ctypes.data_as(capi.c_int32_p), bd.ctypes.data_as(capi.c_float_p),
+                                 mb.ctypes.data_as(capi.c_int32_p), md.ctypes.data_as(capi.c_float_p))
+    return bi, bd, mb, md
+
+
+def ref_match_matrix(D, skipA=None, skipB=None, thr=60.0, ratio=3.0, use_ratio=False, threads=1):
+    lib = load_ref_matcher()
+    assert lib is not None
+    D = np.ascontiguousarray(D, dtype=np.float32)
+    nA, nB = D.shape
+    mb, md = np.zeros(nB, np.int32), np.zeros(nB, np.float32)
+    lib.svin_ref_dense_match(nA, nB, D.ctypes.data_as(capi.c_float_p), _u8(skipA), _u8(skipB), thr, ratio,
+                             int(use_ratio), threads, mb.ctypes.data_as(capi.c_int32_p),
+                             md.ctypes.data_as(capi.c_float_p))
+    return mb, md
+
+
+class MatchArgs:
+    """Keeps the numpy arrays of one SvinMatchProblem alive."""
+
+    def __init__(self, type_, descA, descB, kpA, kpB, intrA, intrB, W, H, skipA=None, skipB=None, landmarksA=None,
+                 T_CbW=None, pose_uncertainty=4e-8, T_CaCb=None, thr=60.0):
+        c = np.ascontiguousarray
+        self.descA, self.descB = c(descA, dtype=np.uint8), c(descB, dtype=np.uint8)
+        self.kpA, self.kpB = c(kpA), c(kpB)
+        self.intrA, self.intrB = c(intrA, dtype=np.float64), c(intrB, dtype=np.float64)
+        self.skipA = c(skipA, dtype=np.uint8) if skipA is not None else None
+        self.skipB = c(skipB, dtype=np.uint8) if skipB is not None else None
+        self.landmarksA = c(landmarksA, dtype=np.float64) if landmarksA is not None else None
+        self.T_CbW = c(T_CbW, dtype=np.float64) if T_CbW is not None else None
+        self.T_CaCb = c(T_CaCb, dtype=np.float64) if T_CaCb is not None else None
+        p = capi.SvinMatchProblem()
+        p.type, p.nA, p.nB = type_, len(self.kpA), len(self.kpB)
+        p.descA, p.descB = _u8(self.descA), _u8(self.descB)
+        p.skipA, p.skipB = _u8(self.skipA), _u8(self.skipB)
+        p.kpA = self.kpA.ctypes.data_as(C.POINTER(capi.SvinKeypoint))
+        p.kpB = self.kpB.ctypes.data_as(C.POINTER(capi.SvinKeypoint))
+        p.distance_threshold = thr
+        p.landmarksA, p.T_CbW = P(self.landmarksA), P(self.T_CbW)
+        p.pose_uncertainty = pose_uncertainty
+        p.intrA, p.intrB, p.T_CaCb = P(self.intrA), P(self.intrB), P(self.T_CaCb)
+        p.image_width, p.image_height = W, H
+        self.c = p
+
+
+def fe_match(args: MatchArgs):
+    lib = load_fe()
+    nA, nB = args.c.nA, args.c.nB
+    bi, bd = np.zeros((nA, 4), np.int32), np.zeros((nA, 4), np.float32)
+    mb, md = np.zeros(nB, np.int32), np.zeros(nB, np.float32)
+    sk = np.zeros(nA, np.uint8)
+    lib.svin_oracle_match(C.byref(args.c), bi.ctypes.data_as(capi.c_int32_p), bd.ctypes.data_as(capi.c_float_p),
+                          mb.ctypes.data_as(capi.c_int32_p), md.ctypes.data_as(capi.c_float_p), _u8(sk))
+    return dict(best_index=bi, best_distance=bd, match_of_B=mb, match_distance=md, skipA=sk)
