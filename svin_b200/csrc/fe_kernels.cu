@@ -1,0 +1,719 @@
+// CUDA kernels of the BRISK-2 style front-end (sm_100a).  Specification: DESIGN.md §A (declared, because
+// brisk 2.0.8 is not vendored in the reference); in-tree arithmetic followed exactly is cited per kernel.
+//
+//   k_harris_nms       32x32 pixel tile per CTA   integer Harris score + 3x3 NMS + threshold -> candidate keys
+//   k_sort_candidates  one CTA per image          bitonic sort of 64-bit keys (score desc, pixel index asc)
+//   k_uniformity       one CTA per image          strongest-first uniformity enforcement, occupancy in smem
+//   k_orient_describe  one warp per keypoint      sub-pixel refinement, Frame::describe orientation
+//                                                 (okvis_cv/include/okvis/implementation/Frame.hpp:113-129),
+//                                                 TMA-staged 32x32 tile -> 60 box samples -> 384 bits via ballots
+//   k_match_setup      one thread per keypoint    VKWMA::doSetup projections / rays (VKWMA.cpp:163-212)
+//   k_match            one warp per A keypoint    Hamming (3 x 128 bit, VKWMA.hpp:258-264) + verifyMatch
+//                                                 (VKWMA.cpp:292-323) + best-4 list (DenseMatcher.hpp impl:216-242)
+//   k_assign           one thread per problem     assignbest (DenseMatcher.cpp:59-97), A ascending
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "ba_math.cuh"
+#include "fe_kernels.cuh"
+
+namespace svin {
+
+// ------------------------------------------------------------------------------------------ Harris + NMS
+constexpr int kTile = 32;
+constexpr int kHalo = 3;  // Sobel 1 + box 1 + NMS 1
+
+__global__ void __launch_bounds__(256) k_harris_nms(FeBatch f) {
+  __shared__ uint8_t px[kTile + 2 * kHalo][kTile + 2 * kHalo + 2];
+  __shared__ int gxx[kTile + 4][kTile + 4 + 1], gyy[kTile + 4][kTile + 4 + 1], gxy[kTile + 4][kTile + 4 + 1];
+  __shared__ int sc[kTile + 2][kTile + 2 + 1];
+  const int img = blockIdx.z;
+  const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+  const int W = f.W, H = f.H;
+  const uint8_t* I = f.images + (size_t)img * f.H * f.pitch;
+  const int tid = threadIdx.x;
+  // pixels with halo 3 (zero outside the image; scores there are forced to 0 anyway)
+  for (int e = tid; e < (kTile + 6) * (kTile + 6); e += 256) {
+    const int ly = e / (kTile + 6), lx = e % (kTile + 6);
+    const int gx = x0 + lx - kHalo, gy = y0 + ly - kHalo;
+    px[ly][lx] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? I[(size_t)gy * f.pitch + gx] : 0;
+  }
+  __syncthreads();
+  // gradient products on (tile + 2*2); valid for image pixels 1..W-2, else 0 (matches the oracle's zero frame)
+  for (int e = tid; e < (kTile + 4) * (kTile + 4); e += 256) {
+    const int ly = e / (kTile + 4), lx = e % (kTile + 4);
+    const int gx_ = x0 + lx - 2, gy_ = y0 + ly - 2;
+    int a = 0, b = 0, c = 0;
+    if (gx_ >= 1 && gx_ < W - 1 && gy_ >= 1 && gy_ < H - 1) {
+      const int cy = ly + 1, cx = lx + 1;  // position in px
+      const int dx = (px[cy - 1][cx + 1] + 2 * px[cy][cx + 1] + px[cy + 1][cx + 1]) -
+                     (px[cy - 1][cx - 1] + 2 * px[cy][cx - 1] + px[cy + 1][cx - 1]);
+      const int dy = (px[cy + 1][cx - 1] + 2 * px[cy + 1][cx] + px[cy + 1][cx + 1]) -
+                     (px[cy - 1][cx - 1] + 2 * px[cy - 1][cx] + px[cy - 1][cx + 1]);
+      a = dx * dx;
+      b = dy * dy;
+      c = dx * dy;
+    }
+    gxx[ly][lx] = a;
+    gyy[ly][lx] = b;
+    gxy[ly][lx] = c;
+  }
+  __syncthreads();
+  // scores on (tile + 2*1)
+  for (int e = tid; e < (kTile + 2) * (kTile + 2); e += 256) {
+    const int ly = e / (kTile + 2), lx = e % (kTile + 2);
+    const int gx_ = x0 + lx - 1, gy_ = y0 + ly - 1;
+    int s = 0;
+    if (gx_ >= 2 && gx_ < W - 2 && gy_ >= 2 && gy_ < H - 2) {
+      long long a = 0, b = 0, c = 0;
+#pragma unroll
+      for (int v = 0; v < 3; ++v)
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          a += gxx[ly + v][lx + u];
+          b += gyy[ly + v][lx + u];
+          c += gxy[ly + v][lx + u];
+        }
+      a >>= 10;
+      b >>= 10;
+      c >>= 10;
+      long long v = (a * b - c * c) - (((a + b) * (a + b)) >> 4);
+      v = v > 2147483647ll ? 2147483647ll : (v < -2147483647ll ? -2147483647ll : v);
+      s = (int)v;
+    }
+    sc[ly][lx] = s;
+    if (lx >= 1 && lx <= kTile && ly >= 1 && ly <= kTile && gx_ < W && gy_ < H)
+      f.scores[((size_t)img * H + gy_) * W + gx_] = s;
+  }
+  __syncthreads();
+  // 3x3 NMS on the tile, inside the descriptor border
+  const int thr = f.abs_threshold;
+  for (int e = tid; e < kTile * kTile; e += 256) {
+    const int ly = e / kTile + 1, lx = e % kTile + 1;
+    const int gx_ = x0 + lx - 1, gy_ = y0 + ly - 1;
+    if (gx_ < f.border || gx_ >= W - f.border || gy_ < f.border || gy_ >= H - f.border) continue;
+    const int s = sc[ly][lx];
+    if (s < thr) continue;
+    if (sc[ly - 1][lx - 1] > s || sc[ly - 1][lx] > s || sc[ly - 1][lx + 1] > s || sc[ly][lx - 1] > s) continue;
+    if (sc[ly][lx + 1] >= s || sc[ly + 1][lx - 1] >= s || sc[ly + 1][lx] >= s || sc[ly + 1][lx + 1] >= s) continue;
+    const unsigned slot = atomicAdd(&f.cand_count[img], 1u);
+    if (slot < (unsigned)f.cand_cap) {
+      const unsigned idx = (unsigned)(gy_ * W + gx_);
+      f.cand_keys[(size_t)img * f.cand_cap + slot] = ((unsigned long long)(unsigned)s << 32) | (0xffffffffu - idx);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ sort
+// Descending bitonic sort of the image's candidate keys (unique), padded with zeros to a power of two.
+__global__ void __launch_bounds__(1024) k_sort_candidates(FeBatch f) {
+  const int img = blockIdx.x;
+  unsigned n = f.cand_count[img];
+  if (n > (unsigned)f.cand_cap) n = f.cand_cap;
+  unsigned long long* K = f.cand_keys + (size_t)img * f.cand_cap;
+  unsigned P = 1;
+  while (P < n) P <<= 1;
+  for (unsigned i = n + threadIdx.x; i < P; i += blockDim.x) K[i] = 0ull;
+  __syncthreads();
+  for (unsigned k = 2; k <= P; k <<= 1)
+    for (unsigned j = k >> 1; j > 0; j >>= 1) {
+      for (unsigned i = threadIdx.x; i < P; i += blockDim.x) {
+        const unsigned l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = K[i], b = K[l];
+          const bool desc = ((i & k) == 0);
+          if (desc ? (a < b) : (a > b)) {
+            K[i] = b;
+            K[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ uniformity
+__global__ void __launch_bounds__(256) k_uniformity(FeBatch f) {
+  extern __shared__ uint8_t occ[];  // (H/2+32) x (W/2+32)
+  __shared__ double lut[31 * 31];
+  __shared__ int first_s;
+  __shared__ int kept_s;
+  const int img = blockIdx.x;
+  const int W = f.W, H = f.H;
+  const int OW = W / 2 + 32, OH = H / 2 + 32;
+  unsigned n = f.cand_count[img];
+  if (n > (unsigned)f.cand_cap) n = f.cand_cap;
+  const unsigned long long* K = f.cand_keys + (size_t)img * f.cand_cap;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < OW * OH; e += 256) occ[e] = 0;
+  const double half_radius = f.uniformity_radius / 2.0;
+  for (int e = tid; e < 31 * 31; e += 256) {
+    const int dy = e / 31 - 15, dx = e % 31 - 15;
+    const double d = sqrt((double)(dx * dx + dy * dy));
+    const double v = 1.0 - d / half_radius;
+    lut[e] = v > 0.0 ? v : 0.0;
+  }
+  if (tid == 0) kept_s = 0;
+  __syncthreads();
+  int* kept_xy = f.kept_xy + (size_t)img * f.max_kp * 2;
+  int* kept_score = f.kept_score + (size_t)img * f.max_kp;
+  if (n == 0) {
+    if (tid == 0) f.kept_count[img] = 0;
+    return;
+  }
+  const double maxScore = (double)(unsigned)(K[0] >> 32);
+  const bool enforce = f.uniformity_radius > 0.0;
+  unsigned i0 = 0;
+  while (i0 < n) {
+    if (tid == 0) first_s = 0x7fffffff;
+    __syncthreads();
+    const unsigned i = i0 + tid;
+    if (i < n) {
+      const unsigned long long key = K[i];
+      const int s = (int)(unsigned)(key >> 32);
+      const unsigned idx = 0xffffffffu - (unsigned)(key & 0xffffffffu);
+      const int y = idx / W, x = idx % W;
+      bool pass = true;
+      if (enforce) {
+        const double s0 = (double)occ[(y / 2 + 16) * OW + (x / 2 + 16)] / 255.0;
+        const double lim = s0 * s0 * s0 * s0 * maxScore;
+        pass = !((double)s < lim);
+      }
+      if (pass) atomicMin(&first_s, (int)i);
+    }
+    __syncthreads();
+    const int first = first_s;
+    if (first == 0x7fffffff) {  // nothing in this window passes; occupancy only grows, so they are all rejected
+      i0 += 256;
+      __syncthreads();
+      continue;
+    }
+    const unsigned long long key = K[first];
+    const int s = (int)(unsigned)(key >> 32);
+    const unsigned idx = 0xffffffffu - (unsigned)(key & 0xffffffffu);
+    const int y = idx / W, x = idx % W;
+    if (enforce) {
+      const double nsc = sqrt(sqrt((double)s / maxScore));
+      const int cy = y / 2 + 16, cx = x / 2 + 16;
+      for (int e = tid; e < 31 * 31; e += 256) {
+        const int dy = e / 31 - 15, dx = e % 31 - 15;
+        const int add = (int)floor(255.0 * nsc * lut[e]);
+        const int o = (cy + dy) * OW + cx + dx;
+        const int v = (int)occ[o] + add;
+        occ[o] = (uint8_t)(v > 255 ? 255 : v);
+      }
+    }
+    const int k = kept_s;
+    __syncthreads();
+    if (tid == 0) {
+      kept_xy[2 * k] = x;
+      kept_xy[2 * k + 1] = y;
+      kept_score[k] = s;
+      kept_s = k + 1;
+    }
+    __syncthreads();
+    if (k + 1 >= f.max_kp) break;
+    i0 = first + 1;
+  }
+  __syncthreads();
+  if (tid == 0) f.kept_count[img] = kept_s;
+}
+
+// ------------------------------------------------------------------------------------------ camera helpers
+// RadialTangentialDistortion::undistort (5 Gauss-Newton iterations) and PinholeCamera::backProject
+__device__ __forceinline__ bool backproject(const double* intr, double ix, double iy, double& rx, double& ry) {
+  const double y0 = (ix - intr[2]) * (1.0 / intr[0]), y1 = (iy - intr[3]) * (1.0 / intr[1]);
+  double x0 = y0, x1 = y1;
+  bool ok = false;
+  for (int i = 0; i < 5; ++i) {
+    double d0, d1, E00, E01, E10, E11;
+    radtan_distort(intr, x0, x1, d0, d1, E00, E01, E10, E11);
+    const double e0 = y0 - d0, e1 = y1 - d1;
+    const double a = E00 * E00 + E10 * E10, b = E00 * E01 + E10 * E11, c = E01 * E01 + E11 * E11;
+    const double det = a * c - b * b;
+    const double i00 = c / det, i01 = -b / det, i11 = a / det;
+    const double M00 = i00 * E00 + i01 * E01, M01 = i00 * E10 + i01 * E11;
+    const double M10 = i01 * E00 + i11 * E01, M11 = i01 * E10 + i11 * E11;
+    x0 += M00 * e0 + M01 * e1;
+    x1 += M10 * e0 + M11 * e1;
+    const double chi2 = e0 * e0 + e1 * e1;
+    if (chi2 < 1e-4) ok = true;
+    if (chi2 < 1e-15) {
+      ok = true;
+      break;
+    }
+  }
+  rx = x0;
+  ry = x1;
+  return ok;
+}
+// PinholeCamera::project with point Jacobian; returns ProjectionStatus (0 Successful, 1 OutsideImage, 3 Behind, 4 Invalid)
+__device__ __forceinline__ int project3(const double* intr, double X, double Y, double Z, int W, int H, double& u,
+                                        double& v, double* J) {
+  if (fabs(Z) < 1.0e-12) return 4;
+  const double rz = 1.0 / Z, rz2 = rz * rz;
+  double d0, d1, D00, D01, D10, D11;
+  radtan_distort(intr, X * rz, Y * rz, d0, d1, D00, D01, D10, D11);
+  if (J) {
+    J[0] = intr[0] * D00 * rz;
+    J[1] = intr[0] * D01 * rz;
+    J[2] = -intr[0] * (X * D00 + Y * D01) * rz2;
+    J[3] = intr[1] * D10 * rz;
+    J[4] = intr[1] * D11 * rz;
+    J[5] = -intr[1] * (X * D10 + Y * D11) * rz2;
+  }
+  u = intr[0] * d0 + intr[2];
+  v = intr[1] * d1 + intr[3];
+  if (W > 0) {
+    if (u < 0.0 || v < 0.0) return 1;
+    if (u >= W || v >= H) return 1;
+  }
+  return Z > 0.0 ? 0 : 3;
+}
+__device__ __forceinline__ int project_h(const double* intr, const double* hp, int W, int H, double& u, double& v,
+                                         double* J) {
+  double X = hp[0], Y = hp[1], Z = hp[2];
+  if (hp[3] < 0) {
+    X = -X;
+    Y = -Y;
+    Z = -Z;
+  }
+  return project3(intr, X, Y, Z, W, H, u, v, J);
+}
+
+// ------------------------------------------------------------------------------------------ describe
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(256) k_orient_describe(FeBatch f, const __grid_constant__ CUtensorMap tmap) {
+  __shared__ __align__(128) uint8_t tiles[8][32 * 32];
+  __shared__ __align__(8) unsigned long long mbar[8];
+  __shared__ int S[8][64];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int img = blockIdx.y;
+  const int k = blockIdx.x * 8 + wid;
+  const int count = f.kept_count[img];
+  const bool valid = k < count;
+  // all warps of the CTA take part in barrier setup
+  if (USE_TMA && lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[wid])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (!valid) return;
+  const int cx = f.kept_xy[((size_t)img * f.max_kp + k) * 2], cy = f.kept_xy[((size_t)img * f.max_kp + k) * 2 + 1];
+  const int W = f.W, H = f.H;
+  uint8_t* tile = tiles[wid];
+  if (USE_TMA) {
+    if (lane == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar[wid])), "r"(1024)
+                   : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"(smem_u32(tile)), "l"(&tmap), "r"(cx - 16), "r"(cy - 16), "r"(img), "r"(smem_u32(&mbar[wid]))
+          : "memory");
+    }
+  } else {
+    const uint8_t* I = f.images + (size_t)img * H * f.pitch;
+    for (int e = lane; e < 1024; e += 32) {
+      const int yy = cy - 16 + (e >> 5), xx = cx - 16 + (e & 31);
+      tile[e] = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? I[(size_t)yy * f.pitch + xx] : 0;
+    }
+  }
+  // while the tile is in flight: sub-pixel refinement and orientation (lane 0), broadcast of the rotation bin
+  float kx = 0, ky = 0, ang = 0, resp = 0;
+  int rot = 0;
+  if (lane == 0) {
+    const int* sc = f.scores + ((size_t)img * H + cy) * W + cx;
+    const double m = (double)sc[0];
+    double ddx = 0.0, ddy = 0.0;
+    {
+      const double l = (double)sc[-1], r = (double)sc[1];
+      const double den = 2.0 * (l - 2.0 * m + r);
+      if (den < 0.0) {
+        ddx = (l - r) / den;
+        ddx = ddx > 0.5 ? 0.5 : (ddx < -0.5 ? -0.5 : ddx);
+      }
+    }
+    {
+      const double l = (double)sc[-W], r = (double)sc[W];
+      const double den = 2.0 * (l - 2.0 * m + r);
+      if (den < 0.0) {
+        ddy = (l - r) / den;
+        ddy = ddy > 0.5 ? 0.5 : (ddy < -0.5 ? -0.5 : ddy);
+      }
+    }
+    kx = (float)((double)cx + ddx);
+    ky = (float)((double)cy + ddy);
+    resp = (float)f.kept_score[(size_t)img * f.max_kp + k];
+    // Frame::describe (Frame.hpp impl:113-129)
+    const double* intr = f.intrinsics + 8 * (size_t)img;
+    const double* g = f.extraction_dir + 3 * (size_t)img;
+    double rx, ry, u, v, J[6] = {0, 0, 0, 0, 0, 0};
+    backproject(intr, (double)kx, (double)ky, rx, ry);
+    project3(intr, rx, ry, 1.0, 0, 0, u, v, J);
+    const double egx = J[0] * g[0] + J[1] * g[1] + J[2] * g[2];
+    const double egy = J[3] * g[0] + J[4] * g[1] + J[5] * g[2];
+    const double angle = atan2(egy, egx);
+    ang = (float)(angle / 3.14159265358979323846 * 180.0);
+    double a = (double)ang;
+    if (a < 0) a += 360.0;
+    rot = (int)(a * 1024.0 / 360.0 + 0.5);
+    rot &= 1023;
+    SvinKeypoint kp;
+    kp.x = kx;
+    kp.y = ky;
+    kp.size = 12.0f;
+    kp.angle = ang;
+    kp.response = resp;
+    kp.octave = 0;
+    kp.class_id = -1;
+    f.keypoints[(size_t)img * f.max_kp + k] = kp;
+  }
+  rot = __shfl_sync(0xffffffffu, rot, 0);
+  if (USE_TMA) {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done)
+          : "r"(smem_u32(&mbar[wid])), "r"(0)
+          : "memory");
+    }
+  }
+  __syncwarp();
+  // 60 box-smoothed samples
+  const int8_t* pdx = f.pat_dx + rot * 60;
+  const int8_t* pdy = f.pat_dy + rot * 60;
+  for (int i = lane; i < 60; i += 32) {
+    const int sx = 16 + pdx[i], sy = 16 + pdy[i], h = f.pat_half[i];
+    int sum = 0;
+    for (int v = -h; v <= h; ++v)
+      for (int u = -h; u <= h; ++u) sum += tile[(sy + v) * 32 + sx + u];
+    S[wid][i] = sum;
+  }
+  __syncwarp();
+  // 384 comparisons -> 12 ballots
+  uint8_t* out = f.descriptors + ((size_t)img * f.max_kp + k) * 48;
+  uint32_t words[12];
+#pragma unroll
+  for (int w = 0; w < 12; ++w) {
+    const int b = w * 32 + lane;
+    const int i = f.pair_i[b], j = f.pair_j[b];
+    const int hi = f.pat_half[i], hj = f.pat_half[j];
+    const int Ai = (2 * hi + 1) * (2 * hi + 1), Aj = (2 * hj + 1) * (2 * hj + 1);
+    const bool bit = S[wid][i] * Aj > S[wid][j] * Ai;
+    words[w] = __ballot_sync(0xffffffffu, bit);
+  }
+  if (lane < 12) {
+    uint32_t wv = words[0];
+#pragma unroll
+    for (int w = 1; w < 12; ++w) wv = (lane == w) ? words[w] : wv;
+    reinterpret_cast<uint32_t*>(out)[lane] = wv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ matching
+// VKWMA::doSetup (VKWMA.cpp:124-265): projections of A's landmarks into B with 2x2 covariance, ray sigmas,
+// back-projected rays for the 2D-2D triangulation.  One thread per keypoint (A then B).
+__global__ void k_match_setup(MatchBatch mb) {
+  const int p = blockIdx.y;
+  const MatchDesc& md = mb.desc[p];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < md.nA) {
+    const int a = md.a0 + t;
+    const SvinKeypoint kp = mb.kpA[a];
+    uint8_t skip = mb.skipA_in ? mb.skipA_in[a] : 0;
+    const double fA = md.intrA[0];
+    mb.sigA[a] = sqrt(sqrt(2.0)) * (0.8 * (double)kp.size / 12.0) / fA;
+    if (md.type == SVIN_MATCH_3D2D) {
+      if (!skip) {
+        const Tf T = tf_load(md.T_CbW);
+        const double* hw = mb.landmarksA + 4 * (size_t)a;
+        const V3 tt = m3v(T.C, V3{hw[0], hw[1], hw[2]});
+        const double s = hw[3];
+        const double hc[4] = {tt.x + T.r.x * s, tt.y + T.r.y * s, tt.z + T.r.z * s, s};
+        double u, v, J[6] = {0, 0, 0, 0, 0, 0};
+        if (project_h(md.intrB, hc, md.W, md.H, u, v, J) != 0) {
+          skip = 1;
+        } else {
+          const double pu = md.pose_uncertainty;
+          mb.proj[2 * (size_t)a] = u;
+          mb.proj[2 * (size_t)a + 1] = v;
+          for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j)
+              mb.cov[4 * (size_t)a + i * 2 + j] =
+                  pu * (J[i * 3] * J[j * 3] + J[i * 3 + 1] * J[j * 3 + 1] + J[i * 3 + 2] * J[j * 3 + 2]);
+        }
+      }
+    } else {
+      double rx, ry;
+      backproject(md.intrA, (double)kp.x, (double)kp.y, rx, ry);
+      mb.rayA[3 * (size_t)a] = rx;
+      mb.rayA[3 * (size_t)a + 1] = ry;
+      mb.rayA[3 * (size_t)a + 2] = 1.0;
+    }
+    mb.skipA[a] = skip;
+  }
+  if (t < md.nB) {
+    const int b = md.b0 + t;
+    const SvinKeypoint kp = mb.kpB[b];
+    mb.sigB[b] = sqrt(sqrt(2.0)) * (0.8 * (double)kp.size / 12.0) / md.intrB[0];
+    if (md.type == SVIN_MATCH_2D2D) {
+      double rx, ry;
+      backproject(md.intrB, (double)kp.x, (double)kp.y, rx, ry);
+      const Tf T = tf_load(md.T_CaCb);
+      const V3 r = m3v(T.C, V3{rx, ry, 1.0});
+      mb.rayB[3 * (size_t)b] = r.x;
+      mb.rayB[3 * (size_t)b + 1] = r.y;
+      mb.rayB[3 * (size_t)b + 2] = r.z;
+    }
+  }
+}
+
+__device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// triangulateFast (stereo_triangulation.cpp:51-125)
+__device__ bool triangulate_fast(const double* p1, const double* e1, const double* p2, const double* e2, double sigma,
+                                 bool& isValid, double* out) {
+  isValid = false;
+  const double t12[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  const double b0 = dot3(t12, e1), b1 = dot3(t12, e2);
+  double A00 = dot3(e1, e1), A10 = dot3(e1, e2), A01 = -A10, A11 = -dot3(e2, e2);
+  if (A10 < 0.0) {
+    A10 = -A10;
+    A01 = -A01;
+  }
+  const double det = A00 * A11 - A01 * A10;
+  const double maxc = fmax(fmax(fabs(A00), fabs(A01)), fmax(fabs(A10), fabs(A11)));
+  const bool invertible = fabs(det) > 1.0e-6 * maxc;
+  double x, y, z, w;
+  if (!invertible) {
+    const double cr[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    if (sqrt(dot3(cr, cr)) < 6 * sigma) isValid = true;
+    x = (e1[0] + e2[0]) / 2.0;
+    y = (e1[1] + e2[1]) / 2.0;
+    z = (e1[2] + e2[2]) / 2.0;
+    w = 1e-3;
+  } else {
+    const double invdet = 1.0 / det;
+    const double i00 = A11 * invdet, i01 = -A01 * invdet, i10 = -A10 * invdet, i11 = A00 * invdet;
+    const double l0 = i00 * b0 + i01 * b1, l1 = i10 * b0 + i11 * b1;
+    double mid[3], err[3], diff[3];
+    for (int k = 0; k < 3; ++k) {
+      const double xm = l0 * e1[k] + p1[k], xn = l1 * e2[k] + p2[k];
+      mid[k] = (xm + xn) / 2.0;
+      err[k] = mid[k] - xm;
+      diff[k] = mid[k] - (p1[k] + 0.5 * t12[k]);
+    }
+    const double diff_sq = dot3(diff, diff);
+    const double chi2 = dot3(err, err) * (1.0 / (diff_sq * sigma * sigma));
+    isValid = true;
+    if (chi2 > 9) isValid = false;
+    if (dot3(diff, e1) < 0)
+      for (int k = 0; k < 3; ++k) mid[k] = (p1[k] + 0.5 * t12[k]) - diff[k];
+    x = mid[0];
+    y = mid[1];
+    z = mid[2];
+    w = 1.0;
+  }
+  const double nrm = sqrt(x * x + y * y + z * z + w * w);
+  out[0] = x / nrm;
+  out[1] = y / nrm;
+  out[2] = z / nrm;
+  out[3] = w / nrm;
+  return invertible;
+}
+
+// computeReprojectionError4 (ProbabilisticStereoTriangulator.cpp:340-365)
+__device__ __forceinline__ bool reproj_err4(const double* intr, int W, int H, const SvinKeypoint& kp, const double* hp,
+                                            double& err) {
+  double u, v;
+  if (project_h(intr, hp, W, H, u, v, nullptr) != 0) return false;
+  const double sd = 0.8 * (double)kp.size / 12.0;
+  const double ic = 1.0 / (sd * sd);
+  const double dx = u - (double)kp.x, dy = v - (double)kp.y;
+  err = dx * (ic * dx) + dy * (ic * dy);
+  return true;
+}
+
+// VKWMA::verifyMatch (VKWMA.cpp:292-323)
+__device__ bool verify_match(const MatchBatch& mb, const MatchDesc& md, int a, int b) {
+  if (md.type == SVIN_MATCH_2D2D) {
+    const double sigmaR = fmax(mb.sigA[a], mb.sigB[b]);
+    const double* ra = mb.rayA + 3 * (size_t)a;
+    const double* rb = mb.rayB + 3 * (size_t)b;
+    const double na = sqrt(dot3(ra, ra)), nb = sqrt(dot3(rb, rb));
+    const double e1[3] = {ra[0] / na, ra[1] / na, ra[2] / na}, e2[3] = {rb[0] / nb, rb[1] / nb, rb[2] / nb};
+    const double p1[3] = {0, 0, 0};
+    const Tf T_AB = tf_load(md.T_CaCb);
+    const double p2[3] = {T_AB.r.x, T_AB.r.y, T_AB.r.z};
+    bool isValid;
+    double hpA[4];
+    triangulate_fast(p1, e1, p2, e2, sigmaR, isValid, hpA);
+    if (!isValid) return false;
+    double errA, errB;
+    if (!reproj_err4(md.intrA, md.W, md.H, mb.kpA[a], hpA, errA)) return false;
+    const Tf T_BA = tf_inverse(T_AB);
+    const V3 t = m3v(T_BA.C, V3{hpA[0], hpA[1], hpA[2]});
+    const double hpB[4] = {t.x + T_BA.r.x * hpA[3], t.y + T_BA.r.y * hpA[3], t.z + T_BA.r.z * hpA[3], hpA[3]};
+    if (!reproj_err4(md.intrB, md.W, md.H, mb.kpB[b], hpB, errB)) return false;
+    if (errA > 4.0 || errB > 4.0) return false;
+    return true;
+  }
+  const SvinKeypoint kb = mb.kpB[b];
+  const double sd = 0.8 * (double)kb.size / 12.0;
+  const double* cv = mb.cov + 4 * (size_t)a;
+  const double U00 = sd * sd + cv[0], U01 = cv[1], U10 = cv[2], U11 = sd * sd + cv[3];
+  const double det = U00 * U11 - U01 * U10;
+  const double i00 = U11 / det, i01 = -U01 / det, i10 = -U10 / det, i11 = U00 / det;
+  const double ex = mb.proj[2 * (size_t)a] - (double)kb.x, ey = mb.proj[2 * (size_t)a + 1] - (double)kb.y;
+  const int chi2 = (int)((ex * i00 + ey * i10) * ex + (ex * i01 + ey * i11) * ey);
+  return chi2 < 4.0;
+}
+
+// One warp per A keypoint: distance() over all B, sorted best-4 list with the reference's insertion order.
+__global__ void __launch_bounds__(128) k_match(MatchBatch mb) {
+  const int p = blockIdx.y;
+  const MatchDesc& md = mb.desc[p];
+  const int lane = threadIdx.x & 31;
+  const int ai = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (ai >= md.nA) return;
+  const int a = md.a0 + ai;
+  int bidx[4] = {-1, -1, -1, -1};
+  float bdist[4] = {md.threshold, md.threshold, md.threshold, md.threshold};
+  if (!mb.skipA[a]) {
+    const unsigned long long* da = reinterpret_cast<const unsigned long long*>(mb.descA + 48 * (size_t)a);
+    const unsigned long long a0 = da[0], a1 = da[1], a2 = da[2], a3 = da[3], a4 = da[4], a5 = da[5];
+    for (int base = 0; base < md.nB; base += 32) {
+      const int bi = base + lane;
+      bool cand = false;
+      float d = 0.f;
+      if (bi < md.nB) {
+        const int b = md.b0 + bi;
+        if (!(mb.skipB && mb.skipB[b])) {
+          const unsigned long long* db = reinterpret_cast<const unsigned long long*>(mb.descB + 48 * (size_t)b);
+          const int h = __popcll(a0 ^ db[0]) + __popcll(a1 ^ db[1]) + __popcll(a2 ^ db[2]) + __popcll(a3 ^ db[3]) +
+                        __popcll(a4 ^ db[4]) + __popcll(a5 ^ db[5]);
+          d = (float)h;
+          if (d < md.threshold) cand = verify_match(mb, md, a, b);
+        }
+      }
+      unsigned mask = __ballot_sync(0xffffffffu, cand);
+      while (mask) {
+        const int l = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float dl = __shfl_sync(0xffffffffu, d, l);
+        const int bl = base + l;
+        // listBIteration: insert if better than the worst kept, before entries of equal distance
+        if (dl < bdist[3]) {
+          int pos = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pos += (bdist[k] < dl) ? 1 : 0;
+#pragma unroll
+          for (int k = 3; k > 0; --k)
+            if (k > pos) {
+              bidx[k] = bidx[k - 1];
+              bdist[k] = bdist[k - 1];
+            }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k == pos) {
+              bidx[k] = bl;
+              bdist[k] = dl;
+            }
+        }
+      }
+    }
+  }
+  if (lane < 4) {
+    int bi = bidx[0];
+    float bd = bdist[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      bi = (lane == k) ? bidx[k] : bi;
+      bd = (lane == k) ? bdist[k] : bd;
+    }
+    mb.best_idx[4 * (size_t)a + lane] = bi;
+    mb.best_dist[4 * (size_t)a + lane] = bd;
+  }
+}
+
+// assignbest + matchBody tail, A ascending, single worker (one thread per problem)
+__global__ void k_assign(MatchBatch mb, int n_problems) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_problems) return;
+  const MatchDesc& md = mb.desc[p];
+  const float FMAXV = 3.402823466e+38f;
+  int* mo = mb.match_of_B + md.b0;
+  float* mdist = mb.match_dist + md.b0;
+  for (int b = 0; b < md.nB; ++b) {
+    mo[b] = -1;
+    mdist[b] = FMAXV;
+  }
+  for (int a0 = 0; a0 < md.nA; ++a0) {
+    if (mb.skipA[md.a0 + a0]) continue;
+    int a = a0, start = 0;
+    while (true) {
+      bool reassigned = false;
+      const int* bi = mb.best_idx + 4 * (size_t)(md.a0 + a);
+      const float* bd = mb.best_dist + 4 * (size_t)(md.a0 + a);
+      for (int index = start; index < 4 && bi[index] != -1; ++index) {
+        const int b = bi[index];
+        if (mo[b] == -1) {
+          mo[b] = a;
+          mdist[b] = bd[index];
+          break;
+        }
+        if (bd[index] < mdist[b]) {
+          const int old = mo[b];
+          mo[b] = a;
+          mdist[b] = bd[index];
+          a = old;
+          start = 1;
+          reassigned = true;
+          break;
+        }
+      }
+      if (!reassigned) break;
+    }
+  }
+  for (int b = 0; b < md.nB; ++b)
+    if (!(mdist[b] < md.threshold)) mo[b] = -1;
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+void fe_launch_detect(const FeBatch& f, int n_images, const CUtensorMap* tmap, bool use_tma, size_t occ_bytes,
+                      cudaStream_t st, cudaEvent_t* ev) {
+  dim3 grid((f.W + kTile - 1) / kTile, (f.H + kTile - 1) / kTile, n_images);
+  if (ev) cudaEventRecord(ev[0], st);
+  k_harris_nms<<<grid, 256, 0, st>>>(f);
+  if (ev) cudaEventRecord(ev[1], st);
+  k_sort_candidates<<<n_images, 1024, 0, st>>>(f);
+  if (ev) cudaEventRecord(ev[2], st);
+  k_uniformity<<<n_images, 256, occ_bytes, st>>>(f);
+  if (ev) cudaEventRecord(ev[3], st);
+  dim3 g2((f.max_kp + 7) / 8, n_images);
+  if (use_tma)
+    k_orient_describe<true><<<g2, 256, 0, st>>>(f, *tmap);
+  else
+    k_orient_describe<false><<<g2, 256, 0, st>>>(f, *tmap);
+  if (ev) cudaEventRecord(ev[4], st);
+}
+cudaError_t fe_configure(size_t occ_bytes) {
+  return cudaFuncSetAttribute(k_uniformity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)occ_bytes);
+}
+void fe_launch_match(const MatchBatch& mb, int n_problems, int max_nA, int max_nAB, cudaStream_t st, cudaEvent_t* ev) {
+  if (ev) cudaEventRecord(ev[0], st);
+  dim3 gs((max_nAB + 127) / 128, n_problems);
+  k_match_setup<<<gs, 128, 0, st>>>(mb);
+  dim3 gm((max_nA + 3) / 4, n_problems);
+  k_match<<<gm, 128, 0, st>>>(mb);
+  if (ev) cudaEventRecord(ev[1], st);
+  k_assign<<<(n_problems + 63) / 64, 64, 0, st>>>(mb, n_problems);
+  if (ev) cudaEventRecord(ev[2], st);
+}
+
+}  // namespace svin

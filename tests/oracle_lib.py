@@ -182,32 +182,7 @@ def ref_match_matrix(D, skipA=None, skipB=None, thr=60.0, ratio=3.0, use_ratio=F
     return mb, md
 
 
-class MatchArgs:
-    """Keeps the numpy arrays of one SvinMatchProblem alive."""
-
-    def __init__(self, type_, descA, descB, kpA, kpB, intrA, intrB, W, H, skipA=None, skipB=None, landmarksA=None,
-                 T_CbW=None, pose_uncertainty=4e-8, T_CaCb=None, thr=60.0):
-        c = np.ascontiguousarray
-        self.descA, self.descB = c(descA, dtype=np.uint8), c(descB, dtype=np.uint8)
-        self.kpA, self.kpB = c(kpA), c(kpB)
-        self.intrA, self.intrB = c(intrA, dtype=np.float64), c(intrB, dtype=np.float64)
-        self.skipA = c(skipA, dtype=np.uint8) if skipA is not None else None
-        self.skipB = c(skipB, dtype=np.uint8) if skipB is not None else None
-        self.landmarksA = c(landmarksA, dtype=np.float64) if landmarksA is not None else None
-        self.T_CbW = c(T_CbW, dtype=np.float64) if T_CbW is not None else None
-        self.T_CaCb = c(T_CaCb, dtype=np.float64) if T_CaCb is not None else None
-        p = capi.SvinMatchProblem()
-        p.type, p.nA, p.nB = type_, len(self.kpA), len(self.kpB)
-        p.descA, p.descB = _u8(self.descA), _u8(self.descB)
-        p.skipA, p.skipB = _u8(self.skipA), _u8(self.skipB)
-        p.kpA = self.kpA.ctypes.data_as(C.POINTER(capi.SvinKeypoint))
-        p.kpB = self.kpB.ctypes.data_as(C.POINTER(capi.SvinKeypoint))
-        p.distance_threshold = thr
-        p.landmarksA, p.T_CbW = P(self.landmarksA), P(self.T_CbW)
-        p.pose_uncertainty = pose_uncertainty
-        p.intrA, p.intrB, p.T_CaCb = P(self.intrA), P(self.intrB), P(self.T_CaCb)
-        p.image_width, p.image_height = W, H
-        self.c = p
+from svin_b200.frontend import MatchProblem as MatchArgs  # noqa: E402  (same container for oracle and engine)
 
 
 def fe_match(args: MatchArgs):
