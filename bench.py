@@ -122,6 +122,157 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# ------------------------------------------------------------------------------------------ front-end
+FE_BYTES_DETECT = 372e3     # read 752x480 + write <= 400 keypoints
+FE_BYTES_DESCRIBE = 380e3   # patches (<= image) + 400 x 48 B
+FE_BYTES_MATCH = 51e3       # one 400 x 400 Hamming top-4 call
+
+
+def _inv(T):
+    Ti = np.eye(4)
+    Ti[:3, :3] = T[:3, :3].T
+    Ti[:3, 3] = -T[:3, :3].T @ T[:3, 3]
+    return Ti
+
+
+def frame_match_problems(seq, feats, fa, fb):
+    """The ~17 DenseMatcher::match calls of one dataAssociationAndInitialization (SURVEY.md §3.2) between
+    frame `fb` (current) and frame `fa` (keyframe / last frame): 3 KF x 2 cams 3D-2D, 2 KF x 2 cams 2D-2D,
+    last frame 2 x (3D-2D + 2D-2D), stereo 2D-2D + 3D-2D + 2D-3D."""
+    from svin_b200 import capi
+    from svin_b200.frontend import MatchProblem
+    from svin_b200.synthetic import T_to_pose
+    from svin_b200.synthetic_images import wall_point
+    W, H = 752, 480
+    intr = seq["intrinsics"]
+    probs = []
+
+    def p3d2d(f0, c0, f1, c1):
+        kA, dA = feats[(f0, c0)]
+        kB, dB = feats[(f1, c1)]
+        pw = wall_point(seq["T_WC"][f0][c0], c0, np.stack([kA["x"], kA["y"]], axis=1))
+        lm = np.concatenate([pw, np.ones((len(pw), 1))], axis=1)
+        return MatchProblem(capi.SVIN_MATCH_3D2D, dA, dB, kA, kB, intr[c0], intr[c1], W, H, landmarksA=lm,
+                            T_CbW=T_to_pose(_inv(seq["T_WC"][f1][c1])), pose_uncertainty=1e-2)
+
+    def p2d2d(f0, c0, f1, c1):
+        kA, dA = feats[(f0, c0)]
+        kB, dB = feats[(f1, c1)]
+        T = _inv(seq["T_WC"][f0][c0]) @ seq["T_WC"][f1][c1]
+        return MatchProblem(capi.SVIN_MATCH_2D2D, dA, dB, kA, kB, intr[c0], intr[c1], W, H, T_CaCb=T_to_pose(T))
+
+    for _ in range(3):
+        for c in range(2):
+            probs.append(p3d2d(fa, c, fb, c))
+    for _ in range(2):
+        for c in range(2):
+            probs.append(p2d2d(fa, c, fb, c))
+    for c in range(2):
+        probs.append(p3d2d(fa, c, fb, c))
+        probs.append(p2d2d(fa, c, fb, c))
+    probs.append(p2d2d(fb, 0, fb, 1))
+    probs.append(p3d2d(fb, 0, fb, 1))
+    probs.append(p3d2d(fb, 1, fb, 0))
+    return probs
+
+
+def run_frontend(args, local, rank, world, dist, barrier):
+    """BRISK detect/describe + the ~17 match calls per stereo frame, batched over `--frames` frames."""
+    from svin_b200.frontend import FeEngine
+    from svin_b200.synthetic_images import make_stereo_sequence
+    F = args.frames
+    nd = 4
+    seq = make_stereo_sequence(seed=20260925 + rank, n_frames=nd)
+    imgs, intr, edir = [], [], []
+    for k in range(F):
+        f = k % nd
+        for c in range(2):
+            imgs.append(seq["images"][f][c])
+            intr.append(seq["intrinsics"][c])
+            edir.append(seq["extraction_dir"][f][c])
+    fe = FeEngine(752, 480, max_images=2 * F, device=local)
+    fe.upload(imgs, intr, edir)
+    for _ in range(3):
+        fe.run()
+    out = fe.download()
+    feats = {(f, c): out[2 * f + c] for f in range(nd) for c in range(2)}
+    nkp = float(np.mean([len(k) for k, _ in out]))
+    probs = []
+    for k in range(F):
+        probs += frame_match_problems(seq, feats, k % nd, (k + 1) % nd)
+    for _ in range(2):
+        fe.match(probs)
+    barrier()
+    t0 = time.perf_counter()
+    dev_detect = dev_match = 0.0
+    kms = {}
+    for _ in range(args.steps):
+        fe.run()
+        t = fe.timings()
+        dev_detect += t["run_ms"]
+        for n, v in t["kernel_ms"].items():
+            kms[n] = kms.get(n, 0.0) + v
+    barrier()
+    t_detect = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fe.match(probs)
+        t = fe.timings()
+        dev_match += t["run_ms"]
+        kms["match"] = kms.get("match", 0.0) + t["kernel_ms"]["match"]
+        kms["assign"] = kms.get("assign", 0.0) + t["kernel_ms"]["assign"]
+    barrier()
+    t_match_e2e = time.perf_counter() - t0
+    mt = fe.timings()
+    # end to end detect: host images in, host keypoints out
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fe.detect_describe(imgs, intr, edir)
+    barrier()
+    t_detect_e2e = time.perf_counter() - t0
+    dt = fe.timings()
+    dev_s = (dev_detect + dev_match) * 1e-3
+    dev_s = max_over_ranks(dist, dev_s, local)
+    e2e_s = max_over_ranks(dist, t_detect_e2e + t_match_e2e, local)
+    value = world * F * args.steps / dev_s
+    e2e = world * F * args.steps / e2e_s
+    peak, peak_src = measured_peak_hbm()
+    n_img = 2 * F
+    harris_gbs = FE_BYTES_DETECT * n_img / (kms["harris"] / args.steps * 1e-3) / 1e9
+    res = {
+        "metric": "BRISK detect+describe+match stereo frames/s (752x480, <=400 kp/image, 17 match calls/frame)",
+        "value": value, "unit": "frames/s", "frames_per_step": F, "keypoints_per_image": nkp,
+        "match_calls_per_frame": len(probs) // F,
+        "device_ms_per_step": {"detect_describe": dev_detect / args.steps, "match": dev_match / args.steps},
+        "wall_ms_per_step_resident_detect": 1e3 * t_detect / args.steps,
+        "e2e": {"value": e2e, "unit": "frames/s",
+                "h2d_bytes_per_step": int(dt["h2d_bytes"] + mt["h2d_bytes"]),
+                "d2h_bytes_per_step": int(dt["d2h_bytes"] + mt["d2h_bytes"])},
+        "kernels_ms_per_step": {k: v / args.steps for k, v in kms.items() if v > 0},
+        "roofline": {"bound": "hbm", "kernel": "harris_nms", "achieved": harris_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": harris_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "note": "images fit the 126 MB L2 only up to ~340 frames; the score image (4 B/px) is extra "
+                             "traffic the algorithmic figure does not count"},
+    }
+    if rank == 0 and world == 1:
+        orc = oracle_solver()
+        t0 = time.perf_counter()
+        nf = 0
+        while time.perf_counter() - t0 < 5.0:
+            f = nf % nd
+            for c in range(2):
+                orc.fe_detect_describe(seq["images"][f][c], seq["intrinsics"][c], seq["extraction_dir"][f][c])
+            for p in frame_match_problems(seq, feats, f, (f + 1) % nd):
+                orc.fe_match(p)
+            nf += 1
+        cdt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": nf / cdt, "unit": "frames/s", "cores": 1, "kind": "port",
+                               "sample": f"{nf} stereo frames (detect+describe both cameras + 17 match calls), "
+                                         f"single-thread CPU restatement (oracle/), {cdt:.1f} s; not brisk"}
+    fe.close()
+    return res
+
+
 def oracle_solver():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
@@ -268,6 +419,7 @@ def run_gpu(args):
             kern[k] = {"ms_total": kt[k]["ms"], "launches": kt[k]["launches"], "share": kt[k]["ms"] / total_ms}
     achieved = kern[dominant]["gbs"]
 
+    frontend = run_frontend(args, local, rank, world, dist, barrier) if args.frames > 0 else None
     if rank == 0:
         cpu_val, cpu_dt = cpu_baseline(batch[:args.cpu_sample], 1) if world == 1 else (None, None)
         line = {
@@ -290,6 +442,8 @@ def run_gpu(args):
                          "algorithmic_bytes_per_observation": BYTES_PER_OBS[dominant]},
             "kernels": kern,
         }
+        if frontend is not None:
+            line["frontend"] = frontend
         if cpu_val is not None:
             line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{args.cpu_sample} windows of the same batch, single-thread CPU "
@@ -310,6 +464,7 @@ def main():
     ap.add_argument("--windows", type=int, default=256, help="windows per GPU per step")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic seeds replicated to fill the batch")
     ap.add_argument("--cpu-sample", type=int, default=4)
+    ap.add_argument("--frames", type=int, default=64, help="stereo frames per front-end step (0 = skip the front-end)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -3,7 +3,6 @@
 // Reference seams: Frame::detect / Frame::describe (okvis_cv/include/okvis/implementation/Frame.hpp:93-135) behind
 // Frontend::detectAndDescribe (okvis_frontend/src/Frontend.cpp:91-113), and DenseMatcher::match over a
 // VioKeyframeWindowMatchingAlgorithm (okvis_matcher/include/okvis/implementation/DenseMatcher.hpp:195-203).
-#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -74,10 +73,6 @@ HostPattern make_pattern() {
   return P;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 }  // namespace
 
 struct svin_fe_ctx {
@@ -90,7 +85,6 @@ struct svin_fe_ctx {
   int pitch = 0;
   size_t occ_bytes = 0;
   bool use_tma = true;
-  CUtensorMap tmap{};
   // device buffers
   uint8_t* d_images = nullptr;
   double *d_intr = nullptr, *d_edir = nullptr;
@@ -172,7 +166,7 @@ int svin_fe_create(int device, const SvinFeOptions* opt_in, svin_fe_ctx** out) {
   for (auto& e : c->ev) SVIN_CUDA(cudaEventCreate(&e));
   int cap = 1;
   while (cap < (W * H) / 4 + 1024) cap <<= 1;
-  SVIN_CUDA(cudaMalloc(&c->d_images, (size_t)M * H * c->pitch));
+  SVIN_CUDA(cudaMalloc(&c->d_images, (size_t)M * H * c->pitch + 256));  // +pad: row segments may overrun by < 16 B
   SVIN_CUDA(cudaMalloc(&c->d_intr, sizeof(double) * 8 * M));
   SVIN_CUDA(cudaMalloc(&c->d_edir, sizeof(double) * 3 * M));
   SVIN_CUDA(cudaMalloc(&c->d_scores, sizeof(int) * (size_t)M * H * W));
@@ -214,29 +208,8 @@ int svin_fe_create(int device, const SvinFeOptions* opt_in, svin_fe_ctx** out) {
     return SVIN_ERR_INVALID_ARGUMENT;
   }
   SVIN_CUDA(fe_configure(c->occ_bytes));
-  // TMA descriptor over the image stack [M][H][pitch] with a 32x32x1 box (descriptor tiles)
+  // descriptor tiles are staged with TMA bulk copies (cp.async.bulk); SVIN_FE_NO_TMA=1 selects plain loads (debug)
   c->use_tma = std::getenv("SVIN_FE_NO_TMA") == nullptr;
-  if (c->use_tma) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
-      cudaGetLastError();
-      set_error("cuTensorMapEncodeTiled is not available from the driver");
-      return SVIN_ERR_CUDA;
-    }
-    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)M};
-    const cuuint64_t strides[2] = {(cuuint64_t)c->pitch, (cuuint64_t)c->pitch * H};
-    const cuuint32_t box[3] = {32, 32, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = ((EncodeTiledFn)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->d_images, dims, strides, box, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
-      return SVIN_ERR_CUDA;
-    }
-  }
   *out = c;
   return SVIN_OK;
 }
@@ -297,7 +270,7 @@ int svin_fe_run(svin_fe_ctx* c) {
   }
   SVIN_CUDA(cudaSetDevice(c->device));
   SVIN_CUDA(cudaMemsetAsync(c->d_cand_count, 0, sizeof(unsigned) * c->n_images, c->stream));
-  fe_launch_detect(c->f, c->n_images, &c->tmap, c->use_tma, c->occ_bytes, c->stream, c->ev);
+  fe_launch_detect(c->f, c->n_images, c->use_tma, c->occ_bytes, c->stream, c->ev);
   SVIN_CUDA(cudaGetLastError());
   SVIN_CUDA(cudaStreamSynchronize(c->stream));
   float ms = 0;
@@ -418,7 +391,6 @@ int svin_match(svin_fe_ctx* c, int32_t np, const SvinMatchProblem* probs, SvinMa
   char* D = (char*)c->d_match;
   MatchDesc* hd = (MatchDesc*)(Hh + o_desc);
   size_t a0 = 0, b0 = 0;
-  bool any_skipB = false;
   for (int p = 0; p < np; ++p) {
     const SvinMatchProblem& q = probs[p];
     MatchDesc& d = hd[p];
@@ -433,7 +405,7 @@ int svin_match(svin_fe_ctx* c, int32_t np, const SvinMatchProblem* probs, SvinMa
     std::memcpy(Hh + o_dA + 48 * a0, q.descA, 48 * (size_t)q.nA);
     std::memcpy(Hh + o_dB + 48 * b0, q.descB, 48 * (size_t)q.nB);
     if (q.skipA) std::memcpy(Hh + o_sA + a0, q.skipA, q.nA); else std::memset(Hh + o_sA + a0, 0, q.nA);
-    if (q.skipB) { std::memcpy(Hh + o_sB + b0, q.skipB, q.nB); any_skipB = true; } else std::memset(Hh + o_sB + b0, 0, q.nB);
+    if (q.skipB) std::memcpy(Hh + o_sB + b0, q.skipB, q.nB); else std::memset(Hh + o_sB + b0, 0, q.nB);
     std::memcpy(Hh + o_kA + sizeof(SvinKeypoint) * a0, q.kpA, sizeof(SvinKeypoint) * (size_t)q.nA);
     std::memcpy(Hh + o_kB + sizeof(SvinKeypoint) * b0, q.kpB, sizeof(SvinKeypoint) * (size_t)q.nB);
     if (q.type == SVIN_MATCH_3D2D) std::memcpy(Hh + o_lm + 32 * a0, q.landmarksA, 32 * (size_t)q.nA);
@@ -441,7 +413,6 @@ int svin_match(svin_fe_ctx* c, int32_t np, const SvinMatchProblem* probs, SvinMa
     a0 += q.nA;
     b0 += q.nB;
   }
-  (void)any_skipB;
   MatchBatch mb{};
   mb.desc = (const MatchDesc*)(D + o_desc);
   mb.descA = (const uint8_t*)(D + o_dA); mb.descB = (const uint8_t*)(D + o_dB);

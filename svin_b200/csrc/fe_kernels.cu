@@ -6,12 +6,11 @@
 //   k_uniformity       one CTA per image          strongest-first uniformity enforcement, occupancy in smem
 //   k_orient_describe  one warp per keypoint      sub-pixel refinement, Frame::describe orientation
 //                                                 (okvis_cv/include/okvis/implementation/Frame.hpp:113-129),
-//                                                 TMA-staged 32x32 tile -> 60 box samples -> 384 bits via ballots
+//                                                 TMA bulk-copied 32x48 tile -> 60 box samples -> 384 bits via ballots
 //   k_match_setup      one thread per keypoint    VKWMA::doSetup projections / rays (VKWMA.cpp:163-212)
 //   k_match            one warp per A keypoint    Hamming (3 x 128 bit, VKWMA.hpp:258-264) + verifyMatch
 //                                                 (VKWMA.cpp:292-323) + best-4 list (DenseMatcher.hpp impl:216-242)
 //   k_assign           one thread per problem     assignbest (DenseMatcher.cpp:59-97), A ascending
-#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -286,9 +285,15 @@ __device__ __forceinline__ int project_h(const double* intr, const double* hp, i
 // ------------------------------------------------------------------------------------------ describe
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Tile staging: each warp pulls the 32 rows x 48 bytes around its keypoint into shared memory with the TMA
+// bulk-copy engine (cp.async.bulk, SASS UBLKCP; one 48-byte row per lane, 16-byte aligned start, all
+// completing on one mbarrier) while lane 0 does the fp64 orientation math.  The tensor-map form
+// (cp.async.bulk.tensor / UTMALDG) raises "illegal instruction" on this pool's B200s even through libcu++'s
+// reference wrapper (tools/tma_probe.cu), so the descriptor-free form is used.
+constexpr int kTileStride = 48;
 template <bool USE_TMA>
-__global__ void __launch_bounds__(256) k_orient_describe(FeBatch f, const __grid_constant__ CUtensorMap tmap) {
-  __shared__ __align__(128) uint8_t tiles[8][32 * 32];
+__global__ void __launch_bounds__(256) k_orient_describe(FeBatch f) {
+  __shared__ __align__(128) uint8_t tiles[8][32 * kTileStride];
   __shared__ __align__(8) unsigned long long mbar[8];
   __shared__ int S[8][64];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -306,20 +311,24 @@ __global__ void __launch_bounds__(256) k_orient_describe(FeBatch f, const __grid
   const int cx = f.kept_xy[((size_t)img * f.max_kp + k) * 2], cy = f.kept_xy[((size_t)img * f.max_kp + k) * 2 + 1];
   const int W = f.W, H = f.H;
   uint8_t* tile = tiles[wid];
+  const int x_start = (cx - 16) & ~15;        // 16-byte aligned row segment [x_start, x_start + 48) covers cx-16 .. cx+15
+  const int xoff = (cx - 16) - x_start;       // 0..15
+  const uint8_t* I = f.images + (size_t)img * H * f.pitch;
   if (USE_TMA) {
-    if (lane == 0) {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar[wid])), "r"(1024)
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar[wid])),
+                   "r"(32 * kTileStride)
                    : "memory");
-      asm volatile(
-          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-          ::"r"(smem_u32(tile)), "l"(&tmap), "r"(cx - 16), "r"(cy - 16), "r"(img), "r"(smem_u32(&mbar[wid]))
-          : "memory");
-    }
+    __syncwarp();
+    const uint8_t* src = I + (size_t)(cy - 16 + lane) * f.pitch + x_start;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(tile + lane * kTileStride)),
+                 "l"(src), "r"(kTileStride), "r"(smem_u32(&mbar[wid]))
+                 : "memory");
   } else {
-    const uint8_t* I = f.images + (size_t)img * H * f.pitch;
-    for (int e = lane; e < 1024; e += 32) {
-      const int yy = cy - 16 + (e >> 5), xx = cx - 16 + (e & 31);
-      tile[e] = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? I[(size_t)yy * f.pitch + xx] : 0;
+    for (int e = lane; e < 32 * kTileStride; e += 32) {
+      const int yy = cy - 16 + e / kTileStride, xx = x_start + e % kTileStride;
+      tile[e] = (xx >= 0 && xx < f.pitch && yy >= 0 && yy < H) ? I[(size_t)yy * f.pitch + xx] : 0;
     }
   }
   // while the tile is in flight: sub-pixel refinement and orientation (lane 0), broadcast of the rotation bin
@@ -388,10 +397,10 @@ __global__ void __launch_bounds__(256) k_orient_describe(FeBatch f, const __grid
   const int8_t* pdx = f.pat_dx + rot * 60;
   const int8_t* pdy = f.pat_dy + rot * 60;
   for (int i = lane; i < 60; i += 32) {
-    const int sx = 16 + pdx[i], sy = 16 + pdy[i], h = f.pat_half[i];
+    const int sx = 16 + xoff + pdx[i], sy = 16 + pdy[i], h = f.pat_half[i];
     int sum = 0;
     for (int v = -h; v <= h; ++v)
-      for (int u = -h; u <= h; ++u) sum += tile[(sy + v) * 32 + sx + u];
+      for (int u = -h; u <= h; ++u) sum += tile[(sy + v) * kTileStride + sx + u];
     S[wid][i] = sum;
   }
   __syncwarp();
@@ -685,8 +694,8 @@ __global__ void k_assign(MatchBatch mb, int n_problems) {
 }
 
 // ------------------------------------------------------------------------------------------ launchers
-void fe_launch_detect(const FeBatch& f, int n_images, const CUtensorMap* tmap, bool use_tma, size_t occ_bytes,
-                      cudaStream_t st, cudaEvent_t* ev) {
+void fe_launch_detect(const FeBatch& f, int n_images, bool use_tma, size_t occ_bytes, cudaStream_t st,
+                      cudaEvent_t* ev) {
   dim3 grid((f.W + kTile - 1) / kTile, (f.H + kTile - 1) / kTile, n_images);
   if (ev) cudaEventRecord(ev[0], st);
   k_harris_nms<<<grid, 256, 0, st>>>(f);
@@ -697,9 +706,9 @@ void fe_launch_detect(const FeBatch& f, int n_images, const CUtensorMap* tmap, b
   if (ev) cudaEventRecord(ev[3], st);
   dim3 g2((f.max_kp + 7) / 8, n_images);
   if (use_tma)
-    k_orient_describe<true><<<g2, 256, 0, st>>>(f, *tmap);
+    k_orient_describe<true><<<g2, 256, 0, st>>>(f);
   else
-    k_orient_describe<false><<<g2, 256, 0, st>>>(f, *tmap);
+    k_orient_describe<false><<<g2, 256, 0, st>>>(f);
   if (ev) cudaEventRecord(ev[4], st);
 }
 cudaError_t fe_configure(size_t occ_bytes) {

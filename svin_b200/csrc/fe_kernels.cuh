@@ -1,6 +1,5 @@
 // Device data model + launchers of the front-end kernels (definitions in fe_kernels.cu).
 #pragma once
-#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -52,8 +51,8 @@ struct MatchBatch {
   float* match_dist;
 };
 
-void fe_launch_detect(const FeBatch& f, int n_images, const CUtensorMap* tmap, bool use_tma, size_t occ_bytes,
-                      cudaStream_t st, cudaEvent_t* ev);
+void fe_launch_detect(const FeBatch& f, int n_images, bool use_tma, size_t occ_bytes, cudaStream_t st,
+                      cudaEvent_t* ev);
 cudaError_t fe_configure(size_t occ_bytes);
 void fe_launch_match(const MatchBatch& mb, int n_problems, int max_nA, int max_nAB, cudaStream_t st, cudaEvent_t* ev);
 
