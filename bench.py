@@ -455,6 +455,60 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_sharded(args):
+    """BASELINE configs[3]: ONE 20-keyframe / 8k-landmark window, landmark blocks sharded over the ranks, the
+    reduced system all-reduced with NCCL every iteration (strong scaling of a single solve)."""
+    import torch
+    world, rank, local, dist = dist_setup(args.gpus)
+    from svin_b200.engine import BaEngine
+    from svin_b200.sharding import shard_window
+    nwin = args.windows if args.windows != 256 else 1
+    base = [make_window(seed=20260925 + i, num_keyframes=20, num_imu_frames=3, num_landmarks=8000, mode="steady")[0]
+            for i in range(min(nwin, 2))]
+    wins = [shard_window(base[i % len(base)], rank, world) for i in range(nwin)]
+    for w in wins:
+        w.c_struct()
+    eng = BaEngine(local)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+        if rank == 0:
+            uid = torch.from_numpy(BaEngine.nccl_unique_id().copy()).to(f"cuda:{local}")
+        dist.broadcast(uid, src=0)
+        eng.comm_init(uid.cpu().numpy(), rank, world)
+    opt = default_options()
+    eng.upload(wins)
+    for _ in range(max(args.warmup, 3)):
+        eng.reset()
+        summ = eng.solve(opt)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(local)
+    t0 = time.perf_counter()
+    dev = 0.0
+    for _ in range(args.steps):
+        eng.reset()
+        summ = eng.solve(opt)
+        dev += eng.timings()["solve_ms"]
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(local)
+    dt = max_over_ranks(dist, time.perf_counter() - t0, local)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC.replace("10 KF, 2k", "20 KF, 8k"), "value": nwin * args.steps / dt, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps,
+            "device_ms_per_step": dev / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "20-KF window (+3 IMU frames), 8k landmarks, landmark-block Schur sharded over the "
+                                   "ranks, NCCL all-reduce of the reduced system per iteration (BASELINE configs[3])",
+                       "windows": nwin, "observations_per_rank": int(np.mean([w.num_obs for w in wins])),
+                       "iterations": summ[0]["iterations"], "parallelism": f"landmark shards x{world}"}}))
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -464,10 +518,14 @@ def main():
     ap.add_argument("--windows", type=int, default=256, help="windows per GPU per step")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic seeds replicated to fill the batch")
     ap.add_argument("--cpu-sample", type=int, default=4)
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
+                    help="replicas: independent windows per GPU (headline); sharded: one window's landmarks split over the GPUs")
     ap.add_argument("--frames", type=int, default=64, help="stereo frames per front-end step (0 = skip the front-end)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "sharded":
+        run_sharded(args)
     else:
         run_gpu(args)
 

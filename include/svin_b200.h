@@ -282,6 +282,16 @@ typedef struct SvinBaKernelTimes {
   double ms[SVIN_BA_K_COUNT];
   int64_t launches[SVIN_BA_K_COUNT];
 } SvinBaKernelTimes;
+/* ---- sharded single-window mode (BASELINE configs[3]): every rank uploads the SAME windows with the same pose /
+ * speed-bias blocks and dense terms but a disjoint subset of the landmarks and their observations.  Each
+ * trust-region iteration then all-reduces (NCCL, on the engine's stream) the reduced system
+ * [H | g_red | g_raw | Hdiag] after the landmark elimination plus three small vectors of per-window scalars;
+ * the Cholesky, the dogleg logic and accept/reject run replicated and bit-identically on every rank.
+ * NCCL is dlopen'ed (libnccl.so.2); the communicator is created from a 128-byte unique id that rank 0 obtains
+ * with svin_nccl_unique_id() and the host distributes (e.g. torch.distributed / MPI / a file). */
+int svin_nccl_unique_id(uint8_t out[128]);
+int svin_ba_comm_init(svin_ba_ctx* ctx, const uint8_t unique_id[128], int32_t rank, int32_t world_size);
+
 int svin_ba_set_profiling(svin_ba_ctx* ctx, int enable);
 int svin_ba_kernel_times(svin_ba_ctx* ctx, SvinBaKernelTimes* out);
 

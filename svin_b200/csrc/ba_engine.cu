@@ -15,6 +15,8 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "ba_kernels.cuh"
 #include "common.hpp"
 
@@ -155,6 +157,42 @@ void order_window(const SvinBaWindow& w, bool group, WindowOrder& out) {
   }
 }
 
+// ---- NCCL, resolved at run time so that the library has no link-time dependency on it -------------------
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ struct NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+struct NcclId {
+  char internal[128];
+};
+constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.lib ? &api : nullptr;
+  tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) return nullptr;
+  api.GetUniqueId = (int (*)(void*))dlsym(api.lib, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(api.lib, "ncclCommInitRank");
+  api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+  api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
+  api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce) {
+    api.lib = nullptr;
+    return nullptr;
+  }
+  return &api;
+}
+
 struct Region {
   size_t bytes = 0;
   size_t add(size_t b) {
@@ -202,6 +240,9 @@ struct svin_ba_ctx {
   bool quality_valid = false;
   bool solved = false;
   SvinBaTimings tm{};
+  // sharded mode
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
   // optional per-kernel profiling
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
@@ -359,6 +400,7 @@ void svin_ba_destroy(svin_ba_ctx* c) {
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->prof_events) cudaEventDestroy(ev);
+  if (c->nccl_comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(c->nccl_comm);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -498,10 +540,25 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
 
   c->obs_perm.resize((size_t)NOBS);
   c->lm_perm.resize((size_t)NL);
-  int cam_base = 0, ot = 0, lt = 0, sw = 0;
-  long long meas_base = 0;
-  std::vector<int> cnt;
-  for (int i = 0; i < B; ++i) {
+  // per-window bases of the running counters, so that windows can be packed by independent host threads
+  std::vector<int> cam_base_v(B), ot_v(B), lt_v(B), sw_v(B);
+  std::vector<long long> meas_base_v(B);
+  {
+    int cb = 0, ot0 = 0, lt0 = 0, sw0 = 0;
+    long long mb0 = 0;
+    for (int i = 0; i < B; ++i) {
+      cam_base_v[i] = cb; ot_v[i] = ot0; lt_v[i] = lt0; sw_v[i] = sw0; meas_base_v[i] = mb0;
+      cb += wins[i].num_cameras;
+      ot0 += (wins[i].num_obs + kObsTile - 1) / kObsTile;
+      lt0 += (wins[i].num_landmarks + kLmTile - 1) / kLmTile;
+      sw0 += (int)orders[i].chunk_begin.size();
+      if (wins[i].num_imu) mb0 += wins[i].imu_meas_offset[wins[i].num_imu];
+    }
+  }
+  auto fill_window = [&](int i) {
+    int cam_base = cam_base_v[i], ot = ot_v[i], lt = lt_v[i], sw = sw_v[i];
+    long long meas_base = meas_base_v[i];
+    std::vector<int> cnt;
     const SvinBaWindow& w = wins[i];
     WinDesc& d = c->h_win[i];
     std::memcpy(h_pose + 7 * (size_t)d.pose_begin, w.pose_blocks, 56 * (size_t)w.num_pose_blocks);
@@ -672,7 +729,18 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     s.radius = 1e4;  // overwritten by svin_ba_solve with the options' initial radius
     s.mu = 1e-8;
     s.last_successful = 1;
-    cam_base += w.num_cameras;
+    (void)cam_base; (void)ot; (void)lt; (void)sw; (void)meas_base;
+  };
+  {
+    const int nt = std::max(1, std::min<int>(B, (int)std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    std::atomic<int> next{0};
+    auto work = [&]() {
+      for (int i = next.fetch_add(1); i < B; i = next.fetch_add(1)) fill_window(i);
+    };
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
   }
 
   // ---------------- work arena
@@ -691,6 +759,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     o_rd[k] = wk.add(8 * NROWS);
   }
   const size_t o_wsw = wk.add(sizeof(WinState) * B), o_imucw = wk.add(sizeof(ImuCache) * NIMU);
+  const size_t o_sacc = wk.add(8 * 8 * (size_t)B), o_gmaxb = wk.add(8 * (size_t)B);
   const size_t o_lms = wk.add(24 * NL), o_lmV = wk.add(48 * NL), o_lmb2 = wk.add(24 * NL), o_lmd = wk.add(24 * NL),
                o_lmg = wk.add(24 * NL), o_lmgn = wk.add(24 * NL);
   // cleared every slot: H, g_red, g_raw, Hdiag (kept contiguous)
@@ -760,6 +829,8 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   c->d_pose_out = (double*)(O + c->out_off_pose); c->d_sb_out = (double*)(O + c->out_off_sb);
   c->d_lm_out = (double*)(O + c->out_off_lm);
   b.lm_quality = (double*)(O + c->out_off_q);
+  b.shard_acc = c->nccl_comm ? (double*)(Wk + o_sacc) : nullptr;
+  b.gmax_buf = (double*)(Wk + o_gmaxb);
   c->d_clear = Wk + o_clear;
   c->clear_bytes = clear_bytes;
   c->in_bytes = in.bytes;
@@ -768,6 +839,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   SVIN_CUDA(cudaEventRecord(c->ev[0], c->stream));
   SVIN_CUDA(cudaMemcpyAsync(c->d_in, c->h_in, in.bytes, cudaMemcpyHostToDevice, c->stream));
   SVIN_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  SVIN_CUDA(cudaMemsetAsync(Wk + o_sacc, 0, 8 * 8 * (size_t)B + 8 * (size_t)B, c->stream));
   // Jd must be zero outside the blocks the terms write (structure is static)
   for (int k = 0; k < 2; ++k) SVIN_CUDA(cudaMemsetAsync(b.Jd[k], 0, 8 * (size_t)NJD + 8, c->stream));
   SVIN_CUDA(cudaMemsetAsync(b.lm_quality, 0, 8 * (size_t)NL + 8, c->stream));
@@ -806,9 +878,20 @@ int svin_ba_reset(svin_ba_ctx* c) {
   if (b.NIMU)
     SVIN_CUDA(cudaMemcpyAsync(b.imu_cache, c->d_imu_cache_init, sizeof(ImuCache) * b.NIMU, cudaMemcpyDeviceToDevice,
                               c->stream));
+  if (b.shard_acc) SVIN_CUDA(cudaMemsetAsync(b.shard_acc, 0, 8 * 8 * (size_t)b.B, c->stream));
   SVIN_CUDA(cudaGetLastError());
   c->solved = false;
   c->quality_valid = false;
+  return SVIN_OK;
+}
+
+static int comm_allreduce(svin_ba_ctx* c, void* buf, size_t count, int op) {
+  NcclApi* api = nccl_api();
+  const int r = api->AllReduce(buf, buf, count, kNcclFloat64, op, c->nccl_comm, c->stream);
+  if (r != 0) {
+    set_error(std::string("ncclAllReduce failed: ") + (api->GetErrorString ? api->GetErrorString(r) : "?"));
+    return SVIN_ERR_CUDA;
+  }
   return SVIN_OK;
 }
 
@@ -838,12 +921,33 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
     ProfScope p(c, SVIN_BA_K_CLEAR);
     SVIN_CUDA(cudaMemsetAsync(c->d_clear, 0, c->clear_bytes, c->stream));
   }
+  const bool sharded = c->nccl_comm != nullptr;
+  int rc;
   { ProfScope p(c, SVIN_BA_K_SCHUR); launch_schur(b, opt, c->stream); }
+  if (sharded) {
+    // the exchange step of the path: reduced system of every window + the landmark gradient max
+    if ((rc = comm_allreduce(c, c->d_clear, c->clear_bytes / 8, kNcclSum)) != SVIN_OK) return rc;
+    launch_gmax_pack(b, 0, c->stream);
+    if ((rc = comm_allreduce(c, b.gmax_buf, (size_t)b.B, kNcclMax)) != SVIN_OK) return rc;
+    launch_gmax_pack(b, 1, c->stream);
+  }
   { ProfScope p(c, SVIN_BA_K_DENSE_SOLVE); launch_dense_solve(b, opt, c->smem_bytes, c->stream); }
   { ProfScope p(c, SVIN_BA_K_BACKSUB); launch_backsub(b, c->stream); }
+  if (sharded) {
+    if ((rc = comm_allreduce(c, b.shard_acc, 8 * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
+    launch_fold(b, 2, c->stream);
+  }
   { ProfScope p(c, SVIN_BA_K_STEP_DENSE); launch_step_dense(b, opt, c->stream); }
   { ProfScope p(c, SVIN_BA_K_STEP_LM); launch_step_lm(b, c->stream); }
+  if (sharded) {
+    if ((rc = comm_allreduce(c, b.shard_acc, 8 * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
+    launch_fold(b, 3, c->stream);
+  }
   { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 1, 0, c->stream); }
+  if (sharded) {
+    if ((rc = comm_allreduce(c, b.shard_acc, 8 * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
+    launch_fold(b, 4, c->stream);
+  }
   { ProfScope p(c, SVIN_BA_K_DENSE_EVAL); launch_dense_eval(b, 1, 0, nullptr, c->stream); }
   { ProfScope p(c, SVIN_BA_K_DECIDE); launch_decide(b, opt, c->stream); }
   c->tm.kernel_launches += 8;
@@ -870,6 +974,11 @@ int svin_ba_solve(svin_ba_ctx* c, const SvinBaOptions* opt_in, SvinBaSummary* su
   // initial evaluation (IterationZero); k_init also installs the options' initial trust-region radius
   c->prof_family.clear();
   { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 0, 0, c->stream); }
+  if (c->nccl_comm) {
+    const int rc0 = comm_allreduce(c, b.shard_acc, 8 * (size_t)b.B, kNcclSum);
+    if (rc0 != SVIN_OK) return rc0;
+    launch_fold(b, 4, c->stream);
+  }
   { ProfScope p(c, SVIN_BA_K_DENSE_EVAL); launch_dense_eval(b, 0, 0, nullptr, c->stream); }
   launch_init(b, opt, c->stream);
   c->tm.kernel_launches += 3;
@@ -1064,6 +1173,48 @@ int svin_ba_evaluate(svin_ba_ctx* c, int32_t wi, SvinBaEvaluation* out) {
   }
   if (imu_dump) cudaFree(imu_dump);
   return svin_ba_reset(c);
+}
+
+int svin_nccl_unique_id(uint8_t out[128]) {
+  NcclApi* api = nccl_api();
+  if (!api) {
+    set_error("libnccl.so.2 could not be loaded (dlopen)");
+    return SVIN_ERR_STATE;
+  }
+  NcclId id;
+  const int r = api->GetUniqueId(&id);
+  if (r != 0) {
+    set_error(std::string("ncclGetUniqueId failed: ") + (api->GetErrorString ? api->GetErrorString(r) : "?"));
+    return SVIN_ERR_CUDA;
+  }
+  std::memcpy(out, id.internal, 128);
+  return SVIN_OK;
+}
+
+int svin_ba_comm_init(svin_ba_ctx* c, const uint8_t unique_id[128], int32_t rank, int32_t world) {
+  if (!c || !unique_id || world < 1 || rank < 0 || rank >= world) {
+    set_error("svin_ba_comm_init: invalid arguments");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  NcclApi* api = nccl_api();
+  if (!api) {
+    set_error("libnccl.so.2 could not be loaded (dlopen)");
+    return SVIN_ERR_STATE;
+  }
+  SVIN_CUDA(cudaSetDevice(c->device));
+  NcclId id;
+  std::memcpy(id.internal, unique_id, 128);
+  void* comm = nullptr;
+  const int r = api->CommInitRank(&comm, world, id, rank);
+  if (r != 0) {
+    set_error(std::string("ncclCommInitRank failed: ") + (api->GetErrorString ? api->GetErrorString(r) : "?"));
+    return SVIN_ERR_CUDA;
+  }
+  c->nccl_comm = comm;
+  c->comm_rank = rank;
+  c->comm_world = world;
+  c->uploaded = false;  // the arena layout depends on the mode
+  return SVIN_OK;
 }
 
 int svin_ba_set_profiling(svin_ba_ctx* c, int enable) {

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kObsTile) k_linearize(Batch b, int which, int 
       for (int k = 0; k < 12; ++k) Je[k * S + o] = R.Je[k];
     }
   }
-  double* const dst[1] = {&ws.cost_cand};
+  double* const dst[1] = {(b.shard_acc && !raw) ? &b.shard_acc[8 * (size_t)w + 7] : &ws.cost_cand};
   block_atomic_add<1, kObsTile>(cost, dst);
 }
 
@@ -1732,7 +1732,9 @@ __global__ void __launch_bounds__(kLmTile) k_backsub(Batch b) {
       if (!isfinite(y0) || !isfinite(y1) || !isfinite(y2)) acc[1] = nan("");
     }
   }
-  double* const dst[4] = {&ws.acc_g2, &ws.acc_n2, &ws.acc_gdot, &ws.acc_Jg2};
+  double* sa = b.shard_acc ? b.shard_acc + 8 * (size_t)w : nullptr;
+  double* const dst[4] = {sa ? sa + 0 : &ws.acc_g2, sa ? sa + 1 : &ws.acc_n2, sa ? sa + 2 : &ws.acc_gdot,
+                          sa ? sa + 3 : &ws.acc_Jg2};
   block_atomic_add<4, kLmTile>(acc, dst);
 }
 
@@ -1905,7 +1907,8 @@ __global__ void __launch_bounds__(kLmTile) k_step_lm(Batch b) {
       acc[0] += m0 * (J.r0 + m0 / 2.0) + m1 * (J.r1 + m1 / 2.0);
     }
   }
-  double* const dst[3] = {&ws.acc_mc, &ws.acc_step2, &ws.acc_xnorm2};
+  double* sa = b.shard_acc ? b.shard_acc + 8 * (size_t)w : nullptr;
+  double* const dst[3] = {sa ? sa + 4 : &ws.acc_mc, sa ? sa + 5 : &ws.acc_step2, sa ? sa + 6 : &ws.acc_xnorm2};
   block_atomic_add<3, kLmTile>(acc, dst);
 }
 
@@ -2036,8 +2039,41 @@ __global__ void __launch_bounds__(kLmTile) k_quality(Batch b) {
   b.lm_quality[l] = (ev[0] < 1.0e-12) ? 0.0 : sqrt(ev[0]) / sqrt(ev[2]);
 }
 
-// ------------------------------------------------------------------------------------------ launchers
 static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------ sharded mode
+// stage 2: after k_backsub; 3: after k_step_lm; 4: after k_linearize.  Adds the all-reduced landmark-side
+// sums to the replicated dense-side sums in WinState and clears them.
+__global__ void k_fold(Batch b, int stage) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= b.B) return;
+  WinState& ws = b.ws[w];
+  double* sa = b.shard_acc + 8 * (size_t)w;
+  if (stage == 2) {
+    ws.acc_g2 += sa[0]; ws.acc_n2 += sa[1]; ws.acc_gdot += sa[2]; ws.acc_Jg2 += sa[3];
+    sa[0] = sa[1] = sa[2] = sa[3] = 0.0;
+  } else if (stage == 3) {
+    ws.acc_mc += sa[4]; ws.acc_step2 += sa[5]; ws.acc_xnorm2 += sa[6];
+    sa[4] = sa[5] = sa[6] = 0.0;
+  } else {
+    ws.cost_cand += sa[7];
+    sa[7] = 0.0;
+  }
+}
+__global__ void k_gmax_pack(Batch b, int unpack) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= b.B) return;
+  if (!unpack)
+    b.gmax_buf[w] = __longlong_as_double((long long)b.ws[w].gmax_bits);
+  else
+    b.ws[w].gmax_bits = (unsigned long long)__double_as_longlong(b.gmax_buf[w]);
+}
+void launch_fold(const Batch& b, int stage, cudaStream_t st) { k_fold<<<div_up(b.B, 64), 64, 0, st>>>(b, stage); }
+void launch_gmax_pack(const Batch& b, int unpack, cudaStream_t st) {
+  k_gmax_pack<<<div_up(b.B, 64), 64, 0, st>>>(b, unpack);
+}
+
+// ------------------------------------------------------------------------------------------ launchers
 
 void launch_linearize(const Batch& b, int which, int raw, cudaStream_t st) {
   if (b.n_obs_tiles == 0) return;

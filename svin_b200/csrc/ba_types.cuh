@@ -165,6 +165,11 @@ struct Batch {
   MargBlock* marg_blk;
   double *marg_J, *marg_e0, *marg_lin;
   double* lm_quality;
+  // Sharded single-window mode (landmarks split over ranks): landmark-side partial sums go here instead of
+  // WinState so that they can be all-reduced before k_fold adds them to the replicated dense-side sums.
+  // [B][8]: g2, n2, gdot, Jg2 (k_backsub) | mc, step2, xnorm2 (k_step_lm) | cost of the reprojection terms.
+  double* shard_acc;  // nullptr when not sharded
+  double* gmax_buf;   // [B] landmark gradient max, all-reduced with MAX
 };
 
 struct SolveParams {

@@ -82,6 +82,18 @@ class BaEngine:
         capi.check(self._lib.svin_ba_timings(self._ctx, C.byref(t)), self._lib)
         return {n: getattr(t, n) for n, _ in t._fields_}
 
+    # ---- sharded single-window mode -----------------------------------------------------------------
+    @staticmethod
+    def nccl_unique_id() -> np.ndarray:
+        lib = capi.load()
+        out = np.zeros(128, dtype=np.uint8)
+        capi.check(lib.svin_nccl_unique_id(out.ctypes.data_as(capi.c_uint8_p)), lib)
+        return out
+
+    def comm_init(self, unique_id: np.ndarray, rank: int, world: int):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        capi.check(self._lib.svin_ba_comm_init(self._ctx, uid.ctypes.data_as(capi.c_uint8_p), rank, world), self._lib)
+
     def set_profiling(self, enable: bool):
         capi.check(self._lib.svin_ba_set_profiling(self._ctx, int(enable)), self._lib)
 

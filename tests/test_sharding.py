@@ -1,0 +1,142 @@
+"""N > 1 path: landmark-block sharding + all-reduce.  CPU part runs with world_size 2 over gloo; the GPU part
+(2 devices, NCCL inside the engine) is marked gpu and skipped when fewer than two devices are visible."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle_lib
+from svin_b200.sharding import landmark_owner, merge_landmarks, shard_window
+from svin_b200.synthetic import make_window
+from svin_b200.window import default_options
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _window():
+    return make_window(seed=77, num_keyframes=5, num_imu_frames=3, num_landmarks=300, mode="steady")[0]
+
+
+def _strip_observations(w):
+    e = shard_window(w, 0, 1)
+    e.landmarks = e.landmarks[:0]
+    e.landmark_fixed = e.landmark_fixed[:0]
+    for name in ("obs_pose", "obs_landmark", "obs_extrinsics", "obs_camera", "obs_measurement", "obs_information"):
+        setattr(e, name, getattr(e, name)[:0])
+    return e.finalize()
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = _window()
+    s = shard_window(w, rank, world)
+    cost_dense = oracle_lib.evaluate(_strip_observations(w))["cost"][0]
+    cost_obs = oracle_lib.evaluate(s)["cost"][0] - cost_dense
+    t = torch.tensor([cost_obs, float(s.num_obs), float(s.num_landmarks)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)   # the exchange step of the sharded path
+    if rank == 0:
+        out.put((t.tolist(), cost_dense))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_costs_all_reduce_to_the_full_window_gloo():
+    w = _window()
+    full = oracle_lib.evaluate(w)["cost"][0]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    (summed, cost_dense) = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert summed[1] == w.num_obs and summed[2] == w.num_landmarks
+    assert abs(summed[0] + cost_dense - full) < 1e-9 * full
+
+
+def test_shards_partition_the_window():
+    w = _window()
+    shards = [shard_window(w, r, 3) for r in range(3)]
+    assert sum(s.num_obs for s in shards) == w.num_obs
+    assert sum(s.num_landmarks for s in shards) == w.num_landmarks
+    owner = landmark_owner(w.num_landmarks, 3)
+    for r, s in enumerate(shards):
+        assert np.array_equal(s.landmarks, w.landmarks[owner == r])
+        assert np.array_equal(s.pose_blocks, w.pose_blocks) and np.array_equal(s.marg_J, w.marg_J)
+        assert s.obs_landmark.max() < s.num_landmarks
+    merged = w.copy()
+    merged.landmarks[:] = 0
+    merge_landmarks(merged, shards)
+    assert np.array_equal(merged.landmarks, w.landmarks)
+
+
+def _nccl_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from svin_b200.engine import BaEngine
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid = torch.from_numpy(BaEngine.nccl_unique_id().copy())
+    dist.broadcast(uid, src=0)
+    w = make_window(seed=78, num_keyframes=6, num_imu_frames=3, num_landmarks=900, mode="steady")[0]
+    s = shard_window(w, rank, world)
+    opt = default_options(max_num_iterations=8)
+    eng = BaEngine(rank)
+    eng.comm_init(uid.numpy(), rank, world)
+    summ, _ = eng.optimize([s], opt)
+    eng.close()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (s.pose_blocks, s.speedbias, s.landmarks, summ[0]))
+    if rank == 0:
+        out.put(gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_solve_equals_single_gpu_solve_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from svin_b200.engine import BaEngine
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    w = make_window(seed=78, num_keyframes=6, num_imu_frames=3, num_landmarks=900, mode="steady")[0]
+    ref = w.copy()
+    opt = default_options(max_num_iterations=8)
+    with BaEngine(0) as eng:
+        s_ref, _ = eng.optimize([ref], opt)
+    shards = []
+    for r in range(2):
+        s = shard_window(w, r, 2)
+        s.pose_blocks[:], s.speedbias[:], s.landmarks[:] = gathered[r][0], gathered[r][1], gathered[r][2]
+        shards.append(s)
+        assert gathered[r][3]["iterations"] == s_ref[0]["iterations"]
+        assert abs(gathered[r][3]["final_cost"] - s_ref[0]["final_cost"]) < 1e-9 * s_ref[0]["final_cost"]
+    assert np.array_equal(gathered[0][0], gathered[1][0])  # replicated decisions -> identical poses on both ranks
+    merged = w.copy()
+    merge_landmarks(merged, shards)
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    assert rel(merged.pose_blocks, ref.pose_blocks) < 1e-8
+    assert rel(merged.landmarks, ref.landmarks) < 1e-8
