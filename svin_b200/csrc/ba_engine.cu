@@ -124,8 +124,17 @@ void order_window(const SvinBaWindow& w, bool group, WindowOrder& out) {
   if (group) {
     int k = 0;
     while (k < L) {
+      // pose runs of this pattern bound the chunk size (both operand tiles of k_schur_mma must fit in shared memory)
+      const int lk = out.lm_perm[k];
+      int runs = 0, prev = -1;
+      for (int q = start[lk]; q < start[lk + 1]; ++q) {
+        const int pz = w.obs_pose[ord[q]];
+        if (pz != prev) ++runs;
+        prev = pz;
+      }
+      const int cap = std::max(1, std::min(32, schur_mma_max_chunk(std::max(runs, 1))));
       int e = k + 1;
-      while (e < L && e - k < 32 && same_pattern(out.lm_perm[k], out.lm_perm[e])) ++e;
+      while (e < L && e - k < cap && same_pattern(out.lm_perm[k], out.lm_perm[e])) ++e;
       out.chunk_begin.push_back(k);
       out.chunk_count.push_back(e - k);
       k = e;
@@ -427,6 +436,10 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   for (int i = 0; i < B && !has_ext; ++i)
     for (int o = 0; o < wins[i].num_obs && !has_ext; ++o)
       if (!wins[i].pose_fixed[wins[i].obs_extrinsics[o]]) has_ext = 1;
+  // pattern grouping (k_schur_mma) needs fixed extrinsics and at most 64 pose runs per landmark
+  bool group = !has_ext;
+  for (int i = 0; i < B; ++i)
+    if (wins[i].num_pose_blocks > 64) group = false;
   std::vector<WindowOrder> orders(B);
   long long NSW = 0;
   {
@@ -435,7 +448,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     std::vector<std::thread> pool;
     std::atomic<int> next{0};
     auto work = [&]() {
-      for (int i = next.fetch_add(1); i < B; i = next.fetch_add(1)) order_window(wins[i], !has_ext, orders[i]);
+      for (int i = next.fetch_add(1); i < B; i = next.fetch_add(1)) order_window(wins[i], group, orders[i]);
     };
     for (int t = 1; t < nt; ++t) pool.emplace_back(work);
     work();
@@ -854,6 +867,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     const size_t need = dense_solve_smem_bytes(c->n_max);
     c->smem_bytes = (need <= 227 * 1024 && c->n_max <= 256 && c->n_max > 0) ? (int)need : 0;
     if (c->smem_bytes > 0) SVIN_CUDA(configure_dense_solve(c->smem_bytes));
+    SVIN_CUDA(configure_schur());
   }
   SVIN_CUDA(cudaStreamSynchronize(c->stream));
   float ms = 0;

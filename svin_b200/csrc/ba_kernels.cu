@@ -826,6 +826,251 @@ __global__ void __launch_bounds__(128) k_schur_warp(Batch b, SvinBaOptions opt) 
   }
 }
 
+// Tensor-core variant of k_schur_warp.  The per-landmark elimination is unchanged, but instead of every lane
+// forming its own O(k^2) pose-pair blocks, the lanes of a chunk deposit Z = W V^-1 and W for all k pose runs in
+// shared memory ([6k x 3c] each, c = landmarks in the chunk) and the warp computes the whole update
+//     C (6k x 6k) = Z_chunk * W_chunk^T          (a dense fp64 contraction, K = 3c)
+// with mma.sync.m8n8k4.f64 (DMMA), then issues one fp64 RED per upper-triangular entry of C.  The chunk size is
+// capped at upload so that both operand tiles fit kSchurMmaDoubles doubles per warp.
+constexpr int kSchurMmaDoubles = 1664;  // per operand matrix and warp (13.3 KB)
+constexpr int kSchurMaxRuns = 64;
+
+__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double bq) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(bq));
+}
+
+__global__ void __launch_bounds__(128) k_schur_mma(Batch b, SvinBaOptions opt) {
+  extern __shared__ double sm_all[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int chunk = blockIdx.x * 4 + wid;
+  if (chunk >= b.n_schur_warps) return;
+  double* Zs = sm_all + (size_t)wid * (2 * kSchurMmaDoubles + kSchurMaxRuns / 2);
+  double* Ws = Zs + kSchurMmaDoubles;
+  int* offs = reinterpret_cast<int*>(Ws + kSchurMmaDoubles);
+  const int w = b.sw_win[chunk];
+  WinState& ws = b.ws[w];
+  if (ws.done || ws.reuse) return;
+  const WinDesc& wd = b.win[w];
+  const int cnt = b.sw_count[chunk];
+  const bool active = lane < cnt;
+  const int l = b.sw_lm_begin[chunk] + (active ? lane : 0);
+  const double wgt = active ? 1.0 : 0.0;
+  const int buf = ws.cur;
+  const int n = wd.n_dense;
+  double* H = b.H + wd.H_off;
+  double* g_red = b.g_red + wd.d_off;
+  double* g_raw = b.g_raw + wd.d_off;
+  double* Hdiag = b.Hdiag + wd.d_off;
+  const int ob = b.lm_obs_first[l];
+  const int ost = b.lm_obs_stride[l];
+  const int nobs = b.lm_obs_cnt[l];
+  const bool lfix = b.lm_fixed[l] != 0;
+  const double mu = ws.mu;
+  const size_t S = b.obs_stride;
+  const double* rP = b.lin_r[buf];
+  const double* JpP = b.lin_Jp[buf];
+  const double* JlP = b.lin_Jl[buf];
+
+  // ---- pass 1: V = sum Jl^T Jl, bl = sum Jl^T r (unscaled)
+  double V[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+  for (int k = 0; k < nobs; ++k) {
+    const int o = ob + k * ost;
+    const double r0 = rP[o], r1 = rP[S + o];
+    double a[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) a[q] = JlP[q * S + o];
+    V[0] += a[0] * a[0] + a[3] * a[3];
+    V[1] += a[0] * a[1] + a[3] * a[4];
+    V[2] += a[0] * a[2] + a[3] * a[5];
+    V[3] += a[1] * a[1] + a[4] * a[4];
+    V[4] += a[1] * a[2] + a[4] * a[5];
+    V[5] += a[2] * a[2] + a[5] * a[5];
+    bl[0] += a[0] * r0 + a[3] * r1;
+    bl[1] += a[1] * r0 + a[4] * r1;
+    bl[2] += a[2] * r0 + a[5] * r1;
+  }
+  double s[3] = {1.0, 1.0, 1.0}, Vi[6] = {0, 0, 0, 0, 0, 0}, bs[3] = {0, 0, 0};
+  if (!lfix) {
+    if (ws.iter == 0 && ws.num_successful == 0 && !ws.invalid) {
+      if (opt.jacobi_scaling) {
+        s[0] = 1.0 / (1.0 + sqrt(V[0]));
+        s[1] = 1.0 / (1.0 + sqrt(V[3]));
+        s[2] = 1.0 / (1.0 + sqrt(V[5]));
+      }
+      if (active) {
+        b.lm_scale[3 * (size_t)l] = s[0];
+        b.lm_scale[3 * (size_t)l + 1] = s[1];
+        b.lm_scale[3 * (size_t)l + 2] = s[2];
+      }
+    } else {
+      s[0] = b.lm_scale[3 * (size_t)l];
+      s[1] = b.lm_scale[3 * (size_t)l + 1];
+      s[2] = b.lm_scale[3 * (size_t)l + 2];
+    }
+    double gm = active ? fmax(fabs(bl[0]), fmax(fabs(bl[1]), fabs(bl[2]))) : 0.0;
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o2));
+    if (lane == 0) atomic_max_nonneg(&ws.gmax_bits, gm);
+    double Vs[6] = {V[0] * s[0] * s[0], V[1] * s[0] * s[1], V[2] * s[0] * s[2],
+                    V[3] * s[1] * s[1], V[4] * s[1] * s[2], V[5] * s[2] * s[2]};
+    const double d0 = sqrt(fmin(fmax(Vs[0], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    const double d1 = sqrt(fmin(fmax(Vs[3], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    const double d2 = sqrt(fmin(fmax(Vs[5], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    Vs[0] += mu * d0 * d0;
+    Vs[3] += mu * d1 * d1;
+    Vs[5] += mu * d2 * d2;
+    spd3_inverse(Vs, Vi);
+    bs[0] = s[0] * bl[0];
+    bs[1] = s[1] * bl[1];
+    bs[2] = s[2] * bl[2];
+    if (active) {
+      double* p = b.lm_Vinv + 6 * (size_t)l;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) p[k] = Vi[k];
+      p = b.lm_bs + 3 * (size_t)l;
+      p[0] = bs[0]; p[1] = bs[1]; p[2] = bs[2];
+      p = b.lm_diag + 3 * (size_t)l;
+      p[0] = d0; p[1] = d1; p[2] = d2;
+      p = b.lm_grad + 3 * (size_t)l;
+      p[0] = bs[0] / d0; p[1] = bs[1] / d1; p[2] = bs[2] / d2;
+    }
+  }
+
+  // operand tiles: row = 6 * run + a, column = 3 * lane + j; leading dimension ld
+  const int K4 = (3 * cnt + 3) >> 2;
+  const int ld = 4 * K4 + 4;
+
+  // ---- pass 2: per pose run: unreduced 6x6 block, gradients (reduce-scatter) ; Z, W -> shared memory
+  int i = 0, nr = 0;
+  while (i < nobs) {
+    const int p = b.obs_pose[ob + i * ost];
+    int j = i + 1;
+    while (j < nobs && b.obs_pose[ob + j * ost] == p) ++j;
+    const int offp = b.pose_off[p];
+    if (lane == 0) offs[nr] = offp;
+    double W[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) W[k] = 0;
+    if (offp >= 0) {
+      double v[32];  // [0,21) unreduced block (upper), [21,27) reduced gradient, [27,32) Hdiag 0..4
+      double ex[7];  // Hdiag 5, raw gradient 0..5
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = 0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) ex[k] = 0;
+      for (int k = i; k < j; ++k) {
+        const int o = ob + k * ost;
+        double Jp[12], Jls[6];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) Jp[q] = JpP[q * S + o];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) Jls[q] = JlP[q * S + o] * s[q % 3];
+        const double r0 = rP[o], r1 = rP[S + o];
+        int idx = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int c = a; c < 6; ++c) v[idx++] += Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) ex[1 + a] += Jp[a] * r0 + Jp[6 + a] * r1;
+        acc_W(Jp, Jls, W);
+      }
+      v[27] = v[0]; v[28] = v[6]; v[29] = v[11]; v[30] = v[15]; v[31] = v[18];
+      ex[0] = v[20];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) v[21 + a] = ex[1 + a];
+      if (!lfix) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          const double w0 = W[a * 3], w1 = W[a * 3 + 1], w2 = W[a * 3 + 2];
+          const double z0 = w0 * Vi[0] + w1 * Vi[1] + w2 * Vi[2];
+          const double z1 = w0 * Vi[1] + w1 * Vi[3] + w2 * Vi[4];
+          const double z2 = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
+          v[21 + a] -= z0 * bs[0] + z1 * bs[1] + z2 * bs[2];
+          if (active) {
+            double* zr = Zs + (6 * nr + a) * ld + 3 * lane;
+            zr[0] = z0; zr[1] = z1; zr[2] = z2;
+            double* wr = Ws + (6 * nr + a) * ld + 3 * lane;
+            wr[0] = w0; wr[1] = w1; wr[2] = w2;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] *= wgt;
+      warp_reduce_scatter32(v, lane);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) ex[k] = warp_sum(ex[k] * wgt);
+      double* dst;
+      if (lane < 21) {
+        const int a = (lane >= 6) + (lane >= 11) + (lane >= 15) + (lane >= 18) + (lane >= 20);
+        const int c = lane - (a * 6 - (a * (a - 1) >> 1)) + a;
+        dst = &H[(size_t)(offp + a) * n + offp + c];
+      } else if (lane < 27) {
+        dst = &g_red[offp + lane - 21];
+      } else {
+        dst = &Hdiag[offp + lane - 27];
+      }
+      atomicAdd(dst, v[0]);
+      if (lane < 7) {
+        double e = ex[0];
+#pragma unroll
+        for (int k = 1; k < 7; ++k) e = (lane == k) ? ex[k] : e;
+        atomicAdd(lane == 0 ? &Hdiag[offp + 5] : &g_raw[offp + lane - 1], e);
+      }
+    } else if (!lfix && active) {
+      for (int a = 0; a < 6; ++a) {
+        double* zr = Zs + (6 * nr + a) * ld + 3 * lane;
+        zr[0] = zr[1] = zr[2] = 0.0;
+        double* wr = Ws + (6 * nr + a) * ld + 3 * lane;
+        wr[0] = wr[1] = wr[2] = 0.0;
+      }
+    }
+    ++nr;
+    i = j;
+  }
+  if (lfix) return;
+  // zero the padding: columns [3 cnt, 4 K4) of every used row, and rows [6 nr, 8 T)
+  const int rows = 6 * nr, T = (rows + 7) >> 3;
+  for (int e = lane; e < rows * (4 * K4 - 3 * cnt); e += 32) {
+    const int r = e / (4 * K4 - 3 * cnt), c = 3 * cnt + e % (4 * K4 - 3 * cnt);
+    Zs[r * ld + c] = 0.0;
+    Ws[r * ld + c] = 0.0;
+  }
+  for (int e = lane; e < (8 * T - rows) * 4 * K4; e += 32) {
+    const int r = rows + e / (4 * K4), c = e % (4 * K4);
+    Zs[r * ld + c] = 0.0;
+    Ws[r * ld + c] = 0.0;
+  }
+  __syncwarp();
+  // ---- C = Z W^T on the tensor cores, upper tiles only; one RED per upper-triangular entry
+  const int fr = lane >> 2, fc = lane & 3;
+  for (int tm = 0; tm < T; ++tm) {
+    const double* za = Zs + (8 * tm + fr) * ld + fc;
+    for (int tn = tm; tn < T; ++tn) {
+      const double* wb = Ws + (8 * tn + fr) * ld + fc;
+      double c0 = 0.0, c1 = 0.0;
+      for (int ks = 0; ks < K4; ++ks) dmma8x8x4(c0, c1, za[4 * ks], wb[4 * ks]);
+      const int gi = 8 * tm + fr;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gj = 8 * tn + 2 * fc + e;
+        if (gi < rows && gj < rows && gi <= gj) {
+          const int rp = gi / 6, rq = gj / 6;
+          const int a = gi - 6 * rp, c = gj - 6 * rq;
+          const int op = offs[rp], oq = offs[rq];
+          if (op >= 0 && oq >= 0) {
+            const double val = e ? c1 : c0;
+            double* dst = (op <= oq) ? &H[(size_t)(op + a) * n + oq + c] : &H[(size_t)(oq + c) * n + op + a];
+            atomicAdd(dst, -val);
+          }
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ dense terms
 // Warp-cooperative 15x15 helpers on shared memory (row-major).
 __device__ __forceinline__ void warp_mm15(const double* A, const double* Bm, double* C, bool transB, int lane) {
@@ -2073,6 +2318,20 @@ void launch_gmax_pack(const Batch& b, int unpack, cudaStream_t st) {
   k_gmax_pack<<<div_up(b.B, 64), 64, 0, st>>>(b, unpack);
 }
 
+size_t schur_mma_smem_bytes() { return 4 * (size_t)(2 * kSchurMmaDoubles + kSchurMaxRuns / 2) * sizeof(double); }
+int schur_mma_max_chunk(int runs) {
+  // largest chunk size c <= 32 with pad8(6 runs) * (pad4(3c) + 4) <= kSchurMmaDoubles
+  if (runs > kSchurMaxRuns) return 0;
+  const int rows = ((6 * runs + 7) / 8) * 8;
+  int best = 0;
+  for (int c = 1; c <= 32; ++c)
+    if (rows * (((3 * c + 3) / 4) * 4 + 4) <= kSchurMmaDoubles) best = c;
+  return best;
+}
+cudaError_t configure_schur() {
+  return cudaFuncSetAttribute(k_schur_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_mma_smem_bytes());
+}
+
 // ------------------------------------------------------------------------------------------ launchers
 
 void launch_linearize(const Batch& b, int which, int raw, cudaStream_t st) {
@@ -2098,7 +2357,7 @@ void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {
   if (b.has_ext)
     k_schur<true><<<b.n_lm_tiles, kLmTile, 0, st>>>(b, opt);
   else if (b.n_schur_warps > 0)
-    k_schur_warp<<<div_up(b.n_schur_warps, 4), 128, 0, st>>>(b, opt);
+    k_schur_mma<<<div_up(b.n_schur_warps, 4), 128, schur_mma_smem_bytes(), st>>>(b, opt);
   else
     k_schur<false><<<b.n_lm_tiles, kLmTile, 0, st>>>(b, opt);
 }

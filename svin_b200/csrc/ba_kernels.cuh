@@ -18,6 +18,9 @@ void launch_decide(const Batch& b, const SvinBaOptions& opt, cudaStream_t st);
 void launch_init(const Batch& b, const SvinBaOptions& opt, cudaStream_t st);
 void launch_count_active(const Batch& b, int* out, cudaStream_t st);
 void launch_quality(const Batch& b, cudaStream_t st);
+size_t schur_mma_smem_bytes();
+int schur_mma_max_chunk(int runs);
+cudaError_t configure_schur();
 void launch_fold(const Batch& b, int stage, cudaStream_t st);
 void launch_gmax_pack(const Batch& b, int unpack, cudaStream_t st);
 }  // namespace svin
