@@ -282,6 +282,36 @@ typedef struct SvinBaKernelTimes {
   double ms[SVIN_BA_K_COUNT];
   int64_t launches[SVIN_BA_K_COUNT];
 } SvinBaKernelTimes;
+/* ---- marginalisation (MarginalizationError.cpp:126-397 addResidualBlock, :463-721 marginalizeOut,
+ * :725-758 updateErrorComputation).  The host keeps the graph book-keeping of
+ * Estimator::applyMarginalizationStrategy (Estimator.cpp:495-814) and hands the numeric core one window that
+ * contains exactly the residual blocks to be linearised into the prior, with every parameter block set to its
+ * linearisation point (first-estimate point where the block is already part of the prior).  All landmarks of
+ * that window are marginalised; dense blocks are marginalised where the flags say so.  The dense ordering is
+ * the engine's: non-fixed pose blocks in index order (6 each), then non-fixed speed/bias blocks (9 each). */
+typedef struct SvinMargSpec {
+  int32_t prior_num_blocks;           /* blocks of the existing prior (0 = none), in the order of prior_H rows */
+  const int32_t* prior_block_kind;    /* SVIN_BLOCK_POSE / SVIN_BLOCK_SPEEDBIAS */
+  const int32_t* prior_block_index;   /* index into the window's pose / speedbias arrays */
+  int32_t prior_dim;
+  const double* prior_H;              /* [prior_dim][prior_dim] H_ */
+  const double* prior_b0;             /* [prior_dim] b0_ */
+  const uint8_t* marginalize_pose;      /* [num_pose_blocks] */
+  const uint8_t* marginalize_speedbias; /* [num_speedbias] */
+} SvinMargSpec;
+typedef struct SvinMargResult {     /* caller-allocated, capacity = the window's dense dimension */
+  int32_t dim;                      /* dimension after marginalisation */
+  int32_t num_blocks;
+  int32_t* block_kind;              /* [<= num_pose_blocks + num_speedbias] kept blocks, dense order */
+  int32_t* block_index;
+  double* H;                        /* [dim][dim] */
+  double* b0;                       /* [dim] */
+  double* J;                        /* [dim][dim]  J_ of updateErrorComputation */
+  double* e0;                       /* [dim] */
+} SvinMargResult;
+/* Runs on window `window_index` of the uploaded batch (svin_ba_upload). */
+int svin_ba_marginalize(svin_ba_ctx* ctx, int32_t window_index, const SvinMargSpec* spec, SvinMargResult* out);
+
 /* ---- sharded single-window mode (BASELINE configs[3]): every rank uploads the SAME windows with the same pose /
  * speed-bias blocks and dense terms but a disjoint subset of the landmarks and their observations.  Each
  * trust-region iteration then all-reduces (NCCL, on the engine's stream) the reduced system

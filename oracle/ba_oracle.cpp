@@ -943,3 +943,250 @@ void svin_oracle_sonar_error(double range, double heading, double information, c
 void svin_oracle_sym3_eigenvalues(const double* A, double* ev) { sym3_eigenvalues(A, ev); }
 
 }  // extern "C"
+
+// ======================================================================================================
+// Marginalisation: MarginalizationError::addResidualBlock (MarginalizationError.cpp:126-397), marginalizeOut
+// (:463-721: landmark part :556-619 with pseudoInverseSymmSqrt on 3x3 blocks, dense part :621-667) and
+// updateErrorComputation (:725-758).  Eigen's SelfAdjointEigenSolver is replaced by a cyclic Jacobi
+// eigen-solver (same spectrum / invariants; eigenvector signs and order are not unique in either).
+// ======================================================================================================
+namespace {
+
+// symmetric eigen-decomposition A = U diag(ev) U^T by cyclic two-sided Jacobi with round-robin pair order
+void jacobi_eigh(std::vector<double>& A, int n, std::vector<double>& U, std::vector<double>& ev) {
+  U.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) U[(size_t)i * n + i] = 1.0;
+  const int m = n + (n & 1);  // players of the round-robin tournament (one dummy when n is odd)
+  std::vector<int> pl(m);
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0, diag = 0;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) (i == j ? diag : off) += A[(size_t)i * n + j] * A[(size_t)i * n + j];
+    if (off <= 1e-30 * diag || off == 0.0) break;
+    for (int i = 0; i < m; ++i) pl[i] = i;
+    for (int round = 0; round < m - 1; ++round) {
+      for (int k = 0; k < m / 2; ++k) {
+        int p = pl[k], q = pl[m - 1 - k];
+        if (p >= n || q >= n) continue;
+        if (p > q) std::swap(p, q);
+        const double apq = A[(size_t)p * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[(size_t)q * n + q] - A[(size_t)p * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int i = 0; i < n; ++i) {  // columns: A <- A G
+          const double aip = A[(size_t)i * n + p], aiq = A[(size_t)i * n + q];
+          A[(size_t)i * n + p] = c * aip - s * aiq;
+          A[(size_t)i * n + q] = s * aip + c * aiq;
+        }
+        for (int i = 0; i < n; ++i) {  // rows: A <- G^T A
+          const double api = A[(size_t)p * n + i], aqi = A[(size_t)q * n + i];
+          A[(size_t)p * n + i] = c * api - s * aqi;
+          A[(size_t)q * n + i] = s * api + c * aqi;
+        }
+        for (int i = 0; i < n; ++i) {  // U <- U G
+          const double uip = U[(size_t)i * n + p], uiq = U[(size_t)i * n + q];
+          U[(size_t)i * n + p] = c * uip - s * uiq;
+          U[(size_t)i * n + q] = s * uip + c * uiq;
+        }
+      }
+      // rotate players 1..m-1
+      const int last = pl[m - 1];
+      for (int i = m - 1; i > 1; --i) pl[i] = pl[i - 1];
+      pl[1] = last;
+    }
+  }
+  ev.resize(n);
+  for (int i = 0; i < n; ++i) ev[i] = A[(size_t)i * n + i];
+}
+
+// Vp = pseudo-inverse of symmetric V (n x n) with tolerance eps * n * lambda_max (pseudoInverseSymm[Sqrt])
+void pinv_symm(const std::vector<double>& V, int n, std::vector<double>& Vp) {
+  std::vector<double> A = V, U, ev;
+  jacobi_eigh(A, n, U, ev);
+  double lmax = -1e300;
+  for (double v : ev) lmax = std::max(lmax, v);
+  const double tol = std::numeric_limits<double>::epsilon() * n * lmax;
+  Vp.assign((size_t)n * n, 0.0);
+  for (int k = 0; k < n; ++k) {
+    if (!(ev[k] > tol)) continue;
+    const double inv = 1.0 / ev[k];
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) Vp[(size_t)i * n + j] += U[(size_t)i * n + k] * inv * U[(size_t)j * n + k];
+  }
+}
+
+}  // namespace
+
+extern "C" int svin_oracle_marginalize(const SvinBaWindow* w, const SvinMargSpec* spec, SvinMargResult* out) {
+  Oracle O(w);
+  Lin L;
+  O.evaluate(O.poses, O.sbs, O.lms, true, &L);  // linearise at the supplied (first-estimate) points, loss-corrected
+  const int n = O.n_dense, NL = w->num_landmarks;
+  std::vector<double> H((size_t)n * n, 0.0), b(n, 0.0);
+  // existing prior, embedded
+  {
+    std::vector<int> map;
+    for (int k = 0; k < spec->prior_num_blocks; ++k) {
+      const int kind = spec->prior_block_kind[k], idx = spec->prior_block_index[k];
+      const int off = kind == SVIN_BLOCK_POSE ? O.pose_off[idx] : O.sb_off[idx];
+      const int dim = kind == SVIN_BLOCK_POSE ? 6 : 9;
+      for (int c = 0; c < dim; ++c) map.push_back(off + c);
+    }
+    for (int i = 0; i < spec->prior_dim; ++i)
+      for (int j = 0; j < spec->prior_dim; ++j) H[(size_t)map[i] * n + map[j]] += spec->prior_H[(size_t)i * spec->prior_dim + j];
+    for (int i = 0; i < spec->prior_dim; ++i) b[map[i]] += spec->prior_b0[i];
+  }
+  // dense terms: H += J^T J, b0 -= J^T r   (MarginalizationError.cpp:333-383)
+  for (const DenseTerm& t : L.dense)
+    for (const DenseBlock& A : t.blocks) {
+      if (A.off < 0) continue;
+      for (int rr = 0; rr < t.m; ++rr)
+        for (int c = 0; c < A.ld; ++c) b[A.off + c] -= A.J[rr * A.ld + c] * t.r[rr];
+      for (const DenseBlock& B : t.blocks) {
+        if (B.off < 0) continue;
+        for (int i = 0; i < A.ld; ++i)
+          for (int j = 0; j < B.ld; ++j) {
+            double s = 0;
+            for (int rr = 0; rr < t.m; ++rr) s += A.J[rr * A.ld + i] * B.J[rr * B.ld + j];
+            H[(size_t)(A.off + i) * n + B.off + j] += s;
+          }
+      }
+    }
+  // reprojection terms, landmark by landmark, eliminated with the preconditioned 3x3 pseudo-inverse
+  std::vector<std::vector<int>> by_lm(NL);
+  for (int o = 0; o < w->num_obs; ++o) by_lm[w->obs_landmark[o]].push_back(o);
+  for (int l = 0; l < NL; ++l) {
+    double V[9] = {0}, bl[3] = {0};
+    struct WB { int off; double W[18]; };
+    std::vector<WB> Ws;
+    for (int o : by_lm[l]) {
+      const int offs[2] = {O.pose_off[w->obs_pose[o]], O.pose_off[w->obs_extrinsics[o]]};
+      const double* Js[2] = {&L.Jp[12 * o], &L.Je[12 * o]};
+      const double* Jl = &L.Jl[6 * o];
+      const double r0 = L.r[2 * o], r1 = L.r[2 * o + 1];
+      for (int a = 0; a < 2; ++a) {
+        if (offs[a] < 0) continue;
+        for (int i = 0; i < 6; ++i) b[offs[a] + i] -= Js[a][i] * r0 + Js[a][6 + i] * r1;
+        for (int c = 0; c < 2; ++c) {
+          if (offs[c] < 0) continue;
+          for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j)
+              H[(size_t)(offs[a] + i) * n + offs[c] + j] += Js[a][i] * Js[c][j] + Js[a][6 + i] * Js[c][6 + j];
+        }
+        WB* wb = nullptr;
+        for (WB& x : Ws)
+          if (x.off == offs[a]) wb = &x;
+        if (!wb) {
+          Ws.push_back(WB{offs[a], {0}});
+          wb = &Ws.back();
+        }
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 3; ++j) wb->W[i * 3 + j] += Js[a][i] * Jl[j] + Js[a][6 + i] * Jl[3 + j];
+      }
+      for (int i = 0; i < 3; ++i) {
+        bl[i] -= Jl[i] * r0 + Jl[3 + i] * r1;
+        for (int j = 0; j < 3; ++j) V[i * 3 + j] += Jl[i] * Jl[j] + Jl[3 + i] * Jl[3 + j];
+      }
+    }
+    // preconditioner of the landmark columns (MarginalizationError.cpp:558-563), pinv in the scaled space
+    double pl[3];
+    for (int i = 0; i < 3; ++i) pl[i] = V[i * 3 + i] > 1.0e-9 ? std::sqrt(V[i * 3 + i]) : 1.0e-3;
+    std::vector<double> Vs(9), Vp;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Vs[i * 3 + j] = V[i * 3 + j] / (pl[i] * pl[j]);
+    pinv_symm(Vs, 3, Vp);
+    double Veff[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Veff[i * 3 + j] = Vp[i * 3 + j] / (pl[i] * pl[j]);
+    for (const WB& A : Ws) {
+      double WV[18];
+      mm(A.W, Veff, WV, 6, 3, 3);
+      for (int i = 0; i < 6; ++i) b[A.off + i] -= WV[i * 3] * bl[0] + WV[i * 3 + 1] * bl[1] + WV[i * 3 + 2] * bl[2];
+      for (const WB& B : Ws)
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 6; ++j)
+            H[(size_t)(A.off + i) * n + B.off + j] -=
+                WV[i * 3] * B.W[j * 3] + WV[i * 3 + 1] * B.W[j * 3 + 1] + WV[i * 3 + 2] * B.W[j * 3 + 2];
+    }
+  }
+  // dense part (MarginalizationError.cpp:621-667)
+  std::vector<int> keep_idx, marg_idx;
+  out->num_blocks = 0;
+  for (int i = 0; i < w->num_pose_blocks; ++i)
+    if (O.pose_off[i] >= 0) {
+      const bool mg = spec->marginalize_pose && spec->marginalize_pose[i];
+      for (int c = 0; c < 6; ++c) (mg ? marg_idx : keep_idx).push_back(O.pose_off[i] + c);
+      if (!mg) {
+        out->block_kind[out->num_blocks] = SVIN_BLOCK_POSE;
+        out->block_index[out->num_blocks++] = i;
+      }
+    }
+  for (int i = 0; i < w->num_speedbias; ++i)
+    if (O.sb_off[i] >= 0) {
+      const bool mg = spec->marginalize_speedbias && spec->marginalize_speedbias[i];
+      for (int c = 0; c < 9; ++c) (mg ? marg_idx : keep_idx).push_back(O.sb_off[i] + c);
+      if (!mg) {
+        out->block_kind[out->num_blocks] = SVIN_BLOCK_SPEEDBIAS;
+        out->block_index[out->num_blocks++] = i;
+      }
+    }
+  const int nk = (int)keep_idx.size(), nm = (int)marg_idx.size();
+  std::vector<double> Hk((size_t)nk * nk), bk(nk);
+  if (nm > 0) {
+    std::vector<double> p(n);
+    for (int i = 0; i < n; ++i) p[i] = H[(size_t)i * n + i] > 1.0e-9 ? std::sqrt(H[(size_t)i * n + i]) : 1.0e-3;
+    std::vector<double> V((size_t)nm * nm), Vp;
+    for (int i = 0; i < nm; ++i)
+      for (int j = 0; j < nm; ++j) {
+        const int gi = marg_idx[i], gj = marg_idx[j];
+        V[(size_t)i * nm + j] = 0.5 * (H[(size_t)gi * n + gj] + H[(size_t)gj * n + gi]) / (p[gi] * p[gj]);
+      }
+    pinv_symm(V, nm, Vp);
+    // W (kept x marg) in the scaled space, b_b scaled
+    std::vector<double> Wm((size_t)nk * nm), WV((size_t)nk * nm), bb(nm);
+    for (int i = 0; i < nk; ++i)
+      for (int j = 0; j < nm; ++j) Wm[(size_t)i * nm + j] = H[(size_t)keep_idx[i] * n + marg_idx[j]] / (p[keep_idx[i]] * p[marg_idx[j]]);
+    for (int j = 0; j < nm; ++j) bb[j] = b[marg_idx[j]] / p[marg_idx[j]];
+    mm(Wm.data(), Vp.data(), WV.data(), nk, nm, nm);
+    for (int i = 0; i < nk; ++i) {
+      double s = b[keep_idx[i]] / p[keep_idx[i]];
+      for (int j = 0; j < nm; ++j) s -= WV[(size_t)i * nm + j] * bb[j];
+      bk[i] = s * p[keep_idx[i]];
+      for (int j = 0; j < nk; ++j) {
+        double h = H[(size_t)keep_idx[i] * n + keep_idx[j]] / (p[keep_idx[i]] * p[keep_idx[j]]);
+        for (int k = 0; k < nm; ++k) h -= WV[(size_t)i * nm + k] * Wm[(size_t)j * nm + k];
+        Hk[(size_t)i * nk + j] = h * p[keep_idx[i]] * p[keep_idx[j]];
+      }
+    }
+  } else {
+    for (int i = 0; i < nk; ++i) {
+      bk[i] = b[keep_idx[i]];
+      for (int j = 0; j < nk; ++j) Hk[(size_t)i * nk + j] = H[(size_t)keep_idx[i] * n + keep_idx[j]];
+    }
+  }
+  // updateErrorComputation (MarginalizationError.cpp:725-758)
+  std::vector<double> p(nk), Hs((size_t)nk * nk), U, ev;
+  for (int i = 0; i < nk; ++i) p[i] = Hk[(size_t)i * nk + i] > 1.0e-9 ? std::sqrt(Hk[(size_t)i * nk + i]) : 1.0e-3;
+  for (int i = 0; i < nk; ++i)
+    for (int j = 0; j < nk; ++j) Hs[(size_t)i * nk + j] = 0.5 * (Hk[(size_t)i * nk + j] + Hk[(size_t)j * nk + i]) / (p[i] * p[j]);
+  jacobi_eigh(Hs, nk, U, ev);
+  double lmax = -1e300;
+  for (double v : ev) lmax = std::max(lmax, v);
+  const double tol = std::numeric_limits<double>::epsilon() * nk * lmax;
+  out->dim = nk;
+  for (int k = 0; k < nk; ++k) {
+    const double S = ev[k] > tol ? ev[k] : 0.0;
+    const double Sp = ev[k] > tol ? 1.0 / ev[k] : 0.0;
+    const double ss = std::sqrt(S), sps = std::sqrt(Sp);
+    double e = 0;
+    for (int i = 0; i < nk; ++i) {
+      out->J[(size_t)k * nk + i] = p[i] * U[(size_t)i * nk + k] * ss;       // J_ = (p U sqrt(S))^T
+      e += sps * U[(size_t)i * nk + k] * (1.0 / p[i]) * bk[i];
+    }
+    out->e0[k] = -e;                                                       // e0_ = -sqrt(S+) U^T p^-1 b0_
+  }
+  std::memcpy(out->H, Hk.data(), sizeof(double) * Hk.size());
+  std::memcpy(out->b0, bk.data(), sizeof(double) * bk.size());
+  return 0;
+}

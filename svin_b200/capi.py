@@ -128,6 +128,17 @@ class SvinFeTimings(C.Structure):
 
 FE_KERNEL_NAMES = ["harris", "nms_compact", "sort", "uniformity", "orient_describe", "match", "assign", "unused"]
 
+class SvinMargSpec(C.Structure):
+    _fields_ = [("prior_num_blocks", C.c_int32), ("prior_block_kind", c_int32_p), ("prior_block_index", c_int32_p),
+                ("prior_dim", C.c_int32), ("prior_H", c_double_p), ("prior_b0", c_double_p),
+                ("marginalize_pose", c_uint8_p), ("marginalize_speedbias", c_uint8_p)]
+
+
+class SvinMargResult(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("num_blocks", C.c_int32), ("block_kind", c_int32_p), ("block_index", c_int32_p),
+                ("H", c_double_p), ("b0", c_double_p), ("J", c_double_p), ("e0", c_double_p)]
+
+
 BA_KERNEL_NAMES = ["linearize", "dense_eval", "schur", "dense_solve", "backsub", "step_dense", "step_lm", "decide",
                    "clear"]
 
@@ -147,6 +158,7 @@ EXPORTED_SYMBOLS = [
     "svin_last_error", "svin_version", "svin_ba_default_options", "svin_ba_create", "svin_ba_destroy",
     "svin_ba_upload", "svin_ba_evaluate", "svin_ba_solve", "svin_ba_download", "svin_ba_reset", "svin_ba_optimize",
     "svin_ba_timings", "svin_ba_set_profiling", "svin_ba_kernel_times", "svin_nccl_unique_id", "svin_ba_comm_init",
+    "svin_ba_marginalize",
     "svin_fe_default_options", "svin_fe_create", "svin_fe_destroy", "svin_fe_detect_describe", "svin_fe_upload",
     "svin_fe_run", "svin_fe_download", "svin_fe_scores", "svin_match", "svin_fe_timings",
 ]
@@ -178,6 +190,7 @@ def load(path: str | None = None) -> C.CDLL:
     lib.svin_ba_optimize.argtypes = [C.c_void_p, C.POINTER(SvinBaWindow), C.c_int32, C.POINTER(SvinBaOptions),
                                      C.POINTER(SvinBaSummary), C.POINTER(c_double_p)]
     lib.svin_ba_timings.argtypes = [C.c_void_p, C.POINTER(SvinBaTimings)]
+    lib.svin_ba_marginalize.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SvinMargSpec), C.POINTER(SvinMargResult)]
     lib.svin_nccl_unique_id.argtypes = [c_uint8_p]
     lib.svin_ba_comm_init.argtypes = [C.c_void_p, c_uint8_p, C.c_int32, C.c_int32]
     lib.svin_ba_set_profiling.argtypes = [C.c_void_p, C.c_int]

@@ -194,3 +194,15 @@ def fe_match(args: MatchArgs):
     lib.svin_oracle_match(C.byref(args.c), bi.ctypes.data_as(capi.c_int32_p), bd.ctypes.data_as(capi.c_float_p),
                           mb.ctypes.data_as(capi.c_int32_p), md.ctypes.data_as(capi.c_float_p), _u8(sk))
     return dict(best_index=bi, best_distance=bd, match_of_B=mb, match_distance=md, skipA=sk)
+
+
+# ------------------------------------------------------------------------------ marginalisation oracle
+def marginalize(window, spec):
+    from svin_b200.marginalization import MargResult
+    lib = load()
+    lib.svin_oracle_marginalize.argtypes = [C.POINTER(capi.SvinBaWindow), C.POINTER(capi.SvinMargSpec),
+                                            C.POINTER(capi.SvinMargResult)]
+    res = MargResult(window)
+    s = window.c_struct()
+    assert lib.svin_oracle_marginalize(C.byref(s), C.byref(spec.c), C.byref(res.c)) == 0
+    return res.unpack()
