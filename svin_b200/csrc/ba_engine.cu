@@ -1189,6 +1189,127 @@ int svin_ba_evaluate(svin_ba_ctx* c, int32_t wi, SvinBaEvaluation* out) {
   return svin_ba_reset(c);
 }
 
+int svin_ba_marginalize(svin_ba_ctx* c, int32_t wi, const SvinMargSpec* spec, SvinMargResult* out) {
+  if (!c || !c->uploaded || !spec || !out || wi < 0 || wi >= c->b.B) {
+    set_error("svin_ba_marginalize: invalid arguments");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  if (!out->block_kind || !out->block_index || !out->H || !out->b0 || !out->J || !out->e0) {
+    set_error("svin_ba_marginalize: result arrays are NULL");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  SVIN_CUDA(cudaSetDevice(c->device));
+  Batch& b = c->b;
+  const WinDesc& d = c->h_win[wi];
+  const int n = d.n_dense;
+  const int npb = d.pose_end - d.pose_begin, nsb = d.sb_end - d.sb_begin;
+  // dense offsets of this window's blocks (engine order: free pose blocks, then free speed/bias blocks)
+  std::vector<int> pose_off(npb > 0 ? npb : 1), sb_off(nsb > 0 ? nsb : 1);
+  if (npb) SVIN_CUDA(cudaMemcpy(pose_off.data(), b.pose_off + d.pose_begin, 4 * (size_t)npb, cudaMemcpyDeviceToHost));
+  if (nsb) SVIN_CUDA(cudaMemcpy(sb_off.data(), b.sb_off + d.sb_begin, 4 * (size_t)nsb, cudaMemcpyDeviceToHost));
+  std::vector<int> keep_idx, marg_idx, prior_map;
+  out->num_blocks = 0;
+  for (int i = 0; i < npb; ++i)
+    if (pose_off[i] >= 0) {
+      const bool mg = spec->marginalize_pose && spec->marginalize_pose[i];
+      for (int k = 0; k < 6; ++k) (mg ? marg_idx : keep_idx).push_back(pose_off[i] + k);
+      if (!mg) {
+        out->block_kind[out->num_blocks] = SVIN_BLOCK_POSE;
+        out->block_index[out->num_blocks++] = i;
+      }
+    }
+  for (int i = 0; i < nsb; ++i)
+    if (sb_off[i] >= 0) {
+      const bool mg = spec->marginalize_speedbias && spec->marginalize_speedbias[i];
+      for (int k = 0; k < 9; ++k) (mg ? marg_idx : keep_idx).push_back(sb_off[i] + k);
+      if (!mg) {
+        out->block_kind[out->num_blocks] = SVIN_BLOCK_SPEEDBIAS;
+        out->block_index[out->num_blocks++] = i;
+      }
+    }
+  for (int k = 0; k < spec->prior_num_blocks; ++k) {
+    const int kind = spec->prior_block_kind[k], idx = spec->prior_block_index[k];
+    const bool pose = kind == SVIN_BLOCK_POSE;
+    if (idx < 0 || idx >= (pose ? npb : nsb) || (pose ? pose_off[idx] : sb_off[idx]) < 0) {
+      set_error("svin_ba_marginalize: prior block is not an estimated block of the window");
+      return SVIN_ERR_INVALID_ARGUMENT;
+    }
+    const int off = pose ? pose_off[idx] : sb_off[idx];
+    for (int k2 = 0; k2 < (pose ? 6 : 9); ++k2) prior_map.push_back(off + k2);
+  }
+  if ((int)prior_map.size() != spec->prior_dim) {
+    set_error("svin_ba_marginalize: prior_dim does not match the prior block list");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  const int nk = (int)keep_idx.size(), nm = (int)marg_idx.size(), pd = spec->prior_dim;
+  out->dim = nk;
+  if (nk == 0) return SVIN_OK;
+  // linearise at the uploaded (first-estimate) points
+  int rc = svin_ba_reset(c);
+  if (rc != SVIN_OK) return rc;
+  launch_linearize(b, 0, 0, c->stream);
+  launch_dense_eval(b, 0, 0, nullptr, c->stream);
+  // scratch arena: doubles then ints
+  const size_t nmax = (size_t)(nk > nm ? nk : nm);
+  const size_t nd = (size_t)n * n + n                 // H, b
+                    + 2 * nmax * nmax + nmax          // A, U, ev
+                    + (size_t)nm * nm + 2 * (size_t)nk * nm + 2 * nmax + 4  // Vp, Wm, WV (also (c,s) scratch)
+                    + n                               // pvec
+                    + (size_t)pd * pd + pd            // prior
+                    + 2 * (size_t)nk * nk + 2 * nk;   // Hk, J, bk, e0
+  const size_t ni = (size_t)nk + nm + pd + nmax + 2;
+  void* scratch = nullptr;
+  SVIN_CUDA(cudaMalloc(&scratch, 8 * nd + 4 * ni + 64));
+  double* p = static_cast<double*>(scratch);
+  MargArgs m{};
+  m.w = wi; m.n = n; m.nk = nk; m.nm = nm; m.prior_dim = pd;
+  m.H = p; p += (size_t)n * n;
+  m.b = p; p += n;
+  m.A = p; p += nmax * nmax;
+  m.U = p; p += nmax * nmax;
+  m.ev = p; p += nmax;
+  m.Vp = p; p += (size_t)nm * nm;
+  m.Wm = p; p += (size_t)nk * nm;
+  m.WV = p; p += (size_t)nk * nm + 2 * nmax + 4;
+  m.pvec = p; p += n;
+  double* d_prior_H = p; p += (size_t)pd * pd;
+  double* d_prior_b = p; p += pd;
+  m.Hk = p; p += (size_t)nk * nk;
+  m.J = p; p += (size_t)nk * nk;
+  m.bk = p; p += nk;
+  m.e0 = p; p += nk;
+  int* ip = reinterpret_cast<int*>(p);
+  int* d_keep = ip; ip += nk;
+  int* d_marg = ip; ip += nm;
+  int* d_map = ip; ip += pd;
+  m.players = ip;
+  m.keep_idx = d_keep; m.marg_idx = d_marg; m.prior_map = d_map;
+  m.prior_H = d_prior_H; m.prior_b = d_prior_b;
+  auto fail = [&](cudaError_t e) {
+    set_error(std::string("svin_ba_marginalize: ") + cudaGetErrorString(e));
+    cudaFree(scratch);
+    return SVIN_ERR_CUDA;
+  };
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(m.H, 0, 8 * ((size_t)n * n + n), c->stream)) != cudaSuccess) return fail(e);
+  if ((e = cudaMemcpyAsync(d_keep, keep_idx.data(), 4 * (size_t)nk, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e);
+  if (nm && (e = cudaMemcpyAsync(d_marg, marg_idx.data(), 4 * (size_t)nm, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e);
+  if (pd) {
+    if ((e = cudaMemcpyAsync(d_map, prior_map.data(), 4 * (size_t)pd, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e);
+    if ((e = cudaMemcpyAsync(d_prior_H, spec->prior_H, 8 * (size_t)pd * pd, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e);
+    if ((e = cudaMemcpyAsync(d_prior_b, spec->prior_b0, 8 * (size_t)pd, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e);
+  }
+  launch_marg(b, m, d.lm_end - d.lm_begin, c->stream);
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail(e);
+  if ((e = cudaMemcpyAsync(out->H, m.Hk, 8 * (size_t)nk * nk, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) return fail(e);
+  if ((e = cudaMemcpyAsync(out->J, m.J, 8 * (size_t)nk * nk, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) return fail(e);
+  if ((e = cudaMemcpyAsync(out->b0, m.bk, 8 * (size_t)nk, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) return fail(e);
+  if ((e = cudaMemcpyAsync(out->e0, m.e0, 8 * (size_t)nk, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) return fail(e);
+  if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return fail(e);
+  cudaFree(scratch);
+  return svin_ba_reset(c);
+}
+
 int svin_nccl_unique_id(uint8_t out[128]) {
   NcclApi* api = nccl_api();
   if (!api) {

@@ -23,4 +23,23 @@ int schur_mma_max_chunk(int runs);
 cudaError_t configure_schur();
 void launch_fold(const Batch& b, int stage, cudaStream_t st);
 void launch_gmax_pack(const Batch& b, int unpack, cudaStream_t st);
+struct MargArgs {
+  int w;                // window
+  int n, nk, nm;        // dense dim, kept, marginalised
+  double* H;            // [n][n] full symmetric accumulation
+  double* b;            // [n]
+  const int* keep_idx;  // [nk]
+  const int* marg_idx;  // [nm]
+  const int* prior_map; // [prior_dim] -> dense index
+  int prior_dim;
+  const double *prior_H, *prior_b;
+  // scratch (global)
+  double *A, *U, *ev;   // eigen-solver work: max(n, nm)^2 each
+  double *Vp, *Wm, *WV, *pvec;
+  int* players;
+  // outputs
+  double *Hk, *bk, *J, *e0;
+};
+
+void launch_marg(const Batch& b, const MargArgs& m, int num_landmarks, cudaStream_t st);
 }  // namespace svin

@@ -77,6 +77,14 @@ class BaEngine:
         capi.check(self._lib.svin_ba_evaluate(self._ctx, index, C.byref(ev)), self._lib)
         return out
 
+    def marginalize(self, spec, index: int = 0) -> dict:
+        """MarginalizationError::{addResidualBlock, marginalizeOut, updateErrorComputation} on uploaded window
+        `index` (okvis_ceres/src/MarginalizationError.cpp:126-758) -> dict(dim, kind, index, H, b0, J, e0)."""
+        from .marginalization import MargResult
+        res = MargResult(self._windows[index])
+        capi.check(self._lib.svin_ba_marginalize(self._ctx, index, C.byref(spec.c), C.byref(res.c)), self._lib)
+        return res.unpack()
+
     def timings(self) -> dict:
         t = capi.SvinBaTimings()
         capi.check(self._lib.svin_ba_timings(self._ctx, C.byref(t)), self._lib)
