@@ -240,6 +240,11 @@ int svin_ba_solve(svin_ba_ctx* ctx, const SvinBaOptions* opt, SvinBaSummary* sum
  * be NULL) receives sqrt(lambda_min/lambda_max) of the landmark Hessian block
  * (Estimator.cpp:903-922). */
 int svin_ba_download(svin_ba_ctx* ctx, int32_t window_index, SvinBaWindow* window, double* landmark_quality);
+/* All windows of the uploaded batch with one device-to-host copy (windows[i] must have the shape of the uploaded
+ * window i; landmark_quality may be NULL or hold one pointer per window).  upload / solve / download_all is
+ * svin_ba_optimize in three stages, for callers that overlap the upload of one batch (on one context) with the
+ * solve of another (on a second context). */
+int svin_ba_download_all(svin_ba_ctx* ctx, SvinBaWindow* windows, int32_t num_windows, double* const* landmark_quality);
 
 /* Reset the estimate on the device to the uploaded initial values (and the IMU
  * pre-integration state) without a new host->device copy: lets a benchmark
@@ -260,6 +265,11 @@ typedef struct SvinBaTimings {
   int64_t kernel_launches;
   int64_t h2d_bytes;
   int64_t d2h_bytes;
+  /* host wall-clock parts of the last svin_ba_upload / svin_ba_optimize (the end-to-end path) */
+  double host_order_ms;   /* validation + landmark pattern ordering */
+  double host_fill_ms;    /* packing the pinned staging arena */
+  double host_upload_ms;  /* whole svin_ba_upload, incl. the H2D copy and work-buffer initialisation */
+  double host_scatter_ms; /* writing results back into the caller's arrays (svin_ba_optimize) */
 } SvinBaTimings;
 int svin_ba_timings(svin_ba_ctx* ctx, SvinBaTimings* out);
 

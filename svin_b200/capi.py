@@ -89,7 +89,9 @@ class SvinBaEvaluation(C.Structure):
 
 class SvinBaTimings(C.Structure):
     _fields_ = [("solve_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
-                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("host_order_ms", C.c_double), ("host_fill_ms", C.c_double), ("host_upload_ms", C.c_double),
+                ("host_scatter_ms", C.c_double)]
 
 
 class SvinKeypoint(C.Structure):
@@ -156,7 +158,7 @@ _lib = None
 # every symbol include/svin_b200.h declares (tests check the .so exports each one)
 EXPORTED_SYMBOLS = [
     "svin_last_error", "svin_version", "svin_ba_default_options", "svin_ba_create", "svin_ba_destroy",
-    "svin_ba_upload", "svin_ba_evaluate", "svin_ba_solve", "svin_ba_download", "svin_ba_reset", "svin_ba_optimize",
+    "svin_ba_upload", "svin_ba_evaluate", "svin_ba_solve", "svin_ba_download", "svin_ba_download_all", "svin_ba_reset", "svin_ba_optimize",
     "svin_ba_timings", "svin_ba_set_profiling", "svin_ba_kernel_times", "svin_nccl_unique_id", "svin_ba_comm_init",
     "svin_ba_marginalize",
     "svin_fe_default_options", "svin_fe_create", "svin_fe_destroy", "svin_fe_detect_describe", "svin_fe_upload",
@@ -186,6 +188,7 @@ def load(path: str | None = None) -> C.CDLL:
     lib.svin_ba_evaluate.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SvinBaEvaluation)]
     lib.svin_ba_solve.argtypes = [C.c_void_p, C.POINTER(SvinBaOptions), C.POINTER(SvinBaSummary)]
     lib.svin_ba_download.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SvinBaWindow), c_double_p]
+    lib.svin_ba_download_all.argtypes = [C.c_void_p, C.POINTER(SvinBaWindow), C.c_int32, C.POINTER(c_double_p)]
     lib.svin_ba_reset.argtypes = [C.c_void_p]
     lib.svin_ba_optimize.argtypes = [C.c_void_p, C.POINTER(SvinBaWindow), C.c_int32, C.POINTER(SvinBaOptions),
                                      C.POINTER(SvinBaSummary), C.POINTER(c_double_p)]

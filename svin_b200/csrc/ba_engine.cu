@@ -5,6 +5,11 @@
 // (okvis_ros/okvis/okvis_ceres/src/Estimator.cpp:876-929, include/okvis/ceres/Map.hpp:347).
 #include <cuda_runtime.h>
 
+#include <chrono>
+#include <mutex>
+#include <functional>
+#include <condition_variable>
+
 #include <algorithm>
 #include <atomic>
 #include <thread>
@@ -56,6 +61,84 @@ void llt_sqrt_information(const double* info, double* U, int n) {
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j) U[(size_t)i * n + j] = (j >= i) ? L[(size_t)j * n + i] : 0.0;
 }
+
+// 2x2 case of llt_sqrt_information without the heap allocation (one call per observation on the upload path).
+inline void llt_sqrt_information2(const double* a, double* U) {
+  double l00 = a[0], l10 = a[2], l11 = a[3];
+  if (a[0] > 0.0) {
+    l00 = std::sqrt(a[0]);
+    l10 = a[2] / l00;
+    const double x = a[3] - l10 * l10;
+    if (x > 0.0) l11 = std::sqrt(x);
+  }
+  U[0] = l00; U[1] = l10; U[2] = 0.0; U[3] = l11;
+}
+
+// Persistent host worker threads of one context: the upload path (ordering, packing) and the result scatter are
+// independent per window, and spawning threads on every call costs more than the work itself.
+class HostPool {
+ public:
+  explicit HostPool(int workers) {
+    for (int i = 0; i < workers; ++i) th_.emplace_back([this] { worker(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_work_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int workers() const { return (int)th_.size(); }
+  // hand items 0..n-1 to the workers; the caller may help() and must wait()
+  void start(int n, std::function<void(int)> fn) {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      fn_ = std::move(fn);
+      n_ = n;
+      next_.store(0);
+      running_ = (int)th_.size();
+      ++gen_;
+    }
+    cv_work_.notify_all();
+  }
+  void help() {
+    for (int i = next_.fetch_add(1); i < n_; i = next_.fetch_add(1)) fn_(i);
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [&] { return running_ == 0; });
+  }
+  void run(int n, std::function<void(int)> fn) {
+    start(n, std::move(fn));
+    help();
+    wait();
+  }
+
+ private:
+  void worker() {
+    uint64_t seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lk(m_);
+      cv_work_.wait(lk, [&] { return stop_ || gen_ != seen; });
+      if (stop_) return;
+      seen = gen_;
+      lk.unlock();
+      help();
+      lk.lock();
+      if (--running_ == 0) cv_done_.notify_all();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_work_, cv_done_;
+  std::function<void(int)> fn_;
+  int n_ = 0;
+  std::atomic<int> next_{0};
+  int running_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
 
 // Internal ordering of one window's landmarks and observations.
 //  * observations sorted by (landmark, pose block, camera)
@@ -249,6 +332,7 @@ struct svin_ba_ctx {
   bool quality_valid = false;
   bool solved = false;
   SvinBaTimings tm{};
+  HostPool* pool = nullptr;
   // sharded mode
   void* nccl_comm = nullptr;
   int comm_rank = 0, comm_world = 1;
@@ -260,6 +344,10 @@ struct svin_ba_ctx {
 };
 
 namespace {
+
+double wall_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 int ensure(void** p, size_t* cap, size_t need, bool pinned) {
   if (*cap >= need && *p) return SVIN_OK;
@@ -391,6 +479,7 @@ int svin_ba_create(int device, svin_ba_ctx** out) {
   for (auto& ev : c->ev) SVIN_CUDA(cudaEventCreate(&ev));
   SVIN_CUDA(cudaMalloc(&c->d_active, sizeof(int)));
   SVIN_CUDA(cudaMallocHost(&c->h_active, sizeof(int)));
+  c->pool = new HostPool(std::max(0, std::min(32, (int)std::thread::hardware_concurrency()) - 1));
   *out = c;
   return SVIN_OK;
 }
@@ -411,6 +500,7 @@ void svin_ba_destroy(svin_ba_ctx* c) {
   for (auto& ev : c->prof_events) cudaEventDestroy(ev);
   if (c->nccl_comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(c->nccl_comm);
   if (c->stream) cudaStreamDestroy(c->stream);
+  delete c->pool;
   delete c;
 }
 
@@ -420,9 +510,20 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     return SVIN_ERR_INVALID_ARGUMENT;
   }
   SVIN_CUDA(cudaSetDevice(c->device));
-  for (int i = 0; i < B; ++i) {
-    const int rc = validate(wins[i], i);
-    if (rc != SVIN_OK) return rc;
+  const double t_begin = wall_ms();
+  {
+    // per window on the pool; the message of the first failing window is re-raised on the calling thread
+    std::vector<int> vrc(B, SVIN_OK);
+    std::vector<std::string> vmsg(B);
+    c->pool->run(B, [&](int i) {
+      vrc[i] = validate(wins[i], i);
+      if (vrc[i] != SVIN_OK) vmsg[i] = svin_last_error();
+    });
+    for (int i = 0; i < B; ++i)
+      if (vrc[i] != SVIN_OK) {
+        set_error(vmsg[i]);
+        return vrc[i];
+      }
   }
   c->uploaded = false;
   c->solved = false;
@@ -433,27 +534,27 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   c->h_win.assign(B, WinDesc{});
   c->n_max = 0;
   int has_ext = 0;
-  for (int i = 0; i < B && !has_ext; ++i)
-    for (int o = 0; o < wins[i].num_obs && !has_ext; ++o)
-      if (!wins[i].pose_fixed[wins[i].obs_extrinsics[o]]) has_ext = 1;
+  {
+    std::atomic<int> any{0};
+    c->pool->run(B, [&](int i) {
+      if (any.load(std::memory_order_relaxed)) return;
+      for (int o = 0; o < wins[i].num_obs; ++o)
+        if (!wins[i].pose_fixed[wins[i].obs_extrinsics[o]]) {
+          any.store(1);
+          return;
+        }
+    });
+    has_ext = any.load();
+  }
   // pattern grouping (k_schur_mma) needs fixed extrinsics and at most 64 pose runs per landmark
   bool group = !has_ext;
   for (int i = 0; i < B; ++i)
     if (wins[i].num_pose_blocks > 64) group = false;
   std::vector<WindowOrder> orders(B);
   long long NSW = 0;
-  {
-    // independent per window: spread over host threads (this is on the end-to-end path)
-    const int nt = std::max(1, std::min<int>(B, (int)std::thread::hardware_concurrency()));
-    std::vector<std::thread> pool;
-    std::atomic<int> next{0};
-    auto work = [&]() {
-      for (int i = next.fetch_add(1); i < B; i = next.fetch_add(1)) order_window(wins[i], group, orders[i]);
-    };
-    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
-    work();
-    for (auto& th : pool) th.join();
-  }
+  // independent per window: spread over the context's host threads (this is on the end-to-end path)
+  c->pool->run(B, [&](int i) { order_window(wins[i], group, orders[i]); });
+  const double t_ordered = wall_ms();
   for (int i = 0; i < B; ++i) NSW += (long long)orders[i].chunk_begin.size();
   for (int i = 0; i < B; ++i) {
     const SvinBaWindow& w = wins[i];
@@ -612,7 +713,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
       h_zx[g] = w.obs_measurement[2 * o];
       h_zy[g] = w.obs_measurement[2 * o + 1];
       double U[4];
-      llt_sqrt_information(w.obs_information + 4 * (size_t)o, U, 2);
+      llt_sqrt_information2(w.obs_information + 4 * (size_t)o, U);
       h_u00[g] = U[0];
       h_u01[g] = U[1];
       h_u11[g] = U[3];
@@ -744,18 +845,22 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     s.last_successful = 1;
     (void)cam_base; (void)ot; (void)lt; (void)sw; (void)meas_base;
   };
-  {
-    const int nt = std::max(1, std::min<int>(B, (int)std::thread::hardware_concurrency()));
-    std::vector<std::thread> pool;
-    std::atomic<int> next{0};
-    auto work = [&]() {
-      for (int i = next.fetch_add(1); i < B; i = next.fetch_add(1)) fill_window(i);
-    };
-    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
-    work();
-    for (auto& th : pool) th.join();
-  }
-
+  // Packing runs on the pool while this thread lays out the work arena; the big observation arrays are copied
+  // group by group as soon as their windows are packed, so that the H2D transfer overlaps the packing.
+  const int G = std::max(1, std::min(8, B / 16));
+  std::vector<std::atomic<int>> group_left(G);
+  auto group_of = [&](int i) { return (int)((long long)i * G / B); };
+  for (int g = 0; g < G; ++g) group_left[g].store(0);
+  for (int i = 0; i < B; ++i) group_left[group_of(i)].fetch_add(1);
+  c->pool->start(B, [&](int i) {
+    fill_window(i);
+    group_left[group_of(i)].fetch_sub(1, std::memory_order_release);
+  });
+  // any early return below must first let the workers finish: they reference this frame
+  struct PoolJoin {
+    HostPool* p;
+    ~PoolJoin() { p->help(); p->wait(); }
+  } pool_join{c->pool};
   // ---------------- work arena
   const size_t S = ((size_t)NOBS + 31) & ~(size_t)31;
   Region wk;
@@ -850,7 +955,31 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
 
   // ---------------- copy + initialise
   SVIN_CUDA(cudaEventRecord(c->ev[0], c->stream));
-  SVIN_CUDA(cudaMemcpyAsync(c->d_in, c->h_in, in.bytes, cudaMemcpyHostToDevice, c->stream));
+  if (c->pool->workers() == 0) c->pool->help();
+  {
+    // the nine per-observation arrays, sliced by window group
+    const size_t obs_arr[9] = {o_opose, o_olm, o_oext, o_ocam, o_zx, o_zy, o_u00, o_u01, o_u11};
+    const size_t obs_elt[9] = {4, 4, 4, 4, 8, 8, 8, 8, 8};
+    int w0 = 0;
+    for (int g = 0; g < G; ++g) {
+      int w1 = w0;
+      while (w1 < B && group_of(w1) == g) ++w1;
+      while (group_left[g].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+      if (w1 > w0) {
+        const size_t e0 = (size_t)c->h_win[w0].obs_begin, e1 = (size_t)c->h_win[w1 - 1].obs_end;
+        for (int a = 0; a < 9 && e1 > e0; ++a)
+          SVIN_CUDA(cudaMemcpyAsync(D + obs_arr[a] + obs_elt[a] * e0, H + obs_arr[a] + obs_elt[a] * e0,
+                                    obs_elt[a] * (e1 - e0), cudaMemcpyHostToDevice, c->stream));
+      }
+      w0 = w1;
+    }
+    c->pool->wait();
+    // everything else: the regions before and after the observation arrays
+    const size_t obs_lo = o_opose, obs_hi = o_lmof;
+    SVIN_CUDA(cudaMemcpyAsync(D, H, obs_lo, cudaMemcpyHostToDevice, c->stream));
+    SVIN_CUDA(cudaMemcpyAsync(D + obs_hi, H + obs_hi, in.bytes - obs_hi, cudaMemcpyHostToDevice, c->stream));
+  }
+  const double t_filled = wall_ms();
   SVIN_CUDA(cudaEventRecord(c->ev[1], c->stream));
   SVIN_CUDA(cudaMemsetAsync(Wk + o_sacc, 0, 8 * 8 * (size_t)B + 8 * (size_t)B, c->stream));
   // Jd must be zero outside the blocks the terms write (structure is static)
@@ -875,6 +1004,9 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   c->tm = SvinBaTimings{};
   c->tm.h2d_ms = ms;
   c->tm.h2d_bytes = (int64_t)in.bytes;
+  c->tm.host_order_ms = t_ordered - t_begin;
+  c->tm.host_fill_ms = t_filled - t_ordered;
+  c->tm.host_upload_ms = wall_ms() - t_begin;
   c->uploaded = true;
   c->quality_valid = false;
   return SVIN_OK;
@@ -1105,16 +1237,35 @@ int svin_ba_download(svin_ba_ctx* c, int32_t i, SvinBaWindow* w, double* quality
   return SVIN_OK;
 }
 
+int svin_ba_download_all(svin_ba_ctx* c, SvinBaWindow* wins, int32_t B, double* const* quality) {
+  if (!c || !c->uploaded || !wins || B != c->b.B) {
+    set_error("svin_ba_download_all: invalid arguments (num_windows must equal the uploaded batch size)");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  for (int i = 0; i < B; ++i) {
+    const WinDesc& d = c->h_win[i];
+    if (wins[i].num_pose_blocks != d.pose_end - d.pose_begin || wins[i].num_speedbias != d.sb_end - d.sb_begin ||
+        wins[i].num_landmarks != d.lm_end - d.lm_begin) {
+      set_error("svin_ba_download_all: window shape differs from the uploaded one");
+      return SVIN_ERR_INVALID_ARGUMENT;
+    }
+  }
+  SVIN_CUDA(cudaSetDevice(c->device));
+  const int rc = fetch_results(c);
+  if (rc != SVIN_OK) return rc;
+  const double t0 = wall_ms();
+  c->pool->run(B, [&](int i) { scatter_window(c, i, &wins[i], quality ? quality[i] : nullptr); });
+  c->tm.host_scatter_ms = wall_ms() - t0;
+  return SVIN_OK;
+}
+
 int svin_ba_optimize(svin_ba_ctx* c, SvinBaWindow* wins, int32_t B, const SvinBaOptions* opt, SvinBaSummary* summaries,
                      double* const* quality) {
   int rc = svin_ba_upload(c, wins, B);
   if (rc != SVIN_OK) return rc;
   rc = svin_ba_solve(c, opt, summaries);
   if (rc != SVIN_OK) return rc;
-  rc = fetch_results(c);
-  if (rc != SVIN_OK) return rc;
-  for (int i = 0; i < B; ++i) scatter_window(c, i, &wins[i], quality ? quality[i] : nullptr);
-  return SVIN_OK;
+  return svin_ba_download_all(c, wins, B, quality);
 }
 
 int svin_ba_evaluate(svin_ba_ctx* c, int32_t wi, SvinBaEvaluation* out) {

@@ -63,6 +63,16 @@ class BaEngine:
                    self._lib)
         return w, q
 
+    def download_all(self):
+        """All windows of the uploaded batch with one D2H copy -> list of landmark-quality arrays."""
+        ws = self._windows
+        qall = np.zeros(sum(w.num_landmarks for w in ws))
+        ends = np.cumsum([w.num_landmarks for w in ws])
+        quals = [qall[e - w.num_landmarks:e] for w, e in zip(ws, ends)]
+        qptr = (capi.c_double_p * len(ws))(*[q.ctypes.data_as(capi.c_double_p) for q in quals])
+        capi.check(self._lib.svin_ba_download_all(self._ctx, self._arr, len(ws), qptr), self._lib)
+        return quals
+
     def evaluate(self, index: int = 0) -> dict:
         w = self._windows[index]
         n, m = w.num_obs, len(w.imu_pose0)
@@ -117,9 +127,70 @@ class BaEngine:
         n = len(windows)
         arr = (capi.SvinBaWindow * n)(*[w.c_struct() for w in windows])
         summ = (capi.SvinBaSummary * n)()
-        quals = [np.zeros(w.num_landmarks) for w in windows]
+        qall = np.zeros(sum(w.num_landmarks for w in windows))     # one allocation, sliced per window
+        ends = np.cumsum([w.num_landmarks for w in windows])
+        quals = [qall[e - w.num_landmarks:e] for w, e in zip(windows, ends)]
         qptr = (capi.c_double_p * n)(*[q.ctypes.data_as(capi.c_double_p) for q in quals])
         capi.check(self._lib.svin_ba_optimize(self._ctx, arr, n, C.byref(opt), summ, qptr), self._lib)
         self._windows = windows
         self._arr = arr
         return [s.as_dict() for s in summ], quals
+
+
+class BaPipeline:
+    """Depth-2 software pipeline over the staged C ABI (svin_ba_upload / svin_ba_solve / svin_ba_download_all).
+
+    Two contexts, each driven by its own host thread; a lock serialises the solves so that the packing + H2D copy
+    of batch k+1 (context B) runs while batch k (context A) is being solved, instead of both contexts solving at the
+    same time.  This is the host-side analogue of ThreadedKFVio's overlap of frontend and optimisation threads
+    (okvis_multisensor_processing/src/ThreadedKFVio.cpp:1071-1141), applied across independent windows."""
+
+    def __init__(self, device: int = 0, depth: int = 2):
+        import threading
+        self._engines = [BaEngine(device) for _ in range(depth)]
+        self._gpu = threading.Lock()
+
+    def close(self):
+        for e in self._engines:
+            e.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def optimize_many(self, batches: list[list[BaWindow]], options: capi.SvinBaOptions | None = None):
+        """Every batch is solved as by BaEngine.optimize; returns [(summaries, qualities)] in batch order."""
+        import threading
+        import time
+        opt = options or default_options()
+        out: list = [None] * len(batches)
+        errors: list = []
+        self.trace = [None] * len(batches)   # per batch: (upload start, upload end, solve start, solve end, done) [s]
+        t_origin = time.perf_counter()
+
+        def drive(j):
+            eng = self._engines[j]
+            try:
+                for k in range(j, len(batches), len(self._engines)):
+                    t0 = time.perf_counter()
+                    eng.upload(batches[k])
+                    t1 = time.perf_counter()
+                    with self._gpu:
+                        t2 = time.perf_counter()
+                        summ = eng.solve(opt)
+                        t3 = time.perf_counter()
+                    out[k] = (summ, eng.download_all())
+                    self.trace[k] = tuple(round(1e3 * (t - t_origin), 2) for t in (t0, t1, t2, t3, time.perf_counter()))
+            except Exception as exc:  # surfaced to the caller below
+                errors.append(exc)
+
+        threads = [threading.Thread(target=drive, args=(j,)) for j in range(len(self._engines))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return out

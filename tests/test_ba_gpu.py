@@ -119,3 +119,22 @@ def test_invalid_window_is_rejected_with_message(engine):
     w.obs_landmark[3] = 10 ** 6
     with pytest.raises(SvinError, match="obs_landmark"):
         engine.upload([w])
+
+
+def test_pipeline_matches_blocking_optimize():
+    """BaPipeline (upload / solve / download_all on two contexts) gives what svin_ba_optimize gives."""
+    from svin_b200.engine import BaEngine, BaPipeline
+    base = [make_window(seed=900 + k, num_keyframes=4, num_imu_frames=2, num_landmarks=150)[0] for k in range(3)]
+    batches = [[w.copy() for w in base[:2]], [w.copy() for w in base[1:]], [w.copy() for w in base]]
+    ref = [[w.copy() for w in b] for b in batches]
+    with BaEngine(0) as eng:
+        ref_out = [eng.optimize(b) for b in ref]
+    with BaPipeline(0) as pipe:
+        out = pipe.optimize_many(batches)
+    for (s0, q0), (s1, q1), b0, b1 in zip(ref_out, out, ref, batches):
+        assert [s["iterations"] for s in s0] == [s["iterations"] for s in s1]
+        for w0, w1, a, b in zip(b0, b1, q0, q1):
+            # not bit-identical: the order of the fp64 atomics differs from run to run
+            assert np.allclose(w0.pose_blocks, w1.pose_blocks, rtol=1e-7, atol=1e-9)
+            assert np.allclose(w0.landmarks, w1.landmarks, rtol=1e-7, atol=1e-9)
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-9)
