@@ -150,6 +150,8 @@ struct WindowOrder {
   std::vector<int> lm_count;  // observations of internal landmark k
   std::vector<int> lm_first, lm_stride;  // window-local position of its first observation, stride between them
   std::vector<int> chunk_begin, chunk_count;  // Schur warp chunks (window-local internal landmark indices)
+  std::vector<int> chunk_run_first, chunk_nruns;  // pose runs of the chunk's pattern -> run_pose / run_k0m
+  std::vector<int> run_pose, run_k0m;             // window-local pose block, (first obs k << 8) | obs count
 };
 
 void order_window(const SvinBaWindow& w, bool group, WindowOrder& out) {
@@ -204,17 +206,29 @@ void order_window(const SvinBaWindow& w, bool group, WindowOrder& out) {
   for (int k = 0; k < L; ++k) out.lm_count[k] = start[out.lm_perm[k] + 1] - start[out.lm_perm[k]];
   out.chunk_begin.clear();
   out.chunk_count.clear();
+  out.chunk_run_first.clear();
+  out.chunk_nruns.clear();
+  out.run_pose.clear();
+  out.run_k0m.clear();
   if (group) {
     int k = 0;
     while (k < L) {
       // pose runs of this pattern bound the chunk size (both operand tiles of k_schur_mma must fit in shared memory)
       const int lk = out.lm_perm[k];
       int runs = 0, prev = -1;
+      out.chunk_run_first.push_back((int)out.run_pose.size());
       for (int q = start[lk]; q < start[lk + 1]; ++q) {
         const int pz = w.obs_pose[ord[q]];
-        if (pz != prev) ++runs;
+        if (pz != prev) {
+          ++runs;
+          out.run_pose.push_back(pz);
+          out.run_k0m.push_back(((q - start[lk]) << 8) | 1);
+        } else {
+          out.run_k0m.back() += 1;
+        }
         prev = pz;
       }
+      out.chunk_nruns.push_back(runs);
       const int cap = std::max(1, std::min(32, schur_mma_max_chunk(std::max(runs, 1))));
       int e = k + 1;
       while (e < L && e - k < cap && same_pattern(out.lm_perm[k], out.lm_perm[e])) ++e;
@@ -555,7 +569,9 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   // independent per window: spread over the context's host threads (this is on the end-to-end path)
   c->pool->run(B, [&](int i) { order_window(wins[i], group, orders[i]); });
   const double t_ordered = wall_ms();
+  long long NRUN = 0;
   for (int i = 0; i < B; ++i) NSW += (long long)orders[i].chunk_begin.size();
+  for (int i = 0; i < B; ++i) NRUN += (long long)orders[i].run_pose.size();
   for (int i = 0; i < B; ++i) {
     const SvinBaWindow& w = wins[i];
     WinDesc& d = c->h_win[i];
@@ -615,6 +631,8 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   const size_t o_otw = in.add(4 * (size_t)n_obs_tiles), o_otb = in.add(4 * (size_t)n_obs_tiles);
   const size_t o_ltw = in.add(4 * (size_t)n_lm_tiles), o_ltb = in.add(4 * (size_t)n_lm_tiles);
   const size_t o_sww = in.add(4 * (size_t)NSW), o_swb = in.add(4 * (size_t)NSW), o_swc = in.add(4 * (size_t)NSW);
+  const size_t o_swnr = in.add(4 * (size_t)NSW), o_swrf = in.add(4 * (size_t)NSW);
+  const size_t o_runoff = in.add(4 * (size_t)NRUN), o_runkm = in.add(4 * (size_t)NRUN);
   const size_t o_imu = in.add(sizeof(ImuTerm) * NIMU), o_imuc = in.add(sizeof(ImuCache) * NIMU);
   const size_t o_mt = in.add(8 * NMEAS), o_mg = in.add(24 * NMEAS), o_ma = in.add(24 * NMEAS);
   const size_t o_pp = in.add(sizeof(PosePrior) * NPP), o_sp = in.add(sizeof(SbPrior) * NSP);
@@ -640,6 +658,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   int *h_lmof = (int*)hp(o_lmof), *h_lmos = (int*)hp(o_lmos), *h_lmoc = (int*)hp(o_lmoc);
   int *h_otw = (int*)hp(o_otw), *h_otb = (int*)hp(o_otb), *h_ltw = (int*)hp(o_ltw), *h_ltb = (int*)hp(o_ltb);
   int *h_sww = (int*)hp(o_sww), *h_swb = (int*)hp(o_swb), *h_swc = (int*)hp(o_swc);
+  int *h_swnr = (int*)hp(o_swnr), *h_swrf = (int*)hp(o_swrf), *h_runoff = (int*)hp(o_runoff), *h_runkm = (int*)hp(o_runkm);
   ImuTerm* h_imu = (ImuTerm*)hp(o_imu);
   ImuCache* h_imuc = (ImuCache*)hp(o_imuc);
   long long* h_mt = (long long*)hp(o_mt);
@@ -655,13 +674,14 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   c->obs_perm.resize((size_t)NOBS);
   c->lm_perm.resize((size_t)NL);
   // per-window bases of the running counters, so that windows can be packed by independent host threads
-  std::vector<int> cam_base_v(B), ot_v(B), lt_v(B), sw_v(B);
+  std::vector<int> cam_base_v(B), ot_v(B), lt_v(B), sw_v(B), run_v(B);
   std::vector<long long> meas_base_v(B);
   {
-    int cb = 0, ot0 = 0, lt0 = 0, sw0 = 0;
+    int cb = 0, ot0 = 0, lt0 = 0, sw0 = 0, run0 = 0;
     long long mb0 = 0;
     for (int i = 0; i < B; ++i) {
-      cam_base_v[i] = cb; ot_v[i] = ot0; lt_v[i] = lt0; sw_v[i] = sw0; meas_base_v[i] = mb0;
+      cam_base_v[i] = cb; ot_v[i] = ot0; lt_v[i] = lt0; sw_v[i] = sw0; meas_base_v[i] = mb0; run_v[i] = run0;
+      run0 += (int)orders[i].run_pose.size();
       cb += wins[i].num_cameras;
       ot0 += (wins[i].num_obs + kObsTile - 1) / kObsTile;
       lt0 += (wins[i].num_landmarks + kLmTile - 1) / kLmTile;
@@ -727,7 +747,13 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
       h_sww[sw] = i;
       h_swb[sw] = d.lm_begin + wo.chunk_begin[k];
       h_swc[sw] = wo.chunk_count[k];
+      h_swnr[sw] = wo.chunk_nruns[k];
+      h_swrf[sw] = run_v[i] + wo.chunk_run_first[k];
       ++sw;
+    }
+    for (size_t k = 0; k < wo.run_pose.size(); ++k) {
+      h_runoff[run_v[i] + k] = h_poff[d.pose_begin + wo.run_pose[k]];
+      h_runkm[run_v[i] + k] = wo.run_k0m[k];
     }
     for (int t0 = 0; t0 < N; t0 += kObsTile) {
       h_otw[ot] = i;
@@ -924,6 +950,8 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   b.lm_tile_win = (int*)(D + o_ltw); b.lm_tile_begin = (int*)(D + o_ltb);
   b.n_schur_warps = (int)NSW;
   b.sw_win = (int*)(D + o_sww); b.sw_lm_begin = (int*)(D + o_swb); b.sw_count = (int*)(D + o_swc);
+  b.sw_nruns = (int*)(D + o_swnr); b.sw_run_first = (int*)(D + o_swrf);
+  b.run_off = (int*)(D + o_runoff); b.run_k0m = (int*)(D + o_runkm);
   b.imu = (ImuTerm*)(D + o_imu);
   c->d_imu_cache_init = (ImuCache*)(D + o_imuc);
   b.imu_cache = (ImuCache*)(Wk + o_imucw);

@@ -588,252 +588,21 @@ __global__ void __launch_bounds__(kLmTile) k_schur(Batch b, SvinBaOptions opt) {
   }
 }
 
-// Warp-aggregated variant for batches whose extrinsics are fixed.  The host groups landmarks of a
-// window by their exact (pose, camera) observation pattern and hands every warp a chunk of <= 32
-// landmarks sharing one pattern, so all lanes walk identical pose runs.  Each lane eliminates its
-// own landmark in registers; the per-run 6x6 / 6-vector contributions are then summed across the
-// warp with a recursive-halving reduce-scatter and only ONE lane per matrix entry issues the
-// fp64 RED to the reduced system (32x fewer atomics than the per-thread kernel above).
-__global__ void __launch_bounds__(128) k_schur_warp(Batch b, SvinBaOptions opt) {
-  const int lane = threadIdx.x & 31;
-  const int chunk = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (chunk >= b.n_schur_warps) return;
-  const int w = b.sw_win[chunk];
-  WinState& ws = b.ws[w];
-  if (ws.done || ws.reuse) return;
-  const WinDesc& wd = b.win[w];
-  const int cnt = b.sw_count[chunk];
-  const bool active = lane < cnt;
-  const int l = b.sw_lm_begin[chunk] + (active ? lane : 0);
-  const double wgt = active ? 1.0 : 0.0;
-  const int buf = ws.cur;
-  const int n = wd.n_dense;
-  double* H = b.H + wd.H_off;
-  double* g_red = b.g_red + wd.d_off;
-  double* g_raw = b.g_raw + wd.d_off;
-  double* Hdiag = b.Hdiag + wd.d_off;
-  const int ob = b.lm_obs_first[l];
-  const int ost = b.lm_obs_stride[l];
-  const int nobs = b.lm_obs_cnt[l];  // identical on every lane of the chunk
-  const bool lfix = b.lm_fixed[l] != 0;         // part of the pattern, hence warp-uniform
-  const double mu = ws.mu;
-  const size_t S = b.obs_stride;
-  const double* rP = b.lin_r[buf];
-  const double* JpP = b.lin_Jp[buf];
-  const double* JlP = b.lin_Jl[buf];
-
-  // ---- pass 1: V = sum Jl^T Jl, bl = sum Jl^T r (unscaled)
-  double V[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
-  for (int k = 0; k < nobs; ++k) {
-    const int o = ob + k * ost;
-    const double r0 = rP[o], r1 = rP[S + o];
-    double a[6];
-#pragma unroll
-    for (int q = 0; q < 6; ++q) a[q] = JlP[q * S + o];
-    V[0] += a[0] * a[0] + a[3] * a[3];
-    V[1] += a[0] * a[1] + a[3] * a[4];
-    V[2] += a[0] * a[2] + a[3] * a[5];
-    V[3] += a[1] * a[1] + a[4] * a[4];
-    V[4] += a[1] * a[2] + a[4] * a[5];
-    V[5] += a[2] * a[2] + a[5] * a[5];
-    bl[0] += a[0] * r0 + a[3] * r1;
-    bl[1] += a[1] * r0 + a[4] * r1;
-    bl[2] += a[2] * r0 + a[5] * r1;
-  }
-  double s[3] = {1.0, 1.0, 1.0}, Vi[6] = {0, 0, 0, 0, 0, 0}, bs[3] = {0, 0, 0};
-  if (!lfix) {
-    if (ws.iter == 0 && ws.num_successful == 0 && !ws.invalid) {
-      if (opt.jacobi_scaling) {
-        s[0] = 1.0 / (1.0 + sqrt(V[0]));
-        s[1] = 1.0 / (1.0 + sqrt(V[3]));
-        s[2] = 1.0 / (1.0 + sqrt(V[5]));
-      }
-      if (active) {
-        b.lm_scale[3 * (size_t)l] = s[0];
-        b.lm_scale[3 * (size_t)l + 1] = s[1];
-        b.lm_scale[3 * (size_t)l + 2] = s[2];
-      }
-    } else {
-      s[0] = b.lm_scale[3 * (size_t)l];
-      s[1] = b.lm_scale[3 * (size_t)l + 1];
-      s[2] = b.lm_scale[3 * (size_t)l + 2];
-    }
-    double gm = active ? fmax(fabs(bl[0]), fmax(fabs(bl[1]), fabs(bl[2]))) : 0.0;
-#pragma unroll
-    for (int o2 = 16; o2 > 0; o2 >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o2));
-    if (lane == 0) atomic_max_nonneg(&ws.gmax_bits, gm);
-    double Vs[6] = {V[0] * s[0] * s[0], V[1] * s[0] * s[1], V[2] * s[0] * s[2],
-                    V[3] * s[1] * s[1], V[4] * s[1] * s[2], V[5] * s[2] * s[2]};
-    const double d0 = sqrt(fmin(fmax(Vs[0], opt.min_lm_diagonal), opt.max_lm_diagonal));
-    const double d1 = sqrt(fmin(fmax(Vs[3], opt.min_lm_diagonal), opt.max_lm_diagonal));
-    const double d2 = sqrt(fmin(fmax(Vs[5], opt.min_lm_diagonal), opt.max_lm_diagonal));
-    Vs[0] += mu * d0 * d0;
-    Vs[3] += mu * d1 * d1;
-    Vs[5] += mu * d2 * d2;
-    spd3_inverse(Vs, Vi);
-    bs[0] = s[0] * bl[0];
-    bs[1] = s[1] * bl[1];
-    bs[2] = s[2] * bl[2];
-    if (active) {
-      double* p = b.lm_Vinv + 6 * (size_t)l;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) p[k] = Vi[k];
-      p = b.lm_bs + 3 * (size_t)l;
-      p[0] = bs[0]; p[1] = bs[1]; p[2] = bs[2];
-      p = b.lm_diag + 3 * (size_t)l;
-      p[0] = d0; p[1] = d1; p[2] = d2;
-      p = b.lm_grad + 3 * (size_t)l;
-      p[0] = bs[0] / d0; p[1] = bs[1] / d1; p[2] = bs[2] / d2;
-    }
-  }
-
-  // ---- pass 2: pose runs (identical structure on every lane)
-  int i = 0;
-  while (i < nobs) {
-    const int p = b.obs_pose[ob + i * ost];
-    int j = i + 1;
-    while (j < nobs && b.obs_pose[ob + j * ost] == p) ++j;
-    const int offp = b.pose_off[p];
-    if (offp >= 0) {
-      double v[32];  // [0,21) H block upper, [21,27) reduced gradient, [27,32) Hdiag 0..4
-      double ex[7];  // Hdiag 5, raw gradient 0..5
-      double W[18];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) v[k] = 0;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) ex[k] = 0;
-#pragma unroll
-      for (int k = 0; k < 18; ++k) W[k] = 0;
-      for (int k = i; k < j; ++k) {
-        const int o = ob + k * ost;
-        double Jp[12], Jls[6];
-#pragma unroll
-        for (int q = 0; q < 12; ++q) Jp[q] = JpP[q * S + o];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) Jls[q] = JlP[q * S + o] * s[q % 3];
-        const double r0 = rP[o], r1 = rP[S + o];
-        int idx = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-          for (int c = a; c < 6; ++c) v[idx++] += Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) ex[1 + a] += Jp[a] * r0 + Jp[6 + a] * r1;
-        acc_W(Jp, Jls, W);
-      }
-      // column square norms = diagonal of the unreduced block
-      v[27] = v[0]; v[28] = v[6]; v[29] = v[11]; v[30] = v[15]; v[31] = v[18];
-      ex[0] = v[20];
-#pragma unroll
-      for (int a = 0; a < 6; ++a) v[21 + a] = ex[1 + a];
-      double Z[18];
-      if (!lfix) {
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-          const double w0 = W[a * 3], w1 = W[a * 3 + 1], w2 = W[a * 3 + 2];
-          Z[a * 3 + 0] = w0 * Vi[0] + w1 * Vi[1] + w2 * Vi[2];
-          Z[a * 3 + 1] = w0 * Vi[1] + w1 * Vi[3] + w2 * Vi[4];
-          Z[a * 3 + 2] = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
-        }
-        int idx = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-          for (int c = a; c < 6; ++c)
-            v[idx++] -= Z[a * 3] * W[c * 3] + Z[a * 3 + 1] * W[c * 3 + 1] + Z[a * 3 + 2] * W[c * 3 + 2];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) v[21 + a] -= Z[a * 3] * bs[0] + Z[a * 3 + 1] * bs[1] + Z[a * 3 + 2] * bs[2];
-      }
-#pragma unroll
-      for (int k = 0; k < 32; ++k) v[k] *= wgt;
-      warp_reduce_scatter32(v, lane);
-#pragma unroll
-      for (int k = 0; k < 7; ++k) ex[k] = warp_sum(ex[k] * wgt);
-      {
-        // lane -> destination of the value it now owns
-        double* dst;
-        if (lane < 21) {
-          const int a = (lane >= 6) + (lane >= 11) + (lane >= 15) + (lane >= 18) + (lane >= 20);
-          const int c = lane - (a * 6 - (a * (a - 1) >> 1)) + a;
-          dst = &H[(size_t)(offp + a) * n + offp + c];
-        } else if (lane < 27) {
-          dst = &g_red[offp + lane - 21];
-        } else {
-          dst = &Hdiag[offp + lane - 27];
-        }
-        atomicAdd(dst, v[0]);
-        if (lane < 7) {
-          double e = ex[0];
-#pragma unroll
-          for (int k = 1; k < 7; ++k) e = (lane == k) ? ex[k] : e;
-          atomicAdd(lane == 0 ? &Hdiag[offp + 5] : &g_raw[offp + lane - 1], e);
-        }
-      }
-      if (!lfix) {
-        int i2 = j;
-        while (i2 < nobs) {
-          const int q = b.obs_pose[ob + i2 * ost];
-          int j2 = i2 + 1;
-          while (j2 < nobs && b.obs_pose[ob + j2 * ost] == q) ++j2;
-          const int offq = b.pose_off[q];
-          if (offq >= 0) {
-            double Wq[18];
-#pragma unroll
-            for (int k = 0; k < 18; ++k) Wq[k] = 0;
-            for (int k = i2; k < j2; ++k) {
-              const int o = ob + k * ost;
-              double Jp[12], Jls[6];
-#pragma unroll
-              for (int t = 0; t < 12; ++t) Jp[t] = JpP[t * S + o];
-#pragma unroll
-              for (int t = 0; t < 6; ++t) Jls[t] = JlP[t * S + o] * s[t % 3];
-              acc_W(Jp, Jls, Wq);
-            }
-            double blk[32], e4[4];
-#pragma unroll
-            for (int a = 0; a < 6; ++a)
-#pragma unroll
-              for (int c = 0; c < 6; ++c) {
-                const double val =
-                    -(Z[a * 3] * Wq[c * 3] + Z[a * 3 + 1] * Wq[c * 3 + 1] + Z[a * 3 + 2] * Wq[c * 3 + 2]) * wgt;
-                if (a * 6 + c < 32)
-                  blk[a * 6 + c] = val;
-                else
-                  e4[a * 6 + c - 32] = val;
-              }
-            warp_reduce_scatter32(blk, lane);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) e4[k] = warp_sum(e4[k]);
-            {
-              const int a = lane / 6, c = lane - a * 6;
-              double* dst = (offp < offq) ? &H[(size_t)(offp + a) * n + offq + c] : &H[(size_t)(offq + c) * n + offp + a];
-              atomicAdd(dst, blk[0]);
-              if (lane < 4) {
-                double e = e4[0];
-#pragma unroll
-                for (int k = 1; k < 4; ++k) e = (lane == k) ? e4[k] : e;
-                const int c2 = 2 + lane;  // entries (5,2)..(5,5)
-                double* d2 = (offp < offq) ? &H[(size_t)(offp + 5) * n + offq + c2] : &H[(size_t)(offq + c2) * n + offp + 5];
-                atomicAdd(d2, e);
-              }
-            }
-          }
-          i2 = j2;
-        }
-      }
-    }
-    i = j;
-  }
-}
-
-// Tensor-core variant of k_schur_warp.  The per-landmark elimination is unchanged, but instead of every lane
-// forming its own O(k^2) pose-pair blocks, the lanes of a chunk deposit Z = W V^-1 and W for all k pose runs in
-// shared memory ([6k x 3c] each, c = landmarks in the chunk) and the warp computes the whole update
-//     C (6k x 6k) = Z_chunk * W_chunk^T          (a dense fp64 contraction, K = 3c)
-// with mma.sync.m8n8k4.f64 (DMMA), then issues one fp64 RED per upper-triangular entry of C.  The chunk size is
-// capped at upload so that both operand tiles fit kSchurMmaDoubles doubles per warp.
-constexpr int kSchurMmaDoubles = 1664;  // per operand matrix and warp (13.3 KB)
-constexpr int kSchurMaxRuns = 64;
+// Tensor-core landmark elimination (fixed extrinsics): one warp per chunk of <= 32 landmarks that share the exact
+// (pose block, camera) observation pattern, so that the pose runs are warp-uniform and the sums over the landmarks
+// of a chunk become the K dimension of fp64 tensor-core contractions (mma.sync.m8n8k4.f64, DMMA):
+//   per run a and observation:  P (8 x 2c) = [Jp^T ; r^T ; 0] columns (row, landmark)  ->  P P^T accumulates
+//        [ Jp^T Jp   Jp^T r ]      the pose-pose block, the raw gradient and diag(J^T J)
+//        [ r^T Jp    r^T r  ]
+//   per chunk:  Y ((6k+1) x 3c), rows 6a..6a+5 = W_a M^T with V^-1 = M^T M (M = inverse Cholesky factor of the
+//        damped landmark block), last row u = M b_l  ->  Y Y^T = [ W V^-1 W^T   W V^-1 b_l ; ... ]
+//        i.e. the whole Schur update of the k x k pose blocks and the reduced-gradient correction in one product.
+// One fp64 RED per produced entry.  The chunk size is capped at upload so that Y fits kSchurYDoubles.
+constexpr int kSchurYDoubles = 1776;   // Y operand per warp (3 CTAs of 4 warps per SM: 3 x 76.3 KB shared memory)
+constexpr int kSchurPld = 68;          // P tile leading dimension: 2 * 32 columns + 4 (bank spread)
+constexpr int kSchurPDoubles = 8 * kSchurPld;
+constexpr int kSchurMaxRuns = 64;      // run descriptors per warp: 2 ints each
+constexpr int kSchurWarpDoubles = kSchurYDoubles + kSchurPDoubles + kSchurMaxRuns;
 
 __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double bq) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -841,22 +610,43 @@ __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, doub
                : "d"(a), "d"(bq));
 }
 
-__global__ void __launch_bounds__(128) k_schur_mma(Batch b, SvinBaOptions opt) {
+// spd3_inverse that also returns the inverse Cholesky factor M (lower: 00 10 11 20 21 22), V^-1 = M^T M
+__device__ __forceinline__ void spd3_inverse_factor(const double* V, double* Vi, double* M) {
+  const double l00 = sqrt(V[0]);
+  const double l10 = V[1] / l00, l20 = V[2] / l00;
+  const double l11 = sqrt(V[3] - l10 * l10);
+  const double l21 = (V[4] - l20 * l10) / l11;
+  const double l22 = sqrt(V[5] - l20 * l20 - l21 * l21);
+  const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+  const double i10 = -l10 * i00 * i11;
+  const double i21 = -l21 * i11 * i22;
+  const double i20 = -(l20 * i00 + l21 * i10) * i22;
+  Vi[0] = i00 * i00 + i10 * i10 + i20 * i20;
+  Vi[1] = i10 * i11 + i20 * i21;
+  Vi[2] = i20 * i22;
+  Vi[3] = i11 * i11 + i21 * i21;
+  Vi[4] = i21 * i22;
+  Vi[5] = i22 * i22;
+  M[0] = i00; M[1] = i10; M[2] = i11; M[3] = i20; M[4] = i21; M[5] = i22;
+}
+
+__global__ void __launch_bounds__(128, 3) k_schur_mma(Batch b, SvinBaOptions opt) {
   extern __shared__ double sm_all[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int chunk = blockIdx.x * 4 + wid;
   if (chunk >= b.n_schur_warps) return;
-  double* Zs = sm_all + (size_t)wid * (2 * kSchurMmaDoubles + kSchurMaxRuns / 2);
-  double* Ws = Zs + kSchurMmaDoubles;
-  int* offs = reinterpret_cast<int*>(Ws + kSchurMmaDoubles);
+  double* Ys = sm_all + (size_t)wid * kSchurWarpDoubles;
+  double* Ps = Ys + kSchurYDoubles;
+  int* rdesc = reinterpret_cast<int*>(Ps + kSchurPDoubles);  // [2r] dense offset of the run's pose block, [2r+1] k0<<8|m
   const int w = b.sw_win[chunk];
   WinState& ws = b.ws[w];
   if (ws.done || ws.reuse) return;
   const WinDesc& wd = b.win[w];
   const int cnt = b.sw_count[chunk];
+  const int nr = b.sw_nruns[chunk];
+  const int rf = b.sw_run_first[chunk];
   const bool active = lane < cnt;
   const int l = b.sw_lm_begin[chunk] + (active ? lane : 0);
-  const double wgt = active ? 1.0 : 0.0;
   const int buf = ws.cur;
   const int n = wd.n_dense;
   double* H = b.H + wd.H_off;
@@ -872,6 +662,11 @@ __global__ void __launch_bounds__(128) k_schur_mma(Batch b, SvinBaOptions opt) {
   const double* rP = b.lin_r[buf];
   const double* JpP = b.lin_Jp[buf];
   const double* JlP = b.lin_Jl[buf];
+  for (int r = lane; r < nr; r += 32) {
+    rdesc[2 * r] = b.run_off[rf + r];
+    rdesc[2 * r + 1] = b.run_k0m[rf + r];
+  }
+  for (int e = lane; e < kSchurPDoubles; e += 32) Ps[e] = 0.0;
 
   // ---- pass 1: V = sum Jl^T Jl, bl = sum Jl^T r (unscaled)
   double V[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
@@ -891,7 +686,7 @@ __global__ void __launch_bounds__(128) k_schur_mma(Batch b, SvinBaOptions opt) {
     bl[1] += a[1] * r0 + a[4] * r1;
     bl[2] += a[2] * r0 + a[5] * r1;
   }
-  double s[3] = {1.0, 1.0, 1.0}, Vi[6] = {0, 0, 0, 0, 0, 0}, bs[3] = {0, 0, 0};
+  double s[3] = {1.0, 1.0, 1.0}, M[6] = {0, 0, 0, 0, 0, 0}, u[3] = {0, 0, 0};
   if (!lfix) {
     if (ws.iter == 0 && ws.num_successful == 0 && !ws.invalid) {
       if (opt.jacobi_scaling) {
@@ -921,46 +716,42 @@ __global__ void __launch_bounds__(128) k_schur_mma(Batch b, SvinBaOptions opt) {
     Vs[0] += mu * d0 * d0;
     Vs[3] += mu * d1 * d1;
     Vs[5] += mu * d2 * d2;
-    spd3_inverse(Vs, Vi);
-    bs[0] = s[0] * bl[0];
-    bs[1] = s[1] * bl[1];
-    bs[2] = s[2] * bl[2];
+    double Vi[6];
+    spd3_inverse_factor(Vs, Vi, M);
+    const double bs0 = s[0] * bl[0], bs1 = s[1] * bl[1], bs2 = s[2] * bl[2];
+    u[0] = M[0] * bs0;
+    u[1] = M[1] * bs0 + M[2] * bs1;
+    u[2] = M[3] * bs0 + M[4] * bs1 + M[5] * bs2;
     if (active) {
       double* p = b.lm_Vinv + 6 * (size_t)l;
 #pragma unroll
       for (int k = 0; k < 6; ++k) p[k] = Vi[k];
       p = b.lm_bs + 3 * (size_t)l;
-      p[0] = bs[0]; p[1] = bs[1]; p[2] = bs[2];
+      p[0] = bs0; p[1] = bs1; p[2] = bs2;
       p = b.lm_diag + 3 * (size_t)l;
       p[0] = d0; p[1] = d1; p[2] = d2;
       p = b.lm_grad + 3 * (size_t)l;
-      p[0] = bs[0] / d0; p[1] = bs[1] / d1; p[2] = bs[2] / d2;
+      p[0] = bs0 / d0; p[1] = bs1 / d1; p[2] = bs2 / d2;
     }
   }
+  __syncwarp();
 
-  // operand tiles: row = 6 * run + a, column = 3 * lane + j; leading dimension ld
-  const int K4 = (3 * cnt + 3) >> 2;
+  const int fr = lane >> 2, fc = lane & 3;
+  const int cntp = (cnt + 3) & ~3;    // landmark columns of the P tile per residual row
+  const int K4p = cntp >> 1;          // k-steps over the 2 * cntp columns
+  const int K4 = (3 * cnt + 3) >> 2;  // k-steps over the 3 * cnt columns of Y
   const int ld = 4 * K4 + 4;
 
-  // ---- pass 2: per pose run: unreduced 6x6 block, gradients (reduce-scatter) ; Z, W -> shared memory
-  int i = 0, nr = 0;
-  while (i < nobs) {
-    const int p = b.obs_pose[ob + i * ost];
-    int j = i + 1;
-    while (j < nobs && b.obs_pose[ob + j * ost] == p) ++j;
-    const int offp = b.pose_off[p];
-    if (lane == 0) offs[nr] = offp;
+  // ---- pass 2: per pose run: P P^T on the tensor cores -> diagonal block / gradients; Y rows -> shared memory
+  for (int a = 0; a < nr; ++a) {
+    const int offp = rdesc[2 * a];
+    const int k0 = rdesc[2 * a + 1] >> 8, m = rdesc[2 * a + 1] & 255;
     double W[18];
 #pragma unroll
     for (int k = 0; k < 18; ++k) W[k] = 0;
     if (offp >= 0) {
-      double v[32];  // [0,21) unreduced block (upper), [21,27) reduced gradient, [27,32) Hdiag 0..4
-      double ex[7];  // Hdiag 5, raw gradient 0..5
-#pragma unroll
-      for (int k = 0; k < 32; ++k) v[k] = 0;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) ex[k] = 0;
-      for (int k = i; k < j; ++k) {
+      double c0 = 0.0, c1 = 0.0;
+      for (int k = k0; k < k0 + m; ++k) {
         const int o = ob + k * ost;
         double Jp[12], Jls[6];
 #pragma unroll
@@ -968,102 +759,93 @@ __global__ void __launch_bounds__(128) k_schur_mma(Batch b, SvinBaOptions opt) {
 #pragma unroll
         for (int q = 0; q < 6; ++q) Jls[q] = JlP[q * S + o] * s[q % 3];
         const double r0 = rP[o], r1 = rP[S + o];
-        int idx = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-          for (int c = a; c < 6; ++c) v[idx++] += Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) ex[1 + a] += Jp[a] * r0 + Jp[6 + a] * r1;
         acc_W(Jp, Jls, W);
+        if (active) {
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            Ps[q * kSchurPld + lane] = Jp[q];
+            Ps[q * kSchurPld + cntp + lane] = Jp[6 + q];
+          }
+          Ps[6 * kSchurPld + lane] = r0;
+          Ps[6 * kSchurPld + cntp + lane] = r1;
+        }
+        __syncwarp();
+        const double* pa = Ps + fr * kSchurPld + fc;
+        for (int ks = 0; ks < K4p; ++ks) {
+          const double x = pa[4 * ks];
+          dmma8x8x4(c0, c1, x, x);
+        }
+        __syncwarp();
       }
-      v[27] = v[0]; v[28] = v[6]; v[29] = v[11]; v[30] = v[15]; v[31] = v[18];
-      ex[0] = v[20];
+      if (fr < 6) {
 #pragma unroll
-      for (int a = 0; a < 6; ++a) v[21 + a] = ex[1 + a];
-      if (!lfix) {
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-          const double w0 = W[a * 3], w1 = W[a * 3 + 1], w2 = W[a * 3 + 2];
-          const double z0 = w0 * Vi[0] + w1 * Vi[1] + w2 * Vi[2];
-          const double z1 = w0 * Vi[1] + w1 * Vi[3] + w2 * Vi[4];
-          const double z2 = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
-          v[21 + a] -= z0 * bs[0] + z1 * bs[1] + z2 * bs[2];
-          if (active) {
-            double* zr = Zs + (6 * nr + a) * ld + 3 * lane;
-            zr[0] = z0; zr[1] = z1; zr[2] = z2;
-            double* wr = Ws + (6 * nr + a) * ld + 3 * lane;
-            wr[0] = w0; wr[1] = w1; wr[2] = w2;
+        for (int e = 0; e < 2; ++e) {
+          const int col = 2 * fc + e;
+          const double val = e ? c1 : c0;
+          if (col < 6) {
+            if (fr <= col) atomicAdd(&H[(size_t)(offp + fr) * n + offp + col], val);
+            if (fr == col) atomicAdd(&Hdiag[offp + fr], val);
+          } else if (col == 6) {
+            atomicAdd(&g_red[offp + fr], val);
+            atomicAdd(&g_raw[offp + fr], val);
           }
         }
       }
+    }
+    if (!lfix && active) {
 #pragma unroll
-      for (int k = 0; k < 32; ++k) v[k] *= wgt;
-      warp_reduce_scatter32(v, lane);
-#pragma unroll
-      for (int k = 0; k < 7; ++k) ex[k] = warp_sum(ex[k] * wgt);
-      double* dst;
-      if (lane < 21) {
-        const int a = (lane >= 6) + (lane >= 11) + (lane >= 15) + (lane >= 18) + (lane >= 20);
-        const int c = lane - (a * 6 - (a * (a - 1) >> 1)) + a;
-        dst = &H[(size_t)(offp + a) * n + offp + c];
-      } else if (lane < 27) {
-        dst = &g_red[offp + lane - 21];
-      } else {
-        dst = &Hdiag[offp + lane - 27];
-      }
-      atomicAdd(dst, v[0]);
-      if (lane < 7) {
-        double e = ex[0];
-#pragma unroll
-        for (int k = 1; k < 7; ++k) e = (lane == k) ? ex[k] : e;
-        atomicAdd(lane == 0 ? &Hdiag[offp + 5] : &g_raw[offp + lane - 1], e);
-      }
-    } else if (!lfix && active) {
-      for (int a = 0; a < 6; ++a) {
-        double* zr = Zs + (6 * nr + a) * ld + 3 * lane;
-        zr[0] = zr[1] = zr[2] = 0.0;
-        double* wr = Ws + (6 * nr + a) * ld + 3 * lane;
-        wr[0] = wr[1] = wr[2] = 0.0;
+      for (int i = 0; i < 6; ++i) {
+        const double w0 = W[i * 3], w1 = W[i * 3 + 1], w2 = W[i * 3 + 2];
+        double* yr = Ys + (6 * a + i) * ld + 3 * lane;
+        yr[0] = w0 * M[0];
+        yr[1] = w0 * M[1] + w1 * M[2];
+        yr[2] = w0 * M[3] + w1 * M[4] + w2 * M[5];
       }
     }
-    ++nr;
-    i = j;
   }
   if (lfix) return;
-  // zero the padding: columns [3 cnt, 4 K4) of every used row, and rows [6 nr, 8 T)
-  const int rows = 6 * nr, T = (rows + 7) >> 3;
-  for (int e = lane; e < rows * (4 * K4 - 3 * cnt); e += 32) {
-    const int r = e / (4 * K4 - 3 * cnt), c = 3 * cnt + e % (4 * K4 - 3 * cnt);
-    Zs[r * ld + c] = 0.0;
-    Ws[r * ld + c] = 0.0;
+  const int R = 6 * nr, RY = R + 1, T = (RY + 7) >> 3;
+  if (active) {
+    double* yr = Ys + R * ld + 3 * lane;
+    yr[0] = u[0]; yr[1] = u[1]; yr[2] = u[2];
   }
-  for (int e = lane; e < (8 * T - rows) * 4 * K4; e += 32) {
-    const int r = rows + e / (4 * K4), c = e % (4 * K4);
-    Zs[r * ld + c] = 0.0;
-    Ws[r * ld + c] = 0.0;
-  }
+  // zero the k padding: columns [3 cnt, 4 K4) of every row
+  for (int r = lane; r < RY; r += 32)
+    for (int c = 3 * cnt; c < 4 * K4; ++c) Ys[r * ld + c] = 0.0;
   __syncwarp();
-  // ---- C = Z W^T on the tensor cores, upper tiles only; one RED per upper-triangular entry
-  const int fr = lane >> 2, fc = lane & 3;
+  // ---- C = Y Y^T on the tensor cores, upper tiles only; one RED per upper-triangular entry
   for (int tm = 0; tm < T; ++tm) {
-    const double* za = Zs + (8 * tm + fr) * ld + fc;
+    const int ra = 8 * tm + fr;
+    const bool va = ra < RY;
+    const double* za = Ys + (va ? ra : 0) * ld + fc;
     for (int tn = tm; tn < T; ++tn) {
-      const double* wb = Ws + (8 * tn + fr) * ld + fc;
+      const int rb = 8 * tn + fr;
+      const bool vb = rb < RY;
+      const double* zb = Ys + (vb ? rb : 0) * ld + fc;
       double c0 = 0.0, c1 = 0.0;
-      for (int ks = 0; ks < K4; ++ks) dmma8x8x4(c0, c1, za[4 * ks], wb[4 * ks]);
-      const int gi = 8 * tm + fr;
+      for (int ks = 0; ks < K4; ++ks) {
+        const double xa = va ? za[4 * ks] : 0.0;
+        const double xb = vb ? zb[4 * ks] : 0.0;
+        dmma8x8x4(c0, c1, xa, xb);
+      }
+      const int gi = ra;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int gj = 8 * tn + 2 * fc + e;
-        if (gi < rows && gj < rows && gi <= gj) {
-          const int rp = gi / 6, rq = gj / 6;
-          const int a = gi - 6 * rp, c = gj - 6 * rq;
-          const int op = offs[rp], oq = offs[rq];
-          if (op >= 0 && oq >= 0) {
-            const double val = e ? c1 : c0;
-            double* dst = (op <= oq) ? &H[(size_t)(op + a) * n + oq + c] : &H[(size_t)(oq + c) * n + op + a];
-            atomicAdd(dst, -val);
+        if (gi < R && gj <= R && gi <= gj) {
+          const double val = e ? c1 : c0;
+          const int rp = gi / 6, ai = gi - 6 * rp;
+          const int op = rdesc[2 * rp];
+          if (op < 0) continue;
+          if (gj == R) {
+            atomicAdd(&g_red[op + ai], -val);
+          } else {
+            const int rq = gj / 6, cj = gj - 6 * rq;
+            const int oq = rdesc[2 * rq];
+            if (oq >= 0) {
+              double* dst = (op <= oq) ? &H[(size_t)(op + ai) * n + oq + cj] : &H[(size_t)(oq + cj) * n + op + ai];
+              atomicAdd(dst, -val);
+            }
           }
         }
       }
@@ -2318,14 +2100,14 @@ void launch_gmax_pack(const Batch& b, int unpack, cudaStream_t st) {
   k_gmax_pack<<<div_up(b.B, 64), 64, 0, st>>>(b, unpack);
 }
 
-size_t schur_mma_smem_bytes() { return 4 * (size_t)(2 * kSchurMmaDoubles + kSchurMaxRuns / 2) * sizeof(double); }
+size_t schur_mma_smem_bytes() { return 4 * (size_t)kSchurWarpDoubles * sizeof(double); }
 int schur_mma_max_chunk(int runs) {
-  // largest chunk size c <= 32 with pad8(6 runs) * (pad4(3c) + 4) <= kSchurMmaDoubles
+  // largest chunk size c <= 32 with (6 runs + 1) * (pad4(3c) + 4) <= kSchurYDoubles
   if (runs > kSchurMaxRuns) return 0;
-  const int rows = ((6 * runs + 7) / 8) * 8;
+  const int rows = 6 * runs + 1;
   int best = 0;
   for (int c = 1; c <= 32; ++c)
-    if (rows * (((3 * c + 3) / 4) * 4 + 4) <= kSchurMmaDoubles) best = c;
+    if (rows * (((3 * c + 3) / 4) * 4 + 4) <= kSchurYDoubles) best = c;
   return best;
 }
 cudaError_t configure_schur() {

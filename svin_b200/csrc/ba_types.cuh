@@ -139,6 +139,8 @@ struct Batch {
   // Schur warp chunks: <= 32 consecutive landmarks with an identical (pose, camera) observation pattern
   int n_schur_warps;
   int *sw_win, *sw_lm_begin, *sw_count;
+  int *sw_nruns, *sw_run_first;  // pose runs of the chunk's pattern: count, first entry in run_off / run_k0m
+  int *run_off, *run_k0m;        // per run: dense offset of its pose block (-1 fixed), (first obs k << 8) | obs count
   // linearisation, two buffers: planes [k][obs_stride]
   double* lin_r[2];   // 2 planes
   double* lin_Jp[2];  // 12 planes
