@@ -903,7 +903,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     o_rd[k] = wk.add(8 * NROWS);
   }
   const size_t o_wsw = wk.add(sizeof(WinState) * B), o_imucw = wk.add(sizeof(ImuCache) * NIMU);
-  const size_t o_sacc = wk.add(8 * 8 * (size_t)B), o_gmaxb = wk.add(8 * (size_t)B);
+  const size_t o_sacc = wk.add(8 * kShardAcc * (size_t)B), o_gmaxb = wk.add(8 * (size_t)B);
   const size_t o_lms = wk.add(24 * NL), o_lmV = wk.add(48 * NL), o_lmb2 = wk.add(24 * NL), o_lmd = wk.add(24 * NL),
                o_lmg = wk.add(24 * NL), o_lmgn = wk.add(24 * NL);
   // cleared every slot: H, g_red, g_raw, Hdiag (kept contiguous)
@@ -1009,7 +1009,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   }
   const double t_filled = wall_ms();
   SVIN_CUDA(cudaEventRecord(c->ev[1], c->stream));
-  SVIN_CUDA(cudaMemsetAsync(Wk + o_sacc, 0, 8 * 8 * (size_t)B + 8 * (size_t)B, c->stream));
+  SVIN_CUDA(cudaMemsetAsync(Wk + o_sacc, 0, 8 * kShardAcc * (size_t)B, c->stream));
   // Jd must be zero outside the blocks the terms write (structure is static)
   for (int k = 0; k < 2; ++k) SVIN_CUDA(cudaMemsetAsync(b.Jd[k], 0, 8 * (size_t)NJD + 8, c->stream));
   SVIN_CUDA(cudaMemsetAsync(b.lm_quality, 0, 8 * (size_t)NL + 8, c->stream));
@@ -1052,7 +1052,7 @@ int svin_ba_reset(svin_ba_ctx* c) {
   if (b.NIMU)
     SVIN_CUDA(cudaMemcpyAsync(b.imu_cache, c->d_imu_cache_init, sizeof(ImuCache) * b.NIMU, cudaMemcpyDeviceToDevice,
                               c->stream));
-  if (b.shard_acc) SVIN_CUDA(cudaMemsetAsync(b.shard_acc, 0, 8 * 8 * (size_t)b.B, c->stream));
+  if (b.shard_acc) SVIN_CUDA(cudaMemsetAsync(b.shard_acc, 0, 8 * kShardAcc * (size_t)b.B, c->stream));
   SVIN_CUDA(cudaGetLastError());
   c->solved = false;
   c->quality_valid = false;
@@ -1108,18 +1108,18 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
   { ProfScope p(c, SVIN_BA_K_DENSE_SOLVE); launch_dense_solve(b, opt, c->smem_bytes, c->stream); }
   { ProfScope p(c, SVIN_BA_K_BACKSUB); launch_backsub(b, c->stream); }
   if (sharded) {
-    if ((rc = comm_allreduce(c, b.shard_acc, 8 * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
+    if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
     launch_fold(b, 2, c->stream);
   }
   { ProfScope p(c, SVIN_BA_K_STEP_DENSE); launch_step_dense(b, opt, c->stream); }
   { ProfScope p(c, SVIN_BA_K_STEP_LM); launch_step_lm(b, c->stream); }
   if (sharded) {
-    if ((rc = comm_allreduce(c, b.shard_acc, 8 * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
+    if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
     launch_fold(b, 3, c->stream);
   }
   { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 1, 0, c->stream); }
   if (sharded) {
-    if ((rc = comm_allreduce(c, b.shard_acc, 8 * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
+    if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
     launch_fold(b, 4, c->stream);
   }
   { ProfScope p(c, SVIN_BA_K_DENSE_EVAL); launch_dense_eval(b, 1, 0, nullptr, c->stream); }
@@ -1149,7 +1149,7 @@ int svin_ba_solve(svin_ba_ctx* c, const SvinBaOptions* opt_in, SvinBaSummary* su
   c->prof_family.clear();
   { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 0, 0, c->stream); }
   if (c->nccl_comm) {
-    const int rc0 = comm_allreduce(c, b.shard_acc, 8 * (size_t)b.B, kNcclSum);
+    const int rc0 = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum);
     if (rc0 != SVIN_OK) return rc0;
     launch_fold(b, 4, c->stream);
   }

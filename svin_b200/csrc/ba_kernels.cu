@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kObsTile) k_linearize(Batch b, int which, int 
       for (int k = 0; k < 12; ++k) Je[k * S + o] = R.Je[k];
     }
   }
-  double* const dst[1] = {(b.shard_acc && !raw) ? &b.shard_acc[8 * (size_t)w + 7] : &ws.cost_cand};
+  double* const dst[1] = {(b.shard_acc && !raw) ? &b.shard_acc[kShardAcc * (size_t)w + 11] : &ws.cost_cand};
   block_atomic_add<1, kObsTile>(cost, dst);
 }
 
@@ -1687,7 +1687,7 @@ __global__ void __launch_bounds__(kLmTile) k_backsub(Batch b) {
   const WinDesc& wd = b.win[w];
   const int l = b.lm_tile_begin[tile] + threadIdx.x;
   const int buf = ws.cur;
-  double acc[4] = {0, 0, 0, 0};  // g2, n2, gdot, Jg2
+  double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // g2, n2, gdot, Jg2, acc_A[0..4]
   if (l < wd.lm_end) {
     const double* u = b.u_d + wd.d_off;
     const double* cv = b.c_d + wd.d_off;
@@ -1702,7 +1702,9 @@ __global__ void __launch_bounds__(kLmTile) k_backsub(Batch b) {
         cl[k] = s[k] * gr[k] / dg[k];
       }
     }
-    double a3[3] = {0, 0, 0};
+    // per landmark: a3 = sum Jl^T t, jg = sum Jl^T mg, jr = sum Jl^T r, V = sum Jl^T Jl   (t = Jp u, mg = J cauchy)
+    double a3[3] = {0, 0, 0}, jg[3] = {0, 0, 0}, jr[3] = {0, 0, 0}, V[6] = {0, 0, 0, 0, 0, 0};
+    double s_tr = 0, s_tt = 0, s_gt = 0;
     const int ob = b.lm_obs_first[l], ost = b.lm_obs_stride[l], nobs = b.lm_obs_cnt[l];
     for (int k = 0; k < nobs; ++k) {
       const int o = ob + k * ost;
@@ -1735,12 +1737,29 @@ __global__ void __launch_bounds__(kLmTile) k_backsub(Batch b) {
       }
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        a3[k] += J.Jl[k] * t0 + J.Jl[3 + k] * t1;
         m0 += J.Jl[k] * cl[k];
         m1 += J.Jl[3 + k] * cl[k];
       }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        a3[k] += J.Jl[k] * t0 + J.Jl[3 + k] * t1;
+        jg[k] += J.Jl[k] * m0 + J.Jl[3 + k] * m1;
+        jr[k] += J.Jl[k] * J.r0 + J.Jl[3 + k] * J.r1;
+      }
+      V[0] += J.Jl[0] * J.Jl[0] + J.Jl[3] * J.Jl[3];
+      V[1] += J.Jl[0] * J.Jl[1] + J.Jl[3] * J.Jl[4];
+      V[2] += J.Jl[0] * J.Jl[2] + J.Jl[3] * J.Jl[5];
+      V[3] += J.Jl[1] * J.Jl[1] + J.Jl[4] * J.Jl[4];
+      V[4] += J.Jl[1] * J.Jl[2] + J.Jl[4] * J.Jl[5];
+      V[5] += J.Jl[2] * J.Jl[2] + J.Jl[5] * J.Jl[5];
       acc[3] += m0 * m0 + m1 * m1;
+      acc[4] += m0 * J.r0 + m1 * J.r1;
+      s_tr += t0 * J.r0 + t1 * J.r1;
+      s_tt += t0 * t0 + t1 * t1;
+      s_gt += m0 * t0 + m1 * t1;
     }
+    acc[6] = acc[3];
+    double q[3] = {0, 0, 0};  // s o y: minus the landmark's Gauss-Newton step in the original parameters
     if (!lfix) {
       const double* Vi = b.lm_Vinv + 6 * (size_t)l;
       const double* bs = b.lm_bs + 3 * (size_t)l;
@@ -1757,12 +1776,21 @@ __global__ void __launch_bounds__(kLmTile) k_backsub(Batch b) {
       acc[1] = g0 * g0 + g1 * g1 + g2 * g2;
       acc[2] = gr[0] * g0 + gr[1] * g1 + gr[2] * g2;
       if (!isfinite(y0) || !isfinite(y1) || !isfinite(y2)) acc[1] = nan("");
+      q[0] = s[0] * y0; q[1] = s[1] * y1; q[2] = s[2] * y2;
     }
+    // an = t + Jl q per observation, summed in closed form
+    const double Vq0 = V[0] * q[0] + V[1] * q[1] + V[2] * q[2];
+    const double Vq1 = V[1] * q[0] + V[3] * q[1] + V[4] * q[2];
+    const double Vq2 = V[2] * q[0] + V[4] * q[1] + V[5] * q[2];
+    acc[5] = s_tr + q[0] * jr[0] + q[1] * jr[1] + q[2] * jr[2];
+    acc[7] = s_gt + q[0] * jg[0] + q[1] * jg[1] + q[2] * jg[2];
+    acc[8] = s_tt + 2.0 * (q[0] * a3[0] + q[1] * a3[1] + q[2] * a3[2]) + q[0] * Vq0 + q[1] * Vq1 + q[2] * Vq2;
   }
-  double* sa = b.shard_acc ? b.shard_acc + 8 * (size_t)w : nullptr;
-  double* const dst[4] = {sa ? sa + 0 : &ws.acc_g2, sa ? sa + 1 : &ws.acc_n2, sa ? sa + 2 : &ws.acc_gdot,
-                          sa ? sa + 3 : &ws.acc_Jg2};
-  block_atomic_add<4, kLmTile>(acc, dst);
+  double* sa = b.shard_acc ? b.shard_acc + kShardAcc * (size_t)w : nullptr;
+  double* const dst[9] = {sa ? sa + 0 : &ws.acc_g2,   sa ? sa + 1 : &ws.acc_n2,   sa ? sa + 2 : &ws.acc_gdot,
+                          sa ? sa + 3 : &ws.acc_Jg2,  sa ? sa + 4 : &ws.acc_A[0], sa ? sa + 5 : &ws.acc_A[1],
+                          sa ? sa + 6 : &ws.acc_A[2], sa ? sa + 7 : &ws.acc_A[3], sa ? sa + 8 : &ws.acc_A[4]};
+  block_atomic_add<9, kLmTile>(acc, dst);
 }
 
 // ------------------------------------------------------------------------------------------ dogleg step
@@ -1870,6 +1898,10 @@ __global__ void __launch_bounds__(128) k_step_dense(Batch b, SvinBaOptions opt) 
     for (int i = 0; i < n; ++i) m += Jd[(size_t)r * n + i] * delta[i];
     acc[0] += m * (rd[r] + m / 2.0);
   }
+  // reprojection rows of the model from the sums k_backsub left: m = cg * mg - cn * an per observation
+  if (tid == 0)
+    acc[0] += cg * ws.acc_A[0] - cn * ws.acc_A[1] +
+              0.5 * (cg * cg * ws.acc_A[2] - 2.0 * cg * cn * ws.acc_A[3] + cn * cn * ws.acc_A[4]);
   double* const dst[3] = {&ws.acc_mc, &ws.acc_step2, &ws.acc_xnorm2};
   block_atomic_add<3, 128>(acc, dst);
 }
@@ -1883,10 +1915,9 @@ __global__ void __launch_bounds__(kLmTile) k_step_lm(Batch b) {
   const WinDesc& wd = b.win[w];
   const int l = b.lm_tile_begin[tile] + threadIdx.x;
   const int buf = ws.cur;
-  double acc[3] = {0, 0, 0};
+  double acc[2] = {0, 0};  // step2, xnorm2 (the model rows of the landmark terms come from k_backsub's sums)
   if (l < wd.lm_end) {
     const double cg = ws.cg, cn = ws.cn;
-    const double* delta = b.delta_d + wd.d_off;
     const bool lfix = b.lm_fixed[l] != 0;
     const double* x = b.lm[buf] + 4 * (size_t)l;
     double* y = b.lm[1 - buf] + 4 * (size_t)l;
@@ -1897,51 +1928,23 @@ __global__ void __launch_bounds__(kLmTile) k_step_lm(Batch b) {
       for (int k = 0; k < 3; ++k)
         dl[k] = b.lm_scale[3 * (size_t)l + k] *
                 (cg * b.lm_grad[3 * (size_t)l + k] + cn * b.lm_gn[3 * (size_t)l + k]) / b.lm_diag[3 * (size_t)l + k];
-      acc[1] = dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2];
-      acc[2] = x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
+      acc[0] = dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2];
+      acc[1] = x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
     }
     y[0] = x0 + dl[0];
     y[1] = x1 + dl[1];
     y[2] = x2 + dl[2];
     y[3] = x3;
-    const int ob = b.lm_obs_first[l], ost = b.lm_obs_stride[l], nobs = b.lm_obs_cnt[l];
-    for (int k = 0; k < nobs; ++k) {
-      const int o = ob + k * ost;
-      ObsJ J;
-      load_obs(b, buf, o, J);
-      double m0 = J.Jl[0] * dl[0] + J.Jl[1] * dl[1] + J.Jl[2] * dl[2];
-      double m1 = J.Jl[3] * dl[0] + J.Jl[4] * dl[1] + J.Jl[5] * dl[2];
-      const int offp = b.pose_off[b.obs_pose[o]];
-      if (offp >= 0) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          m0 += J.Jp[k] * delta[offp + k];
-          m1 += J.Jp[6 + k] * delta[offp + k];
-        }
-      }
-      if (HAS_EXT) {
-        const int offe = b.pose_off[b.obs_ext[o]];
-        if (offe >= 0) {
-          double Je[12];
-          load_Je(b, buf, o, Je);
-#pragma unroll
-          for (int k = 0; k < 6; ++k) {
-            m0 += Je[k] * delta[offe + k];
-            m1 += Je[6 + k] * delta[offe + k];
-          }
-        }
-      }
-      acc[0] += m0 * (J.r0 + m0 / 2.0) + m1 * (J.r1 + m1 / 2.0);
-    }
   }
-  double* sa = b.shard_acc ? b.shard_acc + 8 * (size_t)w : nullptr;
-  double* const dst[3] = {sa ? sa + 4 : &ws.acc_mc, sa ? sa + 5 : &ws.acc_step2, sa ? sa + 6 : &ws.acc_xnorm2};
-  block_atomic_add<3, kLmTile>(acc, dst);
+  double* sa = b.shard_acc ? b.shard_acc + kShardAcc * (size_t)w : nullptr;
+  double* const dst[2] = {sa ? sa + 9 : &ws.acc_step2, sa ? sa + 10 : &ws.acc_xnorm2};
+  block_atomic_add<2, kLmTile>(acc, dst);
 }
 
 // ------------------------------------------------------------------------------------------ accept / reject
 __device__ __forceinline__ void clear_accumulators(WinState& ws) {
   ws.acc_g2 = ws.acc_n2 = ws.acc_gdot = ws.acc_Jg2 = 0.0;
+  ws.acc_A[0] = ws.acc_A[1] = ws.acc_A[2] = ws.acc_A[3] = ws.acc_A[4] = 0.0;
 }
 __global__ void k_decide(Batch b, SvinBaOptions opt) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2075,16 +2078,17 @@ __global__ void k_fold(Batch b, int stage) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= b.B) return;
   WinState& ws = b.ws[w];
-  double* sa = b.shard_acc + 8 * (size_t)w;
+  double* sa = b.shard_acc + kShardAcc * (size_t)w;
   if (stage == 2) {
     ws.acc_g2 += sa[0]; ws.acc_n2 += sa[1]; ws.acc_gdot += sa[2]; ws.acc_Jg2 += sa[3];
-    sa[0] = sa[1] = sa[2] = sa[3] = 0.0;
+    for (int k = 0; k < 5; ++k) ws.acc_A[k] += sa[4 + k];
+    for (int k = 0; k < 9; ++k) sa[k] = 0.0;
   } else if (stage == 3) {
-    ws.acc_mc += sa[4]; ws.acc_step2 += sa[5]; ws.acc_xnorm2 += sa[6];
-    sa[4] = sa[5] = sa[6] = 0.0;
+    ws.acc_step2 += sa[9]; ws.acc_xnorm2 += sa[10];
+    sa[9] = sa[10] = 0.0;
   } else {
-    ws.cost_cand += sa[7];
-    sa[7] = 0.0;
+    ws.cost_cand += sa[11];
+    sa[11] = 0.0;
   }
 }
 __global__ void k_gmax_pack(Batch b, int unpack) {

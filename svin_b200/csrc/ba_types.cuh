@@ -58,6 +58,10 @@ struct WinState {
   double initial_cost;
   // accumulators (cleared by k_decide / k_init)
   double acc_g2, acc_n2, acc_gdot, acc_Jg2, acc_mc, acc_step2, acc_xnorm2;
+  // reprojection rows of the model, split so that k_step_dense can evaluate them for any dogleg (cg, cn)
+  // without another pass over the Jacobians: sum mg.r, sum an.r, sum |mg|^2, sum mg.an, sum |an|^2
+  // (mg = J * Cauchy direction, an = J * (-Gauss-Newton step), both per observation)
+  double acc_A[5];
   unsigned long long gmax_bits;
   unsigned long long t_start_ns, t_iter_start_ns, t_last_iter_ns;
 };
@@ -110,6 +114,8 @@ struct MargBlock {
 };
 
 // All device pointers of a batch.
+constexpr int kShardAcc = 12;  // [0..3] g2 n2 gdot Jg2, [4..8] acc_A, [9] step2, [10] xnorm2, [11] candidate cost
+
 struct Batch {
   int B, NPB, NSB, NL, NC, NOBS, NIMU, NMEAS;
   int n_obs_tiles, n_lm_tiles;
@@ -170,7 +176,7 @@ struct Batch {
   // Sharded single-window mode (landmarks split over ranks): landmark-side partial sums go here instead of
   // WinState so that they can be all-reduced before k_fold adds them to the replicated dense-side sums.
   // [B][8]: g2, n2, gdot, Jg2 (k_backsub) | mc, step2, xnorm2 (k_step_lm) | cost of the reprojection terms.
-  double* shard_acc;  // nullptr when not sharded
+  double* shard_acc;  // nullptr when not sharded; kShardAcc doubles per window
   double* gmax_buf;   // [B] landmark gradient max, all-reduced with MAX
 };
 
