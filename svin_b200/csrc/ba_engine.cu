@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <cstdlib>
 #include <mutex>
 #include <functional>
 #include <condition_variable>
@@ -313,6 +314,8 @@ struct Region {
 struct svin_ba_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;  // dense-term evaluation runs here, concurrently with k_linearize
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   Batch b{};
   bool uploaded = false;
@@ -490,6 +493,15 @@ int svin_ba_create(int device, svin_ba_ctx** out) {
   svin_ba_ctx* c = new svin_ba_ctx();
   c->device = device;
   SVIN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    // higher priority: its small grid must be dispatched ahead of the remaining k_linearize CTAs, otherwise the
+    // work distributor only starts it in k_linearize's tail
+    int lo = 0, hi = 0;
+    SVIN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    SVIN_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));
+  }
+  SVIN_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  SVIN_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   for (auto& ev : c->ev) SVIN_CUDA(cudaEventCreate(&ev));
   SVIN_CUDA(cudaMalloc(&c->d_active, sizeof(int)));
   SVIN_CUDA(cudaMallocHost(&c->h_active, sizeof(int)));
@@ -513,6 +525,9 @@ void svin_ba_destroy(svin_ba_ctx* c) {
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->prof_events) cudaEventDestroy(ev);
   if (c->nccl_comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(c->nccl_comm);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->side) cudaStreamDestroy(c->side);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c->pool;
   delete c;
@@ -631,7 +646,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   const size_t o_otw = in.add(4 * (size_t)n_obs_tiles), o_otb = in.add(4 * (size_t)n_obs_tiles);
   const size_t o_ltw = in.add(4 * (size_t)n_lm_tiles), o_ltb = in.add(4 * (size_t)n_lm_tiles);
   const size_t o_sww = in.add(4 * (size_t)NSW), o_swb = in.add(4 * (size_t)NSW), o_swc = in.add(4 * (size_t)NSW);
-  const size_t o_swnr = in.add(4 * (size_t)NSW), o_swrf = in.add(4 * (size_t)NSW);
+  const size_t o_swnr = in.add(4 * (size_t)NSW), o_swrf = in.add(4 * (size_t)NSW), o_swlist = in.add(4 * (size_t)NSW);
   const size_t o_runoff = in.add(4 * (size_t)NRUN), o_runkm = in.add(4 * (size_t)NRUN);
   const size_t o_imu = in.add(sizeof(ImuTerm) * NIMU), o_imuc = in.add(sizeof(ImuCache) * NIMU);
   const size_t o_mt = in.add(8 * NMEAS), o_mg = in.add(24 * NMEAS), o_ma = in.add(24 * NMEAS);
@@ -871,6 +886,17 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     s.last_successful = 1;
     (void)cam_base; (void)ot; (void)lt; (void)sw; (void)meas_base;
   };
+  // chunk ids by lane-mapping class (one k_schur_mma<G> launch per class)
+  int sw_class_count[3] = {0, 0, 0};
+  {
+    int* h_swlist = (int*)hp(o_swlist);
+    for (int i = 0; i < B; ++i)
+      for (int cc : orders[i].chunk_count) sw_class_count[schur_chunk_class(cc)]++;
+    int pos[3] = {0, sw_class_count[0], sw_class_count[0] + sw_class_count[1]};
+    for (int i = 0; i < B; ++i)
+      for (size_t k = 0; k < orders[i].chunk_count.size(); ++k)
+        h_swlist[pos[schur_chunk_class(orders[i].chunk_count[k])]++] = sw_v[i] + (int)k;
+  }
   // Packing runs on the pool while this thread lays out the work arena; the big observation arrays are copied
   // group by group as soon as their windows are packed, so that the H2D transfer overlaps the packing.
   const int G = std::max(1, std::min(8, B / 16));
@@ -903,6 +929,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     o_rd[k] = wk.add(8 * NROWS);
   }
   const size_t o_wsw = wk.add(sizeof(WinState) * B), o_imucw = wk.add(sizeof(ImuCache) * NIMU);
+  const size_t o_opoff = wk.add(4 * S);
   const size_t o_sacc = wk.add(8 * kShardAcc * (size_t)B), o_gmaxb = wk.add(8 * (size_t)B);
   const size_t o_lms = wk.add(24 * NL), o_lmV = wk.add(48 * NL), o_lmb2 = wk.add(24 * NL), o_lmd = wk.add(24 * NL),
                o_lmg = wk.add(24 * NL), o_lmgn = wk.add(24 * NL);
@@ -943,14 +970,16 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   b.intr = (double*)(D + o_intr);
   b.obs_pose = (int*)(D + o_opose); b.obs_lm = (int*)(D + o_olm); b.obs_ext = (int*)(D + o_oext);
   b.obs_cam = (int*)(D + o_ocam);
+  b.obs_poff = (int*)(Wk + o_opoff);
   b.obs_zx = (double*)(D + o_zx); b.obs_zy = (double*)(D + o_zy);
   b.obs_u00 = (double*)(D + o_u00); b.obs_u01 = (double*)(D + o_u01); b.obs_u11 = (double*)(D + o_u11);
   b.lm_obs_first = (int*)(D + o_lmof); b.lm_obs_stride = (int*)(D + o_lmos); b.lm_obs_cnt = (int*)(D + o_lmoc);
   b.obs_tile_win = (int*)(D + o_otw); b.obs_tile_begin = (int*)(D + o_otb);
   b.lm_tile_win = (int*)(D + o_ltw); b.lm_tile_begin = (int*)(D + o_ltb);
   b.n_schur_warps = (int)NSW;
+  for (int k = 0; k < 3; ++k) b.sw_class_count[k] = sw_class_count[k];
   b.sw_win = (int*)(D + o_sww); b.sw_lm_begin = (int*)(D + o_swb); b.sw_count = (int*)(D + o_swc);
-  b.sw_nruns = (int*)(D + o_swnr); b.sw_run_first = (int*)(D + o_swrf);
+  b.sw_nruns = (int*)(D + o_swnr); b.sw_run_first = (int*)(D + o_swrf); b.sw_list = (int*)(D + o_swlist);
   b.run_off = (int*)(D + o_runoff); b.run_k0m = (int*)(D + o_runkm);
   b.imu = (ImuTerm*)(D + o_imu);
   c->d_imu_cache_init = (ImuCache*)(D + o_imuc);
@@ -1014,6 +1043,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   for (int k = 0; k < 2; ++k) SVIN_CUDA(cudaMemsetAsync(b.Jd[k], 0, 8 * (size_t)NJD + 8, c->stream));
   SVIN_CUDA(cudaMemsetAsync(b.lm_quality, 0, 8 * (size_t)NL + 8, c->stream));
   launch_reset_state(b, c->stream);
+  launch_obs_poff(b, c->stream);
   SVIN_CUDA(cudaMemcpyAsync(b.ws, c->d_ws_init, sizeof(WinState) * B, cudaMemcpyDeviceToDevice, c->stream));
   if (NIMU)
     SVIN_CUDA(cudaMemcpyAsync(b.imu_cache, c->d_imu_cache_init, sizeof(ImuCache) * NIMU, cudaMemcpyDeviceToDevice,
@@ -1117,12 +1147,28 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
     if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
     launch_fold(b, 3, c->stream);
   }
+  // candidate evaluation: the reprojection terms (k_linearize) and the dense terms (k_dense_eval, a small
+  // latency-bound grid) are independent -> run them concurrently on two streams.  Serial when profiling (per-kernel
+  // events) or sharded (the fold into cost_cand is not atomic).
+  static const bool no_fork = std::getenv("SVIN_BA_NO_FORK") != nullptr;  // debugging knob
+  const bool fork = !c->profiling && !sharded && !no_fork;
+  if (fork) {
+    SVIN_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    SVIN_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    launch_dense_eval(b, 1, 0, nullptr, c->side);
+    SVIN_CUDA(cudaEventRecord(c->ev_join, c->side));
+  }
   { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 1, 0, c->stream); }
   if (sharded) {
     if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
     launch_fold(b, 4, c->stream);
   }
-  { ProfScope p(c, SVIN_BA_K_DENSE_EVAL); launch_dense_eval(b, 1, 0, nullptr, c->stream); }
+  if (fork) {
+    SVIN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  } else {
+    ProfScope p(c, SVIN_BA_K_DENSE_EVAL);
+    launch_dense_eval(b, 1, 0, nullptr, c->stream);
+  }
   { ProfScope p(c, SVIN_BA_K_DECIDE); launch_decide(b, opt, c->stream); }
   c->tm.kernel_launches += 8;
   return SVIN_OK;

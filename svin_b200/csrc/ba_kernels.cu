@@ -197,6 +197,12 @@ template <bool HAS_EXT>
 __global__ void __launch_bounds__(kObsTile) k_linearize(Batch b, int which, int raw) {
   const int tile = blockIdx.x;
   const int w = b.obs_tile_win[tile];
+  const int o = b.obs_tile_begin[tile] + threadIdx.x;
+  // the observation record does not depend on the window state: issue its loads together with the state's
+  // (one dependent-load level less; the kernel is bound by this latency chain, not by bandwidth or fp64)
+  const int oc = min(o, b.NOBS - 1);
+  const int ip = b.obs_pose[oc], il = b.obs_lm[oc], ie = b.obs_ext[oc], ic = b.obs_cam[oc];
+  const double zx = b.obs_zx[oc], zy = b.obs_zy[oc], u00 = b.obs_u00[oc], u01 = b.obs_u01[oc], u11 = b.obs_u11[oc];
   WinState& ws = b.ws[w];
   if (!raw) {
     if (ws.done) return;
@@ -205,14 +211,12 @@ __global__ void __launch_bounds__(kObsTile) k_linearize(Batch b, int which, int 
   const WinDesc& wd = b.win[w];
   const int buf = (which == 0) ? ws.cur : 1 - ws.cur;
   const int sbuf = raw ? ws.cur : buf;  // state to read
-  const int o = b.obs_tile_begin[tile] + threadIdx.x;
   double cost[1] = {0.0};
   if (o < wd.obs_end) {
     Reproj R;
-    const int ip = b.obs_pose[o], il = b.obs_lm[o], ie = b.obs_ext[o], ic = b.obs_cam[o];
     reproj_eval<true, HAS_EXT>(b.pose[sbuf] + 7 * (size_t)ip, b.lm[sbuf] + 4 * (size_t)il,
-                               b.pose[sbuf] + 7 * (size_t)ie, b.intr + 8 * (size_t)ic, b.obs_zx[o], b.obs_zy[o],
-                               b.obs_u00[o], b.obs_u01[o], b.obs_u11[o], wd.loss_type, wd.loss_scale, raw != 0, R);
+                               b.pose[sbuf] + 7 * (size_t)ie, b.intr + 8 * (size_t)ic, zx, zy, u00, u01, u11,
+                               wd.loss_type, wd.loss_scale, raw != 0, R);
     cost[0] = R.cost;
     const size_t S = b.obs_stride;
     double* r = b.lin_r[buf];
@@ -598,9 +602,8 @@ __global__ void __launch_bounds__(kLmTile) k_schur(Batch b, SvinBaOptions opt) {
 //        damped landmark block), last row u = M b_l  ->  Y Y^T = [ W V^-1 W^T   W V^-1 b_l ; ... ]
 //        i.e. the whole Schur update of the k x k pose blocks and the reduced-gradient correction in one product.
 // One fp64 RED per produced entry.  The chunk size is capped at upload so that Y fits kSchurYDoubles.
-constexpr int kSchurYDoubles = 1776;   // Y operand per warp (3 CTAs of 4 warps per SM: 3 x 76.3 KB shared memory)
-constexpr int kSchurPld = 68;          // P tile leading dimension: 2 * 32 columns + 4 (bank spread)
-constexpr int kSchurPDoubles = 8 * kSchurPld;
+constexpr int kSchurYDoubles = 1680;   // Y operand per warp (3 CTAs of 4 warps per SM: 3 x 76.3 KB shared memory)
+constexpr int kSchurPDoubles = 640;    // P tiles: G x 8 x (2 * pad4(cnt) + 4) doubles, G * pad4(cnt) <= 32
 constexpr int kSchurMaxRuns = 64;      // run descriptors per warp: 2 ints each
 constexpr int kSchurWarpDoubles = kSchurYDoubles + kSchurPDoubles + kSchurMaxRuns;
 
@@ -630,23 +633,18 @@ __device__ __forceinline__ void spd3_inverse_factor(const double* V, double* Vi,
   M[0] = i00; M[1] = i10; M[2] = i11; M[3] = i20; M[4] = i21; M[5] = i22;
 }
 
-__global__ void __launch_bounds__(128, 3) k_schur_mma(Batch b, SvinBaOptions opt) {
-  extern __shared__ double sm_all[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int chunk = blockIdx.x * 4 + wid;
-  if (chunk >= b.n_schur_warps) return;
-  double* Ys = sm_all + (size_t)wid * kSchurWarpDoubles;
-  double* Ps = Ys + kSchurYDoubles;
-  int* rdesc = reinterpret_cast<int*>(Ps + kSchurPDoubles);  // [2r] dense offset of the run's pose block, [2r+1] k0<<8|m
-  const int w = b.sw_win[chunk];
-  WinState& ws = b.ws[w];
-  if (ws.done || ws.reuse) return;
-  const WinDesc& wd = b.win[w];
-  const int cnt = b.sw_count[chunk];
-  const int nr = b.sw_nruns[chunk];
-  const int rf = b.sw_run_first[chunk];
-  const bool active = lane < cnt;
-  const int l = b.sw_lm_begin[chunk] + (active ? lane : 0);
+// One chunk on one warp.  G lanes share a landmark when the chunk holds <= 32 / G landmarks: lane = j * CG + i
+// (i = landmark slot, j = sub-lane).  The sub-lanes split the observations in pass 1 (then xor-reduce) and the pose
+// runs in pass 2 (run a = t * G + j in round t, one P tile per sub-lane), so that the rare long-track patterns -
+// few landmarks, many runs - keep all 32 lanes busy instead of 2..8.
+template <int G>
+__device__ __forceinline__ void schur_chunk(const Batch& b, const SvinBaOptions& opt, WinState& ws, const WinDesc& wd,
+                                            int chunk, int cnt, int nr, double* Ys, double* Ps, const int* rdesc,
+                                            int lane) {
+  constexpr int CG = 32 / G;
+  const int i = lane & (CG - 1), j = lane / CG;
+  const bool active = i < cnt;
+  const int l = b.sw_lm_begin[chunk] + (active ? i : 0);
   const int buf = ws.cur;
   const int n = wd.n_dense;
   double* H = b.H + wd.H_off;
@@ -662,20 +660,27 @@ __global__ void __launch_bounds__(128, 3) k_schur_mma(Batch b, SvinBaOptions opt
   const double* rP = b.lin_r[buf];
   const double* JpP = b.lin_Jp[buf];
   const double* JlP = b.lin_Jl[buf];
-  for (int r = lane; r < nr; r += 32) {
-    rdesc[2 * r] = b.run_off[rf + r];
-    rdesc[2 * r + 1] = b.run_k0m[rf + r];
-  }
-  for (int e = lane; e < kSchurPDoubles; e += 32) Ps[e] = 0.0;
+  const int cntp = (cnt + 3) & ~3;    // landmark columns of a P tile per residual row
+  const int K4p = cntp >> 1;          // k-steps over its 2 * cntp columns
+  const int ldp = 2 * cntp + 4;
+  const int K4 = (3 * cnt + 3) >> 2;  // k-steps over the 3 * cnt columns of Y
+  const int ld = 4 * K4 + 4;
+  for (int e = lane; e < G * ldp; e += 32) Ps[(e / ldp) * 8 * ldp + 7 * ldp + (e % ldp)] = 0.0;  // row 7 of every tile
 
-  // ---- pass 1: V = sum Jl^T Jl, bl = sum Jl^T r (unscaled)
+  // ---- pass 1: V = sum Jl^T Jl, bl = sum Jl^T r (unscaled); the sub-lanes take every G-th observation
   double V[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
-  for (int k = 0; k < nobs; ++k) {
+  for (int k = j; k < nobs; k += 2 * G) {  // two observations in flight per trip
     const int o = ob + k * ost;
+    const bool two = k + G < nobs;
+    const int ob2 = two ? o + G * ost : o;
     const double r0 = rP[o], r1 = rP[S + o];
-    double a[6];
+    const double q0 = rP[ob2], q1 = rP[S + ob2];
+    double a[6], c[6];
 #pragma unroll
     for (int q = 0; q < 6; ++q) a[q] = JlP[q * S + o];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) c[q] = JlP[q * S + ob2];
+    const double w2 = two ? 1.0 : 0.0;
     V[0] += a[0] * a[0] + a[3] * a[3];
     V[1] += a[0] * a[1] + a[3] * a[4];
     V[2] += a[0] * a[2] + a[3] * a[5];
@@ -685,16 +690,35 @@ __global__ void __launch_bounds__(128, 3) k_schur_mma(Batch b, SvinBaOptions opt
     bl[0] += a[0] * r0 + a[3] * r1;
     bl[1] += a[1] * r0 + a[4] * r1;
     bl[2] += a[2] * r0 + a[5] * r1;
+    V[0] += w2 * (c[0] * c[0] + c[3] * c[3]);
+    V[1] += w2 * (c[0] * c[1] + c[3] * c[4]);
+    V[2] += w2 * (c[0] * c[2] + c[3] * c[5]);
+    V[3] += w2 * (c[1] * c[1] + c[4] * c[4]);
+    V[4] += w2 * (c[1] * c[2] + c[4] * c[5]);
+    V[5] += w2 * (c[2] * c[2] + c[5] * c[5]);
+    bl[0] += w2 * (c[0] * q0 + c[3] * q1);
+    bl[1] += w2 * (c[1] * q0 + c[4] * q1);
+    bl[2] += w2 * (c[2] * q0 + c[5] * q1);
+  }
+  if (G > 1) {
+#pragma unroll
+    for (int o2 = CG; o2 < 32; o2 <<= 1) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) V[q] += __shfl_xor_sync(0xffffffffu, V[q], o2);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) bl[q] += __shfl_xor_sync(0xffffffffu, bl[q], o2);
+    }
   }
   double s[3] = {1.0, 1.0, 1.0}, M[6] = {0, 0, 0, 0, 0, 0}, u[3] = {0, 0, 0};
   if (!lfix) {
+    const bool owner = active && j == 0;
     if (ws.iter == 0 && ws.num_successful == 0 && !ws.invalid) {
       if (opt.jacobi_scaling) {
         s[0] = 1.0 / (1.0 + sqrt(V[0]));
         s[1] = 1.0 / (1.0 + sqrt(V[3]));
         s[2] = 1.0 / (1.0 + sqrt(V[5]));
       }
-      if (active) {
+      if (owner) {
         b.lm_scale[3 * (size_t)l] = s[0];
         b.lm_scale[3 * (size_t)l + 1] = s[1];
         b.lm_scale[3 * (size_t)l + 2] = s[2];
@@ -722,7 +746,7 @@ __global__ void __launch_bounds__(128, 3) k_schur_mma(Batch b, SvinBaOptions opt
     u[0] = M[0] * bs0;
     u[1] = M[1] * bs0 + M[2] * bs1;
     u[2] = M[3] * bs0 + M[4] * bs1 + M[5] * bs2;
-    if (active) {
+    if (owner) {
       double* p = b.lm_Vinv + 6 * (size_t)l;
 #pragma unroll
       for (int k = 0; k < 6; ++k) p[k] = Vi[k];
@@ -737,66 +761,95 @@ __global__ void __launch_bounds__(128, 3) k_schur_mma(Batch b, SvinBaOptions opt
   __syncwarp();
 
   const int fr = lane >> 2, fc = lane & 3;
-  const int cntp = (cnt + 3) & ~3;    // landmark columns of the P tile per residual row
-  const int K4p = cntp >> 1;          // k-steps over the 2 * cntp columns
-  const int K4 = (3 * cnt + 3) >> 2;  // k-steps over the 3 * cnt columns of Y
-  const int ld = 4 * K4 + 4;
-
+  double* Pt = Ps + j * 8 * ldp;  // this sub-lane's tile
   // ---- pass 2: per pose run: P P^T on the tensor cores -> diagonal block / gradients; Y rows -> shared memory
-  for (int a = 0; a < nr; ++a) {
-    const int offp = rdesc[2 * a];
-    const int k0 = rdesc[2 * a + 1] >> 8, m = rdesc[2 * a + 1] & 255;
+  for (int t = 0; t * G < nr; ++t) {
+    const int a = t * G + j;
+    const bool vr = a < nr;
+    const int offp = vr ? rdesc[2 * a] : -1;
+    const int k0 = vr ? (rdesc[2 * a + 1] >> 8) : 0, m = vr ? (rdesc[2 * a + 1] & 255) : 0;
+    int mmax = 0;  // warp-uniform: most observations of any estimated run of this round
+#pragma unroll
+    for (int jj = 0; jj < G; ++jj) {
+      const int a2 = t * G + jj;
+      if (a2 < nr && rdesc[2 * a2] >= 0) mmax = max(mmax, rdesc[2 * a2 + 1] & 255);
+    }
     double W[18];
 #pragma unroll
     for (int k = 0; k < 18; ++k) W[k] = 0;
-    if (offp >= 0) {
-      double c0 = 0.0, c1 = 0.0;
-      for (int k = k0; k < k0 + m; ++k) {
-        const int o = ob + k * ost;
+    double c[G][2];
+#pragma unroll
+    for (int jj = 0; jj < G; ++jj) c[jj][0] = c[jj][1] = 0.0;
+    for (int q = 0; q < mmax; ++q) {
+      if (offp >= 0 && q < m) {
+        const int o = ob + (k0 + q) * ost;
         double Jp[12], Jls[6];
 #pragma unroll
-        for (int q = 0; q < 12; ++q) Jp[q] = JpP[q * S + o];
+        for (int e = 0; e < 12; ++e) Jp[e] = JpP[e * S + o];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) Jls[q] = JlP[q * S + o] * s[q % 3];
+        for (int e = 0; e < 6; ++e) Jls[e] = JlP[e * S + o] * s[e % 3];
         const double r0 = rP[o], r1 = rP[S + o];
         acc_W(Jp, Jls, W);
-        if (active) {
+        if (i < cntp) {
+          const double wgt = active ? 1.0 : 0.0;
 #pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            Ps[q * kSchurPld + lane] = Jp[q];
-            Ps[q * kSchurPld + cntp + lane] = Jp[6 + q];
+          for (int e = 0; e < 6; ++e) {
+            Pt[e * ldp + i] = wgt * Jp[e];
+            Pt[e * ldp + cntp + i] = wgt * Jp[6 + e];
           }
-          Ps[6 * kSchurPld + lane] = r0;
-          Ps[6 * kSchurPld + cntp + lane] = r1;
+          Pt[6 * ldp + i] = wgt * r0;
+          Pt[6 * ldp + cntp + i] = wgt * r1;
         }
-        __syncwarp();
-        const double* pa = Ps + fr * kSchurPld + fc;
-        for (int ks = 0; ks < K4p; ++ks) {
-          const double x = pa[4 * ks];
-          dmma8x8x4(c0, c1, x, x);
+      } else if (i < cntp) {
+#pragma unroll
+        for (int e = 0; e < 7; ++e) {
+          Pt[e * ldp + i] = 0.0;
+          Pt[e * ldp + cntp + i] = 0.0;
         }
-        __syncwarp();
       }
-      if (fr < 6) {
+      __syncwarp();
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int col = 2 * fc + e;
-          const double val = e ? c1 : c0;
-          if (col < 6) {
-            if (fr <= col) atomicAdd(&H[(size_t)(offp + fr) * n + offp + col], val);
-            if (fr == col) atomicAdd(&Hdiag[offp + fr], val);
-          } else if (col == 6) {
-            atomicAdd(&g_red[offp + fr], val);
-            atomicAdd(&g_raw[offp + fr], val);
+      for (int jj = 0; jj < G; ++jj) {
+        const int a2 = t * G + jj;
+        if (a2 < nr && rdesc[2 * a2] >= 0 && q < (rdesc[2 * a2 + 1] & 255)) {  // warp-uniform
+          // two independent accumulator pairs (K4p is even): the DMMA chain is latency-, not throughput-limited
+          const double* pa = Ps + jj * 8 * ldp + fr * ldp + fc;
+          double e0 = 0.0, e1 = 0.0;
+          for (int ks = 0; ks < K4p; ks += 2) {
+            const double x = pa[4 * ks], y = pa[4 * ks + 4];
+            dmma8x8x4(c[jj][0], c[jj][1], x, x);
+            dmma8x8x4(e0, e1, y, y);
           }
+          c[jj][0] += e0;
+          c[jj][1] += e1;
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int jj = 0; jj < G; ++jj) {
+      const int a2 = t * G + jj;
+      if (a2 >= nr) continue;
+      const int off2 = rdesc[2 * a2];
+      if (off2 < 0 || fr >= 6) continue;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = 2 * fc + e;
+        const double val = e ? c[jj][1] : c[jj][0];
+        if (col < 6) {
+          if (fr <= col) atomicAdd(&H[(size_t)(off2 + fr) * n + off2 + col], val);
+          if (fr == col) atomicAdd(&Hdiag[off2 + fr], val);
+        } else if (col == 6) {
+          atomicAdd(&g_red[off2 + fr], val);
+          atomicAdd(&g_raw[off2 + fr], val);
         }
       }
     }
-    if (!lfix && active) {
+    if (vr && !lfix && active) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const double w0 = W[i * 3], w1 = W[i * 3 + 1], w2 = W[i * 3 + 2];
-        double* yr = Ys + (6 * a + i) * ld + 3 * lane;
+      for (int e = 0; e < 6; ++e) {
+        const double w0 = W[e * 3], w1 = W[e * 3 + 1], w2 = W[e * 3 + 2];
+        double* yr = Ys + (6 * a + e) * ld + 3 * i;
         yr[0] = w0 * M[0];
         yr[1] = w0 * M[1] + w1 * M[2];
         yr[2] = w0 * M[3] + w1 * M[4] + w2 * M[5];
@@ -805,52 +858,81 @@ __global__ void __launch_bounds__(128, 3) k_schur_mma(Batch b, SvinBaOptions opt
   }
   if (lfix) return;
   const int R = 6 * nr, RY = R + 1, T = (RY + 7) >> 3;
-  if (active) {
-    double* yr = Ys + R * ld + 3 * lane;
+  if (active && j == 0) {
+    double* yr = Ys + R * ld + 3 * i;
     yr[0] = u[0]; yr[1] = u[1]; yr[2] = u[2];
   }
   // zero the k padding: columns [3 cnt, 4 K4) of every row
   for (int r = lane; r < RY; r += 32)
-    for (int c = 3 * cnt; c < 4 * K4; ++c) Ys[r * ld + c] = 0.0;
+    for (int cc = 3 * cnt; cc < 4 * K4; ++cc) Ys[r * ld + cc] = 0.0;
+  // row -> dense index of the reduced system (-1: fixed block); lives in the P tiles, which are free now
+  int* rowmap = reinterpret_cast<int*>(Ps);
+  for (int r = lane; r < R; r += 32) {
+    const int op = rdesc[2 * (r / 6)];
+    rowmap[r] = op < 0 ? -1 : op + r % 6;
+  }
   __syncwarp();
-  // ---- C = Y Y^T on the tensor cores, upper tiles only; one RED per upper-triangular entry
+  // ---- C = Y Y^T on the tensor cores, upper tiles only; one RED per upper-triangular entry.
+  // Rows >= RY of the last tile read whatever follows in this warp's shared memory: entry (gi, gj) depends on rows
+  // gi and gj only and those entries are never written out.
   for (int tm = 0; tm < T; ++tm) {
-    const int ra = 8 * tm + fr;
-    const bool va = ra < RY;
-    const double* za = Ys + (va ? ra : 0) * ld + fc;
+    const int gi = 8 * tm + fr;
+    const double* za = Ys + (gi < RY ? gi : 0) * ld + fc;
+    const int ri = gi < R ? rowmap[gi] : -1;
     for (int tn = tm; tn < T; ++tn) {
       const int rb = 8 * tn + fr;
-      const bool vb = rb < RY;
-      const double* zb = Ys + (vb ? rb : 0) * ld + fc;
-      double c0 = 0.0, c1 = 0.0;
-      for (int ks = 0; ks < K4; ++ks) {
-        const double xa = va ? za[4 * ks] : 0.0;
-        const double xb = vb ? zb[4 * ks] : 0.0;
-        dmma8x8x4(c0, c1, xa, xb);
+      const double* zb = Ys + (rb < RY ? rb : 0) * ld + fc;
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+      int ks = 0;
+      for (; ks + 1 < K4; ks += 2) {
+        dmma8x8x4(c0, c1, za[4 * ks], zb[4 * ks]);
+        dmma8x8x4(e0, e1, za[4 * ks + 4], zb[4 * ks + 4]);
       }
-      const int gi = ra;
+      if (ks < K4) dmma8x8x4(c0, c1, za[4 * ks], zb[4 * ks]);
+      c0 += e0;
+      c1 += e1;
+      if (ri < 0) continue;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int gj = 8 * tn + 2 * fc + e;
-        if (gi < R && gj <= R && gi <= gj) {
-          const double val = e ? c1 : c0;
-          const int rp = gi / 6, ai = gi - 6 * rp;
-          const int op = rdesc[2 * rp];
-          if (op < 0) continue;
-          if (gj == R) {
-            atomicAdd(&g_red[op + ai], -val);
-          } else {
-            const int rq = gj / 6, cj = gj - 6 * rq;
-            const int oq = rdesc[2 * rq];
-            if (oq >= 0) {
-              double* dst = (op <= oq) ? &H[(size_t)(op + ai) * n + oq + cj] : &H[(size_t)(oq + cj) * n + op + ai];
-              atomicAdd(dst, -val);
-            }
-          }
+        if (gj > R || gi > gj) continue;
+        const double val = e ? c1 : c0;
+        if (gj == R) {
+          atomicAdd(&g_red[ri], -val);
+        } else {
+          const int rj = rowmap[gj];
+          if (rj >= 0) atomicAdd(&H[min(ri, rj) * n + max(ri, rj)], -val);
         }
       }
     }
   }
+}
+
+// One kernel per lane mapping (chunks are listed by class at upload): keeps each kernel's SASS small enough for
+// the instruction cache - the three mappings in one kernel were 120 KB and 18 % of the stalls were "no instruction".
+template <int G>
+__global__ void __launch_bounds__(128, 3) k_schur_mma(Batch b, SvinBaOptions opt, const int* list, int count) {
+  extern __shared__ double sm_all[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int slot = blockIdx.x * 4 + wid;
+  if (slot >= count) return;
+  const int chunk = list[slot];
+  double* Ys = sm_all + (size_t)wid * kSchurWarpDoubles;
+  double* Ps = Ys + kSchurYDoubles;
+  int* rdesc = reinterpret_cast<int*>(Ps + kSchurPDoubles);  // [2r] dense offset of the run's pose block, [2r+1] k0<<8|m
+  const int w = b.sw_win[chunk];
+  WinState& ws = b.ws[w];
+  if (ws.done || ws.reuse) return;
+  const WinDesc& wd = b.win[w];
+  const int cnt = b.sw_count[chunk];
+  const int nr = b.sw_nruns[chunk];
+  const int rf = b.sw_run_first[chunk];
+  for (int r = lane; r < nr; r += 32) {
+    rdesc[2 * r] = b.run_off[rf + r];
+    rdesc[2 * r + 1] = b.run_k0m[rf + r];
+  }
+  __syncwarp();
+  schur_chunk<G>(b, opt, ws, wd, chunk, cnt, nr, Ys, Ps, rdesc, lane);
 }
 
 // ------------------------------------------------------------------------------------------ dense terms
@@ -1710,7 +1792,7 @@ __global__ void __launch_bounds__(kLmTile) k_backsub(Batch b) {
       const int o = ob + k * ost;
       ObsJ J;
       load_obs(b, buf, o, J);
-      const int offp = b.pose_off[b.obs_pose[o]];
+      const int offp = b.obs_poff[o];
       double t0 = 0, t1 = 0, m0 = 0, m1 = 0;
       if (offp >= 0) {
 #pragma unroll
@@ -2099,6 +2181,13 @@ __global__ void k_gmax_pack(Batch b, int unpack) {
   else
     b.ws[w].gmax_bits = (unsigned long long)__double_as_longlong(b.gmax_buf[w]);
 }
+__global__ void k_obs_poff(Batch b) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o < b.NOBS) b.obs_poff[o] = b.pose_off[b.obs_pose[o]];
+}
+void launch_obs_poff(const Batch& b, cudaStream_t st) {
+  if (b.NOBS) k_obs_poff<<<div_up(b.NOBS, 256), 256, 0, st>>>(b);
+}
 void launch_fold(const Batch& b, int stage, cudaStream_t st) { k_fold<<<div_up(b.B, 64), 64, 0, st>>>(b, stage); }
 void launch_gmax_pack(const Batch& b, int unpack, cudaStream_t st) {
   k_gmax_pack<<<div_up(b.B, 64), 64, 0, st>>>(b, unpack);
@@ -2115,8 +2204,14 @@ int schur_mma_max_chunk(int runs) {
   return best;
 }
 cudaError_t configure_schur() {
-  return cudaFuncSetAttribute(k_schur_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_mma_smem_bytes());
+  cudaError_t e = cudaFuncSetAttribute(k_schur_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_mma_smem_bytes());
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_schur_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_mma_smem_bytes());
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_schur_mma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_mma_smem_bytes());
+  return e;
 }
+int schur_chunk_class(int count) { return count <= 8 ? 2 : (count <= 16 ? 1 : 0); }
 
 // ------------------------------------------------------------------------------------------ launchers
 
@@ -2142,8 +2237,16 @@ void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {
   if (b.n_lm_tiles == 0) return;
   if (b.has_ext)
     k_schur<true><<<b.n_lm_tiles, kLmTile, 0, st>>>(b, opt);
-  else if (b.n_schur_warps > 0)
-    k_schur_mma<<<div_up(b.n_schur_warps, 4), 128, schur_mma_smem_bytes(), st>>>(b, opt);
+  else if (b.n_schur_warps > 0) {
+    // class 0: > 16 landmarks per chunk (lane = landmark), 1: 9..16 (2 lanes / landmark), 2: <= 8 (4 lanes / landmark)
+    const int* list = b.sw_list;
+    const size_t sm = schur_mma_smem_bytes();
+    if (b.sw_class_count[0]) k_schur_mma<1><<<div_up(b.sw_class_count[0], 4), 128, sm, st>>>(b, opt, list, b.sw_class_count[0]);
+    list += b.sw_class_count[0];
+    if (b.sw_class_count[1]) k_schur_mma<2><<<div_up(b.sw_class_count[1], 4), 128, sm, st>>>(b, opt, list, b.sw_class_count[1]);
+    list += b.sw_class_count[1];
+    if (b.sw_class_count[2]) k_schur_mma<4><<<div_up(b.sw_class_count[2], 4), 128, sm, st>>>(b, opt, list, b.sw_class_count[2]);
+  }
   else
     k_schur<false><<<b.n_lm_tiles, kLmTile, 0, st>>>(b, opt);
 }

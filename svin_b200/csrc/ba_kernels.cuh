@@ -21,7 +21,9 @@ void launch_quality(const Batch& b, cudaStream_t st);
 size_t schur_mma_smem_bytes();
 int schur_mma_max_chunk(int runs);
 cudaError_t configure_schur();
+int schur_chunk_class(int count);  // which k_schur_mma<G> handles a chunk of `count` landmarks
 void launch_fold(const Batch& b, int stage, cudaStream_t st);
+void launch_obs_poff(const Batch& b, cudaStream_t st);  // obs_poff[o] = pose_off[obs_pose[o]], once per upload
 void launch_gmax_pack(const Batch& b, int unpack, cudaStream_t st);
 struct MargArgs {
   int w;                // window

@@ -135,6 +135,7 @@ struct Batch {
   double* intr;  // [NC*8]
   // observations (sorted by landmark, pose, camera)
   int *obs_pose, *obs_lm, *obs_ext, *obs_cam;
+  int* obs_poff;  // dense offset of the observation's pose block (pose_off[obs_pose]), filled on the device at upload
   double *obs_zx, *obs_zy, *obs_u00, *obs_u01, *obs_u11;
   // observations of landmark l are  lm_obs_first[l] + k * lm_obs_stride[l],  k < lm_obs_cnt[l].
   // Inside a Schur chunk (landmarks sharing one observation pattern) they are stored pattern-major
@@ -145,6 +146,8 @@ struct Batch {
   // Schur warp chunks: <= 32 consecutive landmarks with an identical (pose, camera) observation pattern
   int n_schur_warps;
   int *sw_win, *sw_lm_begin, *sw_count;
+  int* sw_list;           // chunk ids ordered by lane-mapping class (schur_chunk_class), sw_class_count each
+  int sw_class_count[3];
   int *sw_nruns, *sw_run_first;  // pose runs of the chunk's pattern: count, first entry in run_off / run_k0m
   int *run_off, *run_k0m;        // per run: dense offset of its pose block (-1 fixed), (first obs k << 8) | obs count
   // linearisation, two buffers: planes [k][obs_stride]
