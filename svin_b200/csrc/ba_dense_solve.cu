@@ -20,42 +20,33 @@ namespace {
 constexpr int kTS = 16;              // thread layout kTS x kTS
 constexpr int kNT = 7;               // accumulators per thread per dimension in one panel
 constexpr int kPanel = kTS * kNT;    // 112 columns per panel
-constexpr int kRT = 8;               // dense-term rows staged per tile
 
 __device__ __forceinline__ int tri(int i, int j) { return (i * (i + 1) >> 1) + j; }  // j <= i
 }  // namespace
 
-size_t dense_solve_smem_bytes(int n) {
-  const size_t a = (size_t)(n + 1) * (n + 2) / 2;
-  return sizeof(double) * (a + (size_t)kRT * n + kRT + 8 * (size_t)n + 16);
-}
+// G = Jd^T Jd (lower triangle of a row-major n x n block at H_off) and gg = Jd^T rd of the dense-term rows of one
+// state buffer.  Runs right after k_dense_eval - for the candidate on the side stream, hidden behind k_linearize -
+// so that k_dense_solve_smem only adds it to the landmark-eliminated blocks.
+constexpr int kGR = 16;  // rows staged per tile
+size_t dense_gram_smem_bytes(int n) { return sizeof(double) * ((size_t)kGR * n + kGR); }
 
-__global__ void __launch_bounds__(kTS* kTS, 2) k_dense_solve_smem(Batch b, SvinBaOptions opt) {
+__global__ void __launch_bounds__(kTS* kTS, 2) k_dense_gram(Batch b, int which) {
   extern __shared__ double smem[];
   const int w = blockIdx.x;
   WinState& ws = b.ws[w];
-  if (ws.done || ws.reuse) return;
+  if (ws.done) return;
+  if (which == 1 && (ws.skip_slot || ws.gn_failed || !(-ws.acc_mc > 0.0))) return;  // as k_dense_eval
   const WinDesc& wd = b.win[w];
-  const int n = wd.n_dense, M = wd.n_rows, buf = ws.cur;
+  const int buf = (which == 0) ? ws.cur : 1 - ws.cur;
+  const int n = wd.n_dense, M = wd.n_rows;
   const int tid = threadIdx.x, tx = tid & (kTS - 1), ty = tid >> 4;
-  const int lane = tid & 31, wid = tid >> 5;
-  double* A = smem;
-  double* Js = A + (size_t)(n + 1) * (n + 2) / 2;
-  double* rds = Js + (size_t)kRT * n;
-  double* v_hd = rds + kRT;     // column square norms
-  double* v_graw = v_hd + n;    // unreduced gradient
-  double* v_gred = v_graw + n;  // reduced rhs
-  double* v_sc = v_gred + n;    // Jacobi scale
-  double* v_dg = v_sc + n;      // dogleg diagonal
-  double* v_c = v_dg + n;       // scale * gradient_ / diag (Cauchy direction, unscaled space)
-  double* v_tmp = v_c + n;
-  const double* Hg = b.H + wd.H_off;
+  double* Js = smem;
+  double* rds = Js + (size_t)kGR * n;
   const double* Jd = b.Jd[buf] + wd.Jd_off;
   const double* rd = b.rd[buf] + wd.rd_off;
-  __shared__ unsigned long long gmax_s;
-
-  // ---- 1. A(lower) = H~ + Jd^T Jd, panel by panel; vectors on the first pass
-  double hd_acc = 0.0, gr_acc = 0.0;  // thread tid < n owns column tid
+  double* G = b.gram[buf] + wd.H_off;
+  double* gg = b.gram_g[buf] + wd.d_off;
+  double gr_acc = 0.0;
   const int n_panels = (n + kPanel - 1) / kPanel;
   for (int ip = 0; ip < n_panels; ++ip)
     for (int jp = 0; jp <= ip; ++jp) {
@@ -65,8 +56,8 @@ __global__ void __launch_bounds__(kTS* kTS, 2) k_dense_solve_smem(Batch b, SvinB
 #pragma unroll
         for (int y = 0; y < kNT; ++y) acc[x][y] = 0.0;
       const bool first = (ip == 0 && jp == 0);
-      for (int r0 = 0; r0 < M; r0 += kRT) {
-        const int rows = min(kRT, M - r0);
+      for (int r0 = 0; r0 < M; r0 += kGR) {
+        const int rows = min(kGR, M - r0);
         __syncthreads();
         for (int e = tid; e < rows * n; e += kTS * kTS) Js[e] = Jd[(size_t)r0 * n + e];
         if (tid < rows) rds[tid] = rd[r0 + tid];
@@ -85,11 +76,7 @@ __global__ void __launch_bounds__(kTS* kTS, 2) k_dense_solve_smem(Batch b, SvinB
           for (int x = 0; x < kNT; ++x)
 #pragma unroll
             for (int y = 0; y < kNT; ++y) acc[x][y] += a[x] * c[y];
-          if (first && tid < n) {
-            const double jv = row[tid];
-            hd_acc += jv * jv;
-            gr_acc += jv * rds[r];
-          }
+          if (first && tid < n) gr_acc += row[tid] * rds[r];
         }
       }
 #pragma unroll
@@ -97,9 +84,52 @@ __global__ void __launch_bounds__(kTS* kTS, 2) k_dense_solve_smem(Batch b, SvinB
 #pragma unroll
         for (int y = 0; y < kNT; ++y) {
           const int i = ip * kPanel + ty + kTS * x, j = jp * kPanel + tx + kTS * y;
-          if (i < n && j <= i) A[tri(i, j)] = acc[x][y] + Hg[(size_t)j * n + i];  // H~ keeps the upper triangle
+          if (i < n && j <= i) G[(size_t)i * n + j] = acc[x][y];
         }
     }
+  if (tid < n) gg[tid] = gr_acc;
+}
+cudaError_t configure_dense_gram(int smem_bytes) {
+  return cudaFuncSetAttribute(k_dense_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+}
+void launch_dense_gram(const Batch& b, int which, int n_max, cudaStream_t st) {
+  k_dense_gram<<<b.B, kTS * kTS, dense_gram_smem_bytes(n_max), st>>>(b, which);
+}
+
+size_t dense_solve_smem_bytes(int n) {
+  const size_t a = (size_t)(n + 1) * (n + 2) / 2;
+  return sizeof(double) * (a + 8 * (size_t)n + 16);
+}
+
+__global__ void __launch_bounds__(kTS* kTS, 2) k_dense_solve_smem(Batch b, SvinBaOptions opt) {
+  extern __shared__ double smem[];
+  const int w = blockIdx.x;
+  WinState& ws = b.ws[w];
+  if (ws.done || ws.reuse) return;
+  const WinDesc& wd = b.win[w];
+  const int n = wd.n_dense, buf = ws.cur;
+  const int tid = threadIdx.x, tx = tid & (kTS - 1), ty = tid >> 4;
+  const int lane = tid & 31, wid = tid >> 5;
+  double* A = smem;
+  double* v_hd = A + (size_t)(n + 1) * (n + 2) / 2;  // column square norms
+  double* v_graw = v_hd + n;    // unreduced gradient
+  double* v_gred = v_graw + n;  // reduced rhs
+  double* v_sc = v_gred + n;    // Jacobi scale
+  double* v_dg = v_sc + n;      // dogleg diagonal
+  double* v_c = v_dg + n;       // scale * gradient_ / diag (Cauchy direction, unscaled space)
+  double* v_tmp = v_c + n;
+  const double* Hg = b.H + wd.H_off;
+  __shared__ unsigned long long gmax_s;
+
+  // ---- 1. A(lower) = H~ + Jd^T Jd; the Gram matrix of the dense rows comes from k_dense_gram
+  const double* G = b.gram[buf] + wd.H_off;
+  for (int i = ty; i < n; i += kTS) {
+    const double* Gi = G + (size_t)i * n;
+    double* Ai = A + tri(i, 0);
+    for (int j = tx; j <= i; j += kTS) Ai[j] = Gi[j] + Hg[(size_t)j * n + i];  // H~ keeps the upper triangle
+  }
+  const double hd_acc = (tid < n) ? G[(size_t)tid * n + tid] : 0.0;
+  const double gr_acc = (tid < n) ? b.gram_g[buf][wd.d_off + tid] : 0.0;
   // ---- 2. vectors
   double gmax_l = 0.0;
   if (tid < n) {
@@ -228,20 +258,15 @@ __global__ void __launch_bounds__(kTS* kTS, 2) k_dense_solve_smem(Batch b, SvinB
     }
     return;
   }
-  // Cauchy point over the dense rows: sum_r (Jd[r,:] . c)^2, one warp per row of each tile
+  // Cauchy point over the dense rows: sum_r (Jd[r,:] . c)^2 = c^T (Jd^T Jd) c with the Gram matrix (lower triangle)
+  __syncthreads();
   double jg2 = 0.0;
-  for (int r0 = 0; r0 < M; r0 += kRT) {
-    const int rows = min(kRT, M - r0);
-    __syncthreads();
-    for (int e = tid; e < rows * n; e += kTS * kTS) Js[e] = Jd[(size_t)r0 * n + e];
-    __syncthreads();
-    if (wid < rows) {
-      const double* row = Js + wid * n;
-      double s = 0.0;
-      for (int i = lane; i < n; i += 32) s += row[i] * v_c[i];
-      s = warp_sum(s);
-      if (lane == 0) jg2 += s * s;
-    }
+  for (int i = wid; i < n; i += kTS * kTS / 32) {
+    const double* Gi = G + (size_t)i * n;
+    double sdot = 0.0;
+    for (int j = lane; j < i; j += 32) sdot += Gi[j] * v_c[j];
+    sdot = warp_sum(sdot);
+    if (lane == 0) jg2 += v_c[i] * (2.0 * sdot + Gi[i] * v_c[i]);
   }
   double v[4] = {g2, n2, gd, jg2};
   double* const dst[4] = {&ws.acc_g2, &ws.acc_n2, &ws.acc_gdot, &ws.acc_Jg2};

@@ -916,7 +916,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   // ---------------- work arena
   const size_t S = ((size_t)NOBS + 31) & ~(size_t)31;
   Region wk;
-  size_t o_poseb[2], o_sbb[2], o_lmb[2], o_r[2], o_Jp[2], o_Jl[2], o_Je[2], o_Jd[2], o_rd[2];
+  size_t o_poseb[2], o_sbb[2], o_lmb[2], o_r[2], o_Jp[2], o_Jl[2], o_Je[2], o_Jd[2], o_rd[2], o_gram[2], o_gramg[2];
   for (int k = 0; k < 2; ++k) {
     o_poseb[k] = wk.add(56 * NPB);
     o_sbb[k] = wk.add(72 * NSB);
@@ -927,6 +927,8 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     o_Je[k] = has_ext ? wk.add(8 * 12 * S) : 0;
     o_Jd[k] = wk.add(8 * NJD);
     o_rd[k] = wk.add(8 * NROWS);
+    o_gram[k] = wk.add(8 * NH);
+    o_gramg[k] = wk.add(8 * ND);
   }
   const size_t o_wsw = wk.add(sizeof(WinState) * B), o_imucw = wk.add(sizeof(ImuCache) * NIMU);
   const size_t o_opoff = wk.add(4 * S);
@@ -993,6 +995,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     b.lin_r[k] = (double*)(Wk + o_r[k]); b.lin_Jp[k] = (double*)(Wk + o_Jp[k]); b.lin_Jl[k] = (double*)(Wk + o_Jl[k]);
     b.lin_Je[k] = has_ext ? (double*)(Wk + o_Je[k]) : nullptr;
     b.Jd[k] = (double*)(Wk + o_Jd[k]); b.rd[k] = (double*)(Wk + o_rd[k]);
+    b.gram[k] = (double*)(Wk + o_gram[k]); b.gram_g[k] = (double*)(Wk + o_gramg[k]);
   }
   b.lm_scale = (double*)(Wk + o_lms); b.lm_Vinv = (double*)(Wk + o_lmV); b.lm_bs = (double*)(Wk + o_lmb2);
   b.lm_diag = (double*)(Wk + o_lmd); b.lm_grad = (double*)(Wk + o_lmg); b.lm_gn = (double*)(Wk + o_lmgn);
@@ -1053,7 +1056,10 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   {
     const size_t need = dense_solve_smem_bytes(c->n_max);
     c->smem_bytes = (need <= 227 * 1024 && c->n_max <= 256 && c->n_max > 0) ? (int)need : 0;
-    if (c->smem_bytes > 0) SVIN_CUDA(configure_dense_solve(c->smem_bytes));
+    if (c->smem_bytes > 0) {
+      SVIN_CUDA(configure_dense_solve(c->smem_bytes));
+      SVIN_CUDA(configure_dense_gram((int)dense_gram_smem_bytes(c->n_max)));
+    }
     SVIN_CUDA(configure_schur());
   }
   SVIN_CUDA(cudaStreamSynchronize(c->stream));
@@ -1156,6 +1162,7 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
     SVIN_CUDA(cudaEventRecord(c->ev_fork, c->stream));
     SVIN_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
     launch_dense_eval(b, 1, 0, nullptr, c->side);
+    if (c->smem_bytes > 0) launch_dense_gram(b, 1, c->n_max, c->side);
     SVIN_CUDA(cudaEventRecord(c->ev_join, c->side));
   }
   { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 1, 0, c->stream); }
@@ -1168,6 +1175,7 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
   } else {
     ProfScope p(c, SVIN_BA_K_DENSE_EVAL);
     launch_dense_eval(b, 1, 0, nullptr, c->stream);
+    if (c->smem_bytes > 0) launch_dense_gram(b, 1, c->n_max, c->stream);
   }
   { ProfScope p(c, SVIN_BA_K_DECIDE); launch_decide(b, opt, c->stream); }
   c->tm.kernel_launches += 8;
@@ -1199,7 +1207,11 @@ int svin_ba_solve(svin_ba_ctx* c, const SvinBaOptions* opt_in, SvinBaSummary* su
     if (rc0 != SVIN_OK) return rc0;
     launch_fold(b, 4, c->stream);
   }
-  { ProfScope p(c, SVIN_BA_K_DENSE_EVAL); launch_dense_eval(b, 0, 0, nullptr, c->stream); }
+  {
+    ProfScope p(c, SVIN_BA_K_DENSE_EVAL);
+    launch_dense_eval(b, 0, 0, nullptr, c->stream);
+    if (c->smem_bytes > 0) launch_dense_gram(b, 0, c->n_max, c->stream);
+  }
   launch_init(b, opt, c->stream);
   c->tm.kernel_launches += 3;
   int slots_done = 0;

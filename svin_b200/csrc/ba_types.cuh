@@ -162,6 +162,8 @@ struct Batch {
   double *g_red, *g_raw, *Hdiag;  // reduced rhs, unreduced gradient, column square norms  (cleared each slot)
   double *scale_d, *diag_d, *grad_d, *gn_d, *u_d, *c_d, *delta_d;
   double* Jd[2];  // dense-term Jacobians, by Jd_off
+  double* gram[2];    // Jd^T Jd per buffer (lower triangle, n x n at H_off), k_dense_gram
+  double* gram_g[2];  // Jd^T rd per buffer (at d_off)
   double* rd[2];  // dense-term residuals, by rd_off
   // terms
   ImuTerm* imu;
