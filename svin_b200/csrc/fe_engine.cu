@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "common.hpp"
+#include "host_pool.hpp"
 #include "fe_kernels.cuh"
 
 using namespace svin;
@@ -85,6 +86,7 @@ struct svin_fe_ctx {
   int pitch = 0;
   size_t occ_bytes = 0;
   bool use_tma = true;
+  svin::HostPool* pool = nullptr;
   // device buffers
   uint8_t* d_images = nullptr;
   double *d_intr = nullptr, *d_edir = nullptr;
@@ -158,6 +160,7 @@ int svin_fe_create(int device, const SvinFeOptions* opt_in, svin_fe_ctx** out) {
   }
   SVIN_CUDA(cudaSetDevice(device));
   svin_fe_ctx* c = new svin_fe_ctx();
+  c->pool = new svin::HostPool(std::max(0, std::min(16, (int)std::thread::hardware_concurrency()) - 1));
   c->device = device;
   c->opt = opt;
   const int W = opt.image_width, H = opt.image_height, M = opt.max_images, K = opt.max_keypoints;
@@ -227,6 +230,7 @@ void svin_fe_destroy(svin_fe_ctx* c) {
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
+  delete c->pool;
   delete c;
 }
 
@@ -238,14 +242,15 @@ int svin_fe_upload(svin_fe_ctx* c, int32_t n, const uint8_t* const* images, int3
   }
   SVIN_CUDA(cudaSetDevice(c->device));
   const int W = c->opt.image_width, H = c->opt.image_height;
-  for (int i = 0; i < n; ++i) {
+  for (int i = 0; i < n; ++i)
     if (!images[i]) {
       set_error("svin_fe_upload: NULL image");
       return SVIN_ERR_INVALID_ARGUMENT;
     }
+  c->pool->run(n, [&](int i) {  // row-wise copy into the pitched pinned staging buffer
     for (int y = 0; y < H; ++y)
       std::memcpy(c->h_images + ((size_t)i * H + y) * c->pitch, images[i] + (size_t)y * stride, W);
-  }
+  });
   std::memcpy(c->h_small, intrinsics, sizeof(double) * 8 * n);
   std::memcpy(c->h_small + 8 * (size_t)c->opt.max_images, edir, sizeof(double) * 3 * n);
   SVIN_CUDA(cudaEventRecord(c->ev[5], c->stream));
@@ -390,9 +395,14 @@ int svin_match(svin_fe_ctx* c, int32_t np, const SvinMatchProblem* probs, SvinMa
   char* Hh = (char*)c->h_match;
   char* D = (char*)c->d_match;
   MatchDesc* hd = (MatchDesc*)(Hh + o_desc);
-  size_t a0 = 0, b0 = 0;
+  std::vector<size_t> offA((size_t)np + 1, 0), offB((size_t)np + 1, 0);
   for (int p = 0; p < np; ++p) {
+    offA[p + 1] = offA[p] + probs[p].nA;
+    offB[p + 1] = offB[p] + probs[p].nB;
+  }
+  c->pool->run(np, [&](int p) {
     const SvinMatchProblem& q = probs[p];
+    const size_t a0 = offA[p], b0 = offB[p];
     MatchDesc& d = hd[p];
     std::memset(&d, 0, sizeof d);
     d.type = q.type; d.nA = q.nA; d.nB = q.nB; d.a0 = (int)a0; d.b0 = (int)b0;
@@ -410,9 +420,7 @@ int svin_match(svin_fe_ctx* c, int32_t np, const SvinMatchProblem* probs, SvinMa
     std::memcpy(Hh + o_kB + sizeof(SvinKeypoint) * b0, q.kpB, sizeof(SvinKeypoint) * (size_t)q.nB);
     if (q.type == SVIN_MATCH_3D2D) std::memcpy(Hh + o_lm + 32 * a0, q.landmarksA, 32 * (size_t)q.nA);
     else std::memset(Hh + o_lm + 32 * a0, 0, 32 * (size_t)q.nA);
-    a0 += q.nA;
-    b0 += q.nB;
-  }
+  });
   MatchBatch mb{};
   mb.desc = (const MatchDesc*)(D + o_desc);
   mb.descA = (const uint8_t*)(D + o_dA); mb.descB = (const uint8_t*)(D + o_dB);
@@ -447,18 +455,16 @@ int svin_match(svin_fe_ctx* c, int32_t np, const SvinMatchProblem* probs, SvinMa
   c->tm.h2d_bytes = (int64_t)in_bytes;
   c->tm.d2h_bytes = (int64_t)out_bytes;
   c->tm.kernel_launches += 3;
-  a0 = b0 = 0;
-  for (int p = 0; p < np; ++p) {
+  c->pool->run(np, [&](int p) {
     const SvinMatchProblem& q = probs[p];
     const SvinMatchResult& r = res[p];
+    const size_t a0 = offA[p], b0 = offB[p];
     if (r.best_index) std::memcpy(r.best_index, Hh + o_bi + 16 * a0, 16 * (size_t)q.nA);
     if (r.best_distance) std::memcpy(r.best_distance, Hh + o_bd + 16 * a0, 16 * (size_t)q.nA);
     if (r.match_of_B) std::memcpy(r.match_of_B, Hh + o_mo + 4 * b0, 4 * (size_t)q.nB);
     if (r.match_distance) std::memcpy(r.match_distance, Hh + o_md + 4 * b0, 4 * (size_t)q.nB);
     if (r.skipA_effective) std::memcpy(r.skipA_effective, Hh + o_se + a0, q.nA);
-    a0 += q.nA;
-    b0 += q.nB;
-  }
+  });
   return SVIN_OK;
 }
 

@@ -48,6 +48,43 @@ class MatchProblem:
         self.c = p
 
 
+class MatchResults:
+    """Pooled outputs of one svin_match call; res[i] -> dict of views for problem i."""
+
+    _DT = np.dtype([("best_index", "<u8"), ("best_distance", "<u8"), ("match_of_B", "<u8"), ("match_distance", "<u8"),
+                    ("skipA_effective", "<u8")])
+
+    def __init__(self, nA, nB):
+        assert self._DT.itemsize == C.sizeof(capi.SvinMatchResult)
+        self.offA = np.concatenate([[0], np.cumsum(nA)])
+        self.offB = np.concatenate([[0], np.cumsum(nB)])
+        tA, tB = int(self.offA[-1]), int(self.offB[-1])
+        self.best_index = np.zeros((tA, 4), np.int32)
+        self.best_distance = np.zeros((tA, 4), np.float32)
+        self.match_of_B = np.zeros(tB, np.int32)
+        self.match_distance = np.zeros(tB, np.float32)
+        self.skipA = np.zeros(tA, np.uint8)
+        t = np.zeros(len(nA), dtype=self._DT)
+        t["best_index"] = self.best_index.ctypes.data + 16 * self.offA[:-1]
+        t["best_distance"] = self.best_distance.ctypes.data + 16 * self.offA[:-1]
+        t["match_of_B"] = self.match_of_B.ctypes.data + 4 * self.offB[:-1]
+        t["match_distance"] = self.match_distance.ctypes.data + 4 * self.offB[:-1]
+        t["skipA_effective"] = self.skipA.ctypes.data + self.offA[:-1]
+        self.table = t
+
+    def __len__(self):
+        return len(self.table)
+
+    def __getitem__(self, i):
+        a0, a1, b0, b1 = self.offA[i], self.offA[i + 1], self.offB[i], self.offB[i + 1]
+        return dict(best_index=self.best_index[a0:a1], best_distance=self.best_distance[a0:a1],
+                    match_of_B=self.match_of_B[b0:b1], match_distance=self.match_distance[b0:b1],
+                    skipA=self.skipA[a0:a1])
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class FeEngine:
     def __init__(self, width=752, height=480, max_images=2, device=0, **opts):
         self._lib = capi.load()
@@ -125,22 +162,21 @@ class FeEngine:
 
     # ---- matching ---------------------------------------------------------------------------------------
     def match(self, problems: list[MatchProblem]):
+        """Returns a MatchResults (indexable like a list of dicts).  Outputs of all problems live in five pooled
+        arrays and the SvinMatchResult pointer table is filled with vectorised address arithmetic: with ~1 000
+        problems per call a per-problem Python loop costs more than the matching itself."""
         n = len(problems)
-        parr = (capi.SvinMatchProblem * n)(*[p.c for p in problems])
-        outs, rarr = [], (capi.SvinMatchResult * n)()
-        for i, p in enumerate(problems):
-            nA, nB = p.c.nA, p.c.nB
-            o = dict(best_index=np.zeros((nA, 4), np.int32), best_distance=np.zeros((nA, 4), np.float32),
-                     match_of_B=np.zeros(nB, np.int32), match_distance=np.zeros(nB, np.float32),
-                     skipA=np.zeros(nA, np.uint8))
-            rarr[i].best_index = o["best_index"].ctypes.data_as(capi.c_int32_p)
-            rarr[i].best_distance = o["best_distance"].ctypes.data_as(capi.c_float_p)
-            rarr[i].match_of_B = o["match_of_B"].ctypes.data_as(capi.c_int32_p)
-            rarr[i].match_distance = o["match_distance"].ctypes.data_as(capi.c_float_p)
-            rarr[i].skipA_effective = _u8(o["skipA"])
-            outs.append(o)
-        capi.check(self._lib.svin_match(self._ctx, n, parr, rarr), self._lib)
-        return outs
+        key = tuple(id(p) for p in problems)
+        if getattr(self, "_match_key", None) != key:     # same problem list as last call: reuse the struct array
+            self._match_parr = (capi.SvinMatchProblem * n)(*[p.c for p in problems])
+            self._match_keep = list(problems)
+            self._match_nA = np.array([p.c.nA for p in problems], dtype=np.int64)
+            self._match_nB = np.array([p.c.nB for p in problems], dtype=np.int64)
+            self._match_key = key
+        res = MatchResults(self._match_nA, self._match_nB)
+        capi.check(self._lib.svin_match(self._ctx, n, self._match_parr,
+                                        C.cast(res.table.ctypes.data, C.POINTER(capi.SvinMatchResult))), self._lib)
+        return res
 
     def timings(self) -> dict:
         t = capi.SvinFeTimings()
