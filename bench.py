@@ -378,7 +378,8 @@ def run_gpu(args):
     # serial: one blocking svin_ba_optimize per step.  pipelined: two contexts, each driven by its own host
     # thread (ctypes releases the GIL), so that packing + H2D of step k+1 overlaps the solve of step k.
     from svin_b200.engine import BaPipeline
-    pipe = BaPipeline(local)
+    pipe_depth = int(os.environ.get("SVIN_PIPE_DEPTH", "2"))
+    pipe = BaPipeline(local, depth=pipe_depth)
     for _ in range(2):
         eng.optimize([w.copy() for w in batch], opt)
     pipe.optimize_many([[w.copy() for w in batch] for _ in range(2)], opt)
@@ -456,7 +457,7 @@ def run_gpu(args):
             "device_ms_per_step": dev_ms / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tm["h2d_bytes"]),
                     "d2h_bytes_per_step": int(tm["d2h_bytes"]), "ms_per_step": 1e3 * dt_e2e / n_e2e,
-                    "steps": n_e2e, "pipeline": "BaPipeline: 2 contexts x 1 host thread, upload of step k+1 overlaps the solve of step k",
+                    "steps": n_e2e, "pipeline": f"BaPipeline: {pipe_depth} contexts x 1 host thread, upload of step k+1 overlaps the solve of step k", "host_cores": os.cpu_count(),
                     "pipeline_trace_ms": pipe_trace,
                     "serial": {"value": e2e_serial, "ms_per_step": 1e3 * dt_serial / n_e2e},
                     "last_step_breakdown_ms": {k: round(float(tm[k]), 3) for k in (

@@ -86,9 +86,12 @@ struct WindowOrder {
   std::vector<int> lm_count;  // observations of internal landmark k
   std::vector<int> lm_first, lm_stride;  // window-local position of its first observation, stride between them
   std::vector<int> chunk_begin, chunk_count;  // Schur warp chunks (window-local internal landmark indices)
+  std::vector<int> chunk_kind;                // lane mapping: schur_chunk_class() or 3 = run-parallel (k_schur_lr)
   std::vector<int> chunk_run_first, chunk_nruns;  // pose runs of the chunk's pattern -> run_pose / run_k0m
   std::vector<int> run_pose, run_k0m;             // window-local pose block, (first obs k << 8) | obs count
 };
+
+constexpr int kSchurLrBelow = 16;  // fewer landmarks of one pattern than this -> run-parallel chunks
 
 void order_window(const SvinBaWindow& w, bool group, WindowOrder& out) {
   const int N = w.num_obs, L = w.num_landmarks;
@@ -146,13 +149,17 @@ void order_window(const SvinBaWindow& w, bool group, WindowOrder& out) {
   out.chunk_nruns.clear();
   out.run_pose.clear();
   out.run_k0m.clear();
+  out.chunk_kind.clear();
   if (group) {
+    // A/B knob: SVIN_SCHUR_LR=0 keeps the lane = landmark mappings for every chunk, 1 adds k_schur_lr only
+    // 2 adds k_schur_wr, 3 (default) also the 2- and 4-warp k_schur_lr
+    static const int use_lr = std::getenv("SVIN_SCHUR_LR") ? std::atoi(std::getenv("SVIN_SCHUR_LR")) : 3;
     int k = 0;
     while (k < L) {
-      // pose runs of this pattern bound the chunk size (both operand tiles of k_schur_mma must fit in shared memory)
+      // pose runs of this pattern (shared by all of its chunks)
       const int lk = out.lm_perm[k];
       int runs = 0, prev = -1;
-      out.chunk_run_first.push_back((int)out.run_pose.size());
+      const int run_first = (int)out.run_pose.size();
       for (int q = start[lk]; q < start[lk + 1]; ++q) {
         const int pz = w.obs_pose[ord[q]];
         if (pz != prev) {
@@ -164,13 +171,45 @@ void order_window(const SvinBaWindow& w, bool group, WindowOrder& out) {
         }
         prev = pz;
       }
-      out.chunk_nruns.push_back(runs);
+      int e_all = k + 1;
+      while (e_all < L && same_pattern(out.lm_perm[k], out.lm_perm[e_all])) ++e_all;
+      // The pattern's landmarks go to lane = landmark chunks (bounded by the operand tiles of k_schur_mma) while at
+      // least kSchurLrBelow of them are left (one warp per run for 2..4 runs, k_schur_wr), the rest to run-parallel
+      // chunks of <= 32 / runs landmarks (k_schur_lr); patterns neither kernel takes keep the lane = landmark mappings.
       const int cap = std::max(1, std::min(32, schur_mma_max_chunk(std::max(runs, 1))));
-      int e = k + 1;
-      while (e < L && e - k < cap && same_pattern(out.lm_perm[k], out.lm_perm[e])) ++e;
-      out.chunk_begin.push_back(k);
-      out.chunk_count.push_back(e - k);
-      k = e;
+      const int lr1 = use_lr ? schur_lr_max_chunk(runs, 1) : 0;
+      const int lr2 = use_lr >= 3 ? schur_lr_max_chunk(runs, 2) : 0;
+      const int lr4 = use_lr >= 3 ? schur_lr_max_chunk(runs, 4) : 0;
+      while (k < e_all) {
+        const int rem = e_all - k;
+        int c, kind;
+        if (use_lr >= 2 && runs >= 2 && runs <= 4 && rem >= kSchurLrBelow) {
+          c = std::min(32, rem);
+          kind = 2 + runs;  // warp per run (k_schur_wr<runs>)
+        } else if (lr1 >= 1 && (use_lr >= 2 || rem < kSchurLrBelow || cap < kSchurLrBelow)) {
+          // run-parallel: the narrowest CTA that takes what is left, else equal parts of the widest
+          if (rem <= lr1 || lr2 < 1) {
+            c = std::min(lr1, rem);
+            kind = 3;
+          } else if (rem <= lr2) {
+            c = rem;
+            kind = 7;
+          } else {
+            const int parts = (rem + lr4 - 1) / lr4;
+            c = (rem + parts - 1) / parts;
+            kind = c <= lr1 ? 3 : (c <= lr2 ? 7 : 8);
+          }
+        } else {
+          c = std::min(cap, rem);
+          kind = schur_chunk_class(c);
+        }
+        out.chunk_run_first.push_back(run_first);
+        out.chunk_nruns.push_back(runs);
+        out.chunk_begin.push_back(k);
+        out.chunk_count.push_back(c);
+        out.chunk_kind.push_back(kind);
+        k += c;
+      }
     }
   }
   out.obs_order.resize(N);
@@ -822,15 +861,16 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     (void)cam_base; (void)ot; (void)lt; (void)sw; (void)meas_base;
   };
   // chunk ids by lane-mapping class (one k_schur_mma<G> launch per class)
-  int sw_class_count[3] = {0, 0, 0};
+  int sw_class_count[kSchurClasses] = {};
   {
     int* h_swlist = (int*)hp(o_swlist);
     for (int i = 0; i < B; ++i)
-      for (int cc : orders[i].chunk_count) sw_class_count[schur_chunk_class(cc)]++;
-    int pos[3] = {0, sw_class_count[0], sw_class_count[0] + sw_class_count[1]};
+      for (int kind : orders[i].chunk_kind) sw_class_count[kind]++;
+    int pos[kSchurClasses] = {};
+    for (int k = 1; k < kSchurClasses; ++k) pos[k] = pos[k - 1] + sw_class_count[k - 1];
     for (int i = 0; i < B; ++i)
       for (size_t k = 0; k < orders[i].chunk_count.size(); ++k)
-        h_swlist[pos[schur_chunk_class(orders[i].chunk_count[k])]++] = sw_v[i] + (int)k;
+        h_swlist[pos[orders[i].chunk_kind[k]]++] = sw_v[i] + (int)k;
   }
   // Packing runs on the pool while this thread lays out the work arena; the big observation arrays are copied
   // group by group as soon as their windows are packed, so that the H2D transfer overlaps the packing.
@@ -914,7 +954,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   b.obs_tile_win = (int*)(D + o_otw); b.obs_tile_begin = (int*)(D + o_otb);
   b.lm_tile_win = (int*)(D + o_ltw); b.lm_tile_begin = (int*)(D + o_ltb);
   b.n_schur_warps = (int)NSW;
-  for (int k = 0; k < 3; ++k) b.sw_class_count[k] = sw_class_count[k];
+  for (int k = 0; k < kSchurClasses; ++k) b.sw_class_count[k] = sw_class_count[k];
   b.sw_win = (int*)(D + o_sww); b.sw_lm_begin = (int*)(D + o_swb); b.sw_count = (int*)(D + o_swc);
   b.sw_nruns = (int*)(D + o_swnr); b.sw_run_first = (int*)(D + o_swrf); b.sw_list = (int*)(D + o_swlist);
   b.run_off = (int*)(D + o_runoff); b.run_k0m = (int*)(D + o_runkm);

@@ -22,6 +22,9 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "ba_device_utils.cuh"
 #include "ba_kernels.cuh"
 #include "ba_math.cuh"
@@ -933,6 +936,513 @@ __global__ void __launch_bounds__(128, 3) k_schur_mma(Batch b, SvinBaOptions opt
   }
   __syncwarp();
   schur_chunk<G>(b, opt, ws, wd, chunk, cnt, nr, Ys, Ps, rdesc, lane);
+}
+
+// ---- low-fill chunks: lanes over (pose run, landmark) pairs -------------------------------------------------
+// Long tracks come in many distinct patterns with a handful of landmarks each (BASELINE configs[1]: 6 % of the
+// landmarks, a third of the chunks, and - with the lane = landmark mappings above - 60 % of the instructions).
+// Here a chunk is capped at upload to c <= 32 / runs landmarks and lane = a * c + i works on run a of landmark i:
+// every run of every landmark is loaded and contracted at once (one load latency per chunk instead of one per
+// run), the per-landmark sums (V, b) and the per-run sums (J_p^T J_p, J_p^T r) are finished through shared memory,
+// and only the Y Y^T product runs on the tensor cores as above.
+// One CTA of WPC warps per chunk, runs * c <= 32 * WPC units (thread = unit).
+template <int WPC>
+struct LrCfg {
+  // Y operand (6 runs + 1) x (pad4(3 c) + 4), aliased by the reduction scratch (27 doubles per unit)
+  static constexpr int kY = WPC == 1 ? 1600 : (WPC == 2 ? 2400 : 3456);
+  static constexpr int kIntDoubles = 128;  // 64 ints of run descriptors + 192 ints of row map
+  static constexpr int kDoubles = kY + kIntDoubles;
+};
+
+template <int WPC>
+__global__ void __launch_bounds__(32 * WPC, 12 / WPC) k_schur_lr(Batch b, SvinBaOptions opt, const int* list) {
+  extern __shared__ double sm_all[];
+  constexpr int NT = 32 * WPC;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, tid = threadIdx.x;
+  const int chunk = list[blockIdx.x];
+  double* Ys = sm_all;
+  int* rdesc = reinterpret_cast<int*>(Ys + LrCfg<WPC>::kY);
+  int* rowmap = rdesc + 64;
+  const int w = b.sw_win[chunk];
+  WinState& ws = b.ws[w];
+  if (ws.done || ws.reuse) return;
+  const WinDesc& wd = b.win[w];
+  const int cnt = b.sw_count[chunk];
+  const int nr = b.sw_nruns[chunk];
+  const int rf = b.sw_run_first[chunk];
+  if (tid < nr) {
+    rdesc[2 * tid] = b.run_off[rf + tid];
+    rdesc[2 * tid + 1] = b.run_k0m[rf + tid];
+  }
+  const bool active = tid < cnt * nr;
+  const int a = active ? tid / cnt : 0;
+  const int i = active ? tid - a * cnt : 0;
+  const int l = b.sw_lm_begin[chunk] + i;
+  const int buf = ws.cur;
+  const int n = wd.n_dense;
+  double* H = b.H + wd.H_off;
+  double* g_red = b.g_red + wd.d_off;
+  double* g_raw = b.g_raw + wd.d_off;
+  double* Hdiag = b.Hdiag + wd.d_off;
+  const int ob = b.lm_obs_first[l];
+  const int ost = b.lm_obs_stride[l];
+  const bool lfix = b.lm_fixed[l] != 0;
+  const double mu = ws.mu;
+  const size_t S = b.obs_stride;
+  const double* rP = b.lin_r[buf];
+  const double* JpP = b.lin_Jp[buf];
+  const double* JlP = b.lin_Jl[buf];
+  __syncthreads();
+  const int offp = rdesc[2 * a];
+  const int k0 = rdesc[2 * a + 1] >> 8, m = active ? (rdesc[2 * a + 1] & 255) : 0;
+
+  // ---- this lane's run: partial landmark block, W, diagonal pose block and gradients
+  double V[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+  double W[18];
+  double D[27];  // upper triangle of J_p^T J_p (21, row-major) | J_p^T r (6)
+#pragma unroll
+  for (int k = 0; k < 18; ++k) W[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 27; ++k) D[k] = 0.0;
+  for (int q = 0; q < m; ++q) {
+    const int o = ob + (k0 + q) * ost;
+    double Jp[12], Jl[6];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) Jp[e] = JpP[e * S + o];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) Jl[e] = JlP[e * S + o];
+    const double r0 = rP[o], r1 = rP[S + o];
+    V[0] += Jl[0] * Jl[0] + Jl[3] * Jl[3];
+    V[1] += Jl[0] * Jl[1] + Jl[3] * Jl[4];
+    V[2] += Jl[0] * Jl[2] + Jl[3] * Jl[5];
+    V[3] += Jl[1] * Jl[1] + Jl[4] * Jl[4];
+    V[4] += Jl[1] * Jl[2] + Jl[4] * Jl[5];
+    V[5] += Jl[2] * Jl[2] + Jl[5] * Jl[5];
+    bl[0] += Jl[0] * r0 + Jl[3] * r1;
+    bl[1] += Jl[1] * r0 + Jl[4] * r1;
+    bl[2] += Jl[2] * r0 + Jl[5] * r1;
+    if (offp >= 0) {
+      acc_W(Jp, Jl, W);
+      int k = 0;
+#pragma unroll
+      for (int x = 0; x < 6; ++x)
+#pragma unroll
+        for (int y = x; y < 6; ++y) D[k++] += Jp[x] * Jp[y] + Jp[6 + x] * Jp[6 + y];
+#pragma unroll
+      for (int x = 0; x < 6; ++x) D[21 + x] += Jp[x] * r0 + Jp[6 + x] * r1;
+    }
+  }
+  // ---- per-run sums over the chunk's landmarks -> reduced system (diagonal block, gradients, column norms)
+#pragma unroll
+  for (int k = 0; k < 27; ++k) Ys[tid * 27 + k] = D[k];
+  __syncthreads();
+  for (int e = tid; e < nr * 27; e += NT) {
+    const int a2 = e / 27, k = e - 27 * a2;
+    const int off2 = rdesc[2 * a2];
+    if (off2 < 0) continue;
+    const double* src = Ys + (size_t)(a2 * cnt) * 27 + k;
+    double val = 0.0;
+    for (int i2 = 0; i2 < cnt; ++i2) val += src[i2 * 27];
+    if (k >= 21) {
+      atomicAdd(&g_red[off2 + k - 21], val);
+      atomicAdd(&g_raw[off2 + k - 21], val);
+    } else {
+      // k -> (row, col) of the upper triangle, rows start at 0 6 11 15 18 20
+      const int fr = (k >= 6) + (k >= 11) + (k >= 15) + (k >= 18) + (k >= 20);
+      const int fc = k - (fr * (13 - fr)) / 2 + fr;
+      atomicAdd(&H[(size_t)(off2 + fr) * n + off2 + fc], val);
+      if (fr == fc) atomicAdd(&Hdiag[off2 + fr], val);
+    }
+  }
+  __syncthreads();
+  // ---- per-landmark sums over the runs: V, b (every unit of a landmark ends up with the full sums)
+#pragma unroll
+  for (int k = 0; k < 6; ++k) Ys[tid * 9 + k] = V[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) Ys[tid * 9 + 6 + k] = bl[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 6; ++k) V[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) bl[k] = 0.0;
+  for (int a2 = 0; a2 < nr; ++a2) {
+    const double* src = Ys + (size_t)(a2 * cnt + i) * 9;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) V[k] += src[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) bl[k] += src[6 + k];
+  }
+  __syncthreads();
+  if (lfix) return;  // chunk-uniform: fixed landmarks are not eliminated
+  double s[3] = {1.0, 1.0, 1.0}, M[6], u[3];
+  const bool owner = active && a == 0;
+  if (ws.iter == 0 && ws.num_successful == 0 && !ws.invalid) {
+    if (opt.jacobi_scaling) {
+      s[0] = 1.0 / (1.0 + sqrt(V[0]));
+      s[1] = 1.0 / (1.0 + sqrt(V[3]));
+      s[2] = 1.0 / (1.0 + sqrt(V[5]));
+    }
+    if (owner) {
+      b.lm_scale[3 * (size_t)l] = s[0];
+      b.lm_scale[3 * (size_t)l + 1] = s[1];
+      b.lm_scale[3 * (size_t)l + 2] = s[2];
+    }
+  } else {
+    s[0] = b.lm_scale[3 * (size_t)l];
+    s[1] = b.lm_scale[3 * (size_t)l + 1];
+    s[2] = b.lm_scale[3 * (size_t)l + 2];
+  }
+  {
+    double gm = owner ? fmax(fabs(bl[0]), fmax(fabs(bl[1]), fabs(bl[2]))) : 0.0;
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o2));
+    if (lane == 0) atomic_max_nonneg(&ws.gmax_bits, gm);
+    double Vs[6] = {V[0] * s[0] * s[0], V[1] * s[0] * s[1], V[2] * s[0] * s[2],
+                    V[3] * s[1] * s[1], V[4] * s[1] * s[2], V[5] * s[2] * s[2]};
+    const double d0 = sqrt(fmin(fmax(Vs[0], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    const double d1 = sqrt(fmin(fmax(Vs[3], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    const double d2 = sqrt(fmin(fmax(Vs[5], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    Vs[0] += mu * d0 * d0;
+    Vs[3] += mu * d1 * d1;
+    Vs[5] += mu * d2 * d2;
+    double Vi[6];
+    spd3_inverse_factor(Vs, Vi, M);
+    const double bs0 = s[0] * bl[0], bs1 = s[1] * bl[1], bs2 = s[2] * bl[2];
+    u[0] = M[0] * bs0;
+    u[1] = M[1] * bs0 + M[2] * bs1;
+    u[2] = M[3] * bs0 + M[4] * bs1 + M[5] * bs2;
+    if (owner) {
+      double* p = b.lm_Vinv + 6 * (size_t)l;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) p[k] = Vi[k];
+      p = b.lm_bs + 3 * (size_t)l;
+      p[0] = bs0; p[1] = bs1; p[2] = bs2;
+      p = b.lm_diag + 3 * (size_t)l;
+      p[0] = d0; p[1] = d1; p[2] = d2;
+      p = b.lm_grad + 3 * (size_t)l;
+      p[0] = bs0 / d0; p[1] = bs1 / d1; p[2] = bs2 / d2;
+    }
+  }
+  // ---- Y = [W_a diag(s) M^T ; (M b)^T]
+  const int K4 = (3 * cnt + 3) >> 2;
+  const int ld = 4 * K4 + 4;
+  const int R = 6 * nr, RY = R + 1, T = (RY + 7) >> 3;
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      const double w0 = W[e * 3] * s[0], w1 = W[e * 3 + 1] * s[1], w2 = W[e * 3 + 2] * s[2];
+      double* yr = Ys + (6 * a + e) * ld + 3 * i;
+      yr[0] = w0 * M[0];
+      yr[1] = w0 * M[1] + w1 * M[2];
+      yr[2] = w0 * M[3] + w1 * M[4] + w2 * M[5];
+    }
+    if (a == 0) {
+      double* yr = Ys + R * ld + 3 * i;
+      yr[0] = u[0]; yr[1] = u[1]; yr[2] = u[2];
+    }
+  }
+  for (int r = tid; r < RY; r += NT)
+    for (int cc = 3 * cnt; cc < 4 * K4; ++cc) Ys[r * ld + cc] = 0.0;
+  for (int r = tid; r < R; r += NT) {
+    const int op = rdesc[2 * (r / 6)];
+    rowmap[r] = op < 0 ? -1 : op + r % 6;
+  }
+  __syncthreads();
+  // ---- C = Y Y^T on the tensor cores (upper tiles, dealt out to the warps), one RED per upper-triangular entry
+  const int fr = lane >> 2, fc = lane & 3;
+  int pidx = 0;
+  for (int tm = 0; tm < T; ++tm) {
+    const int gi = 8 * tm + fr;
+    const double* za = Ys + (gi < RY ? gi : 0) * ld + fc;
+    const int ri = gi < R ? rowmap[gi] : -1;
+    for (int tn = tm; tn < T; ++tn, ++pidx) {
+      if (WPC > 1 && pidx % WPC != wid) continue;
+      const int rb = 8 * tn + fr;
+      const double* zb = Ys + (rb < RY ? rb : 0) * ld + fc;
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+      int ks = 0;
+      for (; ks + 1 < K4; ks += 2) {
+        dmma8x8x4(c0, c1, za[4 * ks], zb[4 * ks]);
+        dmma8x8x4(e0, e1, za[4 * ks + 4], zb[4 * ks + 4]);
+      }
+      if (ks < K4) dmma8x8x4(c0, c1, za[4 * ks], zb[4 * ks]);
+      c0 += e0;
+      c1 += e1;
+      if (ri < 0) continue;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gj = 8 * tn + 2 * fc + e;
+        if (gj > R || gi > gj) continue;
+        const double val = e ? c1 : c0;
+        if (gj == R) {
+          atomicAdd(&g_red[ri], -val);
+        } else {
+          const int rj = rowmap[gj];
+          if (rj >= 0) atomicAdd(&H[min(ri, rj) * n + max(ri, rj)], -val);
+        }
+      }
+    }
+  }
+}
+
+// ---- wide chunks of short tracks: one CTA per chunk, one warp per pose run --------------------------------
+// Patterns with <= 4 pose runs hold most of the observations (two-view tracks alone are 63 % of the landmarks of
+// BASELINE configs[1]).  Warp a takes run a of <= 32 landmarks (lane = landmark): all observations of the chunk are
+// in flight at once, the runs' P P^T products (diagonal block, gradients) run concurrently on the tensor cores,
+// V and b are summed over the warps through shared memory, and the Y Y^T tile pairs are dealt out to the warps.
+template <int NR>
+struct WrCfg {
+  static constexpr int R = 6 * NR, RY = R + 1, T = (RY + 7) / 8;
+  static constexpr int kY = RY * 100;        // Y operand, ld <= 4 * ceil(96 / 4) + 4
+  static constexpr int kP = NR * 8 * 68;     // one P tile per warp
+  static constexpr int kInts = 8 * NR;       // 2 NR run descriptors + 6 NR row map
+  static constexpr int kDoubles = kY + kP + (kInts + 1) / 2;
+  static constexpr int kMinBlocks = NR == 2 ? 8 : (NR == 3 ? 5 : 4);
+};
+
+template <int NR>
+__global__ void __launch_bounds__(32 * NR, WrCfg<NR>::kMinBlocks) k_schur_wr(Batch b, SvinBaOptions opt,
+                                                                              const int* list) {
+  using C = WrCfg<NR>;
+  extern __shared__ double sm_all[];
+  double* Ys = sm_all;
+  double* Ps = Ys + C::kY;
+  int* rdesc = reinterpret_cast<int*>(Ps + C::kP);
+  int* rowmap = rdesc + 2 * NR;
+  const int lane = threadIdx.x & 31, a = threadIdx.x >> 5;
+  const int chunk = list[blockIdx.x];
+  const int w = b.sw_win[chunk];
+  WinState& ws = b.ws[w];
+  if (ws.done || ws.reuse) return;  // CTA-uniform
+  const WinDesc& wd = b.win[w];
+  const int cnt = b.sw_count[chunk];
+  const int rf = b.sw_run_first[chunk];
+  const int offp = b.run_off[rf + a];
+  const int k0m = b.run_k0m[rf + a];
+  const int k0 = k0m >> 8, m = k0m & 255;
+  const bool active = lane < cnt;
+  const int l = b.sw_lm_begin[chunk] + (active ? lane : 0);
+  const int buf = ws.cur;
+  const int n = wd.n_dense;
+  double* H = b.H + wd.H_off;
+  double* g_red = b.g_red + wd.d_off;
+  double* g_raw = b.g_raw + wd.d_off;
+  double* Hdiag = b.Hdiag + wd.d_off;
+  const int ob = b.lm_obs_first[l];
+  const int ost = b.lm_obs_stride[l];
+  const bool lfix = b.lm_fixed[l] != 0;
+  const double mu = ws.mu;
+  const size_t S = b.obs_stride;
+  const double* rP = b.lin_r[buf];
+  const double* JpP = b.lin_Jp[buf];
+  const double* JlP = b.lin_Jl[buf];
+  const int cntp = (cnt + 3) & ~3;
+  const int K4p = cntp >> 1;
+  const int ldp = 2 * cntp + 4;
+  const int K4 = (3 * cnt + 3) >> 2;
+  const int ld = 4 * K4 + 4;
+  const int fr = lane >> 2, fc = lane & 3;
+  double* Pt = Ps + a * (8 * 68);
+  if (lane == 0) {
+    rdesc[2 * a] = offp;
+    rdesc[2 * a + 1] = k0m;
+  }
+  for (int e = lane; e < ldp; e += 32) Pt[7 * ldp + e] = 0.0;
+
+  // ---- this warp's run: partial V, b; W; P P^T -> diagonal block, gradients
+  double V[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+  double W[18];
+#pragma unroll
+  for (int k = 0; k < 18; ++k) W[k] = 0.0;
+  double c0 = 0.0, c1 = 0.0;
+  const double wgt = active ? 1.0 : 0.0;
+  for (int q = 0; q < m; ++q) {
+    const int o = ob + (k0 + q) * ost;
+    double Jp[12], Jl[6];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) Jp[e] = wgt * JpP[e * S + o];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) Jl[e] = wgt * JlP[e * S + o];
+    const double r0 = wgt * rP[o], r1 = wgt * rP[S + o];
+    V[0] += Jl[0] * Jl[0] + Jl[3] * Jl[3];
+    V[1] += Jl[0] * Jl[1] + Jl[3] * Jl[4];
+    V[2] += Jl[0] * Jl[2] + Jl[3] * Jl[5];
+    V[3] += Jl[1] * Jl[1] + Jl[4] * Jl[4];
+    V[4] += Jl[1] * Jl[2] + Jl[4] * Jl[5];
+    V[5] += Jl[2] * Jl[2] + Jl[5] * Jl[5];
+    bl[0] += Jl[0] * r0 + Jl[3] * r1;
+    bl[1] += Jl[1] * r0 + Jl[4] * r1;
+    bl[2] += Jl[2] * r0 + Jl[5] * r1;
+    if (offp >= 0) {  // warp-uniform
+      acc_W(Jp, Jl, W);
+      if (lane < cntp) {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) {
+          Pt[e * ldp + lane] = Jp[e];
+          Pt[e * ldp + cntp + lane] = Jp[6 + e];
+        }
+        Pt[6 * ldp + lane] = r0;
+        Pt[6 * ldp + cntp + lane] = r1;
+      }
+      __syncwarp();
+      const double* pa = Pt + fr * ldp + fc;
+      double e0 = 0.0, e1 = 0.0;
+      for (int ks = 0; ks < K4p; ks += 2) {
+        const double x = pa[4 * ks], y = pa[4 * ks + 4];
+        dmma8x8x4(c0, c1, x, x);
+        dmma8x8x4(e0, e1, y, y);
+      }
+      c0 += e0;
+      c1 += e1;
+      __syncwarp();
+    }
+  }
+  if (offp >= 0 && fr < 6) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = 2 * fc + e;
+      const double val = e ? c1 : c0;
+      if (col < 6) {
+        if (fr <= col) atomicAdd(&H[(size_t)(offp + fr) * n + offp + col], val);
+        if (fr == col) atomicAdd(&Hdiag[offp + fr], val);
+      } else if (col == 6) {
+        atomicAdd(&g_red[offp + fr], val);
+        atomicAdd(&g_raw[offp + fr], val);
+      }
+    }
+  }
+  if (lfix) return;  // chunk-uniform: fixed landmarks are not eliminated
+  // ---- V, b over the runs
+  {
+    double* dst = Ys + (size_t)(a * 32 + lane) * 9;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dst[k] = V[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dst[6 + k] = bl[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 6; ++k) V[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) bl[k] = 0.0;
+#pragma unroll
+  for (int a2 = 0; a2 < NR; ++a2) {
+    const double* src = Ys + (size_t)(a2 * 32 + lane) * 9;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) V[k] += src[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) bl[k] += src[6 + k];
+  }
+  __syncthreads();
+  double s[3] = {1.0, 1.0, 1.0}, M[6], u[3];
+  const bool owner = active && a == 0;
+  if (ws.iter == 0 && ws.num_successful == 0 && !ws.invalid) {
+    if (opt.jacobi_scaling) {
+      s[0] = 1.0 / (1.0 + sqrt(V[0]));
+      s[1] = 1.0 / (1.0 + sqrt(V[3]));
+      s[2] = 1.0 / (1.0 + sqrt(V[5]));
+    }
+    if (owner) {
+      b.lm_scale[3 * (size_t)l] = s[0];
+      b.lm_scale[3 * (size_t)l + 1] = s[1];
+      b.lm_scale[3 * (size_t)l + 2] = s[2];
+    }
+  } else {
+    s[0] = b.lm_scale[3 * (size_t)l];
+    s[1] = b.lm_scale[3 * (size_t)l + 1];
+    s[2] = b.lm_scale[3 * (size_t)l + 2];
+  }
+  {
+    if (a == 0) {
+      double gm = active ? fmax(fabs(bl[0]), fmax(fabs(bl[1]), fabs(bl[2]))) : 0.0;
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o2));
+      if (lane == 0) atomic_max_nonneg(&ws.gmax_bits, gm);
+    }
+    double Vs[6] = {V[0] * s[0] * s[0], V[1] * s[0] * s[1], V[2] * s[0] * s[2],
+                    V[3] * s[1] * s[1], V[4] * s[1] * s[2], V[5] * s[2] * s[2]};
+    const double d0 = sqrt(fmin(fmax(Vs[0], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    const double d1 = sqrt(fmin(fmax(Vs[3], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    const double d2 = sqrt(fmin(fmax(Vs[5], opt.min_lm_diagonal), opt.max_lm_diagonal));
+    Vs[0] += mu * d0 * d0;
+    Vs[3] += mu * d1 * d1;
+    Vs[5] += mu * d2 * d2;
+    double Vi[6];
+    spd3_inverse_factor(Vs, Vi, M);
+    const double bs0 = s[0] * bl[0], bs1 = s[1] * bl[1], bs2 = s[2] * bl[2];
+    u[0] = M[0] * bs0;
+    u[1] = M[1] * bs0 + M[2] * bs1;
+    u[2] = M[3] * bs0 + M[4] * bs1 + M[5] * bs2;
+    if (owner) {
+      double* p = b.lm_Vinv + 6 * (size_t)l;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) p[k] = Vi[k];
+      p = b.lm_bs + 3 * (size_t)l;
+      p[0] = bs0; p[1] = bs1; p[2] = bs2;
+      p = b.lm_diag + 3 * (size_t)l;
+      p[0] = d0; p[1] = d1; p[2] = d2;
+      p = b.lm_grad + 3 * (size_t)l;
+      p[0] = bs0 / d0; p[1] = bs1 / d1; p[2] = bs2 / d2;
+    }
+  }
+  // ---- Y = [W_a diag(s) M^T ; (M b)^T]
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      const double w0 = W[e * 3] * s[0], w1 = W[e * 3 + 1] * s[1], w2 = W[e * 3 + 2] * s[2];
+      double* yr = Ys + (6 * a + e) * ld + 3 * lane;
+      yr[0] = w0 * M[0];
+      yr[1] = w0 * M[1] + w1 * M[2];
+      yr[2] = w0 * M[3] + w1 * M[4] + w2 * M[5];
+    }
+    if (a == 0) {
+      double* yr = Ys + C::R * ld + 3 * lane;
+      yr[0] = u[0]; yr[1] = u[1]; yr[2] = u[2];
+    }
+  }
+  for (int r = threadIdx.x; r < C::RY; r += 32 * NR)
+    for (int cc = 3 * cnt; cc < 4 * K4; ++cc) Ys[r * ld + cc] = 0.0;
+  for (int r = threadIdx.x; r < C::R; r += 32 * NR) {
+    const int op = rdesc[2 * (r / 6)];
+    rowmap[r] = op < 0 ? -1 : op + r % 6;
+  }
+  __syncthreads();
+  // ---- C = Y Y^T on the tensor cores: the upper tile pairs are dealt out to the warps
+  int pidx = 0;
+#pragma unroll
+  for (int tm = 0; tm < C::T; ++tm) {
+#pragma unroll
+    for (int tn = tm; tn < C::T; ++tn, ++pidx) {
+      if (pidx % NR != a) continue;
+      const int gi = 8 * tm + fr;
+      const double* za = Ys + (gi < C::RY ? gi : 0) * ld + fc;
+      const int ri = gi < C::R ? rowmap[gi] : -1;
+      const int rb = 8 * tn + fr;
+      const double* zb = Ys + (rb < C::RY ? rb : 0) * ld + fc;
+      double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+      int ks = 0;
+      for (; ks + 1 < K4; ks += 2) {
+        dmma8x8x4(d0, d1, za[4 * ks], zb[4 * ks]);
+        dmma8x8x4(e0, e1, za[4 * ks + 4], zb[4 * ks + 4]);
+      }
+      if (ks < K4) dmma8x8x4(d0, d1, za[4 * ks], zb[4 * ks]);
+      d0 += e0;
+      d1 += e1;
+      if (ri < 0) continue;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gj = 8 * tn + 2 * fc + e;
+        if (gj > C::R || gi > gj) continue;
+        const double val = e ? d1 : d0;
+        if (gj == C::R) {
+          atomicAdd(&g_red[ri], -val);
+        } else {
+          const int rj = rowmap[gj];
+          if (rj >= 0) atomicAdd(&H[min(ri, rj) * n + max(ri, rj)], -val);
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ dense terms
@@ -2194,6 +2704,14 @@ void launch_gmax_pack(const Batch& b, int unpack, cudaStream_t st) {
 }
 
 size_t schur_mma_smem_bytes() { return 4 * (size_t)kSchurWarpDoubles * sizeof(double); }
+int schur_lr_max_chunk(int runs, int wpc) {
+  // landmarks per run-parallel chunk of wpc warps: runs * c <= 32 * wpc units, c <= 32, and Y fits the operand buffer
+  if (runs < 1 || runs > 32) return 0;
+  const int ycap = wpc == 1 ? LrCfg<1>::kY : (wpc == 2 ? LrCfg<2>::kY : LrCfg<4>::kY);
+  int c = std::min(32, 32 * wpc / runs);
+  while (c > 0 && (6 * runs + 1) * (((3 * c + 3) / 4) * 4 + 4) > ycap) --c;
+  return c;
+}
 int schur_mma_max_chunk(int runs) {
   // largest chunk size c <= 32 with (6 runs + 1) * (pad4(3c) + 4) <= kSchurYDoubles
   if (runs > kSchurMaxRuns) return 0;
@@ -2238,14 +2756,24 @@ void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {
   if (b.has_ext)
     k_schur<true><<<b.n_lm_tiles, kLmTile, 0, st>>>(b, opt);
   else if (b.n_schur_warps > 0) {
-    // class 0: > 16 landmarks per chunk (lane = landmark), 1: 9..16 (2 lanes / landmark), 2: <= 8 (4 lanes / landmark)
-    const int* list = b.sw_list;
+    // class 0: > 16 landmarks per chunk (lane = landmark), 1: 9..16 (2 lanes / landmark), 2: <= 8 (4 lanes / landmark),
+    // 3, 7, 8: run-parallel chunks of 1, 2, 4 warps (k_schur_lr), 4..6: warp-per-run chunks of 2..4 runs (k_schur_wr).  The expensive low-fill classes go first so that the cheap full chunks fill the tail of the grid.
+    // SVIN_SCHUR_CLASSMASK (diagnostics only: results are wrong when a class is skipped) times the classes separately.
+    static const int mask = std::getenv("SVIN_SCHUR_CLASSMASK") ? std::atoi(std::getenv("SVIN_SCHUR_CLASSMASK")) : 511;
+    const int* lst[kSchurClasses];
+    lst[0] = b.sw_list;
+    for (int k = 1; k < kSchurClasses; ++k) lst[k] = lst[k - 1] + b.sw_class_count[k - 1];
+    const int* cc = b.sw_class_count;
     const size_t sm = schur_mma_smem_bytes();
-    if (b.sw_class_count[0]) k_schur_mma<1><<<div_up(b.sw_class_count[0], 4), 128, sm, st>>>(b, opt, list, b.sw_class_count[0]);
-    list += b.sw_class_count[0];
-    if (b.sw_class_count[1]) k_schur_mma<2><<<div_up(b.sw_class_count[1], 4), 128, sm, st>>>(b, opt, list, b.sw_class_count[1]);
-    list += b.sw_class_count[1];
-    if (b.sw_class_count[2]) k_schur_mma<4><<<div_up(b.sw_class_count[2], 4), 128, sm, st>>>(b, opt, list, b.sw_class_count[2]);
+    if (cc[8] && (mask & 256)) k_schur_lr<4><<<cc[8], 128, LrCfg<4>::kDoubles * sizeof(double), st>>>(b, opt, lst[8]);
+    if (cc[7] && (mask & 128)) k_schur_lr<2><<<cc[7], 64, LrCfg<2>::kDoubles * sizeof(double), st>>>(b, opt, lst[7]);
+    if (cc[3] && (mask & 8)) k_schur_lr<1><<<cc[3], 32, LrCfg<1>::kDoubles * sizeof(double), st>>>(b, opt, lst[3]);
+    if (cc[6] && (mask & 64)) k_schur_wr<4><<<cc[6], 128, WrCfg<4>::kDoubles * sizeof(double), st>>>(b, opt, lst[6]);
+    if (cc[5] && (mask & 32)) k_schur_wr<3><<<cc[5], 96, WrCfg<3>::kDoubles * sizeof(double), st>>>(b, opt, lst[5]);
+    if (cc[4] && (mask & 16)) k_schur_wr<2><<<cc[4], 64, WrCfg<2>::kDoubles * sizeof(double), st>>>(b, opt, lst[4]);
+    if (cc[2] && (mask & 4)) k_schur_mma<4><<<div_up(cc[2], 4), 128, sm, st>>>(b, opt, lst[2], cc[2]);
+    if (cc[1] && (mask & 2)) k_schur_mma<2><<<div_up(cc[1], 4), 128, sm, st>>>(b, opt, lst[1], cc[1]);
+    if (cc[0] && (mask & 1)) k_schur_mma<1><<<div_up(cc[0], 4), 128, sm, st>>>(b, opt, lst[0], cc[0]);
   }
   else
     k_schur<false><<<b.n_lm_tiles, kLmTile, 0, st>>>(b, opt);

@@ -23,6 +23,7 @@ void launch_count_active(const Batch& b, int* out, cudaStream_t st);
 void launch_quality(const Batch& b, cudaStream_t st);
 size_t schur_mma_smem_bytes();
 int schur_mma_max_chunk(int runs);
+int schur_lr_max_chunk(int runs, int wpc);  // landmarks per run-parallel (k_schur_lr<wpc>) chunk, 0 = not eligible
 cudaError_t configure_schur();
 int schur_chunk_class(int count);  // which k_schur_mma<G> handles a chunk of `count` landmarks
 void launch_fold(const Batch& b, int stage, cudaStream_t st);

@@ -9,6 +9,7 @@ namespace svin {
 constexpr int kObsTile = 128;  // observations per CTA (linearise)
 constexpr int kLmTile = 128;   // landmarks per CTA (Schur / back-substitution / step)
 constexpr int kDenseThreads = 256;
+constexpr int kSchurClasses = 9;  // lane mappings of the Schur chunk kernels
 
 struct ImuP {
   double sigma_g_c, sigma_a_c, sigma_gw_c, sigma_aw_c, g, g_max, a_max;
@@ -147,7 +148,7 @@ struct Batch {
   int n_schur_warps;
   int *sw_win, *sw_lm_begin, *sw_count;
   int* sw_list;           // chunk ids ordered by lane-mapping class (schur_chunk_class), sw_class_count each
-  int sw_class_count[3];
+  int sw_class_count[kSchurClasses];  // 0..2 k_schur_mma<1|2|4>, 3/7/8 k_schur_lr<1|2|4>, 4..6 k_schur_wr<2..4>
   int *sw_nruns, *sw_run_first;  // pose runs of the chunk's pattern: count, first entry in run_off / run_k0m
   int *run_off, *run_k0m;        // per run: dense offset of its pose block (-1 fixed), (first obs k << 8) | obs count
   // linearisation, two buffers: planes [k][obs_stride]

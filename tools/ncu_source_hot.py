@@ -7,7 +7,7 @@ import sys
 
 
 def main(rep, kernel, top=40):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kernel, "--launch-count", "1",
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name-base", "demangled", "--kernel-name", kernel, "--launch-count", "1",
                           "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     cur_file, hdr, agg = None, None, {}
