@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <cstdlib>
+
 #include "ba_device_utils.cuh"
 #include "ba_kernels.cuh"
 
@@ -89,11 +91,118 @@ __global__ void __launch_bounds__(kTS* kTS, 2) k_dense_gram(Batch b, int which) 
     }
   if (tid < n) gg[tid] = gr_acc;
 }
+// Tensor-core version (fp64 mma.sync.m8n8k4, SASS DMMA): G = P^T P with P = [Jd | rd] staged kGP rows at a time;
+// each warp owns every 8th 8x8 tile pair of the lower triangle and keeps it in registers over all row panels, so the
+// Gram matrix costs ~1.5 k warp instructions per warp instead of the ~22 k of the register-tiled FMA version
+// (ncu r1t: 89 us -> see profiles/).  The extra column rd yields gg = Jd^T rd in the same product.
+constexpr int kGP = 32;         // rows per staged panel (8 k-steps)
+constexpr int kGPairTable = 288; // tile pairs of the lower triangle: T (T + 1) / 2 <= 288  ->  n + 1 <= 184
+__host__ __device__ inline int gram_ld(int n) {  // >= n + 1, = 4 (mod 16): conflict-free fragment loads
+  int ld = n + 1;
+  while ((ld & 15) != 4) ++ld;
+  return ld;
+}
+size_t dense_gram_mma_smem_bytes(int n) {
+  return sizeof(double) * (size_t)kGP * gram_ld(n) + sizeof(int) * kGPairTable;
+}
+static int gram_pairs(int n) {
+  const int T = (n + 1 + 7) / 8;
+  return T * (T + 1) / 2;
+}
+
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double bq) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(bq));
+}
+
+// NP = tile pairs per warp (8 warps)
+template <int NP>
+__global__ void __launch_bounds__(256, NP <= 16 ? 2 : 1) k_dense_gram_mma(Batch b, int which) {
+  extern __shared__ double smem[];
+  const int w = blockIdx.x;
+  WinState& ws = b.ws[w];
+  if (ws.done) return;
+  if (which == 1 && (ws.skip_slot || ws.gn_failed || !(-ws.acc_mc > 0.0))) return;  // as k_dense_eval
+  const WinDesc& wd = b.win[w];
+  const int buf = (which == 0) ? ws.cur : 1 - ws.cur;
+  const int n = wd.n_dense, M = wd.n_rows;
+  const int ld = gram_ld(n);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const double* Jd = b.Jd[buf] + wd.Jd_off;
+  const double* rd = b.rd[buf] + wd.rd_off;
+  double* G = b.gram[buf] + wd.H_off;
+  double* gg = b.gram_g[buf] + wd.d_off;
+  const int T = (n + 1 + 7) >> 3;
+  const int npairs = T * (T + 1) / 2;
+  // pair p -> (tm >= tn), row-major over the lower triangle of the T x T tile grid
+  int* pair_tab = reinterpret_cast<int*>(smem + (size_t)kGP * ld);
+  for (int p = tid; p < npairs; p += 256) {
+    int tm = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+    while (tm * (tm + 1) / 2 > p) --tm;
+    while ((tm + 1) * (tm + 2) / 2 <= p) ++tm;
+    pair_tab[p] = (tm << 8) | (p - tm * (tm + 1) / 2);
+  }
+  double acc[NP][2];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) acc[q][0] = acc[q][1] = 0.0;
+  for (int r0 = 0; r0 < M; r0 += kGP) {
+    const int rows = min(kGP, M - r0);
+    __syncthreads();
+    for (int e = tid; e < kGP * ld; e += 256) {
+      const int r = e / ld, c = e - r * ld;
+      double v = 0.0;
+      if (r < rows) {
+        if (c < n)
+          v = Jd[(size_t)(r0 + r) * n + c];
+        else if (c == n)
+          v = rd[r0 + r];
+      }
+      smem[e] = v;
+    }
+    __syncthreads();
+    const int ksteps = (rows + 3) >> 2;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      if (wid + 8 * q < npairs) {  // warp-uniform
+        const int tt = pair_tab[wid + 8 * q];
+        const double* pa = smem + t * ld + 8 * (tt >> 8) + g;
+        const double* pb = smem + t * ld + 8 * (tt & 255) + g;
+        for (int ks = 0; ks < ksteps; ++ks) dmma_884(acc[q][0], acc[q][1], pa[4 * ks * ld], pb[4 * ks * ld]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    if (wid + 8 * q < npairs) {
+      const int tt = pair_tab[wid + 8 * q];
+      const int i = 8 * (tt >> 8) + g;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = 8 * (tt & 255) + 2 * t + e;
+        const double v = acc[q][e];
+        if (i == n && j < n)
+          gg[j] = v;
+        else if (i < n && j <= i)
+          G[(size_t)i * n + j] = v;
+      }
+    }
+  }
+}
 cudaError_t configure_dense_gram(int smem_bytes) {
   return cudaFuncSetAttribute(k_dense_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 }
 void launch_dense_gram(const Batch& b, int which, int n_max, cudaStream_t st) {
-  k_dense_gram<<<b.B, kTS * kTS, dense_gram_smem_bytes(n_max), st>>>(b, which);
+  static const bool no_mma = std::getenv("SVIN_GRAM_FMA") != nullptr;  // A/B knob
+  const int pairs = gram_pairs(n_max);
+  const size_t sm = dense_gram_mma_smem_bytes(n_max);
+  if (!no_mma && pairs <= 8 * 16 && sm <= 48 * 1024)
+    k_dense_gram_mma<16><<<b.B, 256, sm, st>>>(b, which);
+  else if (!no_mma && pairs <= kGPairTable && sm <= 48 * 1024)
+    k_dense_gram_mma<36><<<b.B, 256, sm, st>>>(b, which);
+  else
+    k_dense_gram<<<b.B, kTS * kTS, dense_gram_smem_bytes(n_max), st>>>(b, which);
 }
 
 size_t dense_solve_smem_bytes(int n) {
@@ -118,6 +227,7 @@ __global__ void __launch_bounds__(kTS* kTS, 2) k_dense_solve_smem(Batch b, SvinB
   double* v_dg = v_sc + n;      // dogleg diagonal
   double* v_c = v_dg + n;       // scale * gradient_ / diag (Cauchy direction, unscaled space)
   double* v_tmp = v_c + n;
+  double* colk = v_tmp + n;     // current Cholesky column, dense copy (n + 1 entries)
   const double* Hg = b.H + wd.H_off;
   __shared__ unsigned long long gmax_s;
 
@@ -196,14 +306,18 @@ __global__ void __launch_bounds__(kTS* kTS, 2) k_dense_solve_smem(Batch b, SvinB
       break;
     }
     const double d = sqrt(akk);
-    for (int i = k + 1 + tid; i <= n; i += kTS * kTS) A[tri(i, k)] /= d;
+    for (int i = k + 1 + tid; i <= n; i += kTS * kTS) {
+      const double v = A[tri(i, k)] / d;
+      A[tri(i, k)] = v;
+      colk[i] = v;  // unit-stride copy: the trailing update below needs no triangular index arithmetic
+    }
     __syncthreads();
     if (tid == 0) A[tri(k, k)] = d;
     for (int i = k + 1 + ty; i <= n; i += kTS) {
-      const double aik = A[tri(i, k)];
+      const double aik = colk[i];
       const int jmax = min(i, n - 1);
       double* Ai = A + tri(i, 0);
-      for (int j = k + 1 + tx; j <= jmax; j += kTS) Ai[j] -= aik * A[tri(j, k)];
+      for (int j = k + 1 + tx; j <= jmax; j += kTS) Ai[j] -= aik * colk[j];
     }
   }
   __syncthreads();

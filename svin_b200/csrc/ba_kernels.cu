@@ -196,8 +196,8 @@ __device__ __forceinline__ void reproj_eval(const double* __restrict__ pose, con
 __device__ __forceinline__ bool step_is_invalid(const WinState& ws) { return ws.gn_failed || !(-ws.acc_mc > 0.0); }
 
 // which: 0 = linearise the current estimate (initialisation), 1 = the candidate.  raw: evaluation dump.
-template <bool HAS_EXT>
-__global__ void __launch_bounds__(kObsTile) k_linearize(Batch b, int which, int raw) {
+template <bool HAS_EXT, int MINB>
+__global__ void __launch_bounds__(kObsTile, MINB) k_linearize(Batch b, int which, int raw) {
   const int tile = blockIdx.x;
   const int w = b.obs_tile_win[tile];
   const int o = b.obs_tile_begin[tile] + threadIdx.x;
@@ -2270,21 +2270,28 @@ __global__ void __launch_bounds__(kDenseThreads) k_dense_solve(Batch b, SvinBaOp
 }
 
 // ------------------------------------------------------------------------------------------ back-substitution
-template <bool HAS_EXT>
-__global__ void __launch_bounds__(kLmTile) k_backsub(Batch b) {
+// SPLIT threads share a landmark (they take every SPLIT-th observation and add their sums with shuffles): the
+// kernel is bound by the per-observation load latency chain, not by bandwidth, so halving the chain pays.
+template <bool HAS_EXT, int SPLIT>
+__global__ void __launch_bounds__(kLmTile * SPLIT) k_backsub(Batch b) {
   const int tile = blockIdx.x;
   const int w = b.lm_tile_win[tile];
   WinState& ws = b.ws[w];
   if (ws.done || ws.reuse || ws.skip_slot || ws.gn_failed) return;
   const WinDesc& wd = b.win[w];
-  const int l = b.lm_tile_begin[tile] + threadIdx.x;
+  const int l = b.lm_tile_begin[tile] + threadIdx.x / SPLIT;
+  const int half = threadIdx.x % SPLIT;
   const int buf = ws.cur;
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // g2, n2, gdot, Jg2, acc_A[0..4]
-  if (l < wd.lm_end) {
+  const bool in_range = l < wd.lm_end;
+  const bool lfix = in_range ? b.lm_fixed[l] != 0 : true;
+  double s[3] = {1, 1, 1}, cl[3] = {0, 0, 0}, gr[3] = {0, 0, 0}, dg[3] = {1, 1, 1};
+  // per landmark: a3 = sum Jl^T t, jg = sum Jl^T mg, jr = sum Jl^T r, V = sum Jl^T Jl   (t = Jp u, mg = J cauchy)
+  double a3[3] = {0, 0, 0}, jg[3] = {0, 0, 0}, jr[3] = {0, 0, 0}, V[6] = {0, 0, 0, 0, 0, 0};
+  double s_tr = 0, s_tt = 0, s_gt = 0;
+  if (in_range) {
     const double* u = b.u_d + wd.d_off;
     const double* cv = b.c_d + wd.d_off;
-    const bool lfix = b.lm_fixed[l] != 0;
-    double s[3] = {1, 1, 1}, cl[3] = {0, 0, 0}, gr[3] = {0, 0, 0}, dg[3] = {1, 1, 1};
     if (!lfix) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -2294,11 +2301,8 @@ __global__ void __launch_bounds__(kLmTile) k_backsub(Batch b) {
         cl[k] = s[k] * gr[k] / dg[k];
       }
     }
-    // per landmark: a3 = sum Jl^T t, jg = sum Jl^T mg, jr = sum Jl^T r, V = sum Jl^T Jl   (t = Jp u, mg = J cauchy)
-    double a3[3] = {0, 0, 0}, jg[3] = {0, 0, 0}, jr[3] = {0, 0, 0}, V[6] = {0, 0, 0, 0, 0, 0};
-    double s_tr = 0, s_tt = 0, s_gt = 0;
     const int ob = b.lm_obs_first[l], ost = b.lm_obs_stride[l], nobs = b.lm_obs_cnt[l];
-    for (int k = 0; k < nobs; ++k) {
+    for (int k = half; k < nobs; k += SPLIT) {
       const int o = ob + k * ost;
       ObsJ J;
       load_obs(b, buf, o, J);
@@ -2350,6 +2354,27 @@ __global__ void __launch_bounds__(kLmTile) k_backsub(Batch b) {
       s_tt += t0 * t0 + t1 * t1;
       s_gt += m0 * t0 + m1 * t1;
     }
+  }
+  if (SPLIT > 1) {
+#pragma unroll
+    for (int o2 = 1; o2 < SPLIT; o2 <<= 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        a3[k] += __shfl_xor_sync(0xffffffffu, a3[k], o2);
+        jg[k] += __shfl_xor_sync(0xffffffffu, jg[k], o2);
+        jr[k] += __shfl_xor_sync(0xffffffffu, jr[k], o2);
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) V[k] += __shfl_xor_sync(0xffffffffu, V[k], o2);
+      s_tr += __shfl_xor_sync(0xffffffffu, s_tr, o2);
+      s_tt += __shfl_xor_sync(0xffffffffu, s_tt, o2);
+      s_gt += __shfl_xor_sync(0xffffffffu, s_gt, o2);
+      acc[3] += __shfl_xor_sync(0xffffffffu, acc[3], o2);
+      acc[4] += __shfl_xor_sync(0xffffffffu, acc[4], o2);
+    }
+    if (half != 0) acc[3] = acc[4] = 0.0;
+  }
+  if (in_range && half == 0) {
     acc[6] = acc[3];
     double q[3] = {0, 0, 0};  // s o y: minus the landmark's Gauss-Newton step in the original parameters
     if (!lfix) {
@@ -2382,7 +2407,7 @@ __global__ void __launch_bounds__(kLmTile) k_backsub(Batch b) {
   double* const dst[9] = {sa ? sa + 0 : &ws.acc_g2,   sa ? sa + 1 : &ws.acc_n2,   sa ? sa + 2 : &ws.acc_gdot,
                           sa ? sa + 3 : &ws.acc_Jg2,  sa ? sa + 4 : &ws.acc_A[0], sa ? sa + 5 : &ws.acc_A[1],
                           sa ? sa + 6 : &ws.acc_A[2], sa ? sa + 7 : &ws.acc_A[3], sa ? sa + 8 : &ws.acc_A[4]};
-  block_atomic_add<9, kLmTile>(acc, dst);
+  block_atomic_add<9, kLmTile * SPLIT>(acc, dst);
 }
 
 // ------------------------------------------------------------------------------------------ dogleg step
@@ -2735,10 +2760,15 @@ int schur_chunk_class(int count) { return count <= 8 ? 2 : (count <= 16 ? 1 : 0)
 
 void launch_linearize(const Batch& b, int which, int raw, cudaStream_t st) {
   if (b.n_obs_tiles == 0) return;
+  static const int minb = std::getenv("SVIN_LIN_MINB") ? std::atoi(std::getenv("SVIN_LIN_MINB")) : 5;  // A/B knob: 5 CTAs/SM (96 registers, 100 B spilled) measured fastest
   if (b.has_ext || (raw && b.lin_Je[1] != nullptr))
-    k_linearize<true><<<b.n_obs_tiles, kObsTile, 0, st>>>(b, which, raw);
+    k_linearize<true, 4><<<b.n_obs_tiles, kObsTile, 0, st>>>(b, which, raw);
+  else if (minb == 5)
+    k_linearize<false, 5><<<b.n_obs_tiles, kObsTile, 0, st>>>(b, which, raw);
+  else if (minb == 6)
+    k_linearize<false, 6><<<b.n_obs_tiles, kObsTile, 0, st>>>(b, which, raw);
   else
-    k_linearize<false><<<b.n_obs_tiles, kObsTile, 0, st>>>(b, which, raw);
+    k_linearize<false, 4><<<b.n_obs_tiles, kObsTile, 0, st>>>(b, which, raw);
 }
 void launch_dense_eval(const Batch& b, int which, int raw, const double* const* dump, cudaStream_t st) {
   ImuEvalOut d{nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -2784,10 +2814,15 @@ void launch_dense_solve_generic(const Batch& b, const SvinBaOptions& opt, cudaSt
 }
 void launch_backsub(const Batch& b, cudaStream_t st) {
   if (b.n_lm_tiles == 0) return;
+  static const int split = std::getenv("SVIN_BACKSUB_SPLIT") ? std::atoi(std::getenv("SVIN_BACKSUB_SPLIT")) : 1;  // A/B knob: 2 and 4 measured slower (r1t)
   if (b.has_ext)
-    k_backsub<true><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
+    k_backsub<true, 1><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
+  else if (split == 2)
+    k_backsub<false, 2><<<b.n_lm_tiles, 2 * kLmTile, 0, st>>>(b);
+  else if (split == 4)
+    k_backsub<false, 4><<<b.n_lm_tiles, 4 * kLmTile, 0, st>>>(b);
   else
-    k_backsub<false><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
+    k_backsub<false, 1><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
 }
 void launch_step_dense(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {
   k_step_dense<<<b.B, 128, 0, st>>>(b, opt);

@@ -1,7 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_dense_eval|k_dense_gram|k_dense_solve_smem|k_step_dense|k_step_lm|k_backsub|k_linearize" -s 14 -c 7 -o gpurun_out/t5_prof -f python tools/schur_probe.py --windows 256 --solves 1 --no-prof > gpurun_out/t5_ncu.log 2>&1; echo "ncu rc=$?"
-SVIN_BA_NO_FORK=1 timeout 300 python tools/schur_probe.py --no-prof --solves 3 >> gpurun_out/t5_probe.log 2>&1
-timeout 300 python tools/schur_probe.py --no-prof --solves 3 >> gpurun_out/t5_probe.log 2>&1
-timeout 300 python tools/schur_probe.py --no-prof --solves 3 --windows 296 >> gpurun_out/t5_probe.log 2>&1
-cat gpurun_out/t5_probe.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t7_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/t7_pytest.log
+for sp in 1 2 4; do echo "split $sp" >> gpurun_out/t7_probe.log; SVIN_BACKSUB_SPLIT=$sp timeout 300 python tools/schur_probe.py >> gpurun_out/t7_probe.log 2>&1; done
+for mb in 5 6; do echo "minb $mb" >> gpurun_out/t7_probe.log; SVIN_LIN_MINB=$mb timeout 300 python tools/schur_probe.py >> gpurun_out/t7_probe.log 2>&1; done
+cat gpurun_out/t7_probe.log
