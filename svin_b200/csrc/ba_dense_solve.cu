@@ -387,12 +387,263 @@ __global__ void __launch_bounds__(kTS* kTS, 2) k_dense_solve_smem(Batch b, SvinB
   block_atomic_add<4, kTS * kTS>(v, dst);
 }
 
+// Register-resident variant for n + 1 <= 16 NB: thread (ty, tx) of the 16 x 16 layout owns the elements (i, j) with
+// i = ty, j = tx (mod 16) of the lower triangle (NB (NB + 1) / 2 blocks -> as many registers), the right-hand side is
+// row n.  Per column only the scaled column travels through shared memory (one vector + the next pivot), the rank-1
+// update is pure register arithmetic: 2 barriers and <= NB (NB + 1) / 2 DFMA per thread per column instead of
+// 4 shared-memory accesses per updated element (ncu r1t: the update loop was 54 % of the smem kernel's instructions).
+template <int NB, int KB>
+__device__ __forceinline__ void chol_column(double (&a)[NB * (NB + 1) / 2], int k, int n, int tx, int ty, double akk,
+                                            double* colk, double* akk_s) {
+  constexpr int DI = KB * (KB + 1) / 2 + KB;  // block (KB, KB)
+  const int kt = k & 15;
+  // owners of column k (one half-warp: tx is the slow thread index) scale it and publish it; one reciprocal per
+  // column instead of a division per element (1 ulp from Eigen's A21 /= x, far inside the 1e-6 parity gate)
+  if (tx == kt) {
+    const double d = sqrt(akk);
+    const double inv = 1.0 / d;
+#pragma unroll
+    for (int x = KB; x < NB; ++x) {
+      const int i = 16 * x + ty;
+      double& e = a[x * (x + 1) / 2 + KB];
+      if (i > k && i <= n) {
+        e = e * inv;
+        colk[i] = e;
+      } else if (i == k) {
+        e = d;
+      }
+    }
+  }
+  __syncthreads();
+  double ri[NB], cj[NB];
+#pragma unroll
+  for (int x = KB; x < NB; ++x) {
+    const int i = 16 * x + ty, j = 16 * x + tx;
+    ri[x] = (i > k && i <= n) ? colk[i] : 0.0;
+    cj[x] = (j > k && j < n) ? colk[j] : 0.0;
+  }
+#pragma unroll
+  for (int x = KB; x < NB; ++x)
+#pragma unroll
+    for (int y = KB; y <= x; ++y) a[x * (x + 1) / 2 + y] -= ri[x] * cj[y];
+  // the next pivot
+  const int nt = (k + 1) & 15;
+  if (ty == nt && tx == nt) {
+    if (kt == 15) {
+      if (KB + 1 < NB) *akk_s = a[(KB + 1 < NB ? KB + 1 : KB) * ((KB + 1 < NB ? KB + 1 : KB) + 1) / 2 + (KB + 1 < NB ? KB + 1 : KB)];
+    } else {
+      *akk_s = a[DI];
+    }
+  }
+  __syncthreads();
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kTS* kTS, 2) k_dense_solve_reg(Batch b, SvinBaOptions opt) {
+  extern __shared__ double smem[];
+  const int w = blockIdx.x;
+  WinState& ws = b.ws[w];
+  if (ws.done || ws.reuse) return;
+  const WinDesc& wd = b.win[w];
+  const int n = wd.n_dense, buf = ws.cur;
+  const int tid = threadIdx.x, ty = tid & (kTS - 1), tx = tid >> 4;  // a column's owners share a half-warp
+  const int lane = tid & 31, wid = tid >> 5;
+  double* A = smem;
+  double* v_hd = A + (size_t)(n + 1) * (n + 2) / 2;  // column square norms
+  double* v_graw = v_hd + n;    // unreduced gradient
+  double* v_gred = v_graw + n;  // reduced rhs
+  double* v_sc = v_gred + n;    // Jacobi scale
+  double* v_dg = v_sc + n;      // dogleg diagonal
+  double* v_c = v_dg + n;       // scale * gradient_ / diag (Cauchy direction, unscaled space)
+  double* v_tmp = v_c + n;
+  double* colk = v_tmp + n;     // current Cholesky column (n + 1 entries)
+  __shared__ double akk_s;
+  const double* Hg = b.H + wd.H_off;
+  __shared__ unsigned long long gmax_s;
+
+  // ---- 1. A(lower) = H~ + Jd^T Jd; the Gram matrix of the dense rows comes from k_dense_gram
+  const double* G = b.gram[buf] + wd.H_off;
+  double a[NB * (NB + 1) / 2];
+#pragma unroll
+  for (int x = 0; x < NB; ++x)
+#pragma unroll
+    for (int y = 0; y <= x; ++y) {
+      const int i = 16 * x + ty, j = 16 * y + tx;
+      a[x * (x + 1) / 2 + y] = (i < n && j <= i) ? G[(size_t)i * n + j] + Hg[(size_t)j * n + i] : 0.0;  // H~: upper
+    }
+  const double hd_acc = (tid < n) ? G[(size_t)tid * n + tid] : 0.0;
+  const double gr_acc = (tid < n) ? b.gram_g[buf][wd.d_off + tid] : 0.0;
+  // ---- 2. vectors
+  double gmax_l = 0.0;
+  if (tid < n) {
+    const double hd = b.Hdiag[wd.d_off + tid] + hd_acc;
+    const double gr = b.g_raw[wd.d_off + tid] + gr_acc;
+    v_hd[tid] = hd;
+    v_graw[tid] = gr;
+    v_gred[tid] = b.g_red[wd.d_off + tid] + gr_acc;
+    gmax_l = fabs(gr);
+  }
+
+  atomic_max_nonneg(&ws.gmax_bits, gmax_l);
+  __syncthreads();
+  if (tid == 0) gmax_s = atomicMax(&ws.gmax_bits, 0ull);  // atomic read (L1 may hold a stale WinState line)
+  __syncthreads();
+  // ---- 3. gradient tolerance (checked after the max-iteration test of the previous slot)
+  if (ws.last_successful && __longlong_as_double((long long)gmax_s) <= opt.gradient_tolerance) {
+    if (tid == 0) {
+      ws.done = 1;
+      ws.termination = SVIN_TERM_CONVERGENCE;
+    }
+    return;
+  }
+  // ---- 4. Jacobi scaling (first Jacobian only), dogleg diagonal, scaled gradient
+  const bool first_jac = (ws.iter == 0 && ws.num_successful == 0 && !ws.invalid);
+  const double mu = ws.mu;
+  if (tid < n) {
+    double s;
+    if (first_jac) {
+      s = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(v_hd[tid])) : 1.0;
+      b.scale_d[wd.d_off + tid] = s;
+    } else {
+      s = b.scale_d[wd.d_off + tid];
+    }
+    const double d = sqrt(fmin(fmax(v_hd[tid] * s * s, opt.min_lm_diagonal), opt.max_lm_diagonal));
+    const double g = s * v_graw[tid] / d;
+    v_sc[tid] = s;
+    v_dg[tid] = d;
+    v_tmp[tid] = g;  // gradient_
+    b.diag_d[wd.d_off + tid] = d;
+    b.grad_d[wd.d_off + tid] = g;
+  }
+  __syncthreads();
+  // ---- 5. scaled system + LM diagonal; rhs row n
+#pragma unroll
+  for (int x = 0; x < NB; ++x)
+#pragma unroll
+    for (int y = 0; y <= x; ++y) {
+      const int i = 16 * x + ty, j = 16 * y + tx;
+      double& e = a[x * (x + 1) / 2 + y];
+      if (i < n && j <= i) {
+        double v = e * v_sc[i] * v_sc[j];
+        if (i == j) v += mu * v_dg[i] * v_dg[i];
+        e = v;
+      } else if (i == n && j < n) {
+        e = v_sc[j] * v_gred[j];
+      }
+    }
+  // ---- 6. right-looking Cholesky in registers, rhs row included (forward substitution)
+  if (tid == 0) akk_s = a[0];
+  __syncthreads();
+  bool fail = false;
+  for (int k = 0; k < n; ++k) {
+    const double akk = akk_s;
+    if (!(akk > 0.0) || !isfinite(akk)) {
+      fail = true;
+      break;
+    }
+    switch (k >> 4) {
+      case 0: chol_column<NB, 0>(a, k, n, tx, ty, akk, colk, &akk_s); break;
+      case 1: if (NB > 1) chol_column<NB, (NB > 1 ? 1 : 0)>(a, k, n, tx, ty, akk, colk, &akk_s); break;
+      case 2: if (NB > 2) chol_column<NB, (NB > 2 ? 2 : 0)>(a, k, n, tx, ty, akk, colk, &akk_s); break;
+      case 3: if (NB > 3) chol_column<NB, (NB > 3 ? 3 : 0)>(a, k, n, tx, ty, akk, colk, &akk_s); break;
+      case 4: if (NB > 4) chol_column<NB, (NB > 4 ? 4 : 0)>(a, k, n, tx, ty, akk, colk, &akk_s); break;
+      case 5: if (NB > 5) chol_column<NB, (NB > 5 ? 5 : 0)>(a, k, n, tx, ty, akk, colk, &akk_s); break;
+      default: if (NB > 6) chol_column<NB, (NB > 6 ? 6 : 0)>(a, k, n, tx, ty, akk, colk, &akk_s); break;
+    }
+  }
+  // the factor (and the forward-substituted rhs row) go to the packed layout the back-substitution reads
+  if (!fail) {
+#pragma unroll
+    for (int x = 0; x < NB; ++x)
+#pragma unroll
+      for (int y = 0; y <= x; ++y) {
+        const int i = 16 * x + ty, j = 16 * y + tx;
+        if (i <= n && j <= i && j < n) A[tri(i, j)] = a[x * (x + 1) / 2 + y];
+      }
+  }
+  __syncthreads();
+  if (fail) {
+    if (tid == 0) {
+      // DoglegStrategy::ComputeGaussNewtonStep: mu *= 10 and retry while mu < max_mu (1.0)
+      ws.mu *= 10.0;
+      if (ws.mu < 1.0)
+        ws.skip_slot = 1;  // re-eliminate next slot, no iteration consumed
+      else
+        ws.gn_failed = 1;  // linear solver FAILURE -> invalid step
+    }
+    return;
+  }
+  // ---- 7. backward solve L^T y = z (row n) by warp 0
+  double* z = A + tri(n, 0);
+  if (wid == 0) {
+    for (int k = n - 1; k >= 0; --k) {
+      const double yk = z[k] / A[tri(k, k)];
+      __syncwarp();
+      if (lane == 0) z[k] = yk;
+      const double* Lk = A + tri(k, 0);
+      for (int i = lane; i < k; i += 32) z[i] -= Lk[i] * yk;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // ---- 8. outputs
+  bool bad = false;
+  double g2 = 0, n2 = 0, gd = 0;
+  if (tid < n) {
+    const double y = z[tid];
+    if (!isfinite(y)) bad = true;
+    const double g = v_tmp[tid];
+    const double gni = -y * v_dg[tid];
+    b.gn_d[wd.d_off + tid] = gni;
+    b.u_d[wd.d_off + tid] = v_sc[tid] * y;
+    const double cv = v_sc[tid] * g / v_dg[tid];
+    b.c_d[wd.d_off + tid] = cv;
+    v_c[tid] = cv;
+    g2 = g * g;
+    n2 = gni * gni;
+    gd = g * gni;
+  }
+  if (__syncthreads_or(bad)) {
+    if (tid == 0) {
+      ws.mu *= 10.0;
+      if (ws.mu < 1.0)
+        ws.skip_slot = 1;
+      else
+        ws.gn_failed = 1;
+    }
+    return;
+  }
+  // Cauchy point over the dense rows: sum_r (Jd[r,:] . c)^2 = c^T (Jd^T Jd) c with the Gram matrix (lower triangle)
+  __syncthreads();
+  double jg2 = 0.0;
+  for (int i = wid; i < n; i += kTS * kTS / 32) {
+    const double* Gi = G + (size_t)i * n;
+    double sdot = 0.0;
+    for (int j = lane; j < i; j += 32) sdot += Gi[j] * v_c[j];
+    sdot = warp_sum(sdot);
+    if (lane == 0) jg2 += v_c[i] * (2.0 * sdot + Gi[i] * v_c[i]);
+  }
+  double v[4] = {g2, n2, gd, jg2};
+  double* const dst[4] = {&ws.acc_g2, &ws.acc_n2, &ws.acc_gdot, &ws.acc_Jg2};
+  block_atomic_add<4, kTS * kTS>(v, dst);
+}
+
 cudaError_t configure_dense_solve(int smem_bytes) {
-  return cudaFuncSetAttribute(k_dense_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  cudaError_t e = cudaFuncSetAttribute(k_dense_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_dense_solve_reg<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_dense_solve_reg<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  return e;
 }
 void launch_dense_solve_generic(const Batch& b, const SvinBaOptions& opt, cudaStream_t st);
-void launch_dense_solve(const Batch& b, const SvinBaOptions& opt, int smem_bytes, cudaStream_t st) {
-  if (smem_bytes > 0)
+void launch_dense_solve(const Batch& b, const SvinBaOptions& opt, int smem_bytes, int n_max, cudaStream_t st) {
+  static const bool no_reg = std::getenv("SVIN_SOLVE_SMEM") != nullptr;  // A/B knob
+  if (smem_bytes > 0 && !no_reg && n_max + 1 <= 16 * 5)
+    k_dense_solve_reg<5><<<b.B, kTS * kTS, smem_bytes, st>>>(b, opt);
+  else if (smem_bytes > 0 && !no_reg && n_max + 1 <= 16 * 7)
+    k_dense_solve_reg<7><<<b.B, kTS * kTS, smem_bytes, st>>>(b, opt);
+  else if (smem_bytes > 0)
     k_dense_solve_smem<<<b.B, kTS * kTS, smem_bytes, st>>>(b, opt);
   else
     launch_dense_solve_generic(b, opt, st);

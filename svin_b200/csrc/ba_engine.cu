@@ -1116,7 +1116,7 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
     if ((rc = comm_allreduce(c, b.gmax_buf, (size_t)b.B, kNcclMax)) != SVIN_OK) return rc;
     launch_gmax_pack(b, 1, c->stream);
   }
-  { ProfScope p(c, SVIN_BA_K_DENSE_SOLVE); launch_dense_solve(b, opt, c->smem_bytes, c->stream); }
+  { ProfScope p(c, SVIN_BA_K_DENSE_SOLVE); launch_dense_solve(b, opt, c->smem_bytes, c->n_max, c->stream); }
   { ProfScope p(c, SVIN_BA_K_BACKSUB); launch_backsub(b, c->stream); }
   if (sharded) {
     if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;

@@ -1321,44 +1321,42 @@ __global__ void __launch_bounds__(32 * NR, WrCfg<NR>::kMinBlocks) k_schur_wr(Bat
     for (int k = 0; k < 3; ++k) dst[6 + k] = bl[k];
   }
   __syncthreads();
+  // warp 0 finishes the landmark blocks (scale, damping, inverse factor) and hands s, M to the other warps
+  double s[3] = {1.0, 1.0, 1.0}, M[6], u[3] = {0.0, 0.0, 0.0};
+  double* sM = Ps;  // the P tiles are free now: [32][9]
+  if (a == 0) {
 #pragma unroll
-  for (int k = 0; k < 6; ++k) V[k] = 0.0;
+    for (int k = 0; k < 6; ++k) V[k] = 0.0;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) bl[k] = 0.0;
+    for (int k = 0; k < 3; ++k) bl[k] = 0.0;
 #pragma unroll
-  for (int a2 = 0; a2 < NR; ++a2) {
-    const double* src = Ys + (size_t)(a2 * 32 + lane) * 9;
+    for (int a2 = 0; a2 < NR; ++a2) {
+      const double* src = Ys + (size_t)(a2 * 32 + lane) * 9;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) V[k] += src[k];
+      for (int k = 0; k < 6; ++k) V[k] += src[k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) bl[k] += src[6 + k];
-  }
-  __syncthreads();
-  double s[3] = {1.0, 1.0, 1.0}, M[6], u[3];
-  const bool owner = active && a == 0;
-  if (ws.iter == 0 && ws.num_successful == 0 && !ws.invalid) {
-    if (opt.jacobi_scaling) {
-      s[0] = 1.0 / (1.0 + sqrt(V[0]));
-      s[1] = 1.0 / (1.0 + sqrt(V[3]));
-      s[2] = 1.0 / (1.0 + sqrt(V[5]));
+      for (int k = 0; k < 3; ++k) bl[k] += src[6 + k];
     }
-    if (owner) {
-      b.lm_scale[3 * (size_t)l] = s[0];
-      b.lm_scale[3 * (size_t)l + 1] = s[1];
-      b.lm_scale[3 * (size_t)l + 2] = s[2];
+    if (ws.iter == 0 && ws.num_successful == 0 && !ws.invalid) {
+      if (opt.jacobi_scaling) {
+        s[0] = 1.0 / (1.0 + sqrt(V[0]));
+        s[1] = 1.0 / (1.0 + sqrt(V[3]));
+        s[2] = 1.0 / (1.0 + sqrt(V[5]));
+      }
+      if (active) {
+        b.lm_scale[3 * (size_t)l] = s[0];
+        b.lm_scale[3 * (size_t)l + 1] = s[1];
+        b.lm_scale[3 * (size_t)l + 2] = s[2];
+      }
+    } else {
+      s[0] = b.lm_scale[3 * (size_t)l];
+      s[1] = b.lm_scale[3 * (size_t)l + 1];
+      s[2] = b.lm_scale[3 * (size_t)l + 2];
     }
-  } else {
-    s[0] = b.lm_scale[3 * (size_t)l];
-    s[1] = b.lm_scale[3 * (size_t)l + 1];
-    s[2] = b.lm_scale[3 * (size_t)l + 2];
-  }
-  {
-    if (a == 0) {
-      double gm = active ? fmax(fabs(bl[0]), fmax(fabs(bl[1]), fabs(bl[2]))) : 0.0;
+    double gm = active ? fmax(fabs(bl[0]), fmax(fabs(bl[1]), fabs(bl[2]))) : 0.0;
 #pragma unroll
-      for (int o2 = 16; o2 > 0; o2 >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o2));
-      if (lane == 0) atomic_max_nonneg(&ws.gmax_bits, gm);
-    }
+    for (int o2 = 16; o2 > 0; o2 >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o2));
+    if (lane == 0) atomic_max_nonneg(&ws.gmax_bits, gm);
     double Vs[6] = {V[0] * s[0] * s[0], V[1] * s[0] * s[1], V[2] * s[0] * s[2],
                     V[3] * s[1] * s[1], V[4] * s[1] * s[2], V[5] * s[2] * s[2]};
     const double d0 = sqrt(fmin(fmax(Vs[0], opt.min_lm_diagonal), opt.max_lm_diagonal));
@@ -1373,7 +1371,7 @@ __global__ void __launch_bounds__(32 * NR, WrCfg<NR>::kMinBlocks) k_schur_wr(Bat
     u[0] = M[0] * bs0;
     u[1] = M[1] * bs0 + M[2] * bs1;
     u[2] = M[3] * bs0 + M[4] * bs1 + M[5] * bs2;
-    if (owner) {
+    if (active) {
       double* p = b.lm_Vinv + 6 * (size_t)l;
 #pragma unroll
       for (int k = 0; k < 6; ++k) p[k] = Vi[k];
@@ -1384,6 +1382,19 @@ __global__ void __launch_bounds__(32 * NR, WrCfg<NR>::kMinBlocks) k_schur_wr(Bat
       p = b.lm_grad + 3 * (size_t)l;
       p[0] = bs0 / d0; p[1] = bs1 / d1; p[2] = bs2 / d2;
     }
+    double* dst = sM + lane * 9;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dst[k] = s[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dst[3 + k] = M[k];
+  }
+  __syncthreads();
+  if (a != 0) {
+    const double* src = sM + lane * 9;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s[k] = src[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) M[k] = src[3 + k];
   }
   // ---- Y = [W_a diag(s) M^T ; (M b)^T]
   if (active) {

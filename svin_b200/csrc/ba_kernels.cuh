@@ -13,7 +13,7 @@ cudaError_t configure_dense_solve(int smem_bytes);
 size_t dense_gram_smem_bytes(int n_max);
 cudaError_t configure_dense_gram(int smem_bytes);
 void launch_dense_gram(const Batch& b, int which, int n_max, cudaStream_t st);  // after launch_dense_eval(which)
-void launch_dense_solve(const Batch& b, const SvinBaOptions& opt, int smem_bytes, cudaStream_t st);
+void launch_dense_solve(const Batch& b, const SvinBaOptions& opt, int smem_bytes, int n_max, cudaStream_t st);
 void launch_backsub(const Batch& b, cudaStream_t st);
 void launch_step_dense(const Batch& b, const SvinBaOptions& opt, cudaStream_t st);
 void launch_step_lm(const Batch& b, cudaStream_t st);
