@@ -275,11 +275,16 @@ def run_frontend(args, local, rank, world, dist, barrier):
 
     barrier()
     t0 = time.perf_counter()
-    th = [threading.Thread(target=detect_loop), threading.Thread(target=match_loop)]
-    for x in th:
-        x.start()
-    for x in th:
-        x.join()
+    if args.skip_e2e:   # single-threaded under ncu
+        n_pipe = 1
+        detect_loop()
+        match_loop()
+    else:
+        th = [threading.Thread(target=detect_loop), threading.Thread(target=match_loop)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
     barrier()
     t_pipe = time.perf_counter() - t0
     if errs:
@@ -446,42 +451,53 @@ def run_gpu(args):
     dt = max_over_ranks(dist, dt, local)
     value = world * B * args.steps / dt
 
-    # ---------------- end to end through the C ABI with host buffers ("e2e")
-    # serial: one blocking svin_ba_optimize per step.  pipelined: two contexts, each driven by its own host
-    # thread (ctypes releases the GIL), so that packing + H2D of step k+1 overlaps the solve of step k.
-    from svin_b200.engine import BaPipeline
-    pipe_depth = int(os.environ.get("SVIN_PIPE_DEPTH", "2"))
-    pipe = BaPipeline(local, depth=pipe_depth)
-    for _ in range(2):
-        eng.optimize([w.copy() for w in batch], opt)
-    pipe.optimize_many([[w.copy() for w in batch] for _ in range(2)], opt)
-    n_e2e = max(args.steps, 16)   # enough steps to amortise the pipeline fill (one upload) and drain
+    e2e_line = None
+    if not args.skip_e2e:
+        # ---------------- end to end through the C ABI with host buffers ("e2e")
+        # serial: one blocking svin_ba_optimize per step.  pipelined: two contexts, each driven by its own host
+        # thread (ctypes releases the GIL), so that packing + H2D of step k+1 overlaps the solve of step k.
+        from svin_b200.engine import BaPipeline
+        pipe_depth = int(os.environ.get("SVIN_PIPE_DEPTH", "3"))
+        pipe = BaPipeline(local, depth=pipe_depth)
+        for _ in range(2):
+            eng.optimize([w.copy() for w in batch], opt)
+        pipe.optimize_many([[w.copy() for w in batch] for _ in range(2 * pipe_depth)], opt)
+        n_e2e = max(args.steps, 16)   # enough steps to amortise the pipeline fill (one upload) and drain
 
-    def fresh_sets():
-        sets = [[w.copy() for w in batch] for _ in range(n_e2e)]
-        for s in sets:
-            for w in s:
-                w.c_struct()
-        return sets
+        def fresh_sets():
+            sets = [[w.copy() for w in batch] for _ in range(n_e2e)]
+            for s in sets:
+                for w in s:
+                    w.c_struct()
+            return sets
 
-    e2e_sets = fresh_sets()
-    barrier()
-    t0 = time.perf_counter()
-    for s in e2e_sets:
-        eng.optimize(s, opt)
-    barrier()
-    dt_serial = max_over_ranks(dist, time.perf_counter() - t0, local)
-    tm = eng.timings()
-    e2e_sets = fresh_sets()
-    barrier()
-    t0 = time.perf_counter()
-    pipe.optimize_many(e2e_sets, opt)
-    barrier()
-    dt_e2e = max_over_ranks(dist, time.perf_counter() - t0, local)
-    pipe_trace = pipe.trace
-    e2e_value = world * B * n_e2e / dt_e2e
-    e2e_serial = world * B * n_e2e / dt_serial
-    pipe.close()
+        e2e_sets = fresh_sets()
+        barrier()
+        t0 = time.perf_counter()
+        for s in e2e_sets:
+            eng.optimize(s, opt)
+        barrier()
+        dt_serial = max_over_ranks(dist, time.perf_counter() - t0, local)
+        tm = eng.timings()
+        e2e_sets = fresh_sets()
+        barrier()
+        t0 = time.perf_counter()
+        pipe.optimize_many(e2e_sets, opt)
+        barrier()
+        dt_e2e = max_over_ranks(dist, time.perf_counter() - t0, local)
+        pipe_trace = pipe.trace
+        e2e_value = world * B * n_e2e / dt_e2e
+        e2e_serial = world * B * n_e2e / dt_serial
+        pipe.close()
+        e2e_line = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tm["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(tm["d2h_bytes"]), "ms_per_step": 1e3 * dt_e2e / n_e2e,
+                    "steps": n_e2e,
+                    "pipeline": f"BaPipeline: {pipe_depth} contexts x 1 driver thread + {pipe.host_threads - 1} packing workers each, uploads of the next steps overlap the solve of step k", "host_cores": os.cpu_count(),
+                    "pipeline_trace_ms": pipe_trace,
+                    "serial": {"value": e2e_serial, "ms_per_step": 1e3 * dt_serial / n_e2e},
+                    "last_step_breakdown_ms": {k: round(float(tm[k]), 3) for k in (
+                        "host_order_ms", "host_fill_ms", "host_upload_ms", "h2d_ms", "solve_ms", "d2h_ms",
+                        "host_scatter_ms")}}
 
     # ---------------- per-kernel times (profiling pass, not part of the timed numbers)
     eng.upload(batch)
@@ -528,14 +544,7 @@ def run_gpu(args):
                        "l2": "working set per step (~%.1f GB of Jacobian/state buffers) exceeds the 126 MB L2"
                              % (B * 5.3e-3)},
             "device_ms_per_step": dev_ms / args.steps,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tm["h2d_bytes"]),
-                    "d2h_bytes_per_step": int(tm["d2h_bytes"]), "ms_per_step": 1e3 * dt_e2e / n_e2e,
-                    "steps": n_e2e, "pipeline": f"BaPipeline: {pipe_depth} contexts x 1 host thread, upload of step k+1 overlaps the solve of step k", "host_cores": os.cpu_count(),
-                    "pipeline_trace_ms": pipe_trace,
-                    "serial": {"value": e2e_serial, "ms_per_step": 1e3 * dt_serial / n_e2e},
-                    "last_step_breakdown_ms": {k: round(float(tm[k]), 3) for k in (
-                        "host_order_ms", "host_fill_ms", "host_upload_ms", "h2d_ms", "solve_ms", "d2h_ms",
-                        "host_scatter_ms")}},
+            "e2e": e2e_line,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -626,6 +635,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline: solve windows of the batch for this long")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
                     help="replicas: independent windows per GPU (headline); sharded: one window's landmarks split over the GPUs")
+    ap.add_argument("--skip-e2e", action="store_true", help="resident solve only (used for the ncu launch list)")
     ap.add_argument("--frames", type=int, default=64, help="stereo frames per front-end step (0 = skip the front-end)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -38,8 +38,10 @@ __global__ void __launch_bounds__(kTS* kTS, 2) k_dense_gram(Batch b, int which) 
   WinState& ws = b.ws[w];
   if (ws.done) return;
   if (which == 1 && (ws.skip_slot || ws.gn_failed || !(-ws.acc_mc > 0.0))) return;  // as k_dense_eval
+  // which == 2: after k_decide, for the (possibly new) current buffer; a rejected step keeps the old system
+  if (which == 2 && ws.reuse) return;
   const WinDesc& wd = b.win[w];
-  const int buf = (which == 0) ? ws.cur : 1 - ws.cur;
+  const int buf = (which == 1) ? 1 - ws.cur : ws.cur;
   const int n = wd.n_dense, M = wd.n_rows;
   const int tid = threadIdx.x, tx = tid & (kTS - 1), ty = tid >> 4;
   double* Js = smem;
@@ -124,8 +126,10 @@ __global__ void __launch_bounds__(256, NP <= 16 ? 2 : 1) k_dense_gram_mma(Batch 
   WinState& ws = b.ws[w];
   if (ws.done) return;
   if (which == 1 && (ws.skip_slot || ws.gn_failed || !(-ws.acc_mc > 0.0))) return;  // as k_dense_eval
+  // which == 2: after k_decide, for the (possibly new) current buffer; a rejected step keeps the old system
+  if (which == 2 && ws.reuse) return;
   const WinDesc& wd = b.win[w];
-  const int buf = (which == 0) ? ws.cur : 1 - ws.cur;
+  const int buf = (which == 1) ? 1 - ws.cur : ws.cur;
   const int n = wd.n_dense, M = wd.n_rows;
   const int ld = gram_ld(n);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;

@@ -289,7 +289,12 @@ struct svin_ba_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;  // dense-term evaluation runs here, concurrently with k_linearize
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_gram = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;  // first solve pass of the current upload (SVIN_BA_GRAPH)
+  bool graph_valid = false, graph_opt_known = false;
+  SvinBaOptions graph_opt{};
+  long long graph_launches = 0;
+  bool gram_pending = false;  // a k_dense_gram launch on the side stream the next reduced-system solve must wait for
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   Batch b{};
   bool uploaded = false;
@@ -476,10 +481,14 @@ int svin_ba_create(int device, svin_ba_ctx** out) {
   }
   SVIN_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   SVIN_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  SVIN_CUDA(cudaEventCreateWithFlags(&c->ev_gram, cudaEventDisableTiming));
   for (auto& ev : c->ev) SVIN_CUDA(cudaEventCreate(&ev));
   SVIN_CUDA(cudaMalloc(&c->d_active, sizeof(int)));
   SVIN_CUDA(cudaMallocHost(&c->h_active, sizeof(int)));
-  c->pool = new HostPool(std::max(0, std::min(32, (int)std::thread::hardware_concurrency()) - 1));
+  // worker threads of the upload / scatter path; SVIN_HOST_THREADS lets several contexts (BaPipeline) share the cores
+  int host_threads = std::min(32, (int)std::thread::hardware_concurrency());
+  if (const char* e = std::getenv("SVIN_HOST_THREADS")) host_threads = std::max(1, std::min(64, std::atoi(e)));
+  c->pool = new HostPool(std::max(0, host_threads - 1));
   *out = c;
   return SVIN_OK;
 }
@@ -501,11 +510,16 @@ void svin_ba_destroy(svin_ba_ctx* c) {
   if (c->nccl_comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(c->nccl_comm);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_gram) cudaEventDestroy(c->ev_gram);
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c->pool;
   delete c;
 }
+
+static bool graph_wanted();
+static int build_graph(svin_ba_ctx* c, const SvinBaOptions& opt);
 
 int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   if (!c || !wins || B <= 0) {
@@ -1047,6 +1061,12 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   c->tm.host_fill_ms = t_filled - t_ordered;
   c->tm.host_upload_ms = wall_ms() - t_begin;
   c->uploaded = true;
+  c->graph_valid = false;
+  c->solved = false;
+  if (graph_wanted() && c->graph_opt_known && !c->profiling && !c->nccl_comm) {
+    const int grc = build_graph(c, c->graph_opt);
+    if (grc != SVIN_OK) return grc;
+  }
   c->quality_valid = false;
   return SVIN_OK;
 }
@@ -1116,6 +1136,10 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
     if ((rc = comm_allreduce(c, b.gmax_buf, (size_t)b.B, kNcclMax)) != SVIN_OK) return rc;
     launch_gmax_pack(b, 1, c->stream);
   }
+  if (c->gram_pending) {
+    SVIN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gram, 0));
+    c->gram_pending = false;
+  }
   { ProfScope p(c, SVIN_BA_K_DENSE_SOLVE); launch_dense_solve(b, opt, c->smem_bytes, c->n_max, c->stream); }
   { ProfScope p(c, SVIN_BA_K_BACKSUB); launch_backsub(b, c->stream); }
   if (sharded) {
@@ -1123,23 +1147,25 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
     launch_fold(b, 2, c->stream);
   }
   { ProfScope p(c, SVIN_BA_K_STEP_DENSE); launch_step_dense(b, opt, c->stream); }
-  { ProfScope p(c, SVIN_BA_K_STEP_LM); launch_step_lm(b, c->stream); }
-  if (sharded) {
-    if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
-    launch_fold(b, 3, c->stream);
-  }
-  // candidate evaluation: the reprojection terms (k_linearize) and the dense terms (k_dense_eval, a small
-  // latency-bound grid) are independent -> run them concurrently on two streams.  Serial when profiling (per-kernel
-  // events) or sharded (the fold into cost_cand is not atomic).
   static const bool no_fork = std::getenv("SVIN_BA_NO_FORK") != nullptr;  // debugging knob
   const bool fork = !c->profiling && !sharded && !no_fork;
   if (fork) {
     SVIN_CUDA(cudaEventRecord(c->ev_fork, c->stream));
     SVIN_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
     launch_dense_eval(b, 1, 0, nullptr, c->side);
-    if (c->smem_bytes > 0) launch_dense_gram(b, 1, c->n_max, c->side);
     SVIN_CUDA(cudaEventRecord(c->ev_join, c->side));
   }
+  { ProfScope p(c, SVIN_BA_K_STEP_LM); launch_step_lm(b, c->stream); }
+  if (sharded) {
+    if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
+    launch_fold(b, 3, c->stream);
+  }
+  // candidate evaluation: the reprojection terms (k_linearize) and the dense terms (k_dense_eval, a small
+  // latency-bound grid) are independent -> run them concurrently on two streams.  The dense terms only need the
+  // candidate poses / speed-biases, so the side stream forks right after k_step_dense; k_decide needs their cost
+  // (join), the Gram matrix is only needed by the next slot's reduced-system solve and is computed after k_decide
+  // (for the buffer that is current by then) beside the next slot's Schur kernels.  Serial when profiling
+  // (per-kernel events) or sharded (the fold into cost_cand is not atomic).
   { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 1, 0, c->stream); }
   if (sharded) {
     if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
@@ -1153,7 +1179,71 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
     if (c->smem_bytes > 0) launch_dense_gram(b, 1, c->n_max, c->stream);
   }
   { ProfScope p(c, SVIN_BA_K_DECIDE); launch_decide(b, opt, c->stream); }
+  if (fork && c->smem_bytes > 0) {
+    SVIN_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    SVIN_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    launch_dense_gram(b, 2, c->n_max, c->side);
+    SVIN_CUDA(cudaEventRecord(c->ev_gram, c->side));
+    c->gram_pending = true;
+  }
   c->tm.kernel_launches += 8;
+  return SVIN_OK;
+}
+
+// One pass of the solver's launch sequence: [initial evaluation] + max_num_iterations slots.
+static int enqueue_pass(svin_ba_ctx* c, const SvinBaOptions& opt, bool with_init) {
+  Batch& b = c->b;
+  const int chunk = std::max(1, opt.max_num_iterations);
+  if (with_init) {
+    { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 0, 0, c->stream); }
+    if (c->nccl_comm) {
+      const int rc0 = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum);
+      if (rc0 != SVIN_OK) return rc0;
+      launch_fold(b, 4, c->stream);
+    }
+    {
+      ProfScope p(c, SVIN_BA_K_DENSE_EVAL);
+      launch_dense_eval(b, 0, 0, nullptr, c->stream);
+      if (c->smem_bytes > 0) launch_dense_gram(b, 0, c->n_max, c->stream);
+    }
+    launch_init(b, opt, c->stream);
+    c->tm.kernel_launches += 3;
+  }
+  for (int s = 0; s < chunk; ++s) {
+    const int rc = enqueue_slot(c, opt);
+    if (rc != SVIN_OK) return rc;
+  }
+  if (c->gram_pending) {
+    SVIN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gram, 0));
+    c->gram_pending = false;
+  }
+  return SVIN_OK;
+}
+
+static bool graph_wanted() {
+  static const bool w = !(std::getenv("SVIN_BA_GRAPH") && std::atoi(std::getenv("SVIN_BA_GRAPH")) == 0);
+  return w;
+}
+// Capture the first pass for the current upload (kernel arguments hold the batch by value) and instantiate it.
+static int build_graph(svin_ba_ctx* c, const SvinBaOptions& opt) {
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  c->graph_exec = nullptr;
+  c->graph_valid = false;
+  const long long l0 = c->tm.kernel_launches;
+  cudaGraph_t g = nullptr;
+  SVIN_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue_pass(c, opt, true);
+  const cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+  c->graph_launches = c->tm.kernel_launches - l0;
+  c->tm.kernel_launches = l0;
+  if (rc != SVIN_OK) return rc;
+  SVIN_CUDA(ce);
+  const cudaError_t ie = cudaGraphInstantiate(&c->graph_exec, g, 0);
+  cudaGraphDestroy(g);
+  SVIN_CUDA(ie);
+  c->graph_opt = opt;
+  c->graph_valid = true;
+  c->graph_opt_known = true;
   return SVIN_OK;
 }
 
@@ -1176,27 +1266,27 @@ int svin_ba_solve(svin_ba_ctx* c, const SvinBaOptions* opt_in, SvinBaSummary* su
   SVIN_CUDA(cudaEventRecord(c->ev[2], c->stream));
   // initial evaluation (IterationZero); k_init also installs the options' initial trust-region radius
   c->prof_family.clear();
-  { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 0, 0, c->stream); }
-  if (c->nccl_comm) {
-    const int rc0 = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum);
-    if (rc0 != SVIN_OK) return rc0;
-    launch_fold(b, 4, c->stream);
-  }
-  {
-    ProfScope p(c, SVIN_BA_K_DENSE_EVAL);
-    launch_dense_eval(b, 0, 0, nullptr, c->stream);
-    if (c->smem_bytes > 0) launch_dense_gram(b, 0, c->n_max, c->stream);
-  }
-  launch_init(b, opt, c->stream);
-  c->tm.kernel_launches += 3;
-  int slots_done = 0;
   const int chunk = std::max(1, opt.max_num_iterations);
   const int hard_cap = opt.max_num_iterations * 10 + 16;
+  // The first pass (initial evaluation + max_num_iterations slots) is a fixed launch sequence - all control flow is
+  // on the device - so it is captured once per upload into a CUDA graph and replayed (SVIN_BA_GRAPH=0 disables).
+  // svin_ba_upload pre-builds it with the options of the previous solve, outside the caller's GPU critical section.
+  const bool use_graph = graph_wanted() && !c->profiling && !c->nccl_comm;
+  int slots_done = 0;
+  bool first = true;
   while (true) {
-    for (int s = 0; s < chunk; ++s) {
-      const int rc = enqueue_slot(c, opt);
+    if (first && use_graph) {
+      if (!c->graph_exec || !c->graph_valid || std::memcmp(&c->graph_opt, &opt, sizeof opt) != 0) {
+        const int rc = build_graph(c, opt);
+        if (rc != SVIN_OK) return rc;
+      }
+      SVIN_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
+      c->tm.kernel_launches += c->graph_launches;
+    } else {
+      const int rc = enqueue_pass(c, opt, first);
       if (rc != SVIN_OK) return rc;
     }
+    first = false;
     slots_done += chunk;
     SVIN_CUDA(cudaMemsetAsync(c->d_active, 0, sizeof(int), c->stream));
     launch_count_active(b, c->d_active, c->stream);

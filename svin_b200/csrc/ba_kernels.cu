@@ -1915,7 +1915,10 @@ __device__ void pose_error_eval(const double* meas, const double* U, const doubl
 
 // One CTA per window evaluates every non-reprojection term at state buffer (which: 0 cur, 1 candidate),
 // writing residuals into rd[buf] and local Jacobians into Jd[buf] (dense rows x n_dense).
-__global__ void __launch_bounds__(128) k_dense_eval(Batch b, int which, int raw, ImuEvalOut dump) {
+// MINB CTAs per SM: at 255 registers two CTAs take a whole SM's register file and lock the concurrently running
+// k_linearize out of it; a tighter cap spills in the serial IMU sections but leaves room for the main stream.
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_dense_eval(Batch b, int which, int raw, ImuEvalOut dump) {
   const int w = blockIdx.x;
   WinState& ws = b.ws[w];
   if (!raw) {
@@ -2790,7 +2793,13 @@ void launch_dense_eval(const Batch& b, int which, int raw, const double* const* 
     d.J2 = const_cast<double*>(dump[3]);
     d.J3 = const_cast<double*>(dump[4]);
   }
-  k_dense_eval<<<b.B, 128, 0, st>>>(b, which, raw, d);
+  static const int minb = std::getenv("SVIN_DENSE_MINB") ? std::atoi(std::getenv("SVIN_DENSE_MINB")) : 2;  // A/B knob
+  if (minb == 4)
+    k_dense_eval<4><<<b.B, 128, 0, st>>>(b, which, raw, d);
+  else if (minb == 3)
+    k_dense_eval<3><<<b.B, 128, 0, st>>>(b, which, raw, d);
+  else
+    k_dense_eval<2><<<b.B, 128, 0, st>>>(b, which, raw, d);
 }
 void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {
   if (b.n_lm_tiles == 0) return;

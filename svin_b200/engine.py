@@ -145,9 +145,22 @@ class BaPipeline:
     same time.  This is the host-side analogue of ThreadedKFVio's overlap of frontend and optimisation threads
     (okvis_multisensor_processing/src/ThreadedKFVio.cpp:1071-1141), applied across independent windows."""
 
-    def __init__(self, device: int = 0, depth: int = 2):
+    def __init__(self, device: int = 0, depth: int = 2, host_threads: int | None = None):
+        import os
         import threading
-        self._engines = [BaEngine(device) for _ in range(depth)]
+        # every context packs its uploads on its own worker pool: split the cores between the contexts
+        prev = os.environ.get("SVIN_HOST_THREADS")
+        if host_threads is None:
+            host_threads = max(2, -(-(os.cpu_count() or 8) // depth))
+        os.environ["SVIN_HOST_THREADS"] = str(host_threads)
+        try:
+            self._engines = [BaEngine(device) for _ in range(depth)]
+        finally:
+            if prev is None:
+                del os.environ["SVIN_HOST_THREADS"]
+            else:
+                os.environ["SVIN_HOST_THREADS"] = prev
+        self.host_threads = host_threads
         self._gpu = threading.Lock()
 
     def close(self):

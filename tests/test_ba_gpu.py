@@ -138,3 +138,73 @@ def test_pipeline_matches_blocking_optimize():
             assert np.allclose(w0.pose_blocks, w1.pose_blocks, rtol=1e-7, atol=1e-9)
             assert np.allclose(w0.landmarks, w1.landmarks, rtol=1e-7, atol=1e-9)
             assert np.allclose(a, b, rtol=1e-5, atol=1e-9)
+
+
+def _drop_observations(w, keep):
+    for name in ("obs_pose", "obs_landmark", "obs_extrinsics", "obs_camera", "obs_measurement", "obs_information"):
+        setattr(w, name, getattr(w, name)[keep].copy())
+    w.finalize()
+
+
+def test_mixed_track_shapes_single_camera_runs_and_single_pose_tracks(engine):
+    # The Schur chunk kernels are keyed by the (pose, camera) pattern of a landmark: make the patterns ragged -
+    # mono observations (one residual block per pose run), landmarks seen from one pose only - and compare with the oracle as above (1e-6 relative, same iteration count).
+    w, _ = make_window(seed=777, num_keyframes=8, num_imu_frames=3, num_landmarks=900, mode="steady")
+    rng = np.random.default_rng(5)
+    keep = np.ones(w.num_obs, dtype=bool)
+    keep &= ~((w.obs_camera == 1) & (rng.random(w.num_obs) < 0.3))          # mono runs
+    first_pose = np.full(w.num_landmarks, 10 ** 9)
+    np.minimum.at(first_pose, w.obs_landmark, w.obs_pose)
+    single = rng.random(w.num_landmarks) < 0.1                                 # tracks of one pose
+    keep &= ~(single[w.obs_landmark] & (w.obs_pose != first_pose[w.obs_landmark]))
+    _drop_observations(w, keep)
+    r = w.copy()
+    opt = default_options(max_num_iterations=8)
+    s_ref, _ = oracle_lib.solve(r, opt)
+    s_gpu, _ = engine.optimize([w], opt)
+    assert s_gpu[0]["iterations"] == s_ref["iterations"]
+    assert s_gpu[0]["termination"] == s_ref["termination"]
+    assert abs(s_gpu[0]["final_cost"] - s_ref["final_cost"]) < 1e-6 * s_ref["final_cost"]
+    assert _rel(w.pose_blocks, r.pose_blocks) < 1e-6
+    assert _rel(w.landmarks, r.landmarks) < 1e-6
+
+
+_VARIANT_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from svin_b200.engine import BaEngine
+from svin_b200.synthetic import make_window
+from svin_b200.window import default_options
+ws = [make_window(seed=202, num_keyframes=5, num_imu_frames=3, num_landmarks=600, mode="steady")[0],
+      make_window(seed=203, num_keyframes=10, num_imu_frames=3, num_landmarks=2000, mode="steady")[0]]
+with BaEngine(0) as e:
+    s, q = e.optimize(ws, default_options(max_num_iterations=10))
+np.savez(sys.argv[2], it=np.array([x["iterations"] for x in s]), cost=np.array([x["final_cost"] for x in s]),
+         p0=ws[0].pose_blocks, p1=ws[1].pose_blocks, l0=ws[0].landmarks, l1=ws[1].landmarks)
+"""
+
+
+@pytest.mark.parametrize("env", [
+    {"SVIN_SCHUR_LR": "0"},        # lane = landmark chunk kernels only (k_schur_mma)
+    {"SVIN_SCHUR_LR": "1"},        # + single-warp run-parallel chunks
+    {"SVIN_SOLVE_SMEM": "1", "SVIN_GRAM_FMA": "1"},  # shared-memory Cholesky, FMA Gram matrix
+    {"SVIN_BA_GRAPH": "0", "SVIN_BA_NO_FORK": "1"},  # no CUDA graph, single stream
+])
+def test_kernel_variants_agree(tmp_path, env):
+    # Every kernel variant behind an A/B knob computes the same solution (different summation orders: 1e-7).
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "variant.py"
+    script.write_text(_VARIANT_SCRIPT)
+    outs = []
+    for k, e in enumerate(({}, env)):
+        out = tmp_path / f"v{k}.npz"
+        subprocess.run([sys.executable, str(script), root, str(out)], check=True, env={**os.environ, **e}, timeout=600)
+        outs.append(np.load(out))
+    a, b = outs
+    assert np.array_equal(a["it"], b["it"])
+    assert np.allclose(a["cost"], b["cost"], rtol=1e-9)
+    for k in ("p0", "p1", "l0", "l1"):
+        assert np.allclose(a[k], b[k], rtol=1e-7, atol=1e-9), k

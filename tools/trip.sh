@@ -1,7 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t10_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/t10_pytest.log
-timeout 300 python tools/schur_probe.py >> gpurun_out/t10_probe.log 2>&1
-timeout 300 python tools/schur_probe.py --no-prof --solves 3 >> gpurun_out/t10_probe.log 2>&1
-timeout 300 python tools/schur_probe.py --no-prof --solves 3 --windows 296 >> gpurun_out/t10_probe.log 2>&1
-cat gpurun_out/t10_probe.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t14_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/t14_pytest.log
+timeout 900 python bench.py > gpurun_out/t14_bench.json 2> gpurun_out/t14_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/t14_bench.err
