@@ -417,6 +417,48 @@ typedef struct SvinMatchResult {
  * (A ascending, single worker).  Host buffers in and out. */
 int svin_match(svin_fe_ctx* ctx, int32_t num_problems, const SvinMatchProblem* problems, SvinMatchResult* results);
 
+/* =====================================================================
+ *  (A0) image pre-processing in front of the detector  
+ *  Replaces the OpenCV chain of Subscriber::imageCallback (okvis_ros/src/Subscriber.cpp:123-147):
+ *    cv::resize(raw, Size(), resizeFactor, resizeFactor)  [INTER_LINEAR; an exact 2x decimation takes OpenCV's
+ *    INTER_AREA fast path]  ->  cv::medianBlur(3) if optimization.useMedianFilter  ->  CLAHE::apply / cv::equalizeHist
+ *  per histogramParams (config_stereorig_v1.yaml:103-106).  8-bit single channel, bit-exact with OpenCV 4.x.
+ * ===================================================================== */
+enum { SVIN_HIST_NONE = 0, SVIN_HIST_EQUALIZE = 1, SVIN_HIST_CLAHE = 2 };
+typedef struct SvinPreOptions {
+  int32_t src_width, src_height;  /* raw image size */
+  double resize_factor;           /* miscParams.resizeFactor (1.0 = no resize) */
+  int32_t median_filter;          /* optimization.useMedianFilter */
+  int32_t histogram_method;       /* SVIN_HIST_* (histogramParams.histogramMethod) */
+  double clahe_clip_limit;        /* histogramParams.claheClipLimit */
+  int32_t clahe_tiles;            /* histogramParams.claheTilesGridSize (tiles x tiles) */
+  int32_t max_images;             /* capacity of one batched call */
+} SvinPreOptions;
+typedef struct SvinPreTimings {
+  double run_ms, h2d_ms, d2h_ms;  /* CUDA events of the last call */
+  int64_t h2d_bytes, d2h_bytes;
+  int64_t kernel_launches;
+  double kernel_ms[5];            /* resize, median, histogram, lut, apply */
+} SvinPreTimings;
+typedef struct svin_pre_ctx svin_pre_ctx;
+int svin_pre_create(int device, const SvinPreOptions* opt, svin_pre_ctx** out);
+void svin_pre_destroy(svin_pre_ctx* ctx);
+int svin_pre_output_size(svin_pre_ctx* ctx, int32_t* width, int32_t* height);
+/* Host buffers in and out: src[i] rows `src_stride` bytes apart, dst[i] dense [height][width]. */
+int svin_pre_process(svin_pre_ctx* ctx, int32_t num_images, const uint8_t* const* src, int32_t src_stride,
+                     uint8_t* const* dst);
+/* Split form for device-resident timing and for chaining into svin_fe_upload_device. */
+int svin_pre_upload(svin_pre_ctx* ctx, int32_t num_images, const uint8_t* const* src, int32_t src_stride);
+int svin_pre_run(svin_pre_ctx* ctx);
+int svin_pre_download(svin_pre_ctx* ctx, uint8_t* const* dst);
+/* Device pointer of the processed images of the last run, dense [num_images][height][width] (valid until the next
+ * call on this context); the stream-ordered hand-over to the detector without a host round trip. */
+const uint8_t* svin_pre_device_output(svin_pre_ctx* ctx);
+int svin_pre_timings(svin_pre_ctx* ctx, SvinPreTimings* out);
+/* svin_fe_upload with the images already on the device (dense rows of image_width bytes), e.g. svin_pre_device_output. */
+int svin_fe_upload_device(svin_fe_ctx* ctx, int32_t num_images, const uint8_t* device_images,
+                          const double* intrinsics, const double* extraction_direction);
+
 typedef struct SvinFeTimings {
   double run_ms;   /* device time of the last svin_fe_run / svin_match (CUDA events) */
   double h2d_ms, d2h_ms;

@@ -105,6 +105,20 @@ class SvinFeOptions(C.Structure):
                 ("rotation_invariance", C.c_int32), ("scale_invariance", C.c_int32), ("max_images", C.c_int32)]
 
 
+SVIN_HIST_NONE, SVIN_HIST_EQUALIZE, SVIN_HIST_CLAHE = 0, 1, 2
+
+
+class SvinPreOptions(C.Structure):
+    _fields_ = [("src_width", C.c_int32), ("src_height", C.c_int32), ("resize_factor", C.c_double),
+                ("median_filter", C.c_int32), ("histogram_method", C.c_int32), ("clahe_clip_limit", C.c_double),
+                ("clahe_tiles", C.c_int32), ("max_images", C.c_int32)]
+
+
+class SvinPreTimings(C.Structure):
+    _fields_ = [("run_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int64), ("kernel_ms", C.c_double * 5)]
+
+
 SVIN_MATCH_3D2D, SVIN_MATCH_2D2D = 0, 1
 c_float_p = C.POINTER(C.c_float)
 
@@ -162,7 +176,9 @@ EXPORTED_SYMBOLS = [
     "svin_ba_timings", "svin_ba_set_profiling", "svin_ba_kernel_times", "svin_nccl_unique_id", "svin_ba_comm_init",
     "svin_ba_marginalize",
     "svin_fe_default_options", "svin_fe_create", "svin_fe_destroy", "svin_fe_detect_describe", "svin_fe_upload",
-    "svin_fe_run", "svin_fe_download", "svin_fe_scores", "svin_match", "svin_fe_timings",
+    "svin_fe_run", "svin_fe_download", "svin_fe_scores", "svin_match", "svin_fe_timings", "svin_fe_upload_device",
+    "svin_pre_create", "svin_pre_destroy", "svin_pre_output_size", "svin_pre_process", "svin_pre_upload",
+    "svin_pre_run", "svin_pre_download", "svin_pre_device_output", "svin_pre_timings",
 ]
 
 
@@ -212,6 +228,18 @@ def load(path: str | None = None) -> C.CDLL:
     lib.svin_fe_scores.argtypes = [C.c_void_p, C.c_int32, c_int32_p]
     lib.svin_match.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SvinMatchProblem), C.POINTER(SvinMatchResult)]
     lib.svin_fe_timings.argtypes = [C.c_void_p, C.POINTER(SvinFeTimings)]
+    lib.svin_fe_upload_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, c_double_p, c_double_p]
+    lib.svin_pre_create.argtypes = [C.c_int, C.POINTER(SvinPreOptions), C.POINTER(C.c_void_p)]
+    lib.svin_pre_destroy.argtypes = [C.c_void_p]
+    lib.svin_pre_destroy.restype = None
+    lib.svin_pre_output_size.argtypes = [C.c_void_p, c_int32_p, c_int32_p]
+    lib.svin_pre_process.argtypes = [C.c_void_p, C.c_int32, pp_u8, C.c_int32, pp_u8]
+    lib.svin_pre_upload.argtypes = [C.c_void_p, C.c_int32, pp_u8, C.c_int32]
+    lib.svin_pre_run.argtypes = [C.c_void_p]
+    lib.svin_pre_download.argtypes = [C.c_void_p, pp_u8]
+    lib.svin_pre_device_output.argtypes = [C.c_void_p]
+    lib.svin_pre_device_output.restype = C.c_void_p
+    lib.svin_pre_timings.argtypes = [C.c_void_p, C.POINTER(SvinPreTimings)]
     if path is None:
         _lib = lib
     return lib

@@ -268,6 +268,33 @@ int svin_fe_upload(svin_fe_ctx* c, int32_t n, const uint8_t* const* images, int3
   return SVIN_OK;
 }
 
+int svin_fe_upload_device(svin_fe_ctx* c, int32_t n, const uint8_t* d_images, const double* intrinsics,
+                          const double* edir) {
+  if (!c || !d_images || !intrinsics || !edir || n < 1 || n > c->opt.max_images) {
+    set_error("svin_fe_upload_device: invalid arguments (num_images must be in [1, max_images])");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  SVIN_CUDA(cudaSetDevice(c->device));
+  const int W = c->opt.image_width, H = c->opt.image_height;
+  std::memcpy(c->h_small, intrinsics, sizeof(double) * 8 * n);
+  std::memcpy(c->h_small + 8 * (size_t)c->opt.max_images, edir, sizeof(double) * 3 * n);
+  SVIN_CUDA(cudaEventRecord(c->ev[5], c->stream));
+  // dense device rows -> the pitched image buffer (same device; the producer's stream was synchronised by its API)
+  SVIN_CUDA(cudaMemcpy2DAsync(c->d_images, c->pitch, d_images, W, W, (size_t)n * H, cudaMemcpyDeviceToDevice,
+                              c->stream));
+  SVIN_CUDA(cudaMemcpyAsync(c->d_intr, c->h_small, sizeof(double) * 8 * n, cudaMemcpyHostToDevice, c->stream));
+  SVIN_CUDA(cudaMemcpyAsync(c->d_edir, c->h_small + 8 * (size_t)c->opt.max_images, sizeof(double) * 3 * n,
+                            cudaMemcpyHostToDevice, c->stream));
+  SVIN_CUDA(cudaEventRecord(c->ev[6], c->stream));
+  SVIN_CUDA(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]);
+  c->tm.h2d_ms = ms;
+  c->tm.h2d_bytes = (int64_t)sizeof(double) * 11 * n;
+  c->n_images = n;
+  return SVIN_OK;
+}
+
 int svin_fe_run(svin_fe_ctx* c) {
   if (!c || c->n_images < 1) {
     set_error("svin_fe_run: nothing uploaded");

@@ -146,6 +146,14 @@ class FeEngine:
                                             _dp(self._edir)), self._lib)
         self._n = n
 
+    def upload_device(self, device_images: int, n: int, intrinsics, extraction_dirs):
+        """Images already on the device (dense rows), e.g. Preprocessor.device_output(): no host round trip."""
+        self._intr = np.ascontiguousarray(intrinsics, dtype=np.float64).reshape(n, 8)
+        self._edir = np.ascontiguousarray(extraction_dirs, dtype=np.float64).reshape(n, 3)
+        capi.check(self._lib.svin_fe_upload_device(self._ctx, n, C.c_void_p(device_images), _dp(self._intr),
+                                                   _dp(self._edir)), self._lib)
+        self._n = n
+
     def run(self):
         capi.check(self._lib.svin_fe_run(self._ctx), self._lib)
 

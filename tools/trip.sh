@@ -1,4 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t14_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/t14_pytest.log
-timeout 900 python bench.py > gpurun_out/t14_bench.json 2> gpurun_out/t14_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/t14_bench.err
+timeout 900 python -m pytest tests/test_pre_gpu.py -m gpu -x -q > gpurun_out/t17_pytest.log 2>&1; echo "pytest rc=$?"; tail -30 gpurun_out/t17_pytest.log
