@@ -337,6 +337,61 @@ def run_frontend(args, local, rank, world, dist, barrier):
     return res
 
 
+def run_preprocess(args, local):
+    """Image pre-processing in front of the detector (Subscriber::imageCallback): config_stereorig_v1 shape,
+    1600x1200 raw -> resize 0.5 -> CLAHE(clip 1.0, 2x2 tiles) -> 800x600, batched over `--frames` stereo frames."""
+    from svin_b200.preprocess import Preprocessor
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import preprocess_oracle as po
+    F = args.frames
+    rng = np.random.default_rng(20260925)
+    y, x = np.mgrid[0:1200, 0:1600]
+    base = [(120 + 90 * np.sin(x / (31.0 + k)) * np.cos(y / 17.0) + rng.normal(0, 20, x.shape)).clip(0, 255)
+            .astype(np.uint8) for k in range(4)]
+    imgs = [base[k % 4] for k in range(2 * F)]
+    kw = dict(resizeFactor=0.5, histogramMethod="CLAHE", claheClipLimit=1.0, claheTilesGridSize=2)
+    with Preprocessor(1600, 1200, max_images=2 * F, device=local, **kw) as pre:
+        pre.upload(imgs)
+        for _ in range(3):
+            pre.run()
+        dev_ms, kms = 0.0, {}
+        for _ in range(args.steps):
+            pre.run()
+            t = pre.timings()
+            dev_ms += t["run_ms"]
+            for n, v in t["kernel_ms"].items():
+                kms[n] = kms.get(n, 0.0) + v
+        out = pre.download()
+        pre.process(imgs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pre.process(imgs)
+        t_e2e = time.perf_counter() - t0
+        tm = pre.timings()
+    ok = bool(np.array_equal(out[0], po.preprocess(base[0], 0.5, False, po.HIST_CLAHE, 1.0, 2)))
+    t0 = time.perf_counter()
+    n_cpu = 0
+    while time.perf_counter() - t0 < 3.0:
+        po.preprocess(base[n_cpu % 4], 0.5, False, po.HIST_CLAHE, 1.0, 2)
+        n_cpu += 1
+    cdt = time.perf_counter() - t0
+    S, D = 1600 * 1200, 800 * 600
+    alg = S + D + D + D + D          # decimate: read S write D; histogram: read D; apply: read D write D
+    peak, peak_src = measured_peak_hbm()
+    gbs = alg * 2 * F / (dev_ms / args.steps * 1e-3) / 1e9
+    return {"metric": "pre-processed stereo frames/s (1600x1200 -> 800x600, CLAHE 2x2, config_stereorig_v1)",
+            "value": F * args.steps / (dev_ms * 1e-3), "unit": "frames/s", "frames_per_step": F,
+            "device_ms_per_step": dev_ms / args.steps, "bit_exact_vs_oracle": ok,
+            "kernels_ms_per_step": {k: v / args.steps for k, v in kms.items()},
+            "e2e": {"value": F * args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(tm["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(tm["d2h_bytes"])},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "algorithmic_bytes_per_image": alg, "peak_source": peak_src, "traffic": None},
+            "cpu_baseline": {"value": n_cpu / 2 / cdt, "unit": "frames/s", "cores": 1, "kind": "port",
+                             "sample": f"{n_cpu} images, numpy restatement of the OpenCV chain (oracle/), {cdt:.1f} s; "
+                                       "not OpenCV's SIMD code"}}
+
+
 def oracle_solver():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
@@ -559,6 +614,7 @@ def run_gpu(args):
         }
         if frontend is not None:
             line["frontend"] = frontend
+            line["preprocess"] = run_preprocess(args, local)
         if cpu_val is not None:
             line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{cpu_n} windows of the same batch, single-thread CPU "
