@@ -44,10 +44,7 @@ struct PreDev {
 
 // ---- resize ---------------------------------------------------------------------------------------------------
 // resizeAreaFast_Invoker with scale 2: (a + b + c + d + 2) >> 2; blocks cut by the border average what exists.
-__global__ void k_pre_decimate2(PreDev p) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
-  if (x >= p.w) return;
-  const uint8_t* s = p.src + ((size_t)img * p.sh) * p.spitch;
+__device__ __forceinline__ uint8_t decimate_px(const PreDev& p, const uint8_t* s, int x, int y) {
   const int x0 = 2 * x, y0 = 2 * y;
   int sum = 0, cnt = 0;
 #pragma unroll
@@ -63,7 +60,29 @@ __global__ void k_pre_decimate2(PreDev p) {
     v = (sum + 2) >> 2;
   else if (cnt > 0)
     v = __float2int_rn(__fdiv_rn((float)sum, (float)cnt));  // saturate_cast<uchar>((float)sum / count)
-  p.a[((size_t)img * p.h + y) * p.w + x] = (uint8_t)min(max(v, 0), 255);
+  return (uint8_t)min(max(v, 0), 255);
+}
+// Four output pixels per thread: two 8-byte row segments in, one 4-byte store out (the source pitch is a multiple
+// of 16 and the stage buffers are dense, so the vector accesses are aligned whenever the output width is a multiple
+// of 4; other widths and the border blocks of odd sources take the scalar path).
+__global__ void k_pre_decimate2(PreDev p) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y, img = blockIdx.z;
+  if (x4 >= p.w) return;
+  const uint8_t* s = p.src + ((size_t)img * p.sh) * p.spitch;
+  uint8_t* d = p.a + ((size_t)img * p.h + y) * p.w;
+  if ((p.w & 3) == 0 && 2 * x4 + 8 <= p.sw && 2 * y + 2 <= p.sh) {
+    const uint2 r0 = *reinterpret_cast<const uint2*>(s + (size_t)(2 * y) * p.spitch + 2 * x4);
+    const uint2 r1 = *reinterpret_cast<const uint2*>(s + (size_t)(2 * y + 1) * p.spitch + 2 * x4);
+    auto quad = [](unsigned a, unsigned b, int k) {  // pixels 2k, 2k+1 of both rows
+      const unsigned s0 = (a >> (16 * k)) & 0xffffu, s1 = (b >> (16 * k)) & 0xffffu;
+      return ((s0 & 255u) + (s0 >> 8) + (s1 & 255u) + (s1 >> 8) + 2u) >> 2;
+    };
+    const unsigned o = quad(r0.x, r1.x, 0) | (quad(r0.x, r1.x, 1) << 8) | (quad(r0.y, r1.y, 0) << 16) |
+                       (quad(r0.y, r1.y, 1) << 24);
+    *reinterpret_cast<unsigned*>(d + x4) = o;
+  } else {
+    for (int x = x4; x < min(x4 + 4, p.w); ++x) d[x] = decimate_px(p, s, x, y);
+  }
 }
 // HResizeLinear<uchar,int,short,2048> + VResizeLinear<uchar,int,short>: taps from the host tables.
 __global__ void k_pre_bilinear(PreDev p) {
@@ -125,10 +144,22 @@ __global__ void __launch_bounds__(256) k_pre_hist(PreDev p, const uint8_t* in) {
   for (int yy = y_begin; yy < y_end; ++yy) {
     int y = ty * th + yy;
     if (y >= p.h) y = 2 * (p.h - 1) - y;  // BORDER_REFLECT_101
-    for (int xx = threadIdx.x; xx < tw; xx += 256) {
-      int x = tx * tw + xx;
-      if (x >= p.w) x = 2 * (p.w - 1) - x;
-      atomicAdd(&sh[s[(size_t)y * p.w + x]], 1u);
+    const uint8_t* r = s + (size_t)y * p.w;
+    const int xb = tx * tw;
+    if (((p.w | xb | tw) & 3) == 0 && xb + tw <= p.w) {   // aligned 4-byte loads, no reflected columns
+      for (int xx = 4 * threadIdx.x; xx < tw; xx += 4 * 256) {
+        const unsigned v4 = *reinterpret_cast<const unsigned*>(r + xb + xx);
+        atomicAdd(&sh[v4 & 255u], 1u);
+        atomicAdd(&sh[(v4 >> 8) & 255u], 1u);
+        atomicAdd(&sh[(v4 >> 16) & 255u], 1u);
+        atomicAdd(&sh[v4 >> 24], 1u);
+      }
+    } else {
+      for (int xx = threadIdx.x; xx < tw; xx += 256) {
+        int x = xb + xx;
+        if (x >= p.w) x = 2 * (p.w - 1) - x;
+        atomicAdd(&sh[r[x]], 1u);
+      }
     }
   }
   __syncthreads();
@@ -202,33 +233,76 @@ __global__ void __launch_bounds__(256) k_pre_lut(PreDev p) {
 }
 
 // ---- apply -----------------------------------------------------------------------------------------------------
-__global__ void k_pre_apply(PreDev p, const uint8_t* in, uint8_t* out) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
-  if (x >= p.w) return;
-  const int v = in[((size_t)img * p.h + y) * p.w + x];
-  int r;
-  if (p.method == SVIN_HIST_EQUALIZE) {
-    r = p.lut[(size_t)img * 256 + v];
-  } else {
-    // CLAHE_Interpolation_Body: bilinear blend of the four surrounding tile LUTs, single precision, no contraction
-    const int T = p.tiles;
-    const float inv_tw = __fdiv_rn(1.0f, (float)p.tw), inv_th = __fdiv_rn(1.0f, (float)p.th);
-    const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
-    const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
-    int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
-    const float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
-    const float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
-    const int tx2 = min(tx1 + 1, T - 1), ty2 = min(ty1 + 1, T - 1);
-    tx1 = max(tx1, 0);
-    ty1 = max(ty1, 0);
-    const uint8_t* L = p.lut + (size_t)img * T * T * 256;
-    const float l11 = L[(ty1 * T + tx1) * 256 + v], l12 = L[(ty1 * T + tx2) * 256 + v];
-    const float l21 = L[(ty2 * T + tx1) * 256 + v], l22 = L[(ty2 * T + tx2) * 256 + v];
-    const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
-    const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
-    r = __float2int_rn(__fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya)));
+// One CTA per strip of kApplyRows rows of one image: the image's LUTs (tiles^2 x 256 bytes, <= 64 KB) are staged in
+// shared memory once per strip, then every thread maps four pixels at a time (one 4-byte load and store when the
+// width is a multiple of 4).
+constexpr int kApplyRows = 8;
+__global__ void __launch_bounds__(256) k_pre_apply(PreDev p, const uint8_t* in, uint8_t* out) {
+  extern __shared__ uint8_t sL[];
+  const int img = blockIdx.y, y0 = blockIdx.x * kApplyRows;
+  const int T = p.method == SVIN_HIST_CLAHE ? p.tiles : 1;
+  {
+    const uint4* g = reinterpret_cast<const uint4*>(p.lut + (size_t)img * T * T * 256);
+    uint4* d = reinterpret_cast<uint4*>(sL);
+    for (int k = threadIdx.x; k < T * T * 16; k += 256) d[k] = g[k];
   }
-  out[((size_t)img * p.h + y) * p.w + x] = (uint8_t)min(max(r, 0), 255);
+  // per-column interpolation terms (tx1, tx2, xa) of CLAHE, computed once per strip
+  float2* colT = reinterpret_cast<float2*>(sL + (size_t)T * T * 256);
+  const float inv_tw = __fdiv_rn(1.0f, (float)max(p.tw, 1)), inv_th = __fdiv_rn(1.0f, (float)max(p.th, 1));
+  if (p.method == SVIN_HIST_CLAHE) {
+    for (int x = threadIdx.x; x < p.w; x += 256) {
+      const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
+      const int tx1 = (int)floorf(txf);
+      const float xa = __fsub_rn(txf, (float)tx1);
+      const int t1 = max(tx1, 0), t2 = min(tx1 + 1, T - 1);
+      colT[x] = make_float2(xa, __int_as_float(t1 | (t2 << 8)));
+    }
+  }
+  __syncthreads();
+  const bool vec = (p.w & 3) == 0;
+  const int quads = (p.w + 3) >> 2;
+  for (int yy = 0; yy < kApplyRows; ++yy) {
+    const int y = y0 + yy;
+    if (y >= p.h) break;
+    const size_t row = ((size_t)img * p.h + y) * p.w;
+    const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+    int ty1 = (int)floorf(tyf);
+    const float ya = __fsub_rn(tyf, (float)ty1), ya1 = __fsub_rn(1.0f, ya);
+    const int ty2 = min(ty1 + 1, T - 1);
+    ty1 = max(ty1, 0);
+    for (int q = threadIdx.x; q < quads; q += 256) {
+      const int x4 = 4 * q, nx = min(4, p.w - x4);
+      unsigned vin = 0;
+      if (vec)
+        vin = *reinterpret_cast<const unsigned*>(in + row + x4);
+      else
+        for (int k = 0; k < nx; ++k) vin |= (unsigned)in[row + x4 + k] << (8 * k);
+      unsigned vout = 0;
+      if (p.method == SVIN_HIST_EQUALIZE) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) vout |= (unsigned)sL[(vin >> (8 * k)) & 255u] << (8 * k);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k >= nx) break;
+          const float2 ct = colT[x4 + k];
+          const int tt = __float_as_int(ct.y), tx1 = tt & 255, tx2 = tt >> 8;
+          const float xa = ct.x, xa1 = __fsub_rn(1.0f, xa);
+          const int v = (vin >> (8 * k)) & 255u;
+          const float l11 = sL[(ty1 * T + tx1) * 256 + v], l12 = sL[(ty1 * T + tx2) * 256 + v];
+          const float l21 = sL[(ty2 * T + tx1) * 256 + v], l22 = sL[(ty2 * T + tx2) * 256 + v];
+          const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+          const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+          const int r = __float2int_rn(__fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya)));
+          vout |= (unsigned)min(max(r, 0), 255) << (8 * k);
+        }
+      }
+      if (vec)
+        *reinterpret_cast<unsigned*>(out + row + x4) = vout;
+      else
+        for (int k = 0; k < nx; ++k) out[row + x4 + k] = (uint8_t)(vout >> (8 * k));
+    }
+  }
 }
 
 // cvRound(float) for non-negative short weights
@@ -377,6 +451,9 @@ int svin_pre_create(int device, const SvinPreOptions* o, svin_pre_ctx** out) {
   p.yw = c->d_yw;
   p.hist = c->d_hist;
   p.lut = c->d_lut;
+  if (p.tiles * p.tiles * 256 + 8 * p.w > 48 * 1024)
+    SVIN_CUDA(cudaFuncSetAttribute(svin::k_pre_apply, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   p.tiles * p.tiles * 256 + 8 * p.w));
   c->pool = new svin::HostPool(std::max(0, std::min(16, (int)std::thread::hardware_concurrency()) - 1));
   *out = c;
   return SVIN_OK;
@@ -439,8 +516,9 @@ static int pre_enqueue(svin_pre_ctx* c) {
   const dim3 blk(128), grid((p.w + 127) / 128, p.h, n);
   cudaEvent_t* ev = c->ev;
   SVIN_CUDA(cudaEventRecord(ev[2], c->stream));
+  const dim3 grid4((p.w + 4 * 128 - 1) / (4 * 128), p.h, n);
   if (p.mode == 1)
-    svin::k_pre_decimate2<<<grid, blk, 0, c->stream>>>(p);
+    svin::k_pre_decimate2<<<grid4, blk, 0, c->stream>>>(p);
   else if (p.mode == 2)
     svin::k_pre_bilinear<<<grid, blk, 0, c->stream>>>(p);
   else
@@ -462,7 +540,8 @@ static int pre_enqueue(svin_pre_ctx* c) {
     SVIN_CUDA(cudaEventRecord(ev[5], c->stream));
     svin::k_pre_lut<<<dim3(T * T, n), 256, 0, c->stream>>>(p);
     SVIN_CUDA(cudaEventRecord(ev[6], c->stream));
-    svin::k_pre_apply<<<grid, blk, 0, c->stream>>>(p, cur, other);
+    svin::k_pre_apply<<<dim3((p.h + svin::kApplyRows - 1) / svin::kApplyRows, n), 256, (size_t)T * T * 256 + sizeof(float2) * p.w, c->stream>>>(
+        p, cur, other);
     std::swap(const_cast<uint8_t*&>(cur), other);
     c->tm.kernel_launches += 3;
   } else {
