@@ -52,8 +52,15 @@ def dist_setup(n_gpus: int):
     if world > 1:
         import torch
         import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION (this image's default): keep stdout to the
+        # one JSON line the driver parses
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
         return world, rank, local, dist
     return 1, 0, 0, None
 
