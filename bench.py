@@ -524,7 +524,7 @@ def run_gpu(args):
         for _ in range(2):
             eng.optimize([w.copy() for w in batch], opt)
         pipe.optimize_many([[w.copy() for w in batch] for _ in range(2 * pipe_depth)], opt)
-        n_e2e = max(args.steps, 16)   # enough steps to amortise the pipeline fill (one upload) and drain
+        n_e2e = max(args.steps, 24)   # enough steps to amortise the pipeline fill (one upload) and drain
 
         def fresh_sets():
             sets = [[w.copy() for w in batch] for _ in range(n_e2e)]

@@ -64,17 +64,7 @@ void llt_sqrt_information(const double* info, double* U, int n) {
     for (int j = 0; j < n; ++j) U[(size_t)i * n + j] = (j >= i) ? L[(size_t)j * n + i] : 0.0;
 }
 
-// 2x2 case of llt_sqrt_information without the heap allocation (one call per observation on the upload path).
-inline void llt_sqrt_information2(const double* a, double* U) {
-  double l00 = a[0], l10 = a[2], l11 = a[3];
-  if (a[0] > 0.0) {
-    l00 = std::sqrt(a[0]);
-    l10 = a[2] / l00;
-    const double x = a[3] - l10 * l10;
-    if (x > 0.0) l11 = std::sqrt(x);
-  }
-  U[0] = l00; U[1] = l10; U[2] = 0.0; U[3] = l11;
-}
+// (the 2x2 case for the observations' information matrices runs on the device: k_pack_obs)
 
 // Internal ordering of one window's landmarks and observations.
 //  * observations sorted by (landmark, pose block, camera)
@@ -630,7 +620,11 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   const size_t o_opose = in.add(4 * NOBS), o_olm = in.add(4 * NOBS), o_oext = in.add(4 * NOBS), o_ocam = in.add(4 * NOBS);
   const size_t o_zx = in.add(8 * NOBS), o_zy = in.add(8 * NOBS), o_u00 = in.add(8 * NOBS), o_u01 = in.add(8 * NOBS),
                o_u11 = in.add(8 * NOBS);
-  const size_t o_lmof = in.add(4 * NL), o_lmos = in.add(4 * NL), o_lmoc = in.add(4 * NL);
+  // raw observation arrays in the caller's order (plain copies on the host); k_pack_obs gathers them into the SoA
+  // planes above on the device - the host no longer touches every observation with a sqrt and a scatter
+  const size_t o_rpose = in.add(4 * NOBS), o_rlm = in.add(4 * NOBS), o_rext = in.add(4 * NOBS), o_rcam = in.add(4 * NOBS);
+  const size_t o_rmeas = in.add(16 * NOBS), o_rinfo = in.add(24 * NOBS), o_rord = in.add(4 * NOBS);
+  const size_t o_lmof = in.add(4 * NL), o_lmos = in.add(4 * NL), o_lmoc = in.add(4 * NL), o_linv = in.add(4 * NL);
   const size_t o_otw = in.add(4 * (size_t)n_obs_tiles), o_otb = in.add(4 * (size_t)n_obs_tiles);
   const size_t o_ltw = in.add(4 * (size_t)n_lm_tiles), o_ltb = in.add(4 * (size_t)n_lm_tiles);
   const size_t o_sww = in.add(4 * (size_t)NSW), o_swb = in.add(4 * (size_t)NSW), o_swc = in.add(4 * (size_t)NSW);
@@ -655,10 +649,10 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   int *h_pwin = (int*)hp(o_pwin), *h_sbwin = (int*)hp(o_sbwin);
   uint8_t* h_lmfix = (uint8_t*)hp(o_lmfix);
   double* h_intr = (double*)hp(o_intr);
-  int *h_opose = (int*)hp(o_opose), *h_olm = (int*)hp(o_olm), *h_oext = (int*)hp(o_oext), *h_ocam = (int*)hp(o_ocam);
-  double *h_zx = (double*)hp(o_zx), *h_zy = (double*)hp(o_zy), *h_u00 = (double*)hp(o_u00), *h_u01 = (double*)hp(o_u01),
-         *h_u11 = (double*)hp(o_u11);
-  int *h_lmof = (int*)hp(o_lmof), *h_lmos = (int*)hp(o_lmos), *h_lmoc = (int*)hp(o_lmoc);
+  int *h_lmof = (int*)hp(o_lmof), *h_lmos = (int*)hp(o_lmos), *h_lmoc = (int*)hp(o_lmoc), *h_linv = (int*)hp(o_linv);
+  int *h_rpose = (int*)hp(o_rpose), *h_rlm = (int*)hp(o_rlm), *h_rext = (int*)hp(o_rext), *h_rcam = (int*)hp(o_rcam);
+  int* h_rord = (int*)hp(o_rord);
+  double *h_rmeas = (double*)hp(o_rmeas), *h_rinfo = (double*)hp(o_rinfo);
   int *h_otw = (int*)hp(o_otw), *h_otb = (int*)hp(o_otb), *h_ltw = (int*)hp(o_ltw), *h_ltb = (int*)hp(o_ltb);
   int *h_sww = (int*)hp(o_sww), *h_swb = (int*)hp(o_swb), *h_swc = (int*)hp(o_swc);
   int *h_swnr = (int*)hp(o_swnr), *h_swrf = (int*)hp(o_swrf), *h_runoff = (int*)hp(o_runoff), *h_runkm = (int*)hp(o_runkm);
@@ -723,24 +717,26 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
       h_lmwin[d.lm_begin + k] = i;
     }
     std::memcpy(h_intr + 8 * (size_t)cam_base, w.intrinsics, 64 * (size_t)w.num_cameras);
-    // observations in internal order (landmark-major, then pose, then camera)
+    // observations: the caller's arrays as they are + the internal order; the gather into the internal
+    // (landmark-major, pattern-major inside a chunk) SoA planes and U = chol(information)^T run on the device
     const int N = w.num_obs;
-    for (int k = 0; k < N; ++k) {
-      const int o = wo.obs_order[k];
-      const size_t g = (size_t)d.obs_begin + k;
-      c->obs_perm[g] = o;
-      h_opose[g] = d.pose_begin + w.obs_pose[o];
-      h_olm[g] = d.lm_begin + inv[w.obs_landmark[o]];
-      h_oext[g] = d.pose_begin + w.obs_extrinsics[o];
-      h_ocam[g] = cam_base + w.obs_camera[o];
-      h_zx[g] = w.obs_measurement[2 * o];
-      h_zy[g] = w.obs_measurement[2 * o + 1];
-      double U[4];
-      llt_sqrt_information2(w.obs_information + 4 * (size_t)o, U);
-      h_u00[g] = U[0];
-      h_u01[g] = U[1];
-      h_u11[g] = U[3];
+    const size_t g0 = (size_t)d.obs_begin;
+    std::memcpy(h_rpose + g0, w.obs_pose, 4 * (size_t)N);
+    std::memcpy(h_rlm + g0, w.obs_landmark, 4 * (size_t)N);
+    std::memcpy(h_rext + g0, w.obs_extrinsics, 4 * (size_t)N);
+    std::memcpy(h_rcam + g0, w.obs_camera, 4 * (size_t)N);
+    std::memcpy(h_rmeas + 2 * g0, w.obs_measurement, 16 * (size_t)N);
+    for (int o = 0; o < N; ++o) {  // the three entries the Cholesky factor reads (row-major 2x2: a00, a10, a11)
+      const double* a = w.obs_information + 4 * (size_t)o;
+      double* t = h_rinfo + 3 * (g0 + o);
+      t[0] = a[0];
+      t[1] = a[2];
+      t[2] = a[3];
     }
+    std::memcpy(h_rord + g0, wo.obs_order.data(), 4 * (size_t)N);
+    std::memcpy(c->obs_perm.data() + g0, wo.obs_order.data(), 4 * (size_t)N);
+    std::memcpy(h_linv + d.lm_begin, inv.data(), 4 * (size_t)w.num_landmarks);
+    d.cam_begin = cam_base;
     for (int k = 0; k < w.num_landmarks; ++k) {
       h_lmof[d.lm_begin + k] = d.obs_begin + wo.lm_first[k];
       h_lmos[d.lm_begin + k] = wo.lm_stride[k];
@@ -1006,9 +1002,9 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   SVIN_CUDA(cudaEventRecord(c->ev[0], c->stream));
   if (c->pool->workers() == 0) c->pool->help();
   {
-    // the nine per-observation arrays, sliced by window group
-    const size_t obs_arr[9] = {o_opose, o_olm, o_oext, o_ocam, o_zx, o_zy, o_u00, o_u01, o_u11};
-    const size_t obs_elt[9] = {4, 4, 4, 4, 8, 8, 8, 8, 8};
+    // the seven raw per-observation arrays, sliced by window group
+    const size_t obs_arr[9] = {o_rpose, o_rlm, o_rext, o_rcam, o_rmeas, o_rinfo, o_rord, 0, 0};
+    const size_t obs_elt[9] = {4, 4, 4, 4, 16, 24, 4, 0, 0};
     int w0 = 0;
     for (int g = 0; g < G; ++g) {
       int w1 = w0;
@@ -1016,7 +1012,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
       while (group_left[g].load(std::memory_order_acquire) > 0) std::this_thread::yield();
       if (w1 > w0) {
         const size_t e0 = (size_t)c->h_win[w0].obs_begin, e1 = (size_t)c->h_win[w1 - 1].obs_end;
-        for (int a = 0; a < 9 && e1 > e0; ++a)
+        for (int a = 0; a < 7 && e1 > e0; ++a)
           SVIN_CUDA(cudaMemcpyAsync(D + obs_arr[a] + obs_elt[a] * e0, H + obs_arr[a] + obs_elt[a] * e0,
                                     obs_elt[a] * (e1 - e0), cudaMemcpyHostToDevice, c->stream));
       }
@@ -1035,6 +1031,12 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   for (int k = 0; k < 2; ++k) SVIN_CUDA(cudaMemsetAsync(b.Jd[k], 0, 8 * (size_t)NJD + 8, c->stream));
   SVIN_CUDA(cudaMemsetAsync(b.lm_quality, 0, 8 * (size_t)NL + 8, c->stream));
   launch_reset_state(b, c->stream);
+  {
+    RawObs raw{(const int*)(D + o_rpose), (const int*)(D + o_rlm), (const int*)(D + o_rext), (const int*)(D + o_rcam),
+               (const double*)(D + o_rmeas), (const double*)(D + o_rinfo), (const int*)(D + o_rord),
+               (const int*)(D + o_linv)};
+    launch_pack_obs(b, raw, c->stream);
+  }
   launch_obs_poff(b, c->stream);
   SVIN_CUDA(cudaMemcpyAsync(b.ws, c->d_ws_init, sizeof(WinState) * B, cudaMemcpyDeviceToDevice, c->stream));
   if (NIMU)
@@ -1056,7 +1058,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
   c->tm = SvinBaTimings{};
   c->tm.h2d_ms = ms;
-  c->tm.h2d_bytes = (int64_t)in.bytes;
+  c->tm.h2d_bytes = (int64_t)(in.bytes - (o_rpose - o_opose));  // the SoA observation planes are produced on the device
   c->tm.host_order_ms = t_ordered - t_begin;
   c->tm.host_fill_ms = t_filled - t_ordered;
   c->tm.host_upload_ms = wall_ms() - t_begin;

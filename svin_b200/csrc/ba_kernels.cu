@@ -2734,6 +2734,38 @@ __global__ void k_obs_poff(Batch b) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o < b.NOBS) b.obs_poff[o] = b.pose_off[b.obs_pose[o]];
 }
+// Upload-time gather: internal observation g of window w takes caller observation order[g] of that window; indices
+// become batch-global, U = upper-triangular sqrt(information) as Eigen's LLT gives it (llt_sqrt_information2 on the
+// host before: sqrt / div / mul / sub in the same order, no contraction, so the bits are the same).
+__global__ void __launch_bounds__(kObsTile) k_pack_obs(Batch b, RawObs raw) {
+  const int tile = blockIdx.x;
+  const int w = b.obs_tile_win[tile];
+  const int g = b.obs_tile_begin[tile] + threadIdx.x;
+  const WinDesc& wd = b.win[w];
+  if (g >= wd.obs_end) return;
+  const int src = wd.obs_begin + raw.order[g];
+  b.obs_pose[g] = wd.pose_begin + raw.pose[src];
+  b.obs_lm[g] = wd.lm_begin + raw.lm_inv[wd.lm_begin + raw.lm[src]];
+  b.obs_ext[g] = wd.pose_begin + raw.ext[src];
+  b.obs_cam[g] = wd.cam_begin + raw.cam[src];
+  b.obs_zx[g] = raw.meas[2 * (size_t)src];
+  b.obs_zy[g] = raw.meas[2 * (size_t)src + 1];
+  const double a0 = raw.info3[3 * (size_t)src], a2 = raw.info3[3 * (size_t)src + 1], a3 = raw.info3[3 * (size_t)src + 2];
+  double l00 = a0, l10 = a2, l11 = a3;
+  if (a0 > 0.0) {
+    l00 = sqrt(a0);
+    l10 = __ddiv_rn(a2, l00);
+    const double x = __dsub_rn(a3, __dmul_rn(l10, l10));
+    if (x > 0.0) l11 = sqrt(x);
+  }
+  b.obs_u00[g] = l00;
+  b.obs_u01[g] = l10;
+  b.obs_u11[g] = l11;
+}
+void launch_pack_obs(const Batch& b, const RawObs& raw, cudaStream_t st) {
+  if (b.n_obs_tiles == 0) return;
+  k_pack_obs<<<b.n_obs_tiles, kObsTile, 0, st>>>(b, raw);
+}
 void launch_obs_poff(const Batch& b, cudaStream_t st) {
   if (b.NOBS) k_obs_poff<<<div_up(b.NOBS, 256), 256, 0, st>>>(b);
 }

@@ -27,6 +27,7 @@ int schur_lr_max_chunk(int runs, int wpc);  // landmarks per run-parallel (k_sch
 cudaError_t configure_schur();
 int schur_chunk_class(int count);  // which k_schur_mma<G> handles a chunk of `count` landmarks
 void launch_fold(const Batch& b, int stage, cudaStream_t st);
+void launch_pack_obs(const Batch& b, const RawObs& raw, cudaStream_t st);  // raw caller arrays -> internal SoA planes
 void launch_obs_poff(const Batch& b, cudaStream_t st);  // obs_poff[o] = pose_off[obs_pose[o]], once per upload
 void launch_gmax_pack(const Batch& b, int unpack, cudaStream_t st);
 struct MargArgs {

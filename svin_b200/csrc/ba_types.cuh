@@ -21,6 +21,7 @@ struct WinDesc {
   int sb_begin, sb_end;
   int lm_begin, lm_end;
   int obs_begin, obs_end;
+  int cam_begin;     // first camera (intrinsics) of the window
   int n_dense;       // reduced-system dimension (6 per free pose block + 9 per free speed/bias block)
   int n_rows;        // rows of the dense-term Jacobian Jd
   int d_off;         // offset of this window in the concatenated dense vectors
@@ -184,6 +185,15 @@ struct Batch {
   // [B][8]: g2, n2, gdot, Jg2 (k_backsub) | mc, step2, xnorm2 (k_step_lm) | cost of the reprojection terms.
   double* shard_acc;  // nullptr when not sharded; kShardAcc doubles per window
   double* gmax_buf;   // [B] landmark gradient max, all-reduced with MAX
+};
+
+// The caller's observation arrays (window by window, caller order) as uploaded; k_pack_obs gathers them.
+struct RawObs {
+  const int *pose, *lm, *ext, *cam;  // window-local indices
+  const double* meas;                // [2] per observation
+  const double* info3;               // a00, a10, a11 of the 2x2 information
+  const int* order;                  // internal observation -> caller observation (window-local)
+  const int* lm_inv;                 // [NL] caller landmark -> internal landmark (window-local)
 };
 
 struct SolveParams {
