@@ -1148,39 +1148,53 @@ __global__ void __launch_bounds__(32 * WPC, 12 / WPC) k_schur_lr(Batch b, SvinBa
     rowmap[r] = op < 0 ? -1 : op + r % 6;
   }
   __syncthreads();
-  // ---- C = Y Y^T on the tensor cores (upper tiles, dealt out to the warps), one RED per upper-triangular entry
+  // ---- C = Y Y^T on the tensor cores (upper tiles, dealt out to the warps), one RED per upper-triangular entry.
+  // Two column tiles per step share the row fragment and give four independent DMMA chains (K is only 2..12 steps
+  // here, the chain latency and the per-pair bookkeeping dominate).
   const int fr = lane >> 2, fc = lane & 3;
-  int pidx = 0;
+  auto emit = [&](int gi, int ri, int tn, double v0, double v1) {
+    if (ri < 0) return;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int gj = 8 * tn + 2 * fc + e;
+      if (gj > R || gi > gj) continue;
+      const double val = e ? v1 : v0;
+      if (gj == R) {
+        atomicAdd(&g_red[ri], -val);
+      } else {
+        const int rj = rowmap[gj];
+        if (rj >= 0) atomicAdd(&H[min(ri, rj) * n + max(ri, rj)], -val);
+      }
+    }
+  };
+  // the (tm, tn >= tm) pairs in row-major order, two at a time; warp wid of a multi-warp chunk takes every WPC-th step
+  int step = 0;
   for (int tm = 0; tm < T; ++tm) {
     const int gi = 8 * tm + fr;
     const double* za = Ys + (gi < RY ? gi : 0) * ld + fc;
     const int ri = gi < R ? rowmap[gi] : -1;
-    for (int tn = tm; tn < T; ++tn, ++pidx) {
-      if (WPC > 1 && pidx % WPC != wid) continue;
-      const int rb = 8 * tn + fr;
-      const double* zb = Ys + (rb < RY ? rb : 0) * ld + fc;
-      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+    for (int tn = tm; tn < T; tn += 2, ++step) {
+      if (WPC > 1 && step % WPC != wid) continue;
+      const bool two = tn + 1 < T;
+      const int rb0 = 8 * tn + fr, rb1 = 8 * (tn + 1) + fr;
+      const double* zb0 = Ys + (rb0 < RY ? rb0 : 0) * ld + fc;
+      const double* zb1 = Ys + ((two && rb1 < RY) ? rb1 : 0) * ld + fc;
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, d0 = 0.0, d1 = 0.0, f0 = 0.0, f1 = 0.0;
       int ks = 0;
       for (; ks + 1 < K4; ks += 2) {
-        dmma8x8x4(c0, c1, za[4 * ks], zb[4 * ks]);
-        dmma8x8x4(e0, e1, za[4 * ks + 4], zb[4 * ks + 4]);
+        const double a0 = za[4 * ks], a1 = za[4 * ks + 4];
+        dmma8x8x4(c0, c1, a0, zb0[4 * ks]);
+        dmma8x8x4(d0, d1, a0, zb1[4 * ks]);
+        dmma8x8x4(e0, e1, a1, zb0[4 * ks + 4]);
+        dmma8x8x4(f0, f1, a1, zb1[4 * ks + 4]);
       }
-      if (ks < K4) dmma8x8x4(c0, c1, za[4 * ks], zb[4 * ks]);
-      c0 += e0;
-      c1 += e1;
-      if (ri < 0) continue;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int gj = 8 * tn + 2 * fc + e;
-        if (gj > R || gi > gj) continue;
-        const double val = e ? c1 : c0;
-        if (gj == R) {
-          atomicAdd(&g_red[ri], -val);
-        } else {
-          const int rj = rowmap[gj];
-          if (rj >= 0) atomicAdd(&H[min(ri, rj) * n + max(ri, rj)], -val);
-        }
+      if (ks < K4) {
+        const double a0 = za[4 * ks];
+        dmma8x8x4(c0, c1, a0, zb0[4 * ks]);
+        dmma8x8x4(d0, d1, a0, zb1[4 * ks]);
       }
+      emit(gi, ri, tn, c0 + e0, c1 + e1);
+      if (two) emit(gi, ri, tn + 1, d0 + f0, d1 + f1);
     }
   }
 }

@@ -1,4 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t24_pytest.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/t24_pytest.log
-timeout 900 python bench.py --frames 0 > gpurun_out/t24_bench.json 2> gpurun_out/t24_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/t24_bench.err
+timeout 900 python -m pytest tests/test_ba_gpu.py tests/test_marg_gpu.py -m gpu -x -q > gpurun_out/t25_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/t25_pytest.log
+timeout 300 python tools/schur_probe.py >> gpurun_out/t25_probe.log 2>&1
+timeout 300 python tools/schur_probe.py --no-prof --solves 3 >> gpurun_out/t25_probe.log 2>&1
+cat gpurun_out/t25_probe.log
