@@ -280,6 +280,7 @@ struct svin_ba_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;  // dense-term evaluation runs here, concurrently with k_linearize
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_gram = nullptr;
+  SchurStreams schur_par{};               // concurrent Schur chunk kernels (SVIN_SCHUR_STREAMS=0 disables)
   cudaGraphExec_t graph_exec = nullptr;  // first solve pass of the current upload (SVIN_BA_GRAPH)
   bool graph_valid = false, graph_opt_known = false;
   SvinBaOptions graph_opt{};
@@ -472,6 +473,12 @@ int svin_ba_create(int device, svin_ba_ctx** out) {
   SVIN_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   SVIN_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   SVIN_CUDA(cudaEventCreateWithFlags(&c->ev_gram, cudaEventDisableTiming));
+  c->schur_par.n = 5;
+  SVIN_CUDA(cudaEventCreateWithFlags(&c->schur_par.fork, cudaEventDisableTiming));
+  for (int k = 0; k < 5; ++k) {
+    SVIN_CUDA(cudaStreamCreateWithFlags(&c->schur_par.aux[k], cudaStreamNonBlocking));
+    SVIN_CUDA(cudaEventCreateWithFlags(&c->schur_par.join[k], cudaEventDisableTiming));
+  }
   for (auto& ev : c->ev) SVIN_CUDA(cudaEventCreate(&ev));
   SVIN_CUDA(cudaMalloc(&c->d_active, sizeof(int)));
   SVIN_CUDA(cudaMallocHost(&c->h_active, sizeof(int)));
@@ -501,6 +508,11 @@ void svin_ba_destroy(svin_ba_ctx* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->ev_gram) cudaEventDestroy(c->ev_gram);
+  if (c->schur_par.fork) cudaEventDestroy(c->schur_par.fork);
+  for (int k = 0; k < 5; ++k) {
+    if (c->schur_par.join[k]) cudaEventDestroy(c->schur_par.join[k]);
+    if (c->schur_par.aux[k]) cudaStreamDestroy(c->schur_par.aux[k]);
+  }
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1130,7 +1142,8 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
   }
   const bool sharded = c->nccl_comm != nullptr;
   int rc;
-  { ProfScope p(c, SVIN_BA_K_SCHUR); launch_schur(b, opt, c->stream); }
+  static const bool schur_par = !(std::getenv("SVIN_SCHUR_STREAMS") && std::atoi(std::getenv("SVIN_SCHUR_STREAMS")) == 0);
+  { ProfScope p(c, SVIN_BA_K_SCHUR); launch_schur(b, opt, c->stream, (schur_par && !sharded) ? &c->schur_par : nullptr); }
   if (sharded) {
     // the exchange step of the path: reduced system of every window + the landmark gradient max
     if ((rc = comm_allreduce(c, c->d_clear, c->clear_bytes / 8, kNcclSum)) != SVIN_OK) return rc;

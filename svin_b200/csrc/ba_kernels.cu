@@ -2847,13 +2847,17 @@ void launch_dense_eval(const Batch& b, int which, int raw, const double* const* 
   else
     k_dense_eval<2><<<b.B, 128, 0, st>>>(b, which, raw, d);
 }
-void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {
+// The chunk kernels of one slot are independent (they only meet in the fp64 REDs into the reduced system): with
+// `par` they run concurrently on the auxiliary streams (forked from / joined to `st` with events, capturable into the
+// solver's graph) so that one kernel's tail overlaps the next one's body instead of six drained boundaries per slot.
+void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st, const SchurStreams* par) {
   if (b.n_lm_tiles == 0) return;
   if (b.has_ext)
     k_schur<true><<<b.n_lm_tiles, kLmTile, 0, st>>>(b, opt);
   else if (b.n_schur_warps > 0) {
     // class 0: > 16 landmarks per chunk (lane = landmark), 1: 9..16 (2 lanes / landmark), 2: <= 8 (4 lanes / landmark),
-    // 3, 7, 8: run-parallel chunks of 1, 2, 4 warps (k_schur_lr), 4..6: warp-per-run chunks of 2..4 runs (k_schur_wr).  The expensive low-fill classes go first so that the cheap full chunks fill the tail of the grid.
+    // 3, 7, 8: run-parallel chunks of 1, 2, 4 warps (k_schur_lr), 4..6: warp-per-run chunks of 2..4 runs (k_schur_wr).
+    // The expensive low-fill classes go first so that the cheap full chunks fill the tail of the grid.
     // SVIN_SCHUR_CLASSMASK (diagnostics only: results are wrong when a class is skipped) times the classes separately.
     static const int mask = std::getenv("SVIN_SCHUR_CLASSMASK") ? std::atoi(std::getenv("SVIN_SCHUR_CLASSMASK")) : 511;
     const int* lst[kSchurClasses];
@@ -2861,15 +2865,35 @@ void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {
     for (int k = 1; k < kSchurClasses; ++k) lst[k] = lst[k - 1] + b.sw_class_count[k - 1];
     const int* cc = b.sw_class_count;
     const size_t sm = schur_mma_smem_bytes();
-    if (cc[8] && (mask & 256)) k_schur_lr<4><<<cc[8], 128, LrCfg<4>::kDoubles * sizeof(double), st>>>(b, opt, lst[8]);
-    if (cc[7] && (mask & 128)) k_schur_lr<2><<<cc[7], 64, LrCfg<2>::kDoubles * sizeof(double), st>>>(b, opt, lst[7]);
-    if (cc[3] && (mask & 8)) k_schur_lr<1><<<cc[3], 32, LrCfg<1>::kDoubles * sizeof(double), st>>>(b, opt, lst[3]);
-    if (cc[6] && (mask & 64)) k_schur_wr<4><<<cc[6], 128, WrCfg<4>::kDoubles * sizeof(double), st>>>(b, opt, lst[6]);
-    if (cc[5] && (mask & 32)) k_schur_wr<3><<<cc[5], 96, WrCfg<3>::kDoubles * sizeof(double), st>>>(b, opt, lst[5]);
-    if (cc[4] && (mask & 16)) k_schur_wr<2><<<cc[4], 64, WrCfg<2>::kDoubles * sizeof(double), st>>>(b, opt, lst[4]);
-    if (cc[2] && (mask & 4)) k_schur_mma<4><<<div_up(cc[2], 4), 128, sm, st>>>(b, opt, lst[2], cc[2]);
-    if (cc[1] && (mask & 2)) k_schur_mma<2><<<div_up(cc[1], 4), 128, sm, st>>>(b, opt, lst[1], cc[1]);
-    if (cc[0] && (mask & 1)) k_schur_mma<1><<<div_up(cc[0], 4), 128, sm, st>>>(b, opt, lst[0], cc[0]);
+    int used = 0;  // kernels launched so far: the first stays on `st`, the others go round-robin over the aux streams
+    bool forked = false;
+    auto next_stream = [&]() -> cudaStream_t {
+      const int k = used++;
+      if (!par || par->n < 1 || k == 0) return st;
+      if (!forked) {
+        cudaEventRecord(par->fork, st);
+        forked = true;
+      }
+      const int a = (k - 1) % par->n;
+      if (k - 1 < par->n) cudaStreamWaitEvent(par->aux[a], par->fork, 0);
+      return par->aux[a];
+    };
+    if (cc[8] && (mask & 256)) k_schur_lr<4><<<cc[8], 128, LrCfg<4>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[8]);
+    if (cc[7] && (mask & 128)) k_schur_lr<2><<<cc[7], 64, LrCfg<2>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[7]);
+    if (cc[3] && (mask & 8)) k_schur_lr<1><<<cc[3], 32, LrCfg<1>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[3]);
+    if (cc[6] && (mask & 64)) k_schur_wr<4><<<cc[6], 128, WrCfg<4>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[6]);
+    if (cc[5] && (mask & 32)) k_schur_wr<3><<<cc[5], 96, WrCfg<3>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[5]);
+    if (cc[4] && (mask & 16)) k_schur_wr<2><<<cc[4], 64, WrCfg<2>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[4]);
+    if (cc[2] && (mask & 4)) k_schur_mma<4><<<div_up(cc[2], 4), 128, sm, next_stream()>>>(b, opt, lst[2], cc[2]);
+    if (cc[1] && (mask & 2)) k_schur_mma<2><<<div_up(cc[1], 4), 128, sm, next_stream()>>>(b, opt, lst[1], cc[1]);
+    if (cc[0] && (mask & 1)) k_schur_mma<1><<<div_up(cc[0], 4), 128, sm, next_stream()>>>(b, opt, lst[0], cc[0]);
+    if (forked) {
+      const int touched = std::min(used - 1, par->n);
+      for (int a = 0; a < touched; ++a) {
+        cudaEventRecord(par->join[a], par->aux[a]);
+        cudaStreamWaitEvent(st, par->join[a], 0);
+      }
+    }
   }
   else
     k_schur<false><<<b.n_lm_tiles, kLmTile, 0, st>>>(b, opt);

@@ -7,7 +7,12 @@
 namespace svin {
 void launch_linearize(const Batch& b, int which, int raw, cudaStream_t st);
 void launch_dense_eval(const Batch& b, int which, int raw, const double* const* dump, cudaStream_t st);
-void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st);
+struct SchurStreams {  // auxiliary streams + events for the concurrent chunk kernels of one slot
+  int n;
+  cudaStream_t aux[5];
+  cudaEvent_t fork, join[5];
+};
+void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st, const SchurStreams* par);
 size_t dense_solve_smem_bytes(int n_max);
 cudaError_t configure_dense_solve(int smem_bytes);
 size_t dense_gram_smem_bytes(int n_max);
