@@ -526,20 +526,22 @@ def run_gpu(args):
         pipe.optimize_many([[w.copy() for w in batch] for _ in range(2 * pipe_depth)], opt)
         n_e2e = max(args.steps, 24)   # enough steps to amortise the pipeline fill (one upload) and drain
 
-        def fresh_sets():
-            sets = [[w.copy() for w in batch] for _ in range(n_e2e)]
+        def fresh_sets(n=None):
+            sets = [[w.copy() for w in batch] for _ in range(n or n_e2e)]
             for s in sets:
                 for w in s:
                     w.c_struct()
             return sets
 
-        e2e_sets = fresh_sets()
+        n_serial = max(args.steps, 8)
+        e2e_sets = fresh_sets(n_serial)
         barrier()
         t0 = time.perf_counter()
         for s in e2e_sets:
             eng.optimize(s, opt)
         barrier()
-        dt_serial = max_over_ranks(dist, time.perf_counter() - t0, local)
+        dt_serial = max_over_ranks(dist, time.perf_counter() - t0, local) * n_e2e / n_serial
+        del e2e_sets
         tm = eng.timings()
         e2e_sets = fresh_sets()
         barrier()
