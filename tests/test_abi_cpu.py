@@ -50,3 +50,33 @@ def test_engine_fails_loudly_without_a_gpu():
     rc = lib.svin_ba_create(0, C.byref(ctx))
     assert rc == -3  # SVIN_ERR_NO_DEVICE
     assert b"no CPU fallback" in lib.svin_last_error()
+
+
+def test_preprocess_engine_fails_loudly_without_a_gpu():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a CUDA device is present")
+    except ImportError:
+        pass
+    lib = capi.load()
+    o = capi.SvinPreOptions()
+    o.src_width, o.src_height, o.resize_factor, o.max_images = 64, 48, 1.0, 1
+    ctx = C.c_void_p()
+    assert lib.svin_pre_create(0, C.byref(o), C.byref(ctx)) == -3  # SVIN_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.svin_last_error()
+
+
+def test_reference_arm_prints_one_json_line():
+    # bench.py --impl reference: the CPU restatement on the host cores, same metric / unit / config keys as the GPU arm
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, check=True).stdout
+    lines = [ln for ln in out.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "keyframes/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
