@@ -954,8 +954,9 @@ struct LrCfg {
   static constexpr int kDoubles = kY + kIntDoubles;
 };
 
-template <int WPC>
-__global__ void __launch_bounds__(32 * WPC, 12 / WPC) k_schur_lr(Batch b, SvinBaOptions opt, const int* list) {
+// WSM = resident warps per SM the register allocation aims at (12 -> 168 registers, 16 -> 128 with a few spills)
+template <int WPC, int WSM = 12>
+__global__ void __launch_bounds__(32 * WPC, WSM / WPC) k_schur_lr(Batch b, SvinBaOptions opt, const int* list) {
   extern __shared__ double sm_all[];
   constexpr int NT = 32 * WPC;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, tid = threadIdx.x;
@@ -2878,9 +2879,16 @@ void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st, con
       if (k - 1 < par->n) cudaStreamWaitEvent(par->aux[a], par->fork, 0);
       return par->aux[a];
     };
-    if (cc[8] && (mask & 256)) k_schur_lr<4><<<cc[8], 128, LrCfg<4>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[8]);
-    if (cc[7] && (mask & 128)) k_schur_lr<2><<<cc[7], 64, LrCfg<2>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[7]);
-    if (cc[3] && (mask & 8)) k_schur_lr<1><<<cc[3], 32, LrCfg<1>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[3]);
+    static const int lr_wsm = std::getenv("SVIN_LR_WARPS") ? std::atoi(std::getenv("SVIN_LR_WARPS")) : 12;  // A/B knob
+    if (lr_wsm == 16) {
+      if (cc[8] && (mask & 256)) k_schur_lr<4, 16><<<cc[8], 128, LrCfg<4>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[8]);
+      if (cc[7] && (mask & 128)) k_schur_lr<2, 16><<<cc[7], 64, LrCfg<2>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[7]);
+      if (cc[3] && (mask & 8)) k_schur_lr<1, 16><<<cc[3], 32, LrCfg<1>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[3]);
+    } else {
+      if (cc[8] && (mask & 256)) k_schur_lr<4><<<cc[8], 128, LrCfg<4>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[8]);
+      if (cc[7] && (mask & 128)) k_schur_lr<2><<<cc[7], 64, LrCfg<2>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[7]);
+      if (cc[3] && (mask & 8)) k_schur_lr<1><<<cc[3], 32, LrCfg<1>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[3]);
+    }
     if (cc[6] && (mask & 64)) k_schur_wr<4><<<cc[6], 128, WrCfg<4>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[6]);
     if (cc[5] && (mask & 32)) k_schur_wr<3><<<cc[5], 96, WrCfg<3>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[5]);
     if (cc[4] && (mask & 16)) k_schur_wr<2><<<cc[4], 64, WrCfg<2>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[4]);
