@@ -15,6 +15,7 @@ barrier / max-over-ranks plumbing.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -280,6 +281,8 @@ def run_frontend(args, local, rank, world, dist, barrier):
         except Exception as e:  # noqa: BLE001
             errs.append(e)
 
+    gc.collect()
+    gc.disable()        # no collector pause inside the timed region (the match path allocates ~10 k ctypes objects a step)
     barrier()
     t0 = time.perf_counter()
     if args.skip_e2e:   # single-threaded under ncu
@@ -294,6 +297,7 @@ def run_frontend(args, local, rank, world, dist, barrier):
             x.join()
     barrier()
     t_pipe = time.perf_counter() - t0
+    gc.enable()
     if errs:
         raise errs[0]
     fe2.close()
@@ -544,15 +548,20 @@ def run_gpu(args):
         del e2e_sets
         tm = eng.timings()
         e2e_sets = fresh_sets()
+        gc.collect()
+        gc.disable()
         barrier()
         t0 = time.perf_counter()
         pipe.optimize_many(e2e_sets, opt)
         barrier()
         dt_e2e = max_over_ranks(dist, time.perf_counter() - t0, local)
+        gc.enable()
         pipe_trace = pipe.trace
         e2e_value = world * B * n_e2e / dt_e2e
         e2e_serial = world * B * n_e2e / dt_serial
         pipe.close()
+        del e2e_sets          # ~7 k windows x 45 arrays: a generation-2 collection over them takes > 100 ms
+        gc.collect()
         e2e_line = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tm["h2d_bytes"]),
                     "d2h_bytes_per_step": int(tm["d2h_bytes"]), "ms_per_step": 1e3 * dt_e2e / n_e2e,
                     "steps": n_e2e,
