@@ -332,6 +332,14 @@ int svin_ba_marginalize(svin_ba_ctx* ctx, int32_t window_index, const SvinMargSp
 int svin_nccl_unique_id(uint8_t out[128]);
 int svin_ba_comm_init(svin_ba_ctx* ctx, const uint8_t unique_id[128], int32_t rank, int32_t world_size);
 
+/* Host-side planning only (no device needed): how svin_ba_upload would order one window's landmarks and cut them
+ * into Schur chunks.  landmark_order [num_landmarks]: internal position -> caller landmark; per chunk (in internal
+ * order) its kernel kind (0..2 lane = landmark, 3/7/8 run-parallel with 1/2/4 warps, 4..6 warp per run for 2..4 runs),
+ * landmark count and pose-run count.  Returns SVIN_ERR_INVALID_ARGUMENT if `capacity` chunks are not enough
+ * (*num_chunks is still set).  Test / diagnostics hook for the ordering logic of the upload path. */
+int svin_ba_plan(const SvinBaWindow* window, int32_t* landmark_order, int32_t capacity, int32_t* chunk_kind,
+                 int32_t* chunk_landmarks, int32_t* chunk_runs, int32_t* num_chunks);
+
 int svin_ba_set_profiling(svin_ba_ctx* ctx, int enable);
 int svin_ba_kernel_times(svin_ba_ctx* ctx, SvinBaKernelTimes* out);
 

@@ -1085,6 +1085,35 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   return SVIN_OK;
 }
 
+int svin_ba_plan(const SvinBaWindow* w, int32_t* lm_order, int32_t cap, int32_t* kind, int32_t* count, int32_t* runs,
+                 int32_t* num_chunks) {
+  if (!w || !num_chunks) {
+    set_error("svin_ba_plan: invalid arguments");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  const int rc = validate(*w, 0);
+  if (rc != SVIN_OK) return rc;
+  bool group = w->num_pose_blocks <= 64;
+  for (int o = 0; o < w->num_obs && group; ++o)
+    if (!w->pose_fixed[w->obs_extrinsics[o]]) group = false;  // estimated extrinsics: no pattern grouping
+  WindowOrder wo;
+  order_window(*w, group, wo);
+  if (lm_order)
+    for (int k = 0; k < w->num_landmarks; ++k) lm_order[k] = wo.lm_perm[k];
+  const int n = (int)wo.chunk_begin.size();
+  *num_chunks = n;
+  if (n > cap) {
+    set_error("svin_ba_plan: capacity too small");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  for (int k = 0; k < n; ++k) {
+    if (kind) kind[k] = wo.chunk_kind[k];
+    if (count) count[k] = wo.chunk_count[k];
+    if (runs) runs[k] = wo.chunk_nruns[k];
+  }
+  return SVIN_OK;
+}
+
 int svin_ba_reset(svin_ba_ctx* c) {
   if (!c || !c->uploaded) {
     set_error("svin_ba_reset: nothing uploaded");
