@@ -470,10 +470,43 @@ def run_reference(args):
                                    "of the reference path (oracle/), not Ceres — Ceres/Eigen are absent from the image"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if args.frames > 0:
+        line["frontend"] = reference_frontend(cores)
     print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def reference_frontend(cores: int, seconds: float = 6.0):
+    """The front-end metric on the CPU path: detect + describe (both cameras) + the 17 match calls per stereo frame
+    with the oracle, one frame per host thread."""
+    from concurrent.futures import ThreadPoolExecutor
+    from svin_b200.synthetic_images import make_stereo_sequence
+    orc = oracle_solver()
+    nd = 4
+    seq = make_stereo_sequence(seed=20260925, n_frames=nd)
+    feats = {(f, c): orc.fe_detect_describe(seq["images"][f][c], seq["intrinsics"][c], seq["extraction_dir"][f][c])
+             for f in range(nd) for c in range(2)}
+    probs = [frame_match_problems(seq, feats, f, (f + 1) % nd) for f in range(nd)]
+
+    def one_frame(k):
+        f = k % nd
+        for c in range(2):
+            orc.fe_detect_describe(seq["images"][f][c], seq["intrinsics"][c], seq["extraction_dir"][f][c])
+        for p in probs[f]:
+            orc.fe_match(p)
+
+    done, t0 = 0, time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        while time.perf_counter() - t0 < seconds:
+            list(ex.map(one_frame, range(done, done + cores)))
+            done += cores
+    dt = time.perf_counter() - t0
+    return {"metric": "BRISK detect+describe+match stereo frames/s (752x480, <=400 kp/image, 17 match calls/frame)",
+            "value": done / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{done} stereo frames, one per host thread ({cores} threads), CPU restatement (oracle/), "
+                      f"{dt:.1f} s; not brisk"}
 
 
 def run_gpu(args):
