@@ -1220,7 +1220,8 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
   const bool sharded = c->nccl_comm != nullptr;
   int rc;
   static const bool schur_par = !(std::getenv("SVIN_SCHUR_STREAMS") && std::atoi(std::getenv("SVIN_SCHUR_STREAMS")) == 0);
-  { ProfScope p(c, SVIN_BA_K_SCHUR); launch_schur(b, opt, c->stream, (schur_par && !sharded) ? &c->schur_par : nullptr); }
+  int n_schur = 0;
+  { ProfScope p(c, SVIN_BA_K_SCHUR); n_schur = launch_schur(b, opt, c->stream, (schur_par && !sharded) ? &c->schur_par : nullptr); }
   if (sharded) {
     // the exchange step of the path: reduced system of every window + the landmark gradient max
     if ((rc = comm_allreduce(c, c->d_clear, c->clear_bytes / 8, kNcclSum)) != SVIN_OK) return rc;
@@ -1278,7 +1279,8 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
     SVIN_CUDA(cudaEventRecord(c->ev_gram, c->side));
     c->gram_pending = true;
   }
-  c->tm.kernel_launches += 8;
+  // dense solve, backsub, step (2), linearise, dense eval, Gram, decide + the Schur chunk kernels
+  c->tm.kernel_launches += 8 + n_schur;
   return SVIN_OK;
 }
 
@@ -1299,7 +1301,7 @@ static int enqueue_pass(svin_ba_ctx* c, const SvinBaOptions& opt, bool with_init
       if (c->smem_bytes > 0) launch_dense_gram(b, 0, c->n_max, c->stream);
     }
     launch_init(b, opt, c->stream);
-    c->tm.kernel_launches += 3;
+    c->tm.kernel_launches += 4;  // linearise, dense eval, Gram, init
   }
   for (int s = 0; s < chunk; ++s) {
     const int rc = enqueue_slot(c, opt);

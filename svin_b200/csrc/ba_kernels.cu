@@ -2851,8 +2851,9 @@ void launch_dense_eval(const Batch& b, int which, int raw, const double* const* 
 // The chunk kernels of one slot are independent (they only meet in the fp64 REDs into the reduced system): with
 // `par` they run concurrently on the auxiliary streams (forked from / joined to `st` with events, capturable into the
 // solver's graph) so that one kernel's tail overlaps the next one's body instead of six drained boundaries per slot.
-void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st, const SchurStreams* par) {
-  if (b.n_lm_tiles == 0) return;
+int launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st, const SchurStreams* par) {
+  if (b.n_lm_tiles == 0) return 0;
+  int launched = 1;
   if (b.has_ext)
     k_schur<true><<<b.n_lm_tiles, kLmTile, 0, st>>>(b, opt);
   else if (b.n_schur_warps > 0) {
@@ -2902,9 +2903,11 @@ void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st, con
         cudaStreamWaitEvent(st, par->join[a], 0);
       }
     }
+    launched = used;
   }
   else
     k_schur<false><<<b.n_lm_tiles, kLmTile, 0, st>>>(b, opt);
+  return launched;  // kernels launched (for the launch accounting of svin_ba_timings)
 }
 // generic fallback (reduced system stays in global memory); the fast path is in ba_dense_solve.cu
 void launch_dense_solve_generic(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {

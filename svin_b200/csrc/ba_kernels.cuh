@@ -12,7 +12,7 @@ struct SchurStreams {  // auxiliary streams + events for the concurrent chunk ke
   cudaStream_t aux[5];
   cudaEvent_t fork, join[5];
 };
-void launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st, const SchurStreams* par);
+int launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st, const SchurStreams* par);  // -> kernels launched
 size_t dense_solve_smem_bytes(int n_max);
 cudaError_t configure_dense_solve(int smem_bytes);
 size_t dense_gram_smem_bytes(int n_max);
