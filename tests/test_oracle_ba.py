@@ -237,3 +237,28 @@ def test_window_variants_solve(tmp_path):
     assert w.dense_dim() == 6 * (6 + 12) + 9 * 3
     s, _ = oracle_lib.solve(w)
     assert s["final_cost"] < s["initial_cost"] and np.isfinite(s["final_cost"])
+
+
+def test_projection_point_jacobian_matches_numeric_differences():
+    # TestPinholeCamera.cpp:79-92: the 2x3 point Jacobian of project() against central differences (dp = 1e-7),
+    # same tolerance (norm < 1e-4), rays back-projected from random pixels of the 752x480 test camera
+    lib = oracle_lib.load()
+    rng = np.random.default_rng(4)
+    dp = 1.0e-7
+    for c in range(2):
+        intr = EUROC_INTRINSICS[c].copy()
+        for _ in range(100):
+            ip = np.array([rng.uniform(0, 751), rng.uniform(0, 479)])
+            ray, ip2, J = np.zeros(3), np.zeros(2), np.zeros((2, 3))
+            assert lib.svin_oracle_backproject(P(intr), P(ip), P(ray)) == 1
+            ray = ray * rng.uniform(1.0, 10.0)          # the test projects the scaled ray
+            assert lib.svin_oracle_project(P(intr), P(ray), P(ip2), P(J), 752, 480) == 0
+            J_num = np.zeros((2, 3))
+            for d in range(3):
+                e = np.zeros(3)
+                e[d] = dp
+                a, b = np.zeros(2), np.zeros(2)
+                lib.svin_oracle_project(P(intr), P(ray + e), P(a), capi.c_double_p(), 752, 480)
+                lib.svin_oracle_project(P(intr), P(ray - e), P(b), capi.c_double_p(), 752, 480)
+                J_num[:, d] = (a - b) / (2 * dp)
+            assert np.linalg.norm(J_num - J) < 1.0e-4
