@@ -208,3 +208,20 @@ def test_kernel_variants_agree(tmp_path, env):
     assert np.allclose(a["cost"], b["cost"], rtol=1e-9)
     for k in ("p0", "p1", "l0", "l1"):
         assert np.allclose(a[k], b[k], rtol=1e-7, atol=1e-9), k
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_TestMarginalization_scene_estimated_extrinsics_no_loss(engine, seed):
+    # The scene of okvis_ceres/test/TestMarginalization.cpp:60-231 (two constant poses, third pose + camera extrinsics
+    # estimated with a PoseError prior, 100 points, no loss function): the CUDA engine takes the general Schur path
+    # (estimated extrinsics), must agree with the oracle and meet the reference test's own tolerances.
+    from scene_marginalization import make_scene, pose_errors
+    w, truth = make_scene(seed)
+    r = w.copy()
+    opt = default_options(max_num_iterations=50)
+    s_ref, _ = oracle_lib.solve(r, opt, quality=False)
+    s, _ = engine.optimize([w], opt)
+    assert s[0]["iterations"] == s_ref["iterations"] and s[0]["termination"] == s_ref["termination"]
+    assert _rel(w.pose_blocks, r.pose_blocks) < 1e-6 and _rel(w.landmarks, r.landmarks) < 1e-6
+    rot, trans = pose_errors(w.pose_blocks[2], truth)
+    assert rot < 1.0e-2 and trans < 1.0e-1          # TestMarginalization.cpp:226-231

@@ -262,3 +262,15 @@ def test_projection_point_jacobian_matches_numeric_differences():
                 lib.svin_oracle_project(P(intr), P(ray - e), P(b), capi.c_double_p(), 752, 480)
                 J_num[:, d] = (a - b) / (2 * dp)
             assert np.linalg.norm(J_num - J) < 1.0e-4
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_solver_converges_like_TestMarginalization(seed):
+    # okvis_ceres/test/TestMarginalization.cpp:60-231: two constant poses, the third pose and the camera extrinsics
+    # estimated, 100 points, no loss function; the reference asserts rot < 1e-2 rad and trans < 1e-1 m after solve()
+    from scene_marginalization import make_scene, pose_errors
+    w, truth = make_scene(seed)
+    s, _ = oracle_lib.solve(w, default_options(max_num_iterations=50), quality=False)
+    rot, trans = pose_errors(w.pose_blocks[2], truth)
+    assert rot < 1.0e-2 and trans < 1.0e-1, (s, rot, trans)
+    assert np.array_equal(w.pose_fixed, [1, 1, 0, 0])
