@@ -665,7 +665,10 @@ def run_gpu(args):
         }
         if frontend is not None:
             line["frontend"] = frontend
-            line["preprocess"] = run_preprocess(args, local)
+            try:   # rank-local side section: never lose the headline line over it
+                line["preprocess"] = run_preprocess(args, local)
+            except Exception as exc:  # noqa: BLE001
+                line["preprocess"] = {"error": f"{type(exc).__name__}: {exc}"}
         if cpu_val is not None:
             line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{cpu_n} windows of the same batch, single-thread CPU "
