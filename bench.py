@@ -561,7 +561,8 @@ def run_gpu(args):
         for _ in range(2):
             eng.optimize([w.copy() for w in batch], opt)
         pipe.optimize_many([[w.copy() for w in batch] for _ in range(2 * pipe_depth)], opt)
-        n_e2e = max(args.steps, 24)   # enough steps to amortise the pipeline fill (one upload) and drain
+        # enough steps to amortise the pipeline fill (one upload) and drain; fewer when many ranks share the host's memory
+        n_e2e = max(args.steps, 24 if world <= 2 else 12)
 
         def fresh_sets(n=None):
             sets = [[w.copy() for w in batch] for _ in range(n or n_e2e)]
