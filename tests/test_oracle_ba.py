@@ -274,3 +274,39 @@ def test_solver_converges_like_TestMarginalization(seed):
     rot, trans = pose_errors(w.pose_blocks[2], truth)
     assert rot < 1.0e-2 and trans < 1.0e-1, (s, rot, trans)
     assert np.array_equal(w.pose_fixed, [1, 1, 0, 0])
+
+
+def test_radtan_camera_matches_opencv_projectpoints():
+    # Independent pin of the camera model on the reprojection path: PinholeCamera<RadialTangentialDistortion>
+    # (PinholeCamera.hpp impl:143-212, RadialTangentialDistortion.hpp impl:90-111) is OpenCV's plumb-bob model with
+    # (k1, k2, p1, p2); cv2.projectPoints / cv2.undistortPoints are the third-party reference.
+    cv2 = pytest.importorskip("cv2")
+    lib = oracle_lib.load()
+    rng = np.random.default_rng(8)
+    for c in range(2):
+        intr = EUROC_INTRINSICS[c].copy()
+        K = np.array([[intr[0], 0, intr[2]], [0, intr[1], intr[3]], [0, 0, 1.0]])
+        dist = intr[4:8].copy()
+        pts = np.stack([rng.uniform(-2, 2, 200), rng.uniform(-1.2, 1.2, 200), rng.uniform(2, 12, 200)], axis=1)
+        ref, Jcv = cv2.projectPoints(pts.reshape(-1, 1, 3), np.zeros(3), np.zeros(3), K, dist)
+        ref = ref.reshape(-1, 2)
+        for k in range(len(pts)):
+            ip, J = np.zeros(2), np.zeros((2, 3))
+            st = lib.svin_oracle_project(P(intr), P(pts[k].copy()), P(ip), P(J), 752, 480)
+            if st != 0:       # outside the image: the reference returns a status, OpenCV does not clip
+                continue
+            assert np.abs(ip - ref[k]).max() < 1e-9
+            # OpenCV's Jacobian w.r.t. the translation (columns 3..5) is the point Jacobian
+            assert np.abs(J - Jcv[2 * k:2 * k + 2, 3:6]).max() < 1e-8
+        # back-projection: the reference's 5-iteration Gauss-Newton undistortion (RadialTangentialDistortion.hpp
+        # impl:183-218) against OpenCV's undistortion run to convergence.  In the central half of the image the two
+        # agree to 1e-6 (normalised coordinates); towards the corners the 5 iterations are not converged (the reference
+        # accepts that: its own test asks for 0.01 px after re-projection, TestPinholeCamera.cpp:78)
+        crit = (cv2.TERM_CRITERIA_COUNT | cv2.TERM_CRITERIA_EPS, 200, 1e-14)
+        for lo, hi, tol in ((0.25, 0.75, 1e-6), (0.03, 0.97, 5e-3)):
+            ips = np.stack([rng.uniform(lo * 752, hi * 752, 100), rng.uniform(lo * 480, hi * 480, 100)], axis=1)
+            und = cv2.undistortPointsIter(ips.reshape(-1, 1, 2), K, dist, None, None, crit).reshape(-1, 2)
+            for k in range(len(ips)):
+                d = np.zeros(3)
+                assert lib.svin_oracle_backproject(P(intr), P(ips[k].copy()), P(d)) == 1
+                assert np.abs(d[:2] / d[2] - und[k]).max() < tol
