@@ -310,3 +310,58 @@ def test_radtan_camera_matches_opencv_projectpoints():
                 d = np.zeros(3)
                 assert lib.svin_oracle_backproject(P(intr), P(ips[k].copy()), P(d)) == 1
                 assert np.abs(d[:2] / d[2] - und[k]).max() < tol
+
+
+def test_oracle_minimiser_matches_scipy_least_squares():
+    # Independent check of the whole solver chain (residuals, minimal Jacobians, manifold, Schur, dogleg): the
+    # TestMarginalization scene is a plain non-linear least-squares problem (no loss); scipy's trust-region solver
+    # minimises a numpy restatement of the same cost over local perturbations, the oracle runs to tight tolerances.
+    # Both must land on the same minimiser.
+    from scipy.optimize import least_squares
+    from scene_marginalization import make_scene
+    from svin_b200.synthetic import pose_oplus, project, quat_mul, quat_to_rot
+    w, _ = make_scene(seed=1, n_points=40)
+    x0_pose, x0_lm = w.pose_blocks.copy(), w.landmarks.copy()
+    intr = w.intrinsics[0]
+    T_meas = w.pose_prior_measurement[0]
+    L = len(x0_lm)
+
+    def T_of(p):
+        T = np.eye(4)
+        T[:3, :3] = quat_to_rot(p[3:7])
+        T[:3, 3] = p[:3]
+        return T
+
+    def residuals(x):
+        poses = x0_pose.copy()
+        poses[2] = pose_oplus(x0_pose[2], x[0:6])
+        poses[3] = pose_oplus(x0_pose[3], x[6:12])
+        lm = x0_lm.copy()
+        lm[:, :3] += x[12:].reshape(L, 3)
+        Ts = [T_of(p) for p in poses]
+        T_SC = Ts[3]
+        r = []
+        for j in range(3):
+            sel = w.obs_pose == j
+            pC = (np.linalg.inv(Ts[j] @ T_SC) @ lm[w.obs_landmark[sel]].T).T
+            r.append((w.obs_measurement[sel] - project(intr, pC[:, :3])).ravel())
+        # PoseError (PoseError.cpp:85-132): dp = T_meas * T^-1, e = [t_meas - t; 2 vec(dq)], sqrt(information) = 100
+        p = poses[3]
+        qi = p[3:7] * np.array([-1, -1, -1, 1])
+        dq = quat_mul(T_meas[3:7], qi)
+        r.append(100.0 * np.concatenate([T_meas[:3] - p[:3], 2 * dq[:3]]))
+        return np.concatenate(r)
+
+    sol = least_squares(residuals, np.zeros(12 + 3 * L), method="trf", xtol=1e-15, ftol=1e-15, gtol=1e-12,
+                        x_scale="jac", max_nfev=200)
+    ref_pose2 = pose_oplus(x0_pose[2], sol.x[0:6])
+    ref_ext = pose_oplus(x0_pose[3], sol.x[6:12])
+    opt = default_options(max_num_iterations=100, function_tolerance=1e-15, parameter_tolerance=1e-14,
+                          gradient_tolerance=1e-14)
+    s, _ = oracle_lib.solve(w, opt, quality=False)
+    assert abs(2 * s["final_cost"] - 2 * sol.cost) < 1e-8 * 2 * sol.cost       # same minimum (cost = 1/2 sum r^2)
+    assert np.abs(w.pose_blocks[2] - ref_pose2).max() < 1e-6
+    assert np.abs(w.pose_blocks[3] - ref_ext).max() < 1e-6
+    lm_ref = x0_lm.copy()
+    lm_ref[:, :3] += sol.x[12:].reshape(L, 3)
+    assert np.abs(w.landmarks - lm_ref).max() < 1e-5 * np.abs(lm_ref).max()
