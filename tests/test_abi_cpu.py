@@ -80,3 +80,20 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "keyframes/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+def test_bench_gpu_arm_refuses_to_run_without_a_gpu():
+    # the product arm of bench.py must not fall back to anything on a machine without CUDA
+    import subprocess
+    import sys
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a CUDA device is present")
+    except ImportError:
+        pytest.skip("torch not importable")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                       timeout=600)
+    assert p.returncode != 0
+    assert "no CPU fallback" in (p.stderr + p.stdout)
+    assert p.stdout.strip() == ""          # and prints no JSON line
