@@ -139,6 +139,66 @@ inline double cone(int dx, int dy, double half_radius) {
 
 extern "C" {
 
+// atan2 of the keypoint orientation, restated with +, -, *, / only (fdlibm's s_atan.c / e_atan2.c argument reduction and
+// 11-term polynomial, < 1 ulp) so that the CUDA kernel (compiled without FMA contraction) and this oracle
+// (-ffp-contract=off) produce the same bits: libm's and CUDA's atan2 agree only to 1-2 ulp, and the angle feeds a
+// float cast and the 1024-step rotation quantiser of the descriptor.  Against std::atan2 (what Frame.hpp impl:124 calls)
+// the result differs by at most 1 ulp in fp64 (tests/test_oracle_fe.py).
+inline double det_atan(double x) {
+  static const double aT[11] = {3.33333333333329318027e-01,  -1.99999999998764832476e-01, 1.42857142725034663711e-01,
+                                -1.11111104054623557880e-01, 9.09088713343650656196e-02,  -7.69187620504482999495e-02,
+                                6.66107313738753120669e-02,  -5.83357013379057348645e-02, 4.97687799461593236017e-02,
+                                -3.65315727442169155270e-02, 1.62858201153657823623e-02};
+  static const double hi[4] = {4.63647609000806093515e-01, 7.85398163397448278999e-01, 9.82793723247329054082e-01,
+                               1.57079632679489655800e+00};
+  static const double lo[4] = {2.26987774529616870924e-17, 3.06161699786838301793e-17, 1.39033110312309984516e-17,
+                               6.12323399573676603587e-17};
+  const bool neg = x < 0.0;
+  const double ax = neg ? -x : x;
+  if (ax >= 73786976294838206464.0) {  // 2^66
+    const double z = hi[3] + lo[3];
+    return neg ? -z : z;
+  }
+  int id = -1;
+  if (ax < 0.4375) {
+    if (ax < 1.862645149230957e-09) return x;  // 2^-29
+  } else {
+    x = ax;
+    if (x < 1.1875) {
+      if (x < 0.6875) {
+        id = 0;
+        x = (2.0 * x - 1.0) / (2.0 + x);
+      } else {
+        id = 1;
+        x = (x - 1.0) / (x + 1.0);
+      }
+    } else {
+      if (x < 2.4375) {
+        id = 2;
+        x = (x - 1.5) / (1.0 + 1.5 * x);
+      } else {
+        id = 3;
+        x = -1.0 / x;
+      }
+    }
+  }
+  const double z = x * x, w = z * z;
+  const double s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
+  const double s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
+  if (id < 0) return x - x * (s1 + s2);
+  const double r = hi[id] - ((x * (s1 + s2) - lo[id]) - x);
+  return neg ? -r : r;
+}
+inline double det_atan2(double y, double x) {
+  const double pi = 3.1415926535897931160e+00, pi_lo = 1.2246467991473531772e-16;
+  if (y == 0.0) return x >= 0.0 ? 0.0 : pi;
+  if (x == 0.0) return y > 0.0 ? 0.5 * pi : -0.5 * pi;
+  const double q = y / x;
+  const double z = det_atan(q < 0.0 ? -q : q);
+  if (x > 0.0) return y > 0.0 ? z : -z;
+  return y > 0.0 ? pi - (z - pi_lo) : (z - pi_lo) - pi;
+}
+
 // Detect + orient + describe one image.  kps/desc capacity = max_keypoints.  Returns the number of keypoints.
 int svin_oracle_fe_detect_describe(const uint8_t* img, int stride, int W, int H, double uniformity_radius,
                                    double absolute_threshold, int max_keypoints, const double* intr,
@@ -219,7 +279,7 @@ int svin_oracle_fe_detect_describe(const uint8_t* img, int stride, int W, int H,
     pinhole_project(intr, ep, rp, J);
     const double egx = J[0] * extraction_dir[0] + J[1] * extraction_dir[1] + J[2] * extraction_dir[2];
     const double egy = J[3] * extraction_dir[0] + J[4] * extraction_dir[1] + J[5] * extraction_dir[2];
-    const double angle = std::atan2(egy, egx);
+    const double angle = det_atan2(egy, egx);  // std::atan2 in the reference, see det_atan2
     k.angle = (float)(angle / M_PI * 180.0);
     // descriptor: rotation bin from the float angle in degrees
     double a = (double)k.angle;
@@ -249,6 +309,9 @@ int svin_oracle_fe_detect_describe(const uint8_t* img, int stride, int W, int H,
   }
   return n;
 }
+
+// the orientation's deterministic atan2 (tests: <= 1 ulp from libm)
+double svin_oracle_atan2(double y, double x) { return det_atan2(y, x); }
 
 // raw Harris score dump (tests)
 void svin_oracle_fe_harris(const uint8_t* img, int stride, int W, int H, int32_t* out) {
@@ -282,10 +345,11 @@ void triangulate_fast(const double p1[3], const double e1[3], const double p2[3]
     A10 = -A10;
     A01 = -A01;
   }
-  // Eigen computeInverseWithCheck(…, 1e-6): invertible iff |det| > 1e-6 * max|coeff|
+  // Eigen computeInverseWithCheck(inverse, invertible, 1e-6) on a fixed-size 2x2 (stereo_triangulation.cpp:77-79):
+  // compute_inverse_and_det_with_check<.., 2> tests the determinant against the threshold ABSOLUTELY,
+  // invertible iff |det| > 1e-6 (no scaling by the largest coefficient), then inverse = adj * (1 / det).
   const double det = A00 * A11 - A01 * A10;
-  const double maxc = std::max(std::max(std::fabs(A00), std::fabs(A01)), std::max(std::fabs(A10), std::fabs(A11)));
-  const bool invertible = std::fabs(det) > 1.0e-6 * maxc;
+  const bool invertible = std::fabs(det) > 1.0e-6;
   auto normalize4 = [&](double x, double y, double z, double w) {
     const double n = std::sqrt(x * x + y * y + z * z + w * w);
     out[0] = x / n;

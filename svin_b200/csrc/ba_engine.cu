@@ -321,6 +321,42 @@ struct Region {
   }
 };
 
+
+// ---- in-process communicator: `world` contexts of ONE process on one device (svin_ba_comm_init_local) -----------------
+// The exchange steps of the sharded mode with every rank's context in this process: each rank's host thread enqueues,
+// on its own stream, "sum the peers' buffers in rank order into my scratch, then copy it back" with two host barriers
+// and cross-stream events in between.  All ranks sum in the same order, so the result is bit-identical on every rank
+// (as NCCL guarantees for its all-reduce).  Used by the single-device parity test of BASELINE configs[3]; the
+// multi-process path is NCCL (svin_ba_comm_init).
+struct LocalGroup {
+  int world = 0;
+  std::mutex m;
+  std::condition_variable cv;
+  int arrived = 0;
+  long long generation = 0;
+  bool failed = false;
+  std::vector<double*> bufs;
+  std::vector<cudaEvent_t> ready, read;
+  void barrier() {
+    std::unique_lock<std::mutex> lk(m);
+    const long long g = generation;
+    if (++arrived == world) {
+      arrived = 0;
+      ++generation;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return generation != g; });
+    }
+  }
+};
+__global__ void k_sum_peers(double* dst, const double* const* src, int world, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = src[0][i];
+  for (int r = 1; r < world; ++r) s += src[r][i];
+  dst[i] = s;
+}
+
 }  // namespace
 
 struct svin_ba_ctx {
@@ -370,7 +406,12 @@ struct svin_ba_ctx {
   HostPool* pool = nullptr;
   // sharded mode
   void* nccl_comm = nullptr;
+  std::shared_ptr<LocalGroup> local_comm;  // in-process communicator (svin_ba_comm_init_local)
+  double* local_tmp = nullptr;             // its reduction scratch
+  const double** local_srcs = nullptr;     // device array of the peers' buffer pointers
+  size_t local_tmp_cap = 0;
   int comm_rank = 0, comm_world = 1;
+  bool sharded() const { return nccl_comm != nullptr || local_comm != nullptr; }
   // optional per-kernel profiling
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
@@ -1007,6 +1048,11 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   b.B = B; b.NPB = (int)NPB; b.NSB = (int)NSB; b.NL = (int)NL; b.NC = (int)NC; b.NOBS = (int)NOBS;
   b.NIMU = (int)NIMU; b.NMEAS = (int)NMEAS;
   b.n_obs_tiles = n_obs_tiles; b.n_lm_tiles = n_lm_tiles; b.has_ext = has_ext; b.obs_stride = S;
+  {
+    // fused linearisation needs the pattern-grouped chunk kernels; SVIN_BA_FUSED=0 keeps the materialised Jacobians (A/B)
+    static const bool fused_wanted = !(std::getenv("SVIN_BA_FUSED") && std::atoi(std::getenv("SVIN_BA_FUSED")) == 0);
+    b.fused = (group && fused_wanted) ? 1 : 0;
+  }
   b.win = (WinDesc*)(D + o_win);
   c->d_ws_init = (WinState*)(D + o_ws);
   b.ws = (WinState*)(Wk + o_wsw);
@@ -1259,7 +1305,7 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
   // (join), the Gram matrix is only needed by the next slot's reduced-system solve and is computed after k_decide
   // (for the buffer that is current by then) beside the next slot's Schur kernels.  Serial when profiling
   // (per-kernel events) or sharded (the fold into cost_cand is not atomic).
-  { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 1, 0, c->stream); }
+  { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 1, 0, c->stream, b.fused != 0); }
   if (sharded) {
     if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
     launch_fold(b, 4, c->stream);
@@ -1289,7 +1335,7 @@ static int enqueue_pass(svin_ba_ctx* c, const SvinBaOptions& opt, bool with_init
   Batch& b = c->b;
   const int chunk = std::max(1, opt.max_num_iterations);
   if (with_init) {
-    { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 0, 0, c->stream); }
+    { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 0, 0, c->stream, b.fused != 0); }
     if (c->nccl_comm) {
       const int rc0 = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum);
       if (rc0 != SVIN_OK) return rc0;

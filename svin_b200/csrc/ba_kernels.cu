@@ -196,7 +196,8 @@ __device__ __forceinline__ void reproj_eval(const double* __restrict__ pose, con
 __device__ __forceinline__ bool step_is_invalid(const WinState& ws) { return ws.gn_failed || !(-ws.acc_mc > 0.0); }
 
 // which: 0 = linearise the current estimate (initialisation), 1 = the candidate.  raw: evaluation dump.
-template <bool HAS_EXT, int MINB>
+// COMPACT: the pose-Jacobian planes are not written (Batch::fused, see obs_rJ).
+template <bool HAS_EXT, int MINB, bool COMPACT = false>
 __global__ void __launch_bounds__(kObsTile, MINB) k_linearize(Batch b, int which, int raw) {
   const int tile = blockIdx.x;
   const int w = b.obs_tile_win[tile];
@@ -225,9 +226,11 @@ __global__ void __launch_bounds__(kObsTile, MINB) k_linearize(Batch b, int which
     double* r = b.lin_r[buf];
     r[o] = R.r0;
     r[S + o] = R.r1;
-    double* Jp = b.lin_Jp[buf];
+    if (!COMPACT) {
+      double* Jp = b.lin_Jp[buf];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) Jp[k * S + o] = R.Jp[k];
+      for (int k = 0; k < 12; ++k) Jp[k * S + o] = R.Jp[k];
+    }
     double* Jl = b.lin_Jl[buf];
 #pragma unroll
     for (int k = 0; k < 6; ++k) Jl[k * S + o] = R.Jl[k];
@@ -283,6 +286,50 @@ __device__ __forceinline__ void load_Je(const Batch& b, int buf, int o, double* 
   const double* p = b.lin_Je[buf];
 #pragma unroll
   for (int k = 0; k < 12; ++k) Je[k] = p[k * S + o];
+}
+
+// Compact linearisation (Batch::fused, fixed extrinsics): k_linearize stores r (2) and the loss-corrected landmark
+// Jacobian Jl (2x3) only - 64 bytes per observation instead of 160.  The pose Jacobian is a linear image of it,
+//   J0_min = sqrt(I) Jh C_CW [ w I, -[p]x ]   and   J1 = -sqrt(I) Jh C_CW     (ReprojectionError.hpp impl:153-170),
+// and the loss corrector multiplies both from the left by the same 2x2 matrix, so  Jp = [ -w Jl, Jl [p]x ]  with
+// p = hw - t_WS w is rebuilt in registers (18 flops) from the landmark and the pose translation of the state buffer.
+// (Recomputing r and J from scratch instead - 56 B per observation - was measured slower: the ~600 fp64 instructions
+// per observation cost more issue slots than the loads cost bandwidth; profiles/r2a_*.)
+struct LmPoint {
+  double x, y, z, w;
+};
+__device__ __forceinline__ LmPoint load_lm(const Batch& b, int buf, int l) {
+  const double* p = b.lm[buf] + 4 * (size_t)l;
+  return LmPoint{p[0], p[1], p[2], p[3]};
+}
+template <bool COMPACT>
+__device__ __forceinline__ void obs_rJ(const Batch& b, int buf, int o, const LmPoint& lm, double& r0, double& r1,
+                                       double (&Jp)[12], double (&Jl)[6]) {
+  const size_t S = b.obs_stride;
+  const double* r = b.lin_r[buf];
+  r0 = r[o];
+  r1 = r[S + o];
+  const double* pJl = b.lin_Jl[buf];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) Jl[k] = pJl[k * S + o];
+  if (COMPACT) {
+    const double* t = b.pose[buf] + 7 * (size_t)b.obs_pose[o];
+    const double px = lm.x - t[0] * lm.w, py = lm.y - t[1] * lm.w, pz = lm.z - t[2] * lm.w;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const double j0 = Jl[i * 3], j1 = Jl[i * 3 + 1], j2 = Jl[i * 3 + 2];
+      Jp[i * 6 + 0] = -j0 * lm.w;
+      Jp[i * 6 + 1] = -j1 * lm.w;
+      Jp[i * 6 + 2] = -j2 * lm.w;
+      Jp[i * 6 + 3] = j1 * pz - j2 * py;
+      Jp[i * 6 + 4] = j2 * px - j0 * pz;
+      Jp[i * 6 + 5] = j0 * py - j1 * px;
+    }
+  } else {
+    const double* pJp = b.lin_Jp[buf];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) Jp[k] = pJp[k * S + o];
+  }
 }
 
 // W(6x3) += Jd^T (2x6)^T * Jls (2x3)
@@ -640,7 +687,7 @@ __device__ __forceinline__ void spd3_inverse_factor(const double* V, double* Vi,
 // (i = landmark slot, j = sub-lane).  The sub-lanes split the observations in pass 1 (then xor-reduce) and the pose
 // runs in pass 2 (run a = t * G + j in round t, one P tile per sub-lane), so that the rare long-track patterns -
 // few landmarks, many runs - keep all 32 lanes busy instead of 2..8.
-template <int G>
+template <int G, bool FUSED>
 __device__ __forceinline__ void schur_chunk(const Batch& b, const SvinBaOptions& opt, WinState& ws, const WinDesc& wd,
                                             int chunk, int cnt, int nr, double* Ys, double* Ps, const int* rdesc,
                                             int lane) {
@@ -657,11 +704,11 @@ __device__ __forceinline__ void schur_chunk(const Batch& b, const SvinBaOptions&
   const int ob = b.lm_obs_first[l];
   const int ost = b.lm_obs_stride[l];
   const int nobs = b.lm_obs_cnt[l];
+  const LmPoint lmp = load_lm(b, buf, l);
   const bool lfix = b.lm_fixed[l] != 0;
   const double mu = ws.mu;
   const size_t S = b.obs_stride;
   const double* rP = b.lin_r[buf];
-  const double* JpP = b.lin_Jp[buf];
   const double* JlP = b.lin_Jl[buf];
   const int cntp = (cnt + 3) & ~3;    // landmark columns of a P tile per residual row
   const int K4p = cntp >> 1;          // k-steps over its 2 * cntp columns
@@ -786,12 +833,10 @@ __device__ __forceinline__ void schur_chunk(const Batch& b, const SvinBaOptions&
     for (int q = 0; q < mmax; ++q) {
       if (offp >= 0 && q < m) {
         const int o = ob + (k0 + q) * ost;
-        double Jp[12], Jls[6];
+        double Jp[12], Jls[6], r0, r1;
+        obs_rJ<FUSED>(b, buf, o, lmp, r0, r1, Jp, Jls);
 #pragma unroll
-        for (int e = 0; e < 12; ++e) Jp[e] = JpP[e * S + o];
-#pragma unroll
-        for (int e = 0; e < 6; ++e) Jls[e] = JlP[e * S + o] * s[e % 3];
-        const double r0 = rP[o], r1 = rP[S + o];
+        for (int e = 0; e < 6; ++e) Jls[e] *= s[e % 3];
         acc_W(Jp, Jls, W);
         if (i < cntp) {
           const double wgt = active ? 1.0 : 0.0;
@@ -913,7 +958,7 @@ __device__ __forceinline__ void schur_chunk(const Batch& b, const SvinBaOptions&
 
 // One kernel per lane mapping (chunks are listed by class at upload): keeps each kernel's SASS small enough for
 // the instruction cache - the three mappings in one kernel were 120 KB and 18 % of the stalls were "no instruction".
-template <int G>
+template <int G, bool FUSED>
 __global__ void __launch_bounds__(128, 3) k_schur_mma(Batch b, SvinBaOptions opt, const int* list, int count) {
   extern __shared__ double sm_all[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -935,7 +980,7 @@ __global__ void __launch_bounds__(128, 3) k_schur_mma(Batch b, SvinBaOptions opt
     rdesc[2 * r + 1] = b.run_k0m[rf + r];
   }
   __syncwarp();
-  schur_chunk<G>(b, opt, ws, wd, chunk, cnt, nr, Ys, Ps, rdesc, lane);
+  schur_chunk<G, FUSED>(b, opt, ws, wd, chunk, cnt, nr, Ys, Ps, rdesc, lane);
 }
 
 // ---- low-fill chunks: lanes over (pose run, landmark) pairs -------------------------------------------------
@@ -955,7 +1000,7 @@ struct LrCfg {
 };
 
 // WSM = resident warps per SM the register allocation aims at (12 -> 168 registers, 16 -> 128 with a few spills)
-template <int WPC, int WSM = 12>
+template <int WPC, int WSM = 12, bool FUSED = true>
 __global__ void __launch_bounds__(32 * WPC, WSM / WPC) k_schur_lr(Batch b, SvinBaOptions opt, const int* list) {
   extern __shared__ double sm_all[];
   constexpr int NT = 32 * WPC;
@@ -987,12 +1032,9 @@ __global__ void __launch_bounds__(32 * WPC, WSM / WPC) k_schur_lr(Batch b, SvinB
   double* Hdiag = b.Hdiag + wd.d_off;
   const int ob = b.lm_obs_first[l];
   const int ost = b.lm_obs_stride[l];
+  const LmPoint lmp = load_lm(b, buf, l);
   const bool lfix = b.lm_fixed[l] != 0;
   const double mu = ws.mu;
-  const size_t S = b.obs_stride;
-  const double* rP = b.lin_r[buf];
-  const double* JpP = b.lin_Jp[buf];
-  const double* JlP = b.lin_Jl[buf];
   __syncthreads();
   const int offp = rdesc[2 * a];
   const int k0 = rdesc[2 * a + 1] >> 8, m = active ? (rdesc[2 * a + 1] & 255) : 0;
@@ -1007,12 +1049,8 @@ __global__ void __launch_bounds__(32 * WPC, WSM / WPC) k_schur_lr(Batch b, SvinB
   for (int k = 0; k < 27; ++k) D[k] = 0.0;
   for (int q = 0; q < m; ++q) {
     const int o = ob + (k0 + q) * ost;
-    double Jp[12], Jl[6];
-#pragma unroll
-    for (int e = 0; e < 12; ++e) Jp[e] = JpP[e * S + o];
-#pragma unroll
-    for (int e = 0; e < 6; ++e) Jl[e] = JlP[e * S + o];
-    const double r0 = rP[o], r1 = rP[S + o];
+    double Jp[12], Jl[6], r0, r1;
+    obs_rJ<FUSED>(b, buf, o, lmp, r0, r1, Jp, Jl);
     V[0] += Jl[0] * Jl[0] + Jl[3] * Jl[3];
     V[1] += Jl[0] * Jl[1] + Jl[3] * Jl[4];
     V[2] += Jl[0] * Jl[2] + Jl[3] * Jl[5];
@@ -1215,7 +1253,7 @@ struct WrCfg {
   static constexpr int kMinBlocks = NR == 2 ? 8 : (NR == 3 ? 5 : 4);
 };
 
-template <int NR>
+template <int NR, bool FUSED = true>
 __global__ void __launch_bounds__(32 * NR, WrCfg<NR>::kMinBlocks) k_schur_wr(Batch b, SvinBaOptions opt,
                                                                               const int* list) {
   using C = WrCfg<NR>;
@@ -1245,12 +1283,9 @@ __global__ void __launch_bounds__(32 * NR, WrCfg<NR>::kMinBlocks) k_schur_wr(Bat
   double* Hdiag = b.Hdiag + wd.d_off;
   const int ob = b.lm_obs_first[l];
   const int ost = b.lm_obs_stride[l];
+  const LmPoint lmp = load_lm(b, buf, l);
   const bool lfix = b.lm_fixed[l] != 0;
   const double mu = ws.mu;
-  const size_t S = b.obs_stride;
-  const double* rP = b.lin_r[buf];
-  const double* JpP = b.lin_Jp[buf];
-  const double* JlP = b.lin_Jl[buf];
   const int cntp = (cnt + 3) & ~3;
   const int K4p = cntp >> 1;
   const int ldp = 2 * cntp + 4;
@@ -1273,12 +1308,14 @@ __global__ void __launch_bounds__(32 * NR, WrCfg<NR>::kMinBlocks) k_schur_wr(Bat
   const double wgt = active ? 1.0 : 0.0;
   for (int q = 0; q < m; ++q) {
     const int o = ob + (k0 + q) * ost;
-    double Jp[12], Jl[6];
+    double Jp[12], Jl[6], r0, r1;
+    obs_rJ<FUSED>(b, buf, o, lmp, r0, r1, Jp, Jl);
 #pragma unroll
-    for (int e = 0; e < 12; ++e) Jp[e] = wgt * JpP[e * S + o];
+    for (int e = 0; e < 12; ++e) Jp[e] *= wgt;
 #pragma unroll
-    for (int e = 0; e < 6; ++e) Jl[e] = wgt * JlP[e * S + o];
-    const double r0 = wgt * rP[o], r1 = wgt * rP[S + o];
+    for (int e = 0; e < 6; ++e) Jl[e] *= wgt;
+    r0 *= wgt;
+    r1 *= wgt;
     V[0] += Jl[0] * Jl[0] + Jl[3] * Jl[3];
     V[1] += Jl[0] * Jl[1] + Jl[3] * Jl[4];
     V[2] += Jl[0] * Jl[2] + Jl[3] * Jl[5];
@@ -2301,7 +2338,7 @@ __global__ void __launch_bounds__(kDenseThreads) k_dense_solve(Batch b, SvinBaOp
 // ------------------------------------------------------------------------------------------ back-substitution
 // SPLIT threads share a landmark (they take every SPLIT-th observation and add their sums with shuffles): the
 // kernel is bound by the per-observation load latency chain, not by bandwidth, so halving the chain pays.
-template <bool HAS_EXT, int SPLIT>
+template <bool HAS_EXT, int SPLIT, bool FUSED = false>
 __global__ void __launch_bounds__(kLmTile * SPLIT) k_backsub(Batch b) {  // 152 registers, 3 CTAs/SM: a 128 cap measured 4 % slower
   const int tile = blockIdx.x;
   const int w = b.lm_tile_win[tile];
@@ -2330,11 +2367,12 @@ __global__ void __launch_bounds__(kLmTile * SPLIT) k_backsub(Batch b) {  // 152 
         cl[k] = s[k] * gr[k] / dg[k];
       }
     }
+    const LmPoint lmp = load_lm(b, buf, l);
     const int ob = b.lm_obs_first[l], ost = b.lm_obs_stride[l], nobs = b.lm_obs_cnt[l];
     for (int k = half; k < nobs; k += SPLIT) {
       const int o = ob + k * ost;
       ObsJ J;
-      load_obs(b, buf, o, J);
+      obs_rJ<FUSED>(b, buf, o, lmp, J.r0, J.r1, J.Jp, J.Jl);
       const int offp = b.obs_poff[o];
       double t0 = 0, t1 = 0, m0 = 0, m1 = 0;
       if (offp >= 0) {
@@ -2808,20 +2846,30 @@ int schur_mma_max_chunk(int runs) {
   return best;
 }
 cudaError_t configure_schur() {
-  cudaError_t e = cudaFuncSetAttribute(k_schur_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_mma_smem_bytes());
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_schur_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_mma_smem_bytes());
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_schur_mma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_mma_smem_bytes());
+  const int sm = (int)schur_mma_smem_bytes();
+  cudaError_t e = cudaSuccess;
+  auto set = [&](const void* f) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  };
+  set((const void*)k_schur_mma<1, false>);
+  set((const void*)k_schur_mma<2, false>);
+  set((const void*)k_schur_mma<4, false>);
+  set((const void*)k_schur_mma<1, true>);
+  set((const void*)k_schur_mma<2, true>);
+  set((const void*)k_schur_mma<4, true>);
   return e;
 }
 int schur_chunk_class(int count) { return count <= 8 ? 2 : (count <= 16 ? 1 : 0); }
 
 // ------------------------------------------------------------------------------------------ launchers
 
-void launch_linearize(const Batch& b, int which, int raw, cudaStream_t st) {
+void launch_linearize(const Batch& b, int which, int raw, cudaStream_t st, bool compact) {
   if (b.n_obs_tiles == 0) return;
   static const int minb = std::getenv("SVIN_LIN_MINB") ? std::atoi(std::getenv("SVIN_LIN_MINB")) : 5;  // A/B knob: 5 CTAs/SM (96 registers, 100 B spilled) measured fastest
+  if (compact && !raw && !b.has_ext) {
+    k_linearize<false, 5, true><<<b.n_obs_tiles, kObsTile, 0, st>>>(b, which, raw);
+    return;
+  }
   if (b.has_ext || (raw && b.lin_Je[1] != nullptr))
     k_linearize<true, 4><<<b.n_obs_tiles, kObsTile, 0, st>>>(b, which, raw);
   else if (minb == 5)
@@ -2880,22 +2928,27 @@ int launch_schur(const Batch& b, const SvinBaOptions& opt, cudaStream_t st, cons
       if (k - 1 < par->n) cudaStreamWaitEvent(par->aux[a], par->fork, 0);
       return par->aux[a];
     };
-    static const int lr_wsm = std::getenv("SVIN_LR_WARPS") ? std::atoi(std::getenv("SVIN_LR_WARPS")) : 12;  // A/B knob
-    if (lr_wsm == 16) {
-      if (cc[8] && (mask & 256)) k_schur_lr<4, 16><<<cc[8], 128, LrCfg<4>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[8]);
-      if (cc[7] && (mask & 128)) k_schur_lr<2, 16><<<cc[7], 64, LrCfg<2>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[7]);
-      if (cc[3] && (mask & 8)) k_schur_lr<1, 16><<<cc[3], 32, LrCfg<1>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[3]);
+    if (b.fused) {
+      if (cc[8] && (mask & 256)) k_schur_lr<4, 12, true><<<cc[8], 128, LrCfg<4>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[8]);
+      if (cc[7] && (mask & 128)) k_schur_lr<2, 12, true><<<cc[7], 64, LrCfg<2>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[7]);
+      if (cc[3] && (mask & 8)) k_schur_lr<1, 12, true><<<cc[3], 32, LrCfg<1>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[3]);
+      if (cc[6] && (mask & 64)) k_schur_wr<4, true><<<cc[6], 128, WrCfg<4>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[6]);
+      if (cc[5] && (mask & 32)) k_schur_wr<3, true><<<cc[5], 96, WrCfg<3>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[5]);
+      if (cc[4] && (mask & 16)) k_schur_wr<2, true><<<cc[4], 64, WrCfg<2>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[4]);
+      if (cc[2] && (mask & 4)) k_schur_mma<4, true><<<div_up(cc[2], 4), 128, sm, next_stream()>>>(b, opt, lst[2], cc[2]);
+      if (cc[1] && (mask & 2)) k_schur_mma<2, true><<<div_up(cc[1], 4), 128, sm, next_stream()>>>(b, opt, lst[1], cc[1]);
+      if (cc[0] && (mask & 1)) k_schur_mma<1, true><<<div_up(cc[0], 4), 128, sm, next_stream()>>>(b, opt, lst[0], cc[0]);
     } else {
-      if (cc[8] && (mask & 256)) k_schur_lr<4><<<cc[8], 128, LrCfg<4>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[8]);
-      if (cc[7] && (mask & 128)) k_schur_lr<2><<<cc[7], 64, LrCfg<2>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[7]);
-      if (cc[3] && (mask & 8)) k_schur_lr<1><<<cc[3], 32, LrCfg<1>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[3]);
+      if (cc[8] && (mask & 256)) k_schur_lr<4, 12, false><<<cc[8], 128, LrCfg<4>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[8]);
+      if (cc[7] && (mask & 128)) k_schur_lr<2, 12, false><<<cc[7], 64, LrCfg<2>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[7]);
+      if (cc[3] && (mask & 8)) k_schur_lr<1, 12, false><<<cc[3], 32, LrCfg<1>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[3]);
+      if (cc[6] && (mask & 64)) k_schur_wr<4, false><<<cc[6], 128, WrCfg<4>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[6]);
+      if (cc[5] && (mask & 32)) k_schur_wr<3, false><<<cc[5], 96, WrCfg<3>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[5]);
+      if (cc[4] && (mask & 16)) k_schur_wr<2, false><<<cc[4], 64, WrCfg<2>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[4]);
+      if (cc[2] && (mask & 4)) k_schur_mma<4, false><<<div_up(cc[2], 4), 128, sm, next_stream()>>>(b, opt, lst[2], cc[2]);
+      if (cc[1] && (mask & 2)) k_schur_mma<2, false><<<div_up(cc[1], 4), 128, sm, next_stream()>>>(b, opt, lst[1], cc[1]);
+      if (cc[0] && (mask & 1)) k_schur_mma<1, false><<<div_up(cc[0], 4), 128, sm, next_stream()>>>(b, opt, lst[0], cc[0]);
     }
-    if (cc[6] && (mask & 64)) k_schur_wr<4><<<cc[6], 128, WrCfg<4>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[6]);
-    if (cc[5] && (mask & 32)) k_schur_wr<3><<<cc[5], 96, WrCfg<3>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[5]);
-    if (cc[4] && (mask & 16)) k_schur_wr<2><<<cc[4], 64, WrCfg<2>::kDoubles * sizeof(double), next_stream()>>>(b, opt, lst[4]);
-    if (cc[2] && (mask & 4)) k_schur_mma<4><<<div_up(cc[2], 4), 128, sm, next_stream()>>>(b, opt, lst[2], cc[2]);
-    if (cc[1] && (mask & 2)) k_schur_mma<2><<<div_up(cc[1], 4), 128, sm, next_stream()>>>(b, opt, lst[1], cc[1]);
-    if (cc[0] && (mask & 1)) k_schur_mma<1><<<div_up(cc[0], 4), 128, sm, next_stream()>>>(b, opt, lst[0], cc[0]);
     if (forked) {
       const int touched = std::min(used - 1, par->n);
       for (int a = 0; a < touched; ++a) {
@@ -2915,15 +2968,12 @@ void launch_dense_solve_generic(const Batch& b, const SvinBaOptions& opt, cudaSt
 }
 void launch_backsub(const Batch& b, cudaStream_t st) {
   if (b.n_lm_tiles == 0) return;
-  static const int split = std::getenv("SVIN_BACKSUB_SPLIT") ? std::atoi(std::getenv("SVIN_BACKSUB_SPLIT")) : 1;  // A/B knob: 2 and 4 measured slower (r1t)
   if (b.has_ext)
-    k_backsub<true, 1><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
-  else if (split == 2)
-    k_backsub<false, 2><<<b.n_lm_tiles, 2 * kLmTile, 0, st>>>(b);
-  else if (split == 4)
-    k_backsub<false, 4><<<b.n_lm_tiles, 4 * kLmTile, 0, st>>>(b);
+    k_backsub<true, 1, false><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
+  else if (b.fused)
+    k_backsub<false, 1, true><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
   else
-    k_backsub<false, 1><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
+    k_backsub<false, 1, false><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
 }
 void launch_step_dense(const Batch& b, const SvinBaOptions& opt, cudaStream_t st) {
   k_step_dense<<<b.B, 128, 0, st>>>(b, opt);

@@ -5,7 +5,8 @@
 #include "ba_types.cuh"
 
 namespace svin {
-void launch_linearize(const Batch& b, int which, int raw, cudaStream_t st);
+// compact: Batch::fused - r and Jl only (64 B per observation); the pose Jacobian is rebuilt where it is consumed
+void launch_linearize(const Batch& b, int which, int raw, cudaStream_t st, bool compact = false);
 void launch_dense_eval(const Batch& b, int which, int raw, const double* const* dump, cudaStream_t st);
 struct SchurStreams {  // auxiliary streams + events for the concurrent chunk kernels of one slot
   int n;

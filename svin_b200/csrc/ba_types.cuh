@@ -122,6 +122,7 @@ struct Batch {
   int B, NPB, NSB, NL, NC, NOBS, NIMU, NMEAS;
   int n_obs_tiles, n_lm_tiles;
   int has_ext;  // any observation whose extrinsics block is estimated
+  int fused;    // compact linearisation: r and Jl planes only, Jp rebuilt from Jl in the Schur / back-substitution kernels
   size_t obs_stride;  // plane stride of the per-observation SoA arrays
   WinDesc* win;
   WinState* ws;

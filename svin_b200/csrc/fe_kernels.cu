@@ -282,6 +282,65 @@ __device__ __forceinline__ int project_h(const double* intr, const double* hp, i
   return project3(intr, X, Y, Z, W, H, u, v, J);
 }
 
+// atan2 of the keypoint orientation (Frame.hpp impl:124) with +, -, *, / only: fdlibm's argument reduction and 11-term
+// polynomial (< 1 ulp).  This translation unit is compiled with -fmad=false, so every fp64 operation here is a single
+// IEEE operation in source order and the angle -> float -> 1024-step rotation bin chain is bit-reproducible against a CPU
+// evaluation of the same expressions; CUDA's own atan2 is only specified to 2 ulp.
+__device__ __forceinline__ double svin_atan(double x) {
+  const double aT[11] = {3.33333333333329318027e-01,  -1.99999999998764832476e-01, 1.42857142725034663711e-01,
+                                -1.11111104054623557880e-01, 9.09088713343650656196e-02,  -7.69187620504482999495e-02,
+                                6.66107313738753120669e-02,  -5.83357013379057348645e-02, 4.97687799461593236017e-02,
+                                -3.65315727442169155270e-02, 1.62858201153657823623e-02};
+  const double hi[4] = {4.63647609000806093515e-01, 7.85398163397448278999e-01, 9.82793723247329054082e-01,
+                               1.57079632679489655800e+00};
+  const double lo[4] = {2.26987774529616870924e-17, 3.06161699786838301793e-17, 1.39033110312309984516e-17,
+                               6.12323399573676603587e-17};
+  const bool neg = x < 0.0;
+  const double ax = neg ? -x : x;
+  if (ax >= 73786976294838206464.0) {  // 2^66
+    const double z = hi[3] + lo[3];
+    return neg ? -z : z;
+  }
+  int id = -1;
+  if (ax < 0.4375) {
+    if (ax < 1.862645149230957e-09) return x;  // 2^-29
+  } else {
+    x = ax;
+    if (x < 1.1875) {
+      if (x < 0.6875) {
+        id = 0;
+        x = (2.0 * x - 1.0) / (2.0 + x);
+      } else {
+        id = 1;
+        x = (x - 1.0) / (x + 1.0);
+      }
+    } else {
+      if (x < 2.4375) {
+        id = 2;
+        x = (x - 1.5) / (1.0 + 1.5 * x);
+      } else {
+        id = 3;
+        x = -1.0 / x;
+      }
+    }
+  }
+  const double z = x * x, w = z * z;
+  const double s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
+  const double s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
+  if (id < 0) return x - x * (s1 + s2);
+  const double r = hi[id] - ((x * (s1 + s2) - lo[id]) - x);
+  return neg ? -r : r;
+}
+__device__ __forceinline__ double svin_atan2(double y, double x) {
+  const double pi = 3.1415926535897931160e+00, pi_lo = 1.2246467991473531772e-16;
+  if (y == 0.0) return x >= 0.0 ? 0.0 : pi;
+  if (x == 0.0) return y > 0.0 ? 0.5 * pi : -0.5 * pi;
+  const double q = y / x;
+  const double z = svin_atan(q < 0.0 ? -q : q);
+  if (x > 0.0) return y > 0.0 ? z : -z;
+  return y > 0.0 ? pi - (z - pi_lo) : (z - pi_lo) - pi;
+}
+
 // ------------------------------------------------------------------------------------------ describe
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -365,7 +424,7 @@ __global__ void __launch_bounds__(256) k_orient_describe(FeBatch f) {
     project3(intr, rx, ry, 1.0, 0, 0, u, v, J);
     const double egx = J[0] * g[0] + J[1] * g[1] + J[2] * g[2];
     const double egy = J[3] * g[0] + J[4] * g[1] + J[5] * g[2];
-    const double angle = atan2(egy, egx);
+    const double angle = svin_atan2(egy, egx);
     ang = (float)(angle / 3.14159265358979323846 * 180.0);
     double a = (double)ang;
     if (a < 0) a += 360.0;
@@ -496,8 +555,7 @@ __device__ bool triangulate_fast(const double* p1, const double* e1, const doubl
     A01 = -A01;
   }
   const double det = A00 * A11 - A01 * A10;
-  const double maxc = fmax(fmax(fabs(A00), fabs(A01)), fmax(fabs(A10), fabs(A11)));
-  const bool invertible = fabs(det) > 1.0e-6 * maxc;
+  const bool invertible = fabs(det) > 1.0e-6;  // Eigen's fixed-size 2x2 computeInverseWithCheck: absolute threshold
   double x, y, z, w;
   if (!invertible) {
     const double cr[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};

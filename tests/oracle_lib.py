@@ -103,6 +103,8 @@ def load_fe():
     lib.svin_oracle_fe_harris.argtypes = [u8p, C.c_int, C.c_int, C.c_int, i32p]
     lib.svin_oracle_hamming48.argtypes = [u8p, u8p]
     lib.svin_oracle_hamming48.restype = C.c_uint32
+    lib.svin_oracle_atan2.argtypes = [C.c_double, C.c_double]
+    lib.svin_oracle_atan2.restype = C.c_double
     lib.svin_oracle_match.argtypes = [C.POINTER(capi.SvinMatchProblem), i32p, fp, i32p, fp, u8p]
     lib.svin_oracle_match_matrix.argtypes = [C.c_int, C.c_int, fp, u8p, u8p, C.c_float, i32p, fp, i32p, fp]
     lib._fe_ready = True

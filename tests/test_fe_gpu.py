@@ -34,9 +34,10 @@ def _inv(T):
 def _check_frame(got, ref):
     (k, d), (kr, dr) = got, ref
     assert len(k) == len(kr)
-    for name in ("x", "y", "size", "response", "octave", "class_id"):
+    # every field exact, the angle included: the fp64 orientation chain is evaluated without FMA contraction and with an
+    # arithmetic-only atan2 on both sides, so the 1024-step rotation bin of the descriptor cannot flip
+    for name in ("x", "y", "size", "angle", "response", "octave", "class_id"):
         assert np.array_equal(k[name], kr[name]), name
-    assert np.abs(k["angle"] - kr["angle"]).max() < 1e-4  # atan2 of libm vs CUDA: last-ulp differences only
     assert np.array_equal(d, dr)                         # descriptor bits: exact
 
 
@@ -137,3 +138,27 @@ def test_match_edge_cases(fe, seq):
         assert np.array_equal(g["match_of_B"], r["match_of_B"])
         assert np.array_equal(g["best_index"], r["best_index"])
         assert (g["match_of_B"] >= 0).sum() == 0
+
+
+def test_orientation_and_descriptors_bit_exact_on_1e5_keypoints(seq):
+    # angle -> float -> 1024-step rotation bin must not flip.  256 uniform-random images (400 keypoints
+    # each, > 10^5 keypoints), varying extraction direction and both cameras' intrinsics: angles and descriptor bits exact.
+    from svin_b200.frontend import FeEngine
+    rng = np.random.default_rng(77)
+    n_img, total = 256, 0
+    with FeEngine(752, 480, max_images=64) as e:
+        for start in range(0, n_img, 64):
+            imgs = [random_image(1000 + start + i) for i in range(64)]
+            intr = [seq["intrinsics"][(start + i) % 2] for i in range(64)]
+            edir = []
+            for i in range(64):
+                g = rng.standard_normal(3)
+                edir.append(g / np.linalg.norm(g))
+            out = e.detect_describe(imgs, intr, edir)
+            for i in range(64):
+                kr, dr = ol.fe_detect_describe(imgs[i], intr[i], edir[i])
+                k, d = out[i]
+                assert len(k) == len(kr)
+                assert np.array_equal(k["angle"], kr["angle"]) and np.array_equal(d, dr)
+                total += len(k)
+    assert total >= 100000
