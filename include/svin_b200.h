@@ -324,13 +324,21 @@ int svin_ba_marginalize(svin_ba_ctx* ctx, int32_t window_index, const SvinMargSp
 
 /* ---- sharded single-window mode (BASELINE configs[3]): every rank uploads the SAME windows with the same pose /
  * speed-bias blocks and dense terms but a disjoint subset of the landmarks and their observations.  Each
- * trust-region iteration then all-reduces (NCCL, on the engine's stream) the reduced system
- * [H | g_red | g_raw | Hdiag] after the landmark elimination plus three small vectors of per-window scalars;
- * the Cholesky, the dogleg logic and accept/reject run replicated and bit-identically on every rank.
+ * trust-region iteration has three exchange steps, each ONE sum all-reduce of one packed buffer on the engine's
+ * stream: (1) after the landmark elimination the reduced system [H | g_red | g_raw | Hdiag] of every window plus one
+ * gradient-max slot per rank, (2) after the landmark back-substitution the nine landmark-side sums the dogleg
+ * coefficients need, (3) before accept/reject the landmark step / state norms and the candidate's reprojection cost.
+ * (2) and (3) cannot be folded into (1): the Gauss-Newton step norm needs the solved reduced system, the candidate cost
+ * needs the step.  The Cholesky, the dogleg logic and accept/reject run replicated and bit-identically on every rank;
+ * the whole pass, collectives included, is one CUDA graph.  time_limit_seconds must be < 0 in this mode (ranks must not
+ * decide on their own clocks).
  * NCCL is dlopen'ed (libnccl.so.2); the communicator is created from a 128-byte unique id that rank 0 obtains
- * with svin_nccl_unique_id() and the host distributes (e.g. torch.distributed / MPI / a file). */
+ * with svin_nccl_unique_id() and the host distributes (e.g. torch.distributed / MPI / a file).
+ * svin_ba_comm_init_local joins `world_size` contexts of THIS process (one device) into an in-process group instead:
+ * rank = position in `ctxs`; their svin_ba_solve calls must then run concurrently on `world_size` host threads. */
 int svin_nccl_unique_id(uint8_t out[128]);
 int svin_ba_comm_init(svin_ba_ctx* ctx, const uint8_t unique_id[128], int32_t rank, int32_t world_size);
+int svin_ba_comm_init_local(svin_ba_ctx* const* ctxs, int32_t world_size);
 
 /* Host-side planning only (no device needed): how svin_ba_upload would order one window's landmarks and cut them
  * into Schur chunks.  landmark_order [num_landmarks]: internal position -> caller landmark; per chunk (in internal

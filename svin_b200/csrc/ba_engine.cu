@@ -288,7 +288,7 @@ struct NcclApi {
 struct NcclId {
   char internal[128];
 };
-constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
 NcclApi* nccl_api() {
   static NcclApi api;
   static bool tried = false;
@@ -451,7 +451,32 @@ int validate(const SvinBaWindow& w, int idx) {
     set_error("window " + std::to_string(idx) + ": " + what);
     return SVIN_ERR_INVALID_ARGUMENT;
   };
-  if (w.num_pose_blocks < 0 || w.num_speedbias < 0 || w.num_landmarks < 0 || w.num_obs < 0) return bad("negative count");
+  if (w.num_pose_blocks < 0 || w.num_speedbias < 0 || w.num_landmarks < 0 || w.num_obs < 0 || w.num_cameras < 0 ||
+      w.num_imu < 0 || w.num_pose_priors < 0 || w.num_speedbias_priors < 0 || w.num_relative_pose < 0 ||
+      w.num_sonar < 0 || w.num_depth < 0 || w.marg_num_blocks < 0 || w.marg_dim < 0)
+    return bad("negative count");
+  // every array must be there whenever its count says it is read (a C caller's malformed window must come back as
+  // SVIN_ERR_INVALID_ARGUMENT, not as a segfault in the packers)
+  if (w.num_imu && (!w.imu_pose0 || !w.imu_pose1 || !w.imu_speedbias0 || !w.imu_speedbias1 || !w.imu_t0_ns ||
+                    !w.imu_t1_ns || !w.imu_meas_offset || !w.imu_meas_t_ns || !w.imu_meas_gyro || !w.imu_meas_accel))
+    return bad("IMU term arrays are NULL");
+  if (w.num_pose_priors && (!w.pose_prior_block || !w.pose_prior_measurement || !w.pose_prior_information))
+    return bad("pose prior arrays are NULL");
+  if (w.num_speedbias_priors &&
+      (!w.speedbias_prior_block || !w.speedbias_prior_measurement || !w.speedbias_prior_information))
+    return bad("speedbias prior arrays are NULL");
+  if (w.num_relative_pose && (!w.relative_pose_block0 || !w.relative_pose_block1 || !w.relative_pose_information))
+    return bad("relative pose arrays are NULL");
+  if (w.num_sonar && (!w.sonar_pose || !w.sonar_range || !w.sonar_heading || !w.sonar_information ||
+                      !w.sonar_landmark_mean || !w.sonar_T_SSo))
+    return bad("sonar arrays are NULL");
+  if (w.num_depth && (!w.depth_pose || !w.depth_measurement || !w.depth_first || !w.depth_information))
+    return bad("depth arrays are NULL");
+  if (w.marg_num_blocks && (!w.marg_block_kind || !w.marg_block_index || !w.marg_linearization_points))
+    return bad("marginalisation prior block arrays are NULL");
+  if (w.marg_dim && (!w.marg_J || !w.marg_e0)) return bad("marg_J / marg_e0 is NULL");
+  if (w.marg_dim && !w.marg_num_blocks) return bad("marg_dim > 0 without prior blocks");
+  if (w.num_imu && w.imu_meas_offset[0] != 0) return bad("imu_meas_offset[0] must be 0");
   if (w.num_pose_blocks && (!w.pose_blocks || !w.pose_fixed)) return bad("pose_blocks/pose_fixed is NULL");
   if (w.num_speedbias && (!w.speedbias || !w.speedbias_fixed)) return bad("speedbias/speedbias_fixed is NULL");
   if (w.num_landmarks && !w.landmarks) return bad("landmarks is NULL");
@@ -470,7 +495,11 @@ int validate(const SvinBaWindow& w, int idx) {
         w.imu_speedbias1[i] < 0 || w.imu_speedbias1[i] >= w.num_speedbias)
       return bad("IMU term block index out of range");
     const int a = w.imu_meas_offset[i], e = w.imu_meas_offset[i + 1];
+    if (a < 0 || e < a) return bad("imu_meas_offset must be non-decreasing");
     if (e - a < 2) return bad("IMU term needs at least two measurements");
+    if (w.imu_t1_ns[i] < w.imu_t0_ns[i]) return bad("IMU term with t1 < t0");
+    for (int k = a + 1; k < e; ++k)
+      if (w.imu_meas_t_ns[k] < w.imu_meas_t_ns[k - 1]) return bad("IMU measurement stamps must be ordered");
     if (w.imu_meas_t_ns[a] > w.imu_t0_ns[i] || w.imu_meas_t_ns[e - 1] < w.imu_t1_ns[i])
       return bad("IMU measurements do not cover [t0, t1] (ImuError.cpp:66-73)");
   }
@@ -594,6 +623,9 @@ void svin_ba_destroy(svin_ba_ctx* c) {
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->prof_events) cudaEventDestroy(ev);
   if (c->nccl_comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(c->nccl_comm);
+  if (c->local_tmp) cudaFree(c->local_tmp);
+  if (c->local_srcs) cudaFree(c->local_srcs);
+  c->local_comm.reset();
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->ev_gram) cudaEventDestroy(c->ev_gram);
@@ -1018,12 +1050,15 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   }
   const size_t o_wsw = wk.add(sizeof(WinState) * B), o_imucw = wk.add(sizeof(ImuCache) * NIMU);
   const size_t o_opoff = wk.add(4 * S);
-  const size_t o_sacc = wk.add(8 * kShardAcc * (size_t)B), o_gmaxb = wk.add(8 * (size_t)B);
+  const size_t o_sacc = wk.add(8 * kShardAcc * (size_t)B);
   const size_t o_lms = wk.add(24 * NL), o_lmV = wk.add(48 * NL), o_lmb2 = wk.add(24 * NL), o_lmd = wk.add(24 * NL),
                o_lmg = wk.add(24 * NL), o_lmgn = wk.add(24 * NL);
   // cleared every slot: H, g_red, g_raw, Hdiag (kept contiguous)
   const size_t o_clear = wk.bytes;
   const size_t o_H = wk.add(8 * NH), o_gred = wk.add(8 * ND), o_graw = wk.add(8 * ND), o_hd = wk.add(8 * ND);
+  // sharded mode: one slot per (window, rank) for the landmark gradient max - every rank fills its own slot, the SUM
+  // all-reduce of the whole clear region then carries all of them and the max is taken locally (k_gmax_pack)
+  const size_t o_gmaxb = wk.add(8 * (size_t)B * (size_t)(c->sharded() ? c->comm_world : 1));
   const size_t clear_bytes = wk.bytes - o_clear;
   const size_t o_sc = wk.add(8 * ND), o_dg = wk.add(8 * ND), o_gr = wk.add(8 * ND), o_gn = wk.add(8 * ND),
                o_u = wk.add(8 * ND), o_c = wk.add(8 * ND), o_dl = wk.add(8 * ND);
@@ -1098,10 +1133,21 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   c->d_pose_out = (double*)(O + c->out_off_pose); c->d_sb_out = (double*)(O + c->out_off_sb);
   c->d_lm_out = (double*)(O + c->out_off_lm);
   b.lm_quality = (double*)(O + c->out_off_q);
-  b.shard_acc = c->nccl_comm ? (double*)(Wk + o_sacc) : nullptr;
+  b.shard_acc = c->sharded() ? (double*)(Wk + o_sacc) : nullptr;
+  b.comm_rank = c->comm_rank;
+  b.comm_world = c->sharded() ? c->comm_world : 1;
   b.gmax_buf = (double*)(Wk + o_gmaxb);
   c->d_clear = Wk + o_clear;
   c->clear_bytes = clear_bytes;
+  if (c->local_comm) {
+    const size_t need = std::max(clear_bytes / 8, kShardAcc * (size_t)B);
+    if (need > c->local_tmp_cap) {
+      if (c->local_tmp) cudaFree(c->local_tmp);
+      c->local_tmp = nullptr;
+      SVIN_CUDA(cudaMalloc(&c->local_tmp, 8 * need));
+      c->local_tmp_cap = need;
+    }
+  }
   c->in_bytes = in.bytes;
 
   // ---------------- copy + initialise
@@ -1171,7 +1217,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   c->uploaded = true;
   c->graph_valid = false;
   c->solved = false;
-  if (graph_wanted() && c->graph_opt_known && !c->profiling && !c->nccl_comm) {
+  if (graph_wanted() && c->graph_opt_known && !c->profiling && !c->local_comm) {
     const int grc = build_graph(c, c->graph_opt);
     if (grc != SVIN_OK) return grc;
   }
@@ -1227,13 +1273,37 @@ int svin_ba_reset(svin_ba_ctx* c) {
   return SVIN_OK;
 }
 
-static int comm_allreduce(svin_ba_ctx* c, void* buf, size_t count, int op) {
-  NcclApi* api = nccl_api();
-  const int r = api->AllReduce(buf, buf, count, kNcclFloat64, op, c->nccl_comm, c->stream);
-  if (r != 0) {
-    set_error(std::string("ncclAllReduce failed: ") + (api->GetErrorString ? api->GetErrorString(r) : "?"));
-    return SVIN_ERR_CUDA;
+// SUM all-reduce of `count` doubles in place on the context's stream: NCCL between processes, or the in-process group.
+static int comm_allreduce(svin_ba_ctx* c, double* buf, size_t count) {
+  if (c->nccl_comm) {
+    NcclApi* api = nccl_api();
+    const int r = api->AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, c->nccl_comm, c->stream);
+    if (r != 0) {
+      set_error(std::string("ncclAllReduce failed: ") + (api->GetErrorString ? api->GetErrorString(r) : "?"));
+      return SVIN_ERR_CUDA;
+    }
+    return SVIN_OK;
   }
+  LocalGroup& g = *c->local_comm;
+  const int me = c->comm_rank;
+  if (count > c->local_tmp_cap) {
+    set_error("svin_ba: in-process all-reduce scratch too small");
+    return SVIN_ERR_STATE;
+  }
+  g.bufs[me] = buf;
+  cudaEventRecord(g.ready[me], c->stream);
+  g.barrier();  // every rank has published its buffer and recorded `ready`
+  std::vector<const double*> srcs(g.bufs.begin(), g.bufs.end());
+  for (int r = 0; r < g.world; ++r)
+    if (r != me) cudaStreamWaitEvent(c->stream, g.ready[r], 0);
+  cudaMemcpyAsync(c->local_srcs, srcs.data(), sizeof(double*) * g.world, cudaMemcpyHostToDevice, c->stream);
+  cudaStreamSynchronize(c->stream);  // srcs is a stack array; the test-only path can afford the sync
+  k_sum_peers<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(c->local_tmp, c->local_srcs, g.world, count);
+  cudaEventRecord(g.read[me], c->stream);
+  g.barrier();  // every rank has enqueued its read of all buffers
+  for (int r = 0; r < g.world; ++r)
+    if (r != me) cudaStreamWaitEvent(c->stream, g.read[r], 0);
+  SVIN_CUDA(cudaMemcpyAsync(buf, c->local_tmp, 8 * count, cudaMemcpyDeviceToDevice, c->stream));
   return SVIN_OK;
 }
 
@@ -1263,16 +1333,16 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
     ProfScope p(c, SVIN_BA_K_CLEAR);
     SVIN_CUDA(cudaMemsetAsync(c->d_clear, 0, c->clear_bytes, c->stream));
   }
-  const bool sharded = c->nccl_comm != nullptr;
+  const bool sharded = c->sharded();
   int rc;
   static const bool schur_par = !(std::getenv("SVIN_SCHUR_STREAMS") && std::atoi(std::getenv("SVIN_SCHUR_STREAMS")) == 0);
   int n_schur = 0;
-  { ProfScope p(c, SVIN_BA_K_SCHUR); n_schur = launch_schur(b, opt, c->stream, (schur_par && !sharded) ? &c->schur_par : nullptr); }
+  { ProfScope p(c, SVIN_BA_K_SCHUR); n_schur = launch_schur(b, opt, c->stream, schur_par ? &c->schur_par : nullptr); }
   if (sharded) {
-    // the exchange step of the path: reduced system of every window + the landmark gradient max
-    if ((rc = comm_allreduce(c, c->d_clear, c->clear_bytes / 8, kNcclSum)) != SVIN_OK) return rc;
+    // exchange 1 of 3 per iteration: the reduced system [H | g_red | g_raw | Hdiag] of every window and the per-rank
+    // landmark gradient maxima, one packed buffer, one all-reduce
     launch_gmax_pack(b, 0, c->stream);
-    if ((rc = comm_allreduce(c, b.gmax_buf, (size_t)b.B, kNcclMax)) != SVIN_OK) return rc;
+    if ((rc = comm_allreduce(c, (double*)c->d_clear, c->clear_bytes / 8)) != SVIN_OK) return rc;
     launch_gmax_pack(b, 1, c->stream);
   }
   if (c->gram_pending) {
@@ -1282,12 +1352,13 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
   { ProfScope p(c, SVIN_BA_K_DENSE_SOLVE); launch_dense_solve(b, opt, c->smem_bytes, c->n_max, c->stream); }
   { ProfScope p(c, SVIN_BA_K_BACKSUB); launch_backsub(b, c->stream); }
   if (sharded) {
-    if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
+    // exchange 2: the landmark-side sums the dogleg coefficients need (step norms, Cauchy point, model rows)
+    if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B)) != SVIN_OK) return rc;
     launch_fold(b, 2, c->stream);
   }
   { ProfScope p(c, SVIN_BA_K_STEP_DENSE); launch_step_dense(b, opt, c->stream); }
   static const bool no_fork = std::getenv("SVIN_BA_NO_FORK") != nullptr;  // debugging knob
-  const bool fork = !c->profiling && !sharded && !no_fork;
+  const bool fork = !c->profiling && !no_fork;
   if (fork) {
     SVIN_CUDA(cudaEventRecord(c->ev_fork, c->stream));
     SVIN_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
@@ -1295,20 +1366,17 @@ static int enqueue_slot(svin_ba_ctx* c, const SvinBaOptions& opt) {
     SVIN_CUDA(cudaEventRecord(c->ev_join, c->side));
   }
   { ProfScope p(c, SVIN_BA_K_STEP_LM); launch_step_lm(b, c->stream); }
-  if (sharded) {
-    if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
-    launch_fold(b, 3, c->stream);
-  }
   // candidate evaluation: the reprojection terms (k_linearize) and the dense terms (k_dense_eval, a small
   // latency-bound grid) are independent -> run them concurrently on two streams.  The dense terms only need the
   // candidate poses / speed-biases, so the side stream forks right after k_step_dense; k_decide needs their cost
   // (join), the Gram matrix is only needed by the next slot's reduced-system solve and is computed after k_decide
   // (for the buffer that is current by then) beside the next slot's Schur kernels.  Serial when profiling
-  // (per-kernel events) or sharded (the fold into cost_cand is not atomic).
+  // (per-kernel events).
   { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 1, 0, c->stream, b.fused != 0); }
   if (sharded) {
-    if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum)) != SVIN_OK) return rc;
-    launch_fold(b, 4, c->stream);
+    // exchange 3: landmark step / state norms (k_step_lm) and the candidate's reprojection cost, both only needed by k_decide
+    if ((rc = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B)) != SVIN_OK) return rc;
+    launch_fold(b, 3, c->stream);
   }
   if (fork) {
     SVIN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
@@ -1336,10 +1404,10 @@ static int enqueue_pass(svin_ba_ctx* c, const SvinBaOptions& opt, bool with_init
   const int chunk = std::max(1, opt.max_num_iterations);
   if (with_init) {
     { ProfScope p(c, SVIN_BA_K_LINEARIZE); launch_linearize(b, 0, 0, c->stream, b.fused != 0); }
-    if (c->nccl_comm) {
-      const int rc0 = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B, kNcclSum);
+    if (c->sharded()) {
+      const int rc0 = comm_allreduce(c, b.shard_acc, kShardAcc * (size_t)b.B);
       if (rc0 != SVIN_OK) return rc0;
-      launch_fold(b, 4, c->stream);
+      launch_fold(b, 3, c->stream);
     }
     {
       ProfScope p(c, SVIN_BA_K_DENSE_EVAL);
@@ -1399,6 +1467,12 @@ int svin_ba_solve(svin_ba_ctx* c, const SvinBaOptions* opt_in, SvinBaSummary* su
   else
     svin_ba_default_options(&opt);
   Batch& b = c->b;
+  if (c->sharded() && opt.time_limit_seconds >= 0.0) {
+    // k_decide stops a window on each rank's own clock: ranks could leave the iteration loop in different slots and
+    // stop issuing the collectives their peers wait for.  The replicated decisions must not depend on local time.
+    set_error("svin_ba_solve: time_limit_seconds is not supported in sharded mode (set it < 0)");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
   if (c->solved) {
     const int rc = svin_ba_reset(c);
     if (rc != SVIN_OK) return rc;
@@ -1411,7 +1485,7 @@ int svin_ba_solve(svin_ba_ctx* c, const SvinBaOptions* opt_in, SvinBaSummary* su
   // The first pass (initial evaluation + max_num_iterations slots) is a fixed launch sequence - all control flow is
   // on the device - so it is captured once per upload into a CUDA graph and replayed (SVIN_BA_GRAPH=0 disables).
   // svin_ba_upload pre-builds it with the options of the previous solve, outside the caller's GPU critical section.
-  const bool use_graph = graph_wanted() && !c->profiling && !c->nccl_comm;
+  const bool use_graph = graph_wanted() && !c->profiling && !c->local_comm;  // NCCL all-reduces are capturable
   int slots_done = 0;
   bool first = true;
   while (true) {
@@ -1506,7 +1580,8 @@ static void scatter_window(svin_ba_ctx* c, int i, SvinBaWindow* w, double* quali
   const int* perm = c->lm_perm.data() + d.lm_begin;
   for (int k = 0; k < d.lm_end - d.lm_begin; ++k) {
     std::memcpy(w->landmarks + 4 * (size_t)perm[k], lm_out + 4 * (size_t)k, 32);
-    if (quality) quality[perm[k]] = q_out[k];
+    // without compute_landmark_quality the device buffer holds an earlier batch's values (or nothing): report "unknown"
+    if (quality) quality[perm[k]] = c->quality_valid ? q_out[k] : std::nan("");
   }
 }
 
@@ -1791,6 +1866,37 @@ int svin_ba_comm_init(svin_ba_ctx* c, const uint8_t unique_id[128], int32_t rank
   c->comm_rank = rank;
   c->comm_world = world;
   c->uploaded = false;  // the arena layout depends on the mode
+  return SVIN_OK;
+}
+
+int svin_ba_comm_init_local(svin_ba_ctx* const* ctxs, int32_t world) {
+  if (!ctxs || world < 1 || world > 64) {
+    set_error("svin_ba_comm_init_local: invalid arguments");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  for (int r = 0; r < world; ++r)
+    if (!ctxs[r] || ctxs[r]->device != ctxs[0]->device || ctxs[r]->sharded()) {
+      set_error("svin_ba_comm_init_local: contexts must be distinct, on one device and without a communicator");
+      return SVIN_ERR_INVALID_ARGUMENT;
+    }
+  SVIN_CUDA(cudaSetDevice(ctxs[0]->device));
+  auto g = std::make_shared<LocalGroup>();
+  g->world = world;
+  g->bufs.assign(world, nullptr);
+  g->ready.resize(world);
+  g->read.resize(world);
+  for (int r = 0; r < world; ++r) {
+    SVIN_CUDA(cudaEventCreateWithFlags(&g->ready[r], cudaEventDisableTiming));
+    SVIN_CUDA(cudaEventCreateWithFlags(&g->read[r], cudaEventDisableTiming));
+  }
+  for (int r = 0; r < world; ++r) {
+    svin_ba_ctx* c = ctxs[r];
+    c->local_comm = g;
+    c->comm_rank = r;
+    c->comm_world = world;
+    c->uploaded = false;  // the arena layout depends on the mode
+    SVIN_CUDA(cudaMalloc(&c->local_srcs, sizeof(double*) * world));
+  }
   return SVIN_OK;
 }
 

@@ -2756,32 +2756,36 @@ __global__ void __launch_bounds__(kLmTile) k_quality(Batch b) {
 static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------------------------------------ sharded mode
-// stage 2: after k_backsub; 3: after k_step_lm; 4: after k_linearize.  Adds the all-reduced landmark-side
-// sums to the replicated dense-side sums in WinState and clears them.
+// stage 2: after k_backsub; 3: after k_linearize (landmark step norms + candidate reprojection cost).  Adds the
+// all-reduced landmark-side sums to the replicated dense-side sums in WinState and clears them.
 __global__ void k_fold(Batch b, int stage) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= b.B) return;
   WinState& ws = b.ws[w];
   double* sa = b.shard_acc + kShardAcc * (size_t)w;
+  // atomics: the dense terms of the candidate are evaluated concurrently on the side stream and add to the same sums
   if (stage == 2) {
-    ws.acc_g2 += sa[0]; ws.acc_n2 += sa[1]; ws.acc_gdot += sa[2]; ws.acc_Jg2 += sa[3];
-    for (int k = 0; k < 5; ++k) ws.acc_A[k] += sa[4 + k];
+    atomicAdd(&ws.acc_g2, sa[0]); atomicAdd(&ws.acc_n2, sa[1]); atomicAdd(&ws.acc_gdot, sa[2]); atomicAdd(&ws.acc_Jg2, sa[3]);
+    for (int k = 0; k < 5; ++k) atomicAdd(&ws.acc_A[k], sa[4 + k]);
     for (int k = 0; k < 9; ++k) sa[k] = 0.0;
-  } else if (stage == 3) {
-    ws.acc_step2 += sa[9]; ws.acc_xnorm2 += sa[10];
-    sa[9] = sa[10] = 0.0;
   } else {
-    ws.cost_cand += sa[11];
-    sa[11] = 0.0;
+    atomicAdd(&ws.acc_step2, sa[9]); atomicAdd(&ws.acc_xnorm2, sa[10]);
+    atomicAdd(&ws.cost_cand, sa[11]);
+    sa[9] = sa[10] = sa[11] = 0.0;
   }
 }
+// unpack = 0: this rank's landmark gradient max into its slot of the (cleared) exchange buffer; 1: max over the ranks' slots
 __global__ void k_gmax_pack(Batch b, int unpack) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= b.B) return;
-  if (!unpack)
-    b.gmax_buf[w] = __longlong_as_double((long long)b.ws[w].gmax_bits);
-  else
-    b.ws[w].gmax_bits = (unsigned long long)__double_as_longlong(b.gmax_buf[w]);
+  double* slots = b.gmax_buf + (size_t)w * b.comm_world;
+  if (!unpack) {
+    slots[b.comm_rank] = __longlong_as_double((long long)b.ws[w].gmax_bits);
+  } else {
+    double m = 0.0;
+    for (int r = 0; r < b.comm_world; ++r) m = fmax(m, slots[r]);
+    b.ws[w].gmax_bits = (unsigned long long)__double_as_longlong(m);
+  }
 }
 __global__ void k_obs_poff(Batch b) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;

@@ -185,7 +185,8 @@ struct Batch {
   // WinState so that they can be all-reduced before k_fold adds them to the replicated dense-side sums.
   // [B][8]: g2, n2, gdot, Jg2 (k_backsub) | mc, step2, xnorm2 (k_step_lm) | cost of the reprojection terms.
   double* shard_acc;  // nullptr when not sharded; kShardAcc doubles per window
-  double* gmax_buf;   // [B] landmark gradient max, all-reduced with MAX
+  double* gmax_buf;   // [B][comm_world] landmark gradient max, one slot per rank (inside the all-reduced clear region)
+  int comm_rank, comm_world;
 };
 
 // The caller's observation arrays (window by window, caller order) as uploaded; k_pack_obs gathers them.

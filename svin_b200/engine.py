@@ -137,6 +137,39 @@ class BaEngine:
         return [s.as_dict() for s in summ], quals
 
 
+def solve_sharded_local(shards: list[BaWindow], options: capi.SvinBaOptions | None = None, device: int = 0):
+    """The sharded solve (BASELINE configs[3]) with every rank's context in THIS process on one device: shards[k] is
+    rank k's window (svin_b200.sharding.shard_window).  The exchange steps run through svin_ba_comm_init_local; one host
+    thread per rank drives upload / solve / download.  Solutions are written into the shards; returns the summaries."""
+    import threading
+    opt = options or default_options()
+    lib = capi.load()
+    engines = [BaEngine(device) for _ in shards]
+    out: list = [None] * len(shards)
+    errors: list = []
+    try:
+        ctxs = (C.c_void_p * len(engines))(*[e._ctx for e in engines])
+        capi.check(lib.svin_ba_comm_init_local(ctxs, len(engines)), lib)
+
+        def drive(k):
+            try:
+                out[k] = engines[k].optimize([shards[k]], opt)[0][0]
+            except Exception as exc:  # noqa: BLE001 - surfaced below
+                errors.append(exc)
+
+        threads = [threading.Thread(target=drive, args=(k,)) for k in range(len(engines))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    finally:
+        for e in engines:
+            e.close()
+    if errors:
+        raise errors[0]
+    return out
+
+
 class BaPipeline:
     """Depth-2 software pipeline over the staged C ABI (svin_ba_upload / svin_ba_solve / svin_ba_download_all).
 

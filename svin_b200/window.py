@@ -50,6 +50,15 @@ class BaWindow:
         ("marg_J", _F64, ()), ("marg_e0", _F64, ()),
     ]
 
+    _ARRAY_NAMES = frozenset(n for n, _, _ in _ARRAYS)
+
+    def __setattr__(self, name, value):
+        # re-assigning an array (w.landmarks = ..., w.obs_* = ...) invalidates the cached C view: its raw pointers would
+        # otherwise keep pointing at the old (possibly freed) buffers
+        if name in self._ARRAY_NAMES or name in ("loss_type", "loss_scale", "marg_dim", "imu_params"):
+            object.__setattr__(self, "_struct", None)
+        object.__setattr__(self, name, value)
+
     def __init__(self):
         for name, dt, tail in self._ARRAYS:
             setattr(self, name, np.zeros((0,) + tail, dtype=dt))

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "multigpu: needs at least two CUDA devices (pytest -m multigpu on a multi-GPU box)")
 
 
 def _cuda_available():
