@@ -34,10 +34,12 @@ from svin_b200.window import default_options  # noqa: E402
 METRIC = "keyframes/sec sliding-window BA solve (10 KF, 2k landmarks)"
 UNIT = "keyframes/s"
 WORKLOAD = "EuRoC-shape synthetic stereo+IMU, 10-KF window (+3 IMU frames), 2k landmarks (BASELINE configs[1])"
-# algorithmic bytes per observation
-BYTES_LINEARIZE = 203.0   # read z 16 + info 8 + idx 12 + landmark ~6.4 ; write r 16 + J_pose 96 + J_lm 48
-BYTES_SCHUR = 160.0       # read J_pose 96 + J_lm 48 + r 16 per observation
-BYTES_PER_OBS = {"linearize": BYTES_LINEARIZE, "schur": BYTES_SCHUR, "backsub": BYTES_SCHUR}
+# Algorithmic bytes per observation.  SURVEY.md §8(d) counts 43 B read per observation
+# (z 16 + info 8 + idx 12 + landmark ~6.4) and 160 B of materialised r / J_pose / J_lm.  With the compact linearisation
+# (r + J_lm planes only, J_pose rebuilt in registers; the default) the per-observation record is 64 B + a 4-byte index.
+FUSED = os.environ.get("SVIN_BA_FUSED", "1") != "0"
+BYTES_PER_OBS = ({"linearize": 43.0 + 64.0, "schur": 64.0 + 4.0, "backsub": 64.0 + 8.0} if FUSED else
+                 {"linearize": 43.0 + 160.0, "schur": 160.0, "backsub": 160.0})
 
 
 def make_batch(n_windows: int, n_distinct: int, seed0: int = 20260925):
@@ -232,7 +234,8 @@ def run_frontend(args, local, rank, world, dist, barrier):
         t = fe.timings()
         dev_detect += t["run_ms"]
         for n, v in t["kernel_ms"].items():
-            kms[n] = kms.get(n, 0.0) + v
+            if n not in ("match", "assign"):      # those belong to svin_match (timed below); here they are stale
+                kms[n] = kms.get(n, 0.0) + v
     barrier()
     t_detect = time.perf_counter() - t0
     t0 = time.perf_counter()
@@ -403,10 +406,97 @@ def run_preprocess(args, local):
                                        "not OpenCV's SIMD code"}}
 
 
+ORACLE_FLAGS = "-O2 -ffp-contract=off (parity build)"
+
+
 def oracle_solver():
+    """The CPU restatement (oracle/) for the CPU legs: the -O3 -march=native timing build of BASELINE.md §3, compiled on
+    the box that runs the bench (falls back to the prebuilt parity build if g++ is not there)."""
+    global ORACLE_FLAGS
+    if "oracle_lib" not in sys.modules and "SVIN_ORACLE_SO" not in os.environ:
+        so = os.path.join(ROOT, "oracle", "_native", "libsvin_oracle_native.so")
+        try:
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "native"],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            os.environ["SVIN_ORACLE_SO"] = so
+            ORACLE_FLAGS = "-O3 -march=native"
+        except Exception:  # noqa: BLE001
+            pass
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     return oracle_lib
+
+
+def latency_section(eng, local):
+    """ONE window per svin_ba_optimize call with host buffers - the shape ThreadedKFVio::optimizationLoop produces
+    (ThreadedKFVio.cpp:1086: one Estimator::optimize per frame) - for BASELINE configs[1] and configs[0], next to the
+    single-thread CPU restatement on the same window."""
+    orc = oracle_solver()
+    opt = default_options()
+    out = {}
+    for label, kw in (("configs[1] 10 KF + 3, 2k landmarks", dict(num_keyframes=10, num_landmarks=2000)),
+                      ("configs[0] 5 KF + 3, 800 landmarks", dict(num_keyframes=5, num_landmarks=800))):
+        w = make_window(seed=20260925, num_imu_frames=3, mode="steady", **kw)[0]
+        for _ in range(10):
+            eng.optimize([w.copy()], opt)
+        wall, dev, up = [], [], []
+        for _ in range(100):
+            x = w.copy()
+            x.c_struct()
+            t0 = time.perf_counter()
+            summ, _ = eng.optimize([x], opt)
+            wall.append(1e3 * (time.perf_counter() - t0))
+            tm = eng.timings()
+            dev.append(tm["solve_ms"])
+            up.append(tm["host_upload_ms"])
+        cpu = []
+        for _ in range(5):
+            x = w.copy()
+            x.c_struct()
+            t0 = time.perf_counter()
+            orc.solve(x, opt, quality=True)
+            cpu.append(1e3 * (time.perf_counter() - t0))
+        p = lambda a, q: float(np.percentile(a, q))
+        out[label] = {"observations": int(w.num_obs), "iterations": int(summ[0]["iterations"]),
+                      "e2e_ms": {"p50": p(wall, 50), "p10": p(wall, 10), "p90": p(wall, 90)},
+                      "device_solve_ms_p50": p(dev, 50), "host_upload_ms_p50": p(up, 50),
+                      "h2d_bytes": int(tm["h2d_bytes"]), "d2h_bytes": int(tm["d2h_bytes"]),
+                      "cpu_1thread_ms_p50": p(cpu, 50), "speedup_vs_cpu_1thread": p(cpu, 50) / p(wall, 50)}
+    out["note"] = ("one window per call, host buffers in and out, upload + graph replay + download inside the timed "
+                   "region; CPU = single-thread restatement (oracle/, %s), not Ceres - it has no intra-solve threading, "
+                   "so the reference's 2-thread setting (ThreadedKFVio.cpp:1086) is reported as throughput in "
+                   "cpu_baseline.threads" % ORACLE_FLAGS)
+    return out
+
+
+def marginalization_section(eng):
+    """B9: svin_ba_marginalize (once per frame on the optimisation thread, ThreadedKFVio.cpp:1115) on the window the
+    marginalisation of the oldest frame of a 10-KF graph linearises, next to the CPU restatement."""
+    from svin_b200.marginalization import MargSpec, marginalization_subwindow
+    orc = oracle_solver()
+    w = make_window(seed=20260925, num_keyframes=10, num_imu_frames=3, num_landmarks=2000, mode="initial")[0]
+    sub, mp, ms = marginalization_subwindow(w, frames_removed=1)
+    spec = MargSpec(sub, mp, ms)
+    for _ in range(3):
+        eng.upload([sub])
+        eng.marginalize(spec)
+    t_up, t_m = [], []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        eng.upload([sub])
+        t1 = time.perf_counter()
+        eng.marginalize(spec)
+        t_m.append(1e3 * (time.perf_counter() - t1))
+        t_up.append(1e3 * (t1 - t0))
+    cpu = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        orc.marginalize(sub, spec)
+        cpu.append(1e3 * (time.perf_counter() - t0))
+    return {"landmarks_marginalised": int(sub.num_landmarks), "observations": int(sub.num_obs),
+            "dense_dim": int(sub.dense_dim()), "upload_ms_p50": float(np.median(t_up)),
+            "marginalize_ms_p50": float(np.median(t_m)), "cpu_1thread_ms_p50": float(np.median(cpu)),
+            "note": "single window, single CTA eigen-solver; once per frame, not on the per-iteration loop"}
 
 
 def cpu_baseline_timed(batch, seconds: float):
@@ -467,7 +557,8 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "windows_per_step": n, "max_num_iterations": 10},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n} windows per step, one solve per host thread ({cores} threads); CPU restatement "
-                                   "of the reference path (oracle/), not Ceres — Ceres/Eigen are absent from the image"},
+                                   f"of the reference path (oracle/, {ORACLE_FLAGS}), not Ceres — Ceres/Eigen are absent "
+                                   "from the image"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     if args.frames > 0:
@@ -638,8 +729,25 @@ def run_gpu(args):
     traffic, traffic_src = ncu_traffic(dominant, B)
 
     frontend = run_frontend(args, local, rank, world, dist, barrier) if args.frames > 0 else None
+    sharded = sharded_section(args, local, rank, world, dist)
     if rank == 0:
         cpu_val, cpu_dt, cpu_n = cpu_baseline_timed(batch, args.cpu_seconds) if world == 1 else (None, None, 0)
+        cpu_threads = None
+        if world == 1 and args.cpu_seconds >= 4:
+            cores = os.cpu_count() or 1
+            n2 = max(2, 2 * int(cpu_val * args.cpu_seconds / 4))          # ~cpu_seconds/2 of work on 2 threads
+            nall = max(cores, int(cores * cpu_val * args.cpu_seconds / 4))
+            v2, _ = cpu_baseline(batch[:1] * n2, 2)
+            vall, _ = cpu_baseline(batch[:1] * nall, cores)
+            cpu_threads = {"1": cpu_val, "2": v2, str(cores): vall, "unit": UNIT,
+                           "note": "one window per thread; 2 = the reference's Ceres thread count (ThreadedKFVio.cpp:1086)"}
+        latency = marg = None
+        if world == 1 and not args.skip_e2e:
+            try:
+                latency = latency_section(eng, local)
+                marg = marginalization_section(eng)
+            except Exception as exc:  # noqa: BLE001 - side sections never lose the headline line
+                latency = {"error": f"{type(exc).__name__}: {exc}"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
@@ -660,6 +768,7 @@ def run_gpu(args):
                          "algorithmic_bytes_per_launch": BYTES_PER_OBS[dominant] * units[dominant]
                          / kt[dominant]["launches"],
                          "algorithmic_bytes_per_observation": BYTES_PER_OBS[dominant],
+                         "linearisation": "compact (r + J_lm planes, 64 B/obs)" if FUSED else "materialised (160 B/obs)",
                          "note": "the schur family is several launches per slot (one per chunk lane mapping); "
                                  "achieved = algorithmic bytes of a slot / summed duration of its launches"},
             "kernels": kern,
@@ -673,12 +782,89 @@ def run_gpu(args):
         if cpu_val is not None:
             line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{cpu_n} windows of the same batch, single-thread CPU "
-                                              f"restatement (oracle/), {cpu_dt:.1f} s; not Ceres"}
+                                              f"restatement (oracle/, {ORACLE_FLAGS}), {cpu_dt:.1f} s; not Ceres",
+                                    "threads": cpu_threads}
+        if latency is not None:
+            line["latency"] = latency
+        if marg is not None:
+            line["marginalization"] = marg
+        if sharded is not None:
+            line["sharded"] = sharded
         print(json.dumps(line))
     eng.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def sharded_section(args, local, rank, world, dist):
+    """BASELINE configs[3] inside the default run so that the driver's scaling sweep records it: ONE 20-keyframe / 8k-
+    landmark window, landmark blocks sharded over the N ranks (l -> rank l % N), three packed all-reduces per iteration
+    (NCCL, captured in the solve graph).  Every rank also solves the whole window alone and asserts that the sharded
+    solution equals it - the hardware proof of the NCCL path (the 1-GPU test box can only run it through the in-process
+    communicator).  N = 1: the single-GPU time only."""
+    import torch
+    from svin_b200.engine import BaEngine
+    from svin_b200.sharding import landmark_owner, shard_window
+    try:
+        full = make_window(seed=20260925, num_keyframes=20, num_imu_frames=3, num_landmarks=8000, mode="steady")[0]
+        opt = default_options()
+        steps = max(args.steps, 10)
+
+        def timed(eng, wins):
+            eng.upload(wins)
+            for _ in range(3):
+                eng.reset()
+                summ = eng.solve(opt)
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize(local)
+            dev = 0.0
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                eng.reset()
+                summ = eng.solve(opt)
+                dev += eng.timings()["solve_ms"]
+            torch.cuda.synchronize(local)
+            wall = time.perf_counter() - t0
+            eng.download_all()
+            return summ[0], max_over_ranks(dist, dev / steps, local), max_over_ranks(dist, 1e3 * wall / steps, local)
+
+        ref = full.copy()
+        with BaEngine(local) as e1:
+            s1, dev1, wall1 = timed(e1, [ref])
+        out = {"workload": "20-KF window (+3 IMU frames), 8k landmarks (BASELINE configs[3])", "n_ranks": world,
+               "observations": int(full.num_obs), "iterations": int(s1["iterations"]),
+               "single_gpu_ms_per_solve": {"device": dev1, "wall": wall1}}
+        if world == 1:
+            return out
+        mine = shard_window(full, rank, world)
+        eng = BaEngine(local)
+        uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+        if rank == 0:
+            uid = torch.from_numpy(BaEngine.nccl_unique_id().copy()).to(f"cuda:{local}")
+        dist.broadcast(uid, src=0)
+        eng.comm_init(uid.cpu().numpy(), rank, world)
+        sN, devN, wallN = timed(eng, [mine])
+        eng.close()
+        rel = lambda a, b: float(np.abs(a - b).max() / max(1e-300, np.abs(b).max()))
+        own = landmark_owner(full.num_landmarks, world) == rank
+        errs = [rel(mine.pose_blocks, ref.pose_blocks), rel(mine.speedbias, ref.speedbias),
+                rel(mine.landmarks, ref.landmarks[own])]
+        ok = float(sN["iterations"] == s1["iterations"] and max(errs) < 1e-7)
+        t = torch.tensor([ok, -max(errs)], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok_all, worst = bool(t[0].item() > 0.5), float(-t[1].item())
+        assert ok_all, f"sharded NCCL solve differs from the single-GPU solve (worst relative difference {worst:.2e})"
+        out.update({"sharded_ms_per_solve": {"device": devN, "wall": wallN}, "speedup_device": dev1 / devN,
+                    "exchanges_per_iteration": 3, "collective": "ncclAllReduce(sum, f64) x3 per iteration, in the CUDA graph",
+                    "parity_vs_single_gpu": {"max_relative_difference": worst, "iterations_equal": True, "tolerance": 1e-7},
+                    "scaling": "strong"})
+        return out
+    except AssertionError:
+        raise
+    except Exception as exc:  # noqa: BLE001 - never lose the headline line over the side section
+        return {"error": f"{type(exc).__name__}: {exc}"}
 
 
 def run_sharded(args):

@@ -434,6 +434,72 @@ typedef struct SvinMatchResult {
 int svin_match(svin_fe_ctx* ctx, int32_t num_problems, const SvinMatchProblem* problems, SvinMatchResult* results);
 
 /* =====================================================================
+ *  (A10) RANSAC between matching and bundle adjustment  
+ *  Replaces the three opengv::sac::Ransac<...>::computeModel calls of
+ *    Frontend::runRansac3d2d               (okvis_frontend/src/Frontend.cpp:617-676)  FrameAbsolutePoseSacProblem
+ *    Frontend::runRansac2d2d               (:832-980)   FrameRotationOnlySacProblem + FrameRelativePoseSacProblem
+ *    Frontend::runRansac2d2dToRefineScale  (:680-830)   the same pair between camera 0 and camera 1
+ *  The adapter flattens its correspondences exactly as FrameNoncentralAbsoluteAdapter / FrameRelativeAdapter do
+ *  (okvis_frontend/src/FrameNoncentralAbsoluteAdapter.cpp:64-131, FrameRelativeAdapter.cpp:60-190): unit bearing
+ *  vectors from backProject, sigma_angle = sqrt(2) (0.8 size / 12)^2 / fu^2, camera extrinsics per correspondence.
+ *  Consensus scores: the in-tree getSelectedDistancesToModel of the three problems, exactly.  The loop
+ *  (most inliers wins, adaptive bound k = log(1 - 0.99) / log(1 - w^sampleSize), <= max_iterations + 1 iterations,
+ *  failed models skipped) follows OpenGV's sac::Ransac.  Minimal solvers (OpenGV is not in the reference tree):
+ *  absolute pose - central P3P (Grunert) on three points of ONE camera + 1 point to pick the solution, consensus over
+ *  all cameras (the reference asks OpenGV for GP3P; samples mixing cameras give no model); relative pose - eight-point
+ *  on 8 samples (OpenGV's STEWENIUS uses 5 + 3; EIGHTPT is another algorithm of the same problem class);
+ *  rotation only - 2 points.  The sample index sets are an INPUT so that results are reproducible: sample j is
+ *  hypothesis j, consumed in order.  All hypotheses are evaluated concurrently on the device and the sequential
+ *  stop rule is replayed over their inlier counts, which selects the hypothesis the sequential loop would.
+ *  Models are row-major 3x4 [R | t]: absolute = body pose in the world (T_WS), relative = T_C1C2 with |t| = 1,
+ *  rotation only = [R12 | 0].
+ * ===================================================================== */
+typedef struct svin_ransac_ctx svin_ransac_ctx;
+typedef struct SvinRansacAbsProblem {
+  int32_t num_correspondences;
+  const double* points;          /* [n][3] landmarks in the world (hp.head<3>() / hp[3]) */
+  const double* bearings;        /* [n][3] unit bearing vectors in their camera frame */
+  const int32_t* camera_index;   /* [n] */
+  const double* sigma_angle;     /* [n] */
+  int32_t num_cameras;
+  const double* camera_rotation; /* [num_cameras][9] row-major C_SC (frame->T_SC(im)->C()) */
+  const double* camera_offset;   /* [num_cameras][3] r_SC */
+  int32_t num_samples;           /* hypotheses offered; OpenGV consumes at most max_iterations + 1 valid ones */
+  const int32_t* samples;        /* [num_samples][4] correspondence indices, the first three in one camera */
+  double threshold;              /* 9 (Frontend.cpp:643) */
+  int32_t max_iterations;        /* 50 (Frontend.cpp:644) */
+} SvinRansacAbsProblem;
+typedef struct SvinRansacRelProblem {
+  int32_t num_correspondences;
+  const double* bearings1;       /* [n][3] unit, frame 1 (older frame / camera A) */
+  const double* bearings2;       /* [n][3] unit, frame 2 */
+  const double* sigma_angle1;    /* [n] */
+  const double* sigma_angle2;    /* [n] */
+  int32_t num_samples;
+  const int32_t* samples_rotation; /* [num_samples][2] */
+  const int32_t* samples_relative; /* [num_samples][8] */
+  double threshold;
+  int32_t max_iterations;
+} SvinRansacRelProblem;
+typedef struct SvinRansacResult {
+  int32_t best_sample;           /* winning hypothesis (-1: no model, inliers all 0) */
+  int32_t num_inliers;
+  int32_t iterations;            /* valid hypotheses the sequential loop would have evaluated */
+  double model[12];
+  uint8_t* inliers;              /* [n] caller-allocated or NULL: selectWithinDistance of the winning model */
+  int32_t* hypothesis_inliers;   /* [num_samples] caller-allocated or NULL: inlier count of every hypothesis */
+  uint8_t* hypothesis_valid;     /* [num_samples] caller-allocated or NULL: the minimal solver produced a model */
+} SvinRansacResult;
+int svin_ransac_create(int device, svin_ransac_ctx** out);
+void svin_ransac_destroy(svin_ransac_ctx* ctx);
+int svin_ransac_absolute(svin_ransac_ctx* ctx, int32_t num_problems, const SvinRansacAbsProblem* problems,
+                         SvinRansacResult* results);
+/* Both RANSACs of runRansac2d2d on every problem; the ratio rule between them (Frontend.cpp:876-905) stays in the caller. */
+int svin_ransac_relative(svin_ransac_ctx* ctx, int32_t num_problems, const SvinRansacRelProblem* problems,
+                         SvinRansacResult* rotation_only, SvinRansacResult* relative_pose);
+int svin_ransac_timings(svin_ransac_ctx* ctx, double* device_ms, int64_t* kernel_launches);
+
+/* =====================================================================
  *  (A0) image pre-processing in front of the detector  
  *  Replaces the OpenCV chain of Subscriber::imageCallback (okvis_ros/src/Subscriber.cpp:123-147):
  *    cv::resize(raw, Size(), resizeFactor, resizeFactor)  [INTER_LINEAR; an exact 2x decimation takes OpenCV's

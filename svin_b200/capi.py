@@ -163,6 +163,26 @@ class SvinBaKernelTimes(C.Structure):
     _fields_ = [("ms", C.c_double * 9), ("launches", C.c_int64 * 9)]
 
 
+class SvinRansacAbsProblem(C.Structure):
+    _fields_ = [("num_correspondences", C.c_int32), ("points", c_double_p), ("bearings", c_double_p),
+                ("camera_index", c_int32_p), ("sigma_angle", c_double_p), ("num_cameras", C.c_int32),
+                ("camera_rotation", c_double_p), ("camera_offset", c_double_p), ("num_samples", C.c_int32),
+                ("samples", c_int32_p), ("threshold", C.c_double), ("max_iterations", C.c_int32)]
+
+
+class SvinRansacRelProblem(C.Structure):
+    _fields_ = [("num_correspondences", C.c_int32), ("bearings1", c_double_p), ("bearings2", c_double_p),
+                ("sigma_angle1", c_double_p), ("sigma_angle2", c_double_p), ("num_samples", C.c_int32),
+                ("samples_rotation", c_int32_p), ("samples_relative", c_int32_p), ("threshold", C.c_double),
+                ("max_iterations", C.c_int32)]
+
+
+class SvinRansacResult(C.Structure):
+    _fields_ = [("best_sample", C.c_int32), ("num_inliers", C.c_int32), ("iterations", C.c_int32),
+                ("model", C.c_double * 12), ("inliers", c_uint8_p), ("hypothesis_inliers", c_int32_p),
+                ("hypothesis_valid", c_uint8_p)]
+
+
 class SvinError(RuntimeError):
     pass
 
@@ -180,6 +200,7 @@ EXPORTED_SYMBOLS = [
     "svin_fe_run", "svin_fe_download", "svin_fe_scores", "svin_match", "svin_fe_timings", "svin_fe_upload_device",
     "svin_pre_create", "svin_pre_destroy", "svin_pre_output_size", "svin_pre_process", "svin_pre_upload",
     "svin_pre_run", "svin_pre_download", "svin_pre_device_output", "svin_pre_timings",
+    "svin_ransac_create", "svin_ransac_destroy", "svin_ransac_absolute", "svin_ransac_relative", "svin_ransac_timings",
 ]
 
 
@@ -243,6 +264,14 @@ def load(path: str | None = None) -> C.CDLL:
     lib.svin_pre_device_output.argtypes = [C.c_void_p]
     lib.svin_pre_device_output.restype = C.c_void_p
     lib.svin_pre_timings.argtypes = [C.c_void_p, C.POINTER(SvinPreTimings)]
+    lib.svin_ransac_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.svin_ransac_destroy.argtypes = [C.c_void_p]
+    lib.svin_ransac_destroy.restype = None
+    lib.svin_ransac_absolute.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SvinRansacAbsProblem),
+                                         C.POINTER(SvinRansacResult)]
+    lib.svin_ransac_relative.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SvinRansacRelProblem),
+                                         C.POINTER(SvinRansacResult), C.POINTER(SvinRansacResult)]
+    lib.svin_ransac_timings.argtypes = [C.c_void_p, c_double_p, C.POINTER(C.c_int64)]
     if path is None:
         _lib = lib
     return lib

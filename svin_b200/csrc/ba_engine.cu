@@ -402,6 +402,7 @@ struct svin_ba_ctx {
   void* d_clear = nullptr;
   bool quality_valid = false;
   bool solved = false;
+  int solves_since_upload = 0;
   SvinBaTimings tm{};
   HostPool* pool = nullptr;
   // sharded mode
@@ -642,6 +643,7 @@ void svin_ba_destroy(svin_ba_ctx* c) {
 }
 
 static bool graph_wanted();
+static int graph_min_windows();
 static int build_graph(svin_ba_ctx* c, const SvinBaOptions& opt);
 
 int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
@@ -1215,9 +1217,10 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   c->tm.host_fill_ms = t_filled - t_ordered;
   c->tm.host_upload_ms = wall_ms() - t_begin;
   c->uploaded = true;
+  c->solves_since_upload = 0;
   c->graph_valid = false;
   c->solved = false;
-  if (graph_wanted() && c->graph_opt_known && !c->profiling && !c->local_comm) {
+  if (graph_wanted() && c->graph_opt_known && !c->profiling && !c->local_comm && B >= graph_min_windows()) {
     const int grc = build_graph(c, c->graph_opt);
     if (grc != SVIN_OK) return grc;
   }
@@ -1432,6 +1435,13 @@ static bool graph_wanted() {
   static const bool w = !(std::getenv("SVIN_BA_GRAPH") && std::atoi(std::getenv("SVIN_BA_GRAPH")) == 0);
   return w;
 }
+// Capturing + instantiating the ~190-node graph costs the host about as much as a small batch takes to solve: a graph
+// pays when the batch is solved more than once per upload or is big enough that launch gaps matter.  Below this many
+// windows a fresh upload is solved with plain stream launches (SVIN_BA_GRAPH_MIN_WINDOWS, measured in DESIGN.md §3.5).
+static int graph_min_windows() {
+  static const int v = std::getenv("SVIN_BA_GRAPH_MIN_WINDOWS") ? std::atoi(std::getenv("SVIN_BA_GRAPH_MIN_WINDOWS")) : 8;
+  return v;
+}
 // Capture the first pass for the current upload (kernel arguments hold the batch by value) and instantiate it.
 static int build_graph(svin_ba_ctx* c, const SvinBaOptions& opt) {
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -1485,7 +1495,9 @@ int svin_ba_solve(svin_ba_ctx* c, const SvinBaOptions* opt_in, SvinBaSummary* su
   // The first pass (initial evaluation + max_num_iterations slots) is a fixed launch sequence - all control flow is
   // on the device - so it is captured once per upload into a CUDA graph and replayed (SVIN_BA_GRAPH=0 disables).
   // svin_ba_upload pre-builds it with the options of the previous solve, outside the caller's GPU critical section.
-  const bool use_graph = graph_wanted() && !c->profiling && !c->local_comm;  // NCCL all-reduces are capturable
+  // NCCL all-reduces are capturable; a small batch only gets a graph from its second solve on (c->solved_once)
+  const bool use_graph = graph_wanted() && !c->profiling && !c->local_comm &&
+                         (b.B >= graph_min_windows() || c->solves_since_upload > 0);
   int slots_done = 0;
   bool first = true;
   while (true) {
@@ -1528,6 +1540,7 @@ int svin_ba_solve(svin_ba_ctx* c, const SvinBaOptions* opt_in, SvinBaSummary* su
   cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
   c->tm.solve_ms = ms;
   c->solved = true;
+  c->solves_since_upload += 1;
   if (c->profiling) {
     c->ktimes = SvinBaKernelTimes{};
     for (size_t i = 0; i < c->prof_family.size(); ++i) {

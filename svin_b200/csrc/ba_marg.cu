@@ -142,93 +142,93 @@ __global__ void __launch_bounds__(128) k_marg_landmarks(Batch b, MargArgs m) {
   }
 }
 
-// ---- CTA-wide Jacobi eigen-decomposition (round-robin ordering), matrices in global memory ------------------------
-__device__ void jacobi_eigh_cta(double* A, int n, double* U, double* ev, int* pl, double* cs /*2*(n/2+1)*/) {
-  const int tid = threadIdx.x, T = blockDim.x;
-  const int mm_ = n + (n & 1);
+// ---- CTA-wide symmetric eigen-decomposition: one-sided (Hestenes) Jacobi, one warp per column pair ------------------
+// A (n x n, symmetric; row-major == column-major) is overwritten by G = A V with mutually orthogonal columns, V (the
+// eigenvectors, column k contiguous) is accumulated in U and transposed at the end into the layout the callers use
+// (U[i * n + k] = component i of eigenvector k); ev[k] = v_k . g_k = v_k^T A v_k keeps the sign of tiny negative
+// eigenvalues.  A rotation touches two contiguous columns only (three warp-reduced dot products, then 2 x 2n updates),
+// the n/2 pairs of a round-robin round are independent and go to the CTA's warps, one barrier per round - against the
+// two-sided variant this replaces (rows AND columns of a matrix in global memory, three barriers and a serial
+// reshuffle per round, 256 threads) the B9 call of bench.py's 10-KF window went from 135 ms to a few ms.
+__device__ void jacobi_eigh_cta(double* A, int n, double* U, double* ev, int* /*unused*/, double* /*unused*/) {
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+  const int mm_ = n + (n & 1);   // players (one dummy when n is odd)
   const int half = mm_ / 2;
-  __shared__ double red[2];
+  __shared__ double worst_s[32];
+  __shared__ int done_s;
   for (int e = tid; e < n * n; e += T) U[e] = (e / n == e % n) ? 1.0 : 0.0;
   __syncthreads();
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    if (tid == 0) red[0] = red[1] = 0.0;
-    __syncthreads();
-    double off = 0, dg = 0;
-    for (int e = tid; e < n * n; e += T) {
-      const double v = A[e] * A[e];
-      if (e / n == e % n) dg += v; else off += v;
-    }
-    off = warp_sum(off);
-    dg = warp_sum(dg);
-    if ((tid & 31) == 0) {
-      atomicAdd(&red[0], off);
-      atomicAdd(&red[1], dg);
-    }
-    __syncthreads();
-    const bool conv = (red[0] <= 1e-30 * red[1]) || red[0] == 0.0;
-    __syncthreads();
-    if (conv) break;
-    for (int i = tid; i < mm_; i += T) pl[i] = i;
-    __syncthreads();
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    double worst = 0.0;   // largest |cos angle| between two columns seen by this warp in the sweep
     for (int round = 0; round < mm_ - 1; ++round) {
-      // rotation parameters of the disjoint pairs of this round
-      for (int k = tid; k < half; k += T) {
-        int p = pl[k], q = pl[mm_ - 1 - k];
-        double c = 1.0, s = 0.0;
-        if (p < n && q < n) {
-          if (p > q) { const int t = p; p = q; q = t; }
-          const double apq = A[(size_t)p * n + q];
-          if (apq != 0.0) {
-            const double theta = (A[(size_t)q * n + q] - A[(size_t)p * n + p]) / (2.0 * apq);
-            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-            c = 1.0 / sqrt(t * t + 1.0);
-            s = t * c;
-          }
+      for (int k = wid; k < half; k += nw) {
+        // circle method: player mm_-1 stays, the others rotate
+        int p = (k == 0) ? mm_ - 1 : (round + k) % (mm_ - 1);
+        int q = (round + mm_ - 1 - k) % (mm_ - 1);
+        if (p >= n || q >= n) continue;   // the dummy
+        if (p > q) { const int t = p; p = q; q = t; }
+        double* gp = A + (size_t)p * n;
+        double* gq = A + (size_t)q * n;
+        double al = 0.0, be = 0.0, ga = 0.0;
+        for (int i = lane; i < n; i += 32) {
+          const double x = gp[i], y = gq[i];
+          al += x * x;
+          be += y * y;
+          ga += x * y;
         }
-        cs[2 * k] = c;
-        cs[2 * k + 1] = s;
+        al = warp_sum(al);
+        be = warp_sum(be);
+        ga = warp_sum(ga);
+        if (ga == 0.0 || al == 0.0 || be == 0.0) continue;
+        const double cosang = fabs(ga) / sqrt(al * be);
+        worst = fmax(worst, cosang);
+        if (cosang < 1.0e-15) continue;
+        const double zeta = (be - al) / (2.0 * ga);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+        double* vp = U + (size_t)p * n;
+        double* vq = U + (size_t)q * n;
+        for (int i = lane; i < n; i += 32) {
+          const double x = gp[i], y = gq[i];
+          gp[i] = c * x - sn * y;
+          gq[i] = sn * x + c * y;
+          const double u = vp[i], v = vq[i];
+          vp[i] = c * u - sn * v;
+          vq[i] = sn * u + c * v;
+        }
       }
       __syncthreads();
-      // columns: A <- A G, U <- U G
-      for (int e = tid; e < half * n; e += T) {
-        const int k = e / n, i = e % n;
-        int p = pl[k], q = pl[mm_ - 1 - k];
-        if (p >= n || q >= n) continue;
-        if (p > q) { const int t = p; p = q; q = t; }
-        const double c = cs[2 * k], s = cs[2 * k + 1];
-        const double aip = A[(size_t)i * n + p], aiq = A[(size_t)i * n + q];
-        A[(size_t)i * n + p] = c * aip - s * aiq;
-        A[(size_t)i * n + q] = s * aip + c * aiq;
-        const double uip = U[(size_t)i * n + p], uiq = U[(size_t)i * n + q];
-        U[(size_t)i * n + p] = c * uip - s * uiq;
-        U[(size_t)i * n + q] = s * uip + c * uiq;
-      }
-      __syncthreads();
-      // rows: A <- G^T A
-      for (int e = tid; e < half * n; e += T) {
-        const int k = e / n, i = e % n;
-        int p = pl[k], q = pl[mm_ - 1 - k];
-        if (p >= n || q >= n) continue;
-        if (p > q) { const int t = p; p = q; q = t; }
-        const double c = cs[2 * k], s = cs[2 * k + 1];
-        const double api = A[(size_t)p * n + i], aqi = A[(size_t)q * n + i];
-        A[(size_t)p * n + i] = c * api - s * aqi;
-        A[(size_t)q * n + i] = s * api + c * aqi;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        const int last = pl[mm_ - 1];
-        for (int i = mm_ - 1; i > 1; --i) pl[i] = pl[i - 1];
-        pl[1] = last;
-      }
-      __syncthreads();
+    }
+    if (lane == 0) worst_s[wid] = worst;
+    __syncthreads();
+    if (tid == 0) {
+      double w = 0.0;
+      for (int i = 0; i < nw; ++i) w = fmax(w, worst_s[i]);
+      done_s = w < 1.0e-14;
+    }
+    __syncthreads();
+    if (done_s) break;
+  }
+  for (int k = wid; k < n; k += nw) {
+    double sdot = 0.0;
+    for (int i = lane; i < n; i += 32) sdot += U[(size_t)k * n + i] * A[(size_t)k * n + i];
+    sdot = warp_sum(sdot);
+    if (lane == 0) ev[k] = sdot;
+  }
+  __syncthreads();
+  // V columns -> U[i][k]
+  for (int e = tid; e < n * n; e += T) {
+    const int i = e / n, k = e % n;
+    if (i < k) {
+      const double x = U[(size_t)i * n + k], y = U[(size_t)k * n + i];
+      U[(size_t)i * n + k] = y;
+      U[(size_t)k * n + i] = x;
     }
   }
-  for (int i = tid; i < n; i += T) ev[i] = A[(size_t)i * n + i];
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_marg_dense(Batch b, MargArgs m) {
+__global__ void __launch_bounds__(1024) k_marg_dense(Batch b, MargArgs m) {
   const WinDesc& wd = b.win[m.w];
   const int buf = b.ws[m.w].cur;
   const int tid = threadIdx.x, T = blockDim.x;
@@ -348,7 +348,7 @@ void launch_marg(const Batch& b, const MargArgs& m, int num_landmarks, cudaStrea
     else
       k_marg_landmarks<false><<<grid, 128, 0, st>>>(b, m);
   }
-  k_marg_dense<<<1, 256, 0, st>>>(b, m);
+  k_marg_dense<<<1, 1024, 0, st>>>(b, m);
 }
 
 }  // namespace svin

@@ -108,6 +108,9 @@ class BaWindow:
     def num_landmarks(self):
         return len(self.landmarks)
 
+    def num_pose_blocks_free(self) -> int:
+        return int((np.asarray(self.pose_fixed) == 0).sum())
+
     def dense_dim(self) -> int:
         return int(6 * np.count_nonzero(self.pose_fixed == 0) + 9 * np.count_nonzero(self.speedbias_fixed == 0))
 

@@ -22,6 +22,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    override = os.environ.get("SVIN_ORACLE_SO")   # bench.py's CPU arm: the -O3 -march=native timing build
+    if override and os.path.exists(override):
+        return _bind(C.CDLL(override))
     srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".cpp", ".hpp"))]
     if (not os.path.exists(ORACLE_SO)) or any(os.path.getmtime(s) > os.path.getmtime(ORACLE_SO) for s in srcs):
         try:
@@ -29,7 +32,11 @@ def load():
         except Exception:
             if not os.path.exists(ORACLE_SO):
                 raise
-    lib = C.CDLL(ORACLE_SO)
+    return _bind(C.CDLL(ORACLE_SO))
+
+
+def _bind(lib):
+    global _lib
     dp = capi.c_double_p
     lib.svin_oracle_default_options.argtypes = [C.POINTER(capi.SvinBaOptions)]
     lib.svin_oracle_ba_evaluate.argtypes = [C.POINTER(capi.SvinBaWindow), C.POINTER(capi.SvinBaEvaluation)]
