@@ -800,7 +800,7 @@ def run_gpu(args):
 def sharded_section(args, local, rank, world, dist):
     """BASELINE configs[3] inside the default run so that the driver's scaling sweep records it: ONE 20-keyframe / 8k-
     landmark window, landmark blocks sharded over the N ranks (l -> rank l % N), three packed all-reduces per iteration
-    (NCCL, captured in the solve graph).  Every rank also solves the whole window alone and asserts that the sharded
+    (NCCL).  Every rank also solves the whole window alone and asserts that the sharded
     solution equals it - the hardware proof of the NCCL path (the 1-GPU test box can only run it through the in-process
     communicator).  N = 1: the single-GPU time only."""
     import torch
@@ -857,7 +857,7 @@ def sharded_section(args, local, rank, world, dist):
         ok_all, worst = bool(t[0].item() > 0.5), float(-t[1].item())
         assert ok_all, f"sharded NCCL solve differs from the single-GPU solve (worst relative difference {worst:.2e})"
         out.update({"sharded_ms_per_solve": {"device": devN, "wall": wallN}, "speedup_device": dev1 / devN,
-                    "exchanges_per_iteration": 3, "collective": "ncclAllReduce(sum, f64) x3 per iteration, in the CUDA graph",
+                    "exchanges_per_iteration": 3, "collective": "ncclAllReduce(sum, f64) x3 per iteration on the solve stream (one packed buffer each)",
                     "parity_vs_single_gpu": {"max_relative_difference": worst, "iterations_equal": True, "tolerance": 1e-7},
                     "scaling": "strong"})
         return out

@@ -329,9 +329,8 @@ int svin_ba_marginalize(svin_ba_ctx* ctx, int32_t window_index, const SvinMargSp
  * gradient-max slot per rank, (2) after the landmark back-substitution the nine landmark-side sums the dogleg
  * coefficients need, (3) before accept/reject the landmark step / state norms and the candidate's reprojection cost.
  * (2) and (3) cannot be folded into (1): the Gauss-Newton step norm needs the solved reduced system, the candidate cost
- * needs the step.  The Cholesky, the dogleg logic and accept/reject run replicated and bit-identically on every rank;
- * the whole pass, collectives included, is one CUDA graph.  time_limit_seconds must be < 0 in this mode (ranks must not
- * decide on their own clocks).
+ * needs the step.  The Cholesky, the dogleg logic and accept/reject run replicated and bit-identically on every rank.
+ * time_limit_seconds must be < 0 in this mode (ranks must not decide on their own clocks).
  * NCCL is dlopen'ed (libnccl.so.2); the communicator is created from a 128-byte unique id that rank 0 obtains
  * with svin_nccl_unique_id() and the host distributes (e.g. torch.distributed / MPI / a file).
  * svin_ba_comm_init_local joins `world_size` contexts of THIS process (one device) into an in-process group instead:

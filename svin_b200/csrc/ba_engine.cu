@@ -603,6 +603,10 @@ int svin_ba_create(int device, svin_ba_ctx** out) {
   SVIN_CUDA(cudaMallocHost(&c->h_active, sizeof(int)));
   // worker threads of the upload / scatter path; SVIN_HOST_THREADS lets several contexts (BaPipeline) share the cores
   int host_threads = std::min(32, (int)std::thread::hardware_concurrency());
+  // one process per GPU (torchrun sets LOCAL_WORLD_SIZE): the ranks of a node share its cores - a full-size pool per
+  // rank oversubscribed the host 8x at 8 ranks and made the end-to-end path host-bound (SCALE_r01: 0.25 efficiency)
+  if (const char* lw = std::getenv("LOCAL_WORLD_SIZE"))
+    host_threads = std::max(2, host_threads / std::max(1, std::atoi(lw)));
   if (const char* e = std::getenv("SVIN_HOST_THREADS")) host_threads = std::max(1, std::min(64, std::atoi(e)));
   c->pool = new HostPool(std::max(0, host_threads - 1));
   *out = c;
@@ -1220,7 +1224,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   c->solves_since_upload = 0;
   c->graph_valid = false;
   c->solved = false;
-  if (graph_wanted() && c->graph_opt_known && !c->profiling && !c->local_comm && B >= graph_min_windows()) {
+  if (graph_wanted() && c->graph_opt_known && !c->profiling && !c->sharded() && B >= graph_min_windows()) {
     const int grc = build_graph(c, c->graph_opt);
     if (grc != SVIN_OK) return grc;
   }
@@ -1495,8 +1499,10 @@ int svin_ba_solve(svin_ba_ctx* c, const SvinBaOptions* opt_in, SvinBaSummary* su
   // The first pass (initial evaluation + max_num_iterations slots) is a fixed launch sequence - all control flow is
   // on the device - so it is captured once per upload into a CUDA graph and replayed (SVIN_BA_GRAPH=0 disables).
   // svin_ba_upload pre-builds it with the options of the previous solve, outside the caller's GPU critical section.
-  // NCCL all-reduces are capturable; a small batch only gets a graph from its second solve on (c->solved_once)
-  const bool use_graph = graph_wanted() && !c->profiling && !c->local_comm &&
+  // A small batch only gets a graph from its second solve on.  Sharded mode runs with plain stream launches: a captured
+  // pass with its ncclAllReduce nodes deadlocked at replay on this image (NCCL 2.28.9, 2 ranks, profiles/r2u_*), the
+  // same launch sequence without capture runs fine.
+  const bool use_graph = graph_wanted() && !c->profiling && !c->sharded() &&
                          (b.B >= graph_min_windows() || c->solves_since_upload > 0);
   int slots_done = 0;
   bool first = true;

@@ -185,7 +185,8 @@ class BaPipeline:
         prev = os.environ.get("SVIN_HOST_THREADS")
         # (measured on a 16-core box, 3 contexts: full pools per context 16.7k windows/s, cores / depth 14.9k)
         if host_threads is None:
-            host_threads = min(32, os.cpu_count() or 8)
+            # the ranks of a node (torchrun: LOCAL_WORLD_SIZE) share its cores
+            host_threads = max(2, min(32, os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
         os.environ["SVIN_HOST_THREADS"] = str(host_threads)
         try:
             self._engines = [BaEngine(device) for _ in range(depth)]
