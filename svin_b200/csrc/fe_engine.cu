@@ -206,7 +206,7 @@ int svin_fe_create(int device, const SvinFeOptions* opt_in, svin_fe_ctx** out) {
   f.kept_score = c->d_kept_score; f.kept_count = c->d_kept_count; f.keypoints = c->d_kps; f.descriptors = c->d_desc;
   f.pat_dx = c->d_pdx; f.pat_dy = c->d_pdy; f.pat_half = c->d_half; f.pair_i = c->d_pi; f.pair_j = c->d_pj;
   c->occ_bytes = (size_t)(W / 2 + 32) * (H / 2 + 32);
-  if (c->occ_bytes > 200 * 1024) {
+  if (c->occ_bytes > 184 * 1024) {  // + 40 KB of static shared memory (cone table, staged candidate tile) <= 227 KB
     set_error("svin_fe_create: image too large for the shared-memory occupancy grid");
     return SVIN_ERR_INVALID_ARGUMENT;
   }

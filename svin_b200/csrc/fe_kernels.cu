@@ -12,6 +12,8 @@
 //                                                 (VKWMA.cpp:292-323) + best-4 list (DenseMatcher.hpp impl:216-242)
 //   k_assign           one thread per problem     assignbest (DenseMatcher.cpp:59-97), A ascending
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <math.h>
 #include <stdint.h>
 
@@ -106,55 +108,118 @@ __global__ void __launch_bounds__(256) k_harris_nms(FeBatch f) {
 }
 
 // ------------------------------------------------------------------------------------------ sort
-// Descending bitonic sort of the image's candidate keys (unique), padded with zeros to a power of two.
-__global__ void __launch_bounds__(1024) k_sort_candidates(FeBatch f) {
-  const int img = blockIdx.x;
-  unsigned n = f.cand_count[img];
+// Descending bitonic sort of an image's candidate keys (unique), zero-padded to a power of two P >= n.  Stages whose
+// partner distance j fits a 4096-key chunk run in shared memory (one CTA per chunk); the few stages with j >= 4096 are
+// one compare-exchange per thread in global memory.  A launch is a no-op for images whose P is below its stage, so the
+// fixed launch sequence (sized for cand_cap) costs a typical image (P <= 8192) two real kernels.  [r1: one CTA per image
+// sorting in global memory, 0.90 ms for a 752x480 noise image.]
+constexpr int kSortChunk = 4096;
+__device__ __forceinline__ unsigned sort_size(const FeBatch& f, int img, unsigned& n) {
+  n = f.cand_count[img];
   if (n > (unsigned)f.cand_cap) n = f.cand_cap;
-  unsigned long long* K = f.cand_keys + (size_t)img * f.cand_cap;
-  unsigned P = 1;
+  unsigned P = kSortChunk;
   while (P < n) P <<= 1;
-  for (unsigned i = n + threadIdx.x; i < P; i += blockDim.x) K[i] = 0ull;
+  return P;
+}
+// K == 0: the complete network up to runs of kSortChunk.  K > 0: the tail (j < kSortChunk) of merge stage K.
+__global__ void __launch_bounds__(1024) k_sort_local(FeBatch f, unsigned K) {
+  __shared__ unsigned long long S[kSortChunk];
+  const int img = blockIdx.y;
+  unsigned n;
+  const unsigned P = sort_size(f, img, n);
+  const unsigned base = blockIdx.x * kSortChunk;
+  if (base >= P || K > P) return;
+  if (n == 0) return;
+  unsigned long long* G = f.cand_keys + (size_t)img * f.cand_cap + base;
+  for (unsigned i = threadIdx.x; i < kSortChunk; i += 1024) S[i] = (base + i < n || K != 0) ? G[i] : 0ull;
   __syncthreads();
-  for (unsigned k = 2; k <= P; k <<= 1)
-    for (unsigned j = k >> 1; j > 0; j >>= 1) {
-      for (unsigned i = threadIdx.x; i < P; i += blockDim.x) {
-        const unsigned l = i ^ j;
-        if (l > i) {
-          const unsigned long long a = K[i], b = K[l];
-          const bool desc = ((i & k) == 0);
-          if (desc ? (a < b) : (a > b)) {
-            K[i] = b;
-            K[l] = a;
-          }
+  const unsigned k_first = K ? K : 2, k_last = K ? K : kSortChunk;
+  for (unsigned k = k_first; k <= k_last; k <<= 1) {
+    for (unsigned j = min(k >> 1, (unsigned)kSortChunk >> 1); j > 0; j >>= 1) {
+      for (unsigned t = threadIdx.x; t < kSortChunk / 2; t += 1024) {
+        const unsigned i = 2 * j * (t / j) + (t % j), l = i + j;
+        const unsigned long long a = S[i], b = S[l];
+        const bool desc = (((base + i) & k) == 0);
+        if (desc ? (a < b) : (a > b)) {
+          S[i] = b;
+          S[l] = a;
         }
       }
       __syncthreads();
     }
+    if (k == 0x80000000u) break;
+  }
+  for (unsigned i = threadIdx.x; i < kSortChunk; i += 1024) G[i] = S[i];
+}
+// one global compare-exchange step (K, j >= kSortChunk)
+__global__ void __launch_bounds__(256) k_sort_global(FeBatch f, unsigned K, unsigned j) {
+  const int img = blockIdx.y;
+  unsigned n;
+  const unsigned P = sort_size(f, img, n);
+  if (K > P) return;
+  const unsigned t = blockIdx.x * 256 + threadIdx.x;
+  const unsigned i = 2 * j * (t / j) + (t % j), l = i + j;
+  if (l >= P) return;
+  unsigned long long* G = f.cand_keys + (size_t)img * f.cand_cap;
+  const unsigned long long a = G[i], b = G[l];
+  const bool desc = ((i & K) == 0);
+  if (desc ? (a < b) : (a > b)) {
+    G[i] = b;
+    G[l] = a;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ uniformity
-__global__ void __launch_bounds__(256) k_uniformity(FeBatch f) {
+// Strongest-first acceptance against the occupancy image.  The reference procedure is sequential in the accepted
+// keypoints (each stamp changes the occupancy later tests read); this kernel produces exactly its result but accepts
+// SEVERAL candidates per round:
+//   * all candidates of a 512-wide window are tested against the current occupancy at once; those that fail now fail
+//     for good (the occupancy only grows);
+//   * the passing ones, in order, are accepted as long as each lies outside the 31x31 stamp footprint of every earlier
+//     passing candidate of the round - its test cannot be changed by those stamps, so the sequential procedure would
+//     accept it too.  The first one that is not (or the 33rd) starts the next round's window, which keeps the order.
+//   * saturating adds commute, so stamps of one round only need a barrier between them where their footprints overlap.
+// Candidates are staged in shared memory a tile at a time, decoded, with their stamp amplitude (two fp64 square roots)
+// precomputed in parallel; the test reads a 256-entry table of (v / 255)^4 instead of dividing.  Bit-exact against the
+// oracle's sequential loop (tests/test_fe_gpu.py).  [r1: one keypoint per round, 256 threads, 0.49 ms per image.]
+constexpr int kUniThreads = 512;
+constexpr int kUniTile = 2048;
+constexpr int kUniList = 32;
+__global__ void __launch_bounds__(kUniThreads) k_uniformity(FeBatch f) {
   extern __shared__ uint8_t occ[];  // (H/2+32) x (W/2+32)
   __shared__ double lut[31 * 31];
-  __shared__ int first_s;
-  __shared__ int kept_s;
+  __shared__ double p4[256];                     // ((s0 s0) s0) s0 with s0 = v / 255.0, the test's own operation order
+  __shared__ double t_amp[kUniTile];             // 255.0 * sqrt(sqrt(score / maxScore))
+  __shared__ int t_xy[kUniTile], t_s[kUniTile];
+  __shared__ int wc[kUniThreads / 32];
+  __shared__ int l_idx[kUniList + 1], l_cx[kUniList + 1], l_cy[kUniList + 1];
+  __shared__ int m_s;
+  __shared__ unsigned ovl_s;
   const int img = blockIdx.x;
   const int W = f.W, H = f.H;
   const int OW = W / 2 + 32, OH = H / 2 + 32;
   unsigned n = f.cand_count[img];
   if (n > (unsigned)f.cand_cap) n = f.cand_cap;
   const unsigned long long* K = f.cand_keys + (size_t)img * f.cand_cap;
-  const int tid = threadIdx.x;
-  for (int e = tid; e < OW * OH; e += 256) occ[e] = 0;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int T = kUniThreads, NW = kUniThreads / 32;
+  {
+    uint32_t* o4 = reinterpret_cast<uint32_t*>(occ);   // the dynamic shared array is 16-byte aligned
+    const int words = (OW * OH) / 4;
+    for (int e = tid; e < words; e += T) o4[e] = 0u;
+    for (int e = 4 * words + tid; e < OW * OH; e += T) occ[e] = 0;
+  }
   const double half_radius = f.uniformity_radius / 2.0;
-  for (int e = tid; e < 31 * 31; e += 256) {
+  for (int e = tid; e < 31 * 31; e += T) {
     const int dy = e / 31 - 15, dx = e % 31 - 15;
     const double d = sqrt((double)(dx * dx + dy * dy));
     const double v = 1.0 - d / half_radius;
     lut[e] = v > 0.0 ? v : 0.0;
   }
-  if (tid == 0) kept_s = 0;
+  for (int v = tid; v < 256; v += T) {
+    const double s0 = (double)v / 255.0;
+    p4[v] = s0 * s0 * s0 * s0;
+  }
   __syncthreads();
   int* kept_xy = f.kept_xy + (size_t)img * f.max_kp * 2;
   int* kept_score = f.kept_score + (size_t)img * f.max_kp;
@@ -164,60 +229,111 @@ __global__ void __launch_bounds__(256) k_uniformity(FeBatch f) {
   }
   const double maxScore = (double)(unsigned)(K[0] >> 32);
   const bool enforce = f.uniformity_radius > 0.0;
-  unsigned i0 = 0;
-  while (i0 < n) {
-    if (tid == 0) first_s = 0x7fffffff;
-    __syncthreads();
-    const unsigned i = i0 + tid;
-    if (i < n) {
-      const unsigned long long key = K[i];
-      const int s = (int)(unsigned)(key >> 32);
-      const unsigned idx = 0xffffffffu - (unsigned)(key & 0xffffffffu);
-      const int y = idx / W, x = idx % W;
-      bool pass = true;
-      if (enforce) {
-        const double s0 = (double)occ[(y / 2 + 16) * OW + (x / 2 + 16)] / 255.0;
-        const double lim = s0 * s0 * s0 * s0 * maxScore;
-        pass = !((double)s < lim);
-      }
-      if (pass) atomicMin(&first_s, (int)i);
-    }
-    __syncthreads();
-    const int first = first_s;
-    if (first == 0x7fffffff) {  // nothing in this window passes; occupancy only grows, so they are all rejected
-      i0 += 256;
+  unsigned i0 = 0, tile0 = 0, tile1 = 0;   // candidates [tile0, tile1) are staged
+  int kept = 0;                            // identical in every thread
+  while (i0 < n && kept < f.max_kp) {
+    if (i0 + T > tile1 && tile1 < n) {     // (re)stage a tile starting at the scan position
       __syncthreads();
+      tile0 = i0;
+      tile1 = min(n, i0 + (unsigned)kUniTile);
+      for (unsigned e = tile0 + tid; e < tile1; e += T) {
+        const unsigned long long key = K[e];
+        const int sc = (int)(unsigned)(key >> 32);
+        const unsigned idx = 0xffffffffu - (unsigned)(key & 0xffffffffu);
+        t_s[e - tile0] = sc;
+        t_xy[e - tile0] = (int)idx;
+        t_amp[e - tile0] = 255.0 * sqrt(sqrt((double)sc / maxScore));
+      }
+      __syncthreads();
+    }
+    // ---- test the window against the current occupancy
+    const unsigned i = i0 + tid;
+    bool pass = false;
+    int cx = 0, cy = 0;
+    if (i < tile1) {
+      const int idx = t_xy[i - tile0];
+      cy = (idx / W) / 2 + 16;
+      cx = (idx % W) / 2 + 16;
+      pass = true;
+      if (enforce) {
+        const double lim = p4[occ[cy * OW + cx]] * maxScore;
+        pass = !((double)t_s[i - tile0] < lim);
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+    if (lane == 0) wc[wid] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const int c = wc[w];
+      before += (w < wid) ? c : 0;
+      total += c;
+    }
+    if (total == 0) {  // nothing in this window passes; occupancy only grows, so they are all rejected
+      i0 = min(i0 + (unsigned)T, tile1);
+      __syncthreads();   // wc is rewritten next round
       continue;
     }
-    const unsigned long long key = K[first];
-    const int s = (int)(unsigned)(key >> 32);
-    const unsigned idx = 0xffffffffu - (unsigned)(key & 0xffffffffu);
-    const int y = idx / W, x = idx % W;
-    if (enforce) {
-      const double nsc = sqrt(sqrt((double)s / maxScore));
-      const int cy = y / 2 + 16, cx = x / 2 + 16;
-      for (int e = tid; e < 31 * 31; e += 256) {
-        const int dy = e / 31 - 15, dx = e % 31 - 15;
-        const int add = (int)floor(255.0 * nsc * lut[e]);
-        const int o = (cy + dy) * OW + cx + dx;
-        const int v = (int)occ[o] + add;
-        occ[o] = (uint8_t)(v > 255 ? 255 : v);
+    const int rank = before + __popc(bal & ((1u << lane) - 1u));
+    if (pass && rank <= kUniList) {   // entry kUniList only marks where the next window starts
+      l_idx[rank] = (int)i;
+      l_cx[rank] = cx;
+      l_cy[rank] = cy;
+    }
+    __syncthreads();
+    // ---- warp 0: longest prefix of passing candidates that are outside each other's stamp footprints
+    const int listed = min(total, kUniList);
+    if (wid == 0) {
+      bool unsafe = false, overlap = false;
+      if (lane < listed && enforce) {
+        const int mx = l_cx[lane], my = l_cy[lane];
+        for (int q = 0; q < lane; ++q) {
+          const int dx = abs(mx - l_cx[q]), dy = abs(my - l_cy[q]);
+          unsafe = unsafe || (dx <= 15 && dy <= 15);
+          overlap = overlap || (dx <= 30 && dy <= 30);
+        }
+      }
+      const unsigned ub = __ballot_sync(0xffffffffu, unsafe), ob = __ballot_sync(0xffffffffu, overlap);
+      if (lane == 0) {
+        m_s = ub ? __ffs(ub) - 1 : listed;
+        ovl_s = ob;
       }
     }
-    const int k = kept_s;
     __syncthreads();
-    if (tid == 0) {
-      kept_xy[2 * k] = x;
-      kept_xy[2 * k + 1] = y;
-      kept_score[k] = s;
-      kept_s = k + 1;
+    const int m = m_s;
+    const unsigned ovl = ovl_s;
+    const int accept = min(m, f.max_kp - kept);
+    for (int r = 0; r < accept; ++r) {
+      const int ci = l_idx[r] - (int)tile0;
+      if (enforce) {
+        if ((ovl >> r) & 1u) __syncthreads();   // this stamp overlaps an earlier one of the round
+        const double amp = t_amp[ci];
+        const int ccy = l_cy[r], ccx = l_cx[r];
+        for (int e = tid; e < 31 * 31; e += T) {
+          const int dy = e / 31 - 15, dx = e % 31 - 15;
+          const int add = (int)floor(amp * lut[e]);
+          const int o = (ccy + dy) * OW + ccx + dx;
+          const int v = (int)occ[o] + add;
+          occ[o] = (uint8_t)(v > 255 ? 255 : v);
+        }
+      }
+      if (tid == 0) {
+        const int idx = t_xy[ci];
+        kept_xy[2 * (kept + r)] = idx % W;
+        kept_xy[2 * (kept + r) + 1] = idx / W;
+        kept_score[kept + r] = t_s[ci];
+      }
     }
-    __syncthreads();
-    if (k + 1 >= f.max_kp) break;
-    i0 = first + 1;
+    kept += accept;
+    // next window: the first passing candidate that was not decided, else past this window
+    if (m < total)
+      i0 = (unsigned)l_idx[m];
+    else
+      i0 = min(i0 + (unsigned)T, tile1);
+    __syncthreads();   // stamps complete, lists free
   }
-  __syncthreads();
-  if (tid == 0) f.kept_count[img] = kept_s;
+  if (tid == 0) f.kept_count[img] = kept;
 }
 
 // ------------------------------------------------------------------------------------------ camera helpers
@@ -758,9 +874,17 @@ void fe_launch_detect(const FeBatch& f, int n_images, bool use_tma, size_t occ_b
   if (ev) cudaEventRecord(ev[0], st);
   k_harris_nms<<<grid, 256, 0, st>>>(f);
   if (ev) cudaEventRecord(ev[1], st);
-  k_sort_candidates<<<n_images, 1024, 0, st>>>(f);
+  {
+    const unsigned cap = (unsigned)f.cand_cap;
+    const dim3 gl(std::max(1u, cap / kSortChunk), n_images), gg(std::max(1u, cap / 2 / 256), n_images);
+    k_sort_local<<<gl, 1024, 0, st>>>(f, 0u);
+    for (unsigned K = 2 * kSortChunk; K <= cap; K <<= 1) {
+      for (unsigned j = K >> 1; j >= (unsigned)kSortChunk; j >>= 1) k_sort_global<<<gg, 256, 0, st>>>(f, K, j);
+      k_sort_local<<<gl, 1024, 0, st>>>(f, K);
+    }
+  }
   if (ev) cudaEventRecord(ev[2], st);
-  k_uniformity<<<n_images, 256, occ_bytes, st>>>(f);
+  k_uniformity<<<n_images, kUniThreads, occ_bytes, st>>>(f);
   if (ev) cudaEventRecord(ev[3], st);
   dim3 g2((f.max_kp + 7) / 8, n_images);
   if (use_tma)
