@@ -2338,8 +2338,8 @@ __global__ void __launch_bounds__(kDenseThreads) k_dense_solve(Batch b, SvinBaOp
 // ------------------------------------------------------------------------------------------ back-substitution
 // SPLIT threads share a landmark (they take every SPLIT-th observation and add their sums with shuffles): the
 // kernel is bound by the per-observation load latency chain, not by bandwidth, so halving the chain pays.
-template <bool HAS_EXT, int SPLIT, bool FUSED = false>
-__global__ void __launch_bounds__(kLmTile * SPLIT) k_backsub(Batch b) {  // 152 registers, 3 CTAs/SM: a 128 cap measured 4 % slower
+template <bool HAS_EXT, int SPLIT, bool FUSED = false, int MINB = 1>
+__global__ void __launch_bounds__(kLmTile * SPLIT, MINB) k_backsub(Batch b) {  // 152 registers, 3 CTAs/SM: a 128 cap measured 4 % slower
   const int tile = blockIdx.x;
   const int w = b.lm_tile_win[tile];
   WinState& ws = b.ws[w];
@@ -2871,7 +2871,8 @@ void launch_linearize(const Batch& b, int which, int raw, cudaStream_t st, bool 
   if (b.n_obs_tiles == 0) return;
   static const int minb = std::getenv("SVIN_LIN_MINB") ? std::atoi(std::getenv("SVIN_LIN_MINB")) : 5;  // A/B knob: 5 CTAs/SM (96 registers, 100 B spilled) measured fastest
   if (compact && !raw && !b.has_ext) {
-    k_linearize<false, 5, true><<<b.n_obs_tiles, kObsTile, 0, st>>>(b, which, raw);
+    // 8 CTAs/SM (64 registers, 170 B spilled): 2.05 ms per 11 launches vs 2.14 at 5 CTAs/SM and 2.27 at 6 (r2aj)
+    k_linearize<false, 8, true><<<b.n_obs_tiles, kObsTile, 0, st>>>(b, which, raw);
     return;
   }
   if (b.has_ext || (raw && b.lin_Je[1] != nullptr))
@@ -2975,7 +2976,8 @@ void launch_backsub(const Batch& b, cudaStream_t st) {
   if (b.has_ext)
     k_backsub<true, 1, false><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
   else if (b.fused)
-    k_backsub<false, 1, true><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
+    // 4 CTAs/SM (128 registers): 1.30 ms per 10 launches; 168 registers 1.72, 96 registers 1.30, 80 registers 1.41 (r2aj)
+    k_backsub<false, 1, true, 4><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
   else
     k_backsub<false, 1, false><<<b.n_lm_tiles, kLmTile, 0, st>>>(b);
 }
