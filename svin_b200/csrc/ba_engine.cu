@@ -763,6 +763,11 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   // planes above on the device - the host no longer touches every observation with a sqrt and a scatter
   const size_t o_rpose = in.add(4 * NOBS), o_rlm = in.add(4 * NOBS), o_rext = in.add(4 * NOBS), o_rcam = in.add(4 * NOBS);
   const size_t o_rmeas = in.add(16 * NOBS), o_rinfo = in.add(24 * NOBS), o_rord = in.add(4 * NOBS);
+  // compact upload: pose | ext << 10 | cam << 20 in one word per observation when every window has <= 1024 pose blocks and
+  // cameras (else the three separate arrays travel), and no per-observation information when a window's is uniform
+  bool packed_idx = true;
+  for (int i = 0; i < B; ++i) packed_idx = packed_idx && wins[i].num_pose_blocks <= 1024 && wins[i].num_cameras <= 1024;
+  const size_t o_rpec = in.add(4 * NOBS);
   const size_t o_lmof = in.add(4 * NL), o_lmos = in.add(4 * NL), o_lmoc = in.add(4 * NL), o_linv = in.add(4 * NL);
   const size_t o_otw = in.add(4 * (size_t)n_obs_tiles), o_otb = in.add(4 * (size_t)n_obs_tiles);
   const size_t o_ltw = in.add(4 * (size_t)n_lm_tiles), o_ltb = in.add(4 * (size_t)n_lm_tiles);
@@ -791,6 +796,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   int *h_lmof = (int*)hp(o_lmof), *h_lmos = (int*)hp(o_lmos), *h_lmoc = (int*)hp(o_lmoc), *h_linv = (int*)hp(o_linv);
   int *h_rpose = (int*)hp(o_rpose), *h_rlm = (int*)hp(o_rlm), *h_rext = (int*)hp(o_rext), *h_rcam = (int*)hp(o_rcam);
   int* h_rord = (int*)hp(o_rord);
+  int* h_rpec = (int*)hp(o_rpec);
   double *h_rmeas = (double*)hp(o_rmeas), *h_rinfo = (double*)hp(o_rinfo);
   int *h_otw = (int*)hp(o_otw), *h_otb = (int*)hp(o_otb), *h_ltw = (int*)hp(o_ltw), *h_ltb = (int*)hp(o_ltb);
   int *h_sww = (int*)hp(o_sww), *h_swb = (int*)hp(o_swb), *h_swc = (int*)hp(o_swc);
@@ -825,6 +831,10 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
       if (wins[i].num_imu) mb0 += wins[i].imu_meas_offset[wins[i].num_imu];
     }
   }
+  const int G = std::max(1, std::min(8, B / 16));   // window groups of the overlapped H2D copy below
+  auto group_of = [&](int i) { return (int)((long long)i * G / B); };
+  std::vector<std::atomic<int>> group_info(G);   // 1: a window of the group has per-observation information
+  for (int g = 0; g < G; ++g) group_info[g].store(0);
   auto fill_window = [&](int i) {
     int cam_base = cam_base_v[i], ot = ot_v[i], lt = lt_v[i], sw = sw_v[i];
     long long meas_base = meas_base_v[i];
@@ -860,17 +870,37 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     // (landmark-major, pattern-major inside a chunk) SoA planes and U = chol(information)^T run on the device
     const int N = w.num_obs;
     const size_t g0 = (size_t)d.obs_begin;
-    std::memcpy(h_rpose + g0, w.obs_pose, 4 * (size_t)N);
     std::memcpy(h_rlm + g0, w.obs_landmark, 4 * (size_t)N);
-    std::memcpy(h_rext + g0, w.obs_extrinsics, 4 * (size_t)N);
-    std::memcpy(h_rcam + g0, w.obs_camera, 4 * (size_t)N);
+    if (packed_idx) {
+      for (int o = 0; o < N; ++o) h_rpec[g0 + o] = w.obs_pose[o] | (w.obs_extrinsics[o] << 10) | (w.obs_camera[o] << 20);
+    } else {
+      std::memcpy(h_rpose + g0, w.obs_pose, 4 * (size_t)N);
+      std::memcpy(h_rext + g0, w.obs_extrinsics, 4 * (size_t)N);
+      std::memcpy(h_rcam + g0, w.obs_camera, 4 * (size_t)N);
+    }
     std::memcpy(h_rmeas + 2 * g0, w.obs_measurement, 16 * (size_t)N);
-    for (int o = 0; o < N; ++o) {  // the three entries the Cholesky factor reads (row-major 2x2: a00, a10, a11)
+    // information: the three entries the Cholesky factor reads (row-major 2x2: a00, a10, a11); one copy per window when
+    // they are all equal (OKVIS: 64 / size^2 * I with one keypoint size, Estimator.hpp impl:64-67)
+    bool uniform = N > 0;
+    for (int o = 1; o < N && uniform; ++o) {
       const double* a = w.obs_information + 4 * (size_t)o;
-      double* t = h_rinfo + 3 * (g0 + o);
-      t[0] = a[0];
-      t[1] = a[2];
-      t[2] = a[3];
+      uniform = a[0] == w.obs_information[0] && a[2] == w.obs_information[2] && a[3] == w.obs_information[3];
+    }
+    d.info_uniform = uniform ? 1 : 0;
+    if (uniform) {
+      d.info3[0] = w.obs_information[0];
+      d.info3[1] = w.obs_information[2];
+      d.info3[2] = w.obs_information[3];
+    } else {
+      d.info3[0] = d.info3[1] = d.info3[2] = 0.0;
+      group_info[group_of(i)].store(1, std::memory_order_relaxed);   // this group's information slice must travel
+      for (int o = 0; o < N; ++o) {
+        const double* a = w.obs_information + 4 * (size_t)o;
+        double* t = h_rinfo + 3 * (g0 + o);
+        t[0] = a[0];
+        t[1] = a[2];
+        t[2] = a[3];
+      }
     }
     std::memcpy(h_rord + g0, wo.obs_order.data(), 4 * (size_t)N);
     std::memcpy(c->obs_perm.data() + g0, wo.obs_order.data(), 4 * (size_t)N);
@@ -1023,9 +1053,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   }
   // Packing runs on the pool while this thread lays out the work arena; the big observation arrays are copied
   // group by group as soon as their windows are packed, so that the H2D transfer overlaps the packing.
-  const int G = std::max(1, std::min(8, B / 16));
   std::vector<std::atomic<int>> group_left(G);
-  auto group_of = [&](int i) { return (int)((long long)i * G / B); };
   for (int g = 0; g < G; ++g) group_left[g].store(0);
   for (int i = 0; i < B; ++i) group_left[group_of(i)].fetch_add(1);
   c->pool->start(B, [&](int i) {
@@ -1158,11 +1186,12 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
 
   // ---------------- copy + initialise
   SVIN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  size_t h2d_skipped = 0;   // slices of the observation arrays that did not have to travel
   if (c->pool->workers() == 0) c->pool->help();
   {
     // the seven raw per-observation arrays, sliced by window group
-    const size_t obs_arr[9] = {o_rpose, o_rlm, o_rext, o_rcam, o_rmeas, o_rinfo, o_rord, 0, 0};
-    const size_t obs_elt[9] = {4, 4, 4, 4, 16, 24, 4, 0, 0};
+    const size_t obs_arr[9] = {o_rpose, o_rlm, o_rext, o_rcam, o_rmeas, o_rinfo, o_rord, o_rpec, 0};
+    const size_t obs_elt[9] = {4, 4, 4, 4, 16, 24, 4, 4, 0};
     int w0 = 0;
     for (int g = 0; g < G; ++g) {
       int w1 = w0;
@@ -1170,9 +1199,16 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
       while (group_left[g].load(std::memory_order_acquire) > 0) std::this_thread::yield();
       if (w1 > w0) {
         const size_t e0 = (size_t)c->h_win[w0].obs_begin, e1 = (size_t)c->h_win[w1 - 1].obs_end;
-        for (int a = 0; a < 7 && e1 > e0; ++a)
+        for (int a = 0; a < 8 && e1 > e0; ++a) {
+          const bool skip = (packed_idx && (a == 0 || a == 2 || a == 3)) || (!packed_idx && a == 7) ||
+                            (a == 5 && group_info[g].load(std::memory_order_acquire) == 0);
+          if (skip) {
+            h2d_skipped += obs_elt[a] * (e1 - e0);
+            continue;
+          }
           SVIN_CUDA(cudaMemcpyAsync(D + obs_arr[a] + obs_elt[a] * e0, H + obs_arr[a] + obs_elt[a] * e0,
                                     obs_elt[a] * (e1 - e0), cudaMemcpyHostToDevice, c->stream));
+        }
       }
       w0 = w1;
     }
@@ -1190,7 +1226,8 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   SVIN_CUDA(cudaMemsetAsync(b.lm_quality, 0, 8 * (size_t)NL + 8, c->stream));
   launch_reset_state(b, c->stream);
   {
-    RawObs raw{(const int*)(D + o_rpose), (const int*)(D + o_rlm), (const int*)(D + o_rext), (const int*)(D + o_rcam),
+    RawObs raw{packed_idx ? (const int*)(D + o_rpec) : nullptr,
+               (const int*)(D + o_rpose), (const int*)(D + o_rlm), (const int*)(D + o_rext), (const int*)(D + o_rcam),
                (const double*)(D + o_rmeas), (const double*)(D + o_rinfo), (const int*)(D + o_rord),
                (const int*)(D + o_linv)};
     launch_pack_obs(b, raw, c->stream);
@@ -1216,7 +1253,8 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
   c->tm = SvinBaTimings{};
   c->tm.h2d_ms = ms;
-  c->tm.h2d_bytes = (int64_t)(in.bytes - (o_rpose - o_opose));  // the SoA observation planes are produced on the device
+  // the SoA observation planes are produced on the device; packed indices / uniform information skip their slices
+  c->tm.h2d_bytes = (int64_t)(in.bytes - (o_rpose - o_opose)) - (int64_t)h2d_skipped;
   c->tm.host_order_ms = t_ordered - t_begin;
   c->tm.host_fill_ms = t_filled - t_ordered;
   c->tm.host_upload_ms = wall_ms() - t_begin;

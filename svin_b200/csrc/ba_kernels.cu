@@ -2801,13 +2801,33 @@ __global__ void __launch_bounds__(kObsTile) k_pack_obs(Batch b, RawObs raw) {
   const WinDesc& wd = b.win[w];
   if (g >= wd.obs_end) return;
   const int src = wd.obs_begin + raw.order[g];
-  b.obs_pose[g] = wd.pose_begin + raw.pose[src];
+  int ip, ie, ic;
+  if (raw.pec) {   // one word per observation: pose | ext << 10 | cam << 20
+    const int v = raw.pec[src];
+    ip = v & 1023;
+    ie = (v >> 10) & 1023;
+    ic = (v >> 20) & 1023;
+  } else {
+    ip = raw.pose[src];
+    ie = raw.ext[src];
+    ic = raw.cam[src];
+  }
+  b.obs_pose[g] = wd.pose_begin + ip;
   b.obs_lm[g] = wd.lm_begin + raw.lm_inv[wd.lm_begin + raw.lm[src]];
-  b.obs_ext[g] = wd.pose_begin + raw.ext[src];
-  b.obs_cam[g] = wd.cam_begin + raw.cam[src];
+  b.obs_ext[g] = wd.pose_begin + ie;
+  b.obs_cam[g] = wd.cam_begin + ic;
   b.obs_zx[g] = raw.meas[2 * (size_t)src];
   b.obs_zy[g] = raw.meas[2 * (size_t)src + 1];
-  const double a0 = raw.info3[3 * (size_t)src], a2 = raw.info3[3 * (size_t)src + 1], a3 = raw.info3[3 * (size_t)src + 2];
+  double a0, a2, a3;
+  if (wd.info_uniform) {   // one information matrix for the whole window (single-scale detector: one keypoint size)
+    a0 = wd.info3[0];
+    a2 = wd.info3[1];
+    a3 = wd.info3[2];
+  } else {
+    a0 = raw.info3[3 * (size_t)src];
+    a2 = raw.info3[3 * (size_t)src + 1];
+    a3 = raw.info3[3 * (size_t)src + 2];
+  }
   double l00 = a0, l10 = a2, l11 = a3;
   if (a0 > 0.0) {
     l00 = sqrt(a0);

@@ -40,7 +40,9 @@ struct WinDesc {
   int marg_e0_off;
   int marg_lin_off;
   int loss_type;
+  int info_uniform;  // every observation of the window carries the same 2x2 information: info3 below, nothing uploaded per observation
   double loss_scale;
+  double info3[3];   // a00, a10, a11 of that information
   ImuP imu;
   double T_SSo[7];
 };
@@ -191,6 +193,7 @@ struct Batch {
 
 // The caller's observation arrays (window by window, caller order) as uploaded; k_pack_obs gathers them.
 struct RawObs {
+  const int* pec;                    // packed pose | ext << 10 | cam << 20 (window-local), or nullptr -> the three arrays below
   const int *pose, *lm, *ext, *cam;  // window-local indices
   const double* meas;                // [2] per observation
   const double* info3;               // a00, a10, a11 of the 2x2 information

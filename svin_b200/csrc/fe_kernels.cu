@@ -169,6 +169,34 @@ __global__ void __launch_bounds__(256) k_sort_global(FeBatch f, unsigned K, unsi
   }
 }
 
+// Batched path (many images per call): one CTA per image sorts in global memory - all SMs are busy across the images and it
+// is ONE launch, where the chunked network above would issue ~20 mostly-empty grids per batch.
+__global__ void __launch_bounds__(1024) k_sort_image(FeBatch f) {
+  const int img = blockIdx.x;
+  unsigned n = f.cand_count[img];
+  if (n > (unsigned)f.cand_cap) n = f.cand_cap;
+  unsigned long long* K = f.cand_keys + (size_t)img * f.cand_cap;
+  unsigned P = 1;
+  while (P < n) P <<= 1;
+  for (unsigned i = n + threadIdx.x; i < P; i += blockDim.x) K[i] = 0ull;
+  __syncthreads();
+  for (unsigned k = 2; k <= P; k <<= 1)
+    for (unsigned j = k >> 1; j > 0; j >>= 1) {
+      for (unsigned i = threadIdx.x; i < P; i += blockDim.x) {
+        const unsigned l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = K[i], b = K[l];
+          const bool desc = ((i & k) == 0);
+          if (desc ? (a < b) : (a > b)) {
+            K[i] = b;
+            K[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------ uniformity
 // Strongest-first acceptance against the occupancy image.  The reference procedure is sequential in the accepted
 // keypoints (each stamp changes the occupancy later tests read); this kernel produces exactly its result but accepts
@@ -874,7 +902,9 @@ void fe_launch_detect(const FeBatch& f, int n_images, bool use_tma, size_t occ_b
   if (ev) cudaEventRecord(ev[0], st);
   k_harris_nms<<<grid, 256, 0, st>>>(f);
   if (ev) cudaEventRecord(ev[1], st);
-  {
+  if (n_images >= 16) {
+    k_sort_image<<<n_images, 1024, 0, st>>>(f);   // throughput path: one launch, one CTA per image
+  } else {
     const unsigned cap = (unsigned)f.cand_cap;
     const dim3 gl(std::max(1u, cap / kSortChunk), n_images), gg(std::max(1u, cap / 2 / 256), n_images);
     k_sort_local<<<gl, 1024, 0, st>>>(f, 0u);

@@ -103,6 +103,29 @@ def test_unsorted_observations_and_fixed_blocks(engine):
     assert np.array_equal(w.pose_blocks[2], r.pose_blocks[2])
 
 
+def test_per_observation_information_and_uniform_windows_in_one_batch(engine):
+    # The upload sends one information matrix per window when all observations share it (one keypoint size) and the
+    # per-observation slice otherwise; a batch mixing both kinds, the second with full 2x2 matrices (off-diagonal terms).
+    wa, _ = make_window(seed=411, num_keyframes=4, num_imu_frames=3, num_landmarks=260, mode="steady")
+    wb, _ = make_window(seed=412, num_keyframes=5, num_imu_frames=3, num_landmarks=300, mode="steady")
+    rng = np.random.default_rng(9)
+    n = wb.num_obs
+    a, c = rng.uniform(0.3, 2.0, n), rng.uniform(0.3, 2.0, n)
+    b_ = rng.uniform(-0.4, 0.4, n) * np.sqrt(a * c)
+    wb.obs_information = np.stack([a, b_, b_, c], axis=1)
+    wb.finalize()
+    ra, rb = wa.copy(), wb.copy()
+    opt = default_options(max_num_iterations=8)
+    sa, _ = oracle_lib.solve(ra, opt)
+    sb, _ = oracle_lib.solve(rb, opt)
+    s, _ = engine.optimize([wa, wb], opt)
+    assert [x["iterations"] for x in s] == [sa["iterations"], sb["iterations"]]
+    for w, r in ((wa, ra), (wb, rb)):
+        assert _rel(w.pose_blocks, r.pose_blocks) < 1e-6 and _rel(w.landmarks, r.landmarks) < 1e-6
+    t = engine.timings()
+    assert t["h2d_bytes"] < 60 * (wa.num_obs + wb.num_obs) + 200000   # packed indices: well below the 75 B/obs of round 1
+
+
 def test_reset_and_resolve_is_repeatable(engine):
     w, _ = make_window(seed=501, num_keyframes=5, num_imu_frames=3, num_landmarks=400, mode="steady")
     engine.upload([w])
