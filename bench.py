@@ -61,9 +61,16 @@ def emit(line: dict):
     out.flush()
 
 
-def make_batch(n_windows: int, n_distinct: int, seed0: int = 20260925):
-    base = [make_window(seed=seed0 + i, num_keyframes=10, num_imu_frames=3, num_landmarks=2000, mode="steady")[0]
-            for i in range(n_distinct)]
+def make_batch(n_windows: int, n_distinct: int, seed0: int = 20260925, prior: str = "random", backend=None):
+    """prior = "chain": `n_distinct` consecutive windows of a closed-loop run (svin_b200.synthetic_sequence.
+    make_chain_windows: real marginalisation prior from running the window forward through `backend`, SURVEY 8(d));
+    "random": round 1's generator (random PSD prior, truth (+) noise initial values)."""
+    if prior == "chain":
+        from svin_b200.synthetic_sequence import make_chain_windows
+        base = make_chain_windows(backend, seed=seed0, n_windows=n_distinct)
+    else:
+        base = [make_window(seed=seed0 + i, num_keyframes=10, num_imu_frames=3, num_landmarks=2000, mode="steady")[0]
+                for i in range(n_distinct)]
     return [base[i % n_distinct].copy() for i in range(n_windows)]
 
 
@@ -561,8 +568,9 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     n = max(cores, 8)
-    oracle_solver()      # builds the -O3 -march=native timing library outside the timed region
-    batch = make_batch(n, min(n, 4))
+    orc = oracle_solver()      # builds the -O3 -march=native timing library outside the timed region
+    from svin_b200.sequence import OracleBackend
+    batch = make_batch(n, min(n, 4), prior=args.prior, backend=OracleBackend(orc))
     for _ in range(args.warmup):
         cpu_baseline(batch[:cores], cores)
     t0 = time.perf_counter()
@@ -574,7 +582,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "windows_per_step": n, "max_num_iterations": 10},
+        "config": {"workload": WORKLOAD, "windows_per_step": n, "max_num_iterations": 10,
+                   "windows_from": args.prior},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n} windows per step, one solve per host thread ({cores} threads); CPU restatement "
                                    f"of the reference path (oracle/, {ORACLE_FLAGS}), not Ceres — Ceres/Eigen are absent "
@@ -628,11 +637,12 @@ def run_gpu(args):
                          "(use --impl reference for the CPU path)")
     from svin_b200.engine import BaEngine
     B = args.windows
-    batch = make_batch(B, args.distinct, seed0=20260925 + 1000 * rank)
-    for w in batch:
-        w.c_struct()
     opt = default_options()
     eng = BaEngine(local)
+    from svin_b200.sequence import CudaBackend
+    batch = make_batch(B, args.distinct, seed0=20260925 + 1000 * rank, prior=args.prior, backend=CudaBackend(eng))
+    for w in batch:
+        w.c_struct()
     n_obs_total = sum(w.num_obs for w in batch)
 
     def barrier():
@@ -773,6 +783,10 @@ def run_gpu(args):
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "windows_per_gpu_per_step": B, "distinct_seeds": args.distinct,
+                       "windows_from": ("closed-loop chain: %d consecutive windows as Estimator::optimize receives them, prior = "
+                                        "svin_ba_marginalize output" % args.distinct) if args.prior == "chain" else
+                                       "round-1 generator: random PSD prior, truth (+) noise",
+                       "landmarks_per_window": float(np.mean([w.num_landmarks for w in batch])),
                        "observations_per_window": float(obs.mean()), "max_num_iterations": 10,
                        "iterations_mean": float(iters.mean()), "successful_steps_mean": float(succ.mean()),
                        "parallelism": f"{world} independent replica ranks, no collective",
@@ -954,6 +968,9 @@ def main():
                     help="replicas: independent windows per GPU (headline); sharded: one window's landmarks split over the GPUs")
     ap.add_argument("--skip-e2e", action="store_true", help="resident solve only (used for the ncu launch list)")
     ap.add_argument("--frames", type=int, default=64, help="stereo frames per front-end step (0 = skip the front-end)")
+    ap.add_argument("--prior", default="chain", choices=["chain", "random"],
+                    help="chain: windows + marginalisation prior from a closed-loop run (SURVEY 8(d)); random: round 1's "
+                         "generator (random PSD prior)")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

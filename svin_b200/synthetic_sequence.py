@@ -14,7 +14,10 @@ from .synthetic import (EUROC_IMAGE, EUROC_IMU, EUROC_INTRINSICS, EUROC_T_SC, T_
 
 
 def make_euroc_sequence(seed=20260925, n_frames=30, frame_dt=0.05, kf_every=3, n_points=4000, max_kp=400,
-                        pixel_noise=1.0):
+                        pixel_noise=1.0, track_p=None, stereo_only=False):
+    """track_p: None = a point is tracked for as long as it is in view (long tracks); a float = every point lives for
+    clip(Geometric(track_p), 2, 13) consecutive frames from a random birth frame (k ~ clip(Geom(0.35), 2, P)),
+    which gives the short-track mix of the BA bench windows."""
     rng = np.random.default_rng(seed)
     t0_ms = 500 + 2
     t_ms = [t0_ms + int(round(k * frame_dt * 1000)) for k in range(n_frames)]
@@ -38,19 +41,30 @@ def make_euroc_sequence(seed=20260925, n_frames=30, frame_dt=0.05, kf_every=3, n
     dirs[:, 1] += (px[:, 1] - np.clip(px[:, 1], 1, H - 2)) / intr[0][1]
     p_c = dirs * rng.uniform(2.0, 15.0, (n_points, 1))
     points = p_c @ Tm[:3, :3].T + Tm[:3, 3]
+    if track_p is not None:
+        birth = rng.integers(-12, n_frames, n_points)
+        death = birth + np.clip(rng.geometric(track_p, n_points), 2, 13)
     frames = []
     for k, ms in enumerate(t_ms):
         T_WS = T_of(ms)
         obs = []
+        oks, ips = [], []
         for c in range(2):
             T_CW = np.linalg.inv(T_WS @ T_SC[c])
             pc = points @ T_CW[:3, :3].T + T_CW[:3, 3]
             ok = pc[:, 2] > 0.5
             ip = project(intr[c], np.where(ok[:, None], pc, np.array([0, 0, 1.0])))
             ok &= (ip[:, 0] > 2) & (ip[:, 0] < W - 3) & (ip[:, 1] > 2) & (ip[:, 1] < H - 3)
-            vis = np.nonzero(ok)[0][:max_kp]                      # lowest ids first: persistent tracks
+            if track_p is not None:
+                ok &= (birth <= k) & (k < death)
+            oks.append(ok)
+            ips.append(ip)
+        if stereo_only:                                           # a point is tracked only while both cameras see it
+            oks = [oks[0] & oks[1]] * 2
+        for c in range(2):
+            vis = np.nonzero(oks[c])[0][:max_kp]                  # lowest ids first: persistent tracks
             for j in vis:
-                obs.append((int(j), c, ip[j] + rng.normal(0, pixel_noise, 2)))
+                obs.append((int(j), c, ips[c][j] + rng.normal(0, pixel_noise, 2)))
         frames.append(dict(t_ns=ms * 1000000, keyframe=(k % kf_every == 0), pose=np.concatenate([traj["r"][ms], traj["q"][ms]]),
                            vel=traj["v"][ms].copy(), obs=obs))
     return dict(points=points, frames=frames, imu=(traj["t_imu"], gyro, accel), bias=(bg, ba), intrinsics=intr,
@@ -80,3 +94,46 @@ def add_frame(sw: SlidingWindow, seq, k: int, lm_ids: dict, rng: np.random.Gener
             lm_ids[j] = sw.add_landmark(np.append(seq["points"][j] + rng.normal(0, landmark_noise, 3), 1.0))
         sw.add_observation(lm_ids[j], fid, c, z)
     return fid
+
+
+def make_chain_windows(backend, seed=20260925, n_windows=8, num_keyframes=10, num_imu_frames=2, max_kp=400,
+                       pose_noise=(0.0, 0.0), landmark_noise=0.0, options=None):
+    """BA windows of the BASELINE configs[1] shape whose marginalisation prior comes from ACTUALLY RUNNING the window
+    forward: a closed-loop chain (every frame a keyframe, so the steady-state window is num_keyframes +
+    num_imu_frames consecutive frames) is driven through `backend` (CudaBackend on the GPU arm, OracleBackend on the CPU
+    arm) for num_keyframes + num_imu_frames + 5 frames; then `n_windows` consecutive windows are captured right after
+    addStates / addObservation, i.e. exactly what Estimator::optimize is handed: the new frame's states come from the IMU
+    propagation, landmarks seen for the first time from the (5 cm noisy) triangulation stand-in, everything else from the
+    previous solve.  num_imu_frames = 2 frames are kept behind the new one, so a window holds num_keyframes + 3 poses, 3
+    speed/bias blocks and 2 IMU terms - the 13-pose / n = 105 shape of BASELINE configs[1].  The states are NOT perturbed
+    by default (SURVEY 8(d)'s "truth (+) noise" cannot be combined with a real prior: the chain's prior pins the old
+    keyframes with information up to 1e14, a 2 cm offset there is a 1e22 cost); pose_noise / landmark_noise add it anyway.
+    The prior's linearisation points, J and e0 are the chain's own (svin_ba_marginalize / the oracle)."""
+    from .synthetic import pose_oplus
+    from .window import default_options
+    P = num_keyframes + num_imu_frames
+    warm = P + 5
+    n_frames = warm + n_windows
+    # ~max_kp live points per image: lifetime ~3.3 frames, ~60 % of the cloud projects into an image
+    n_points = int(max_kp * (n_frames + 12) / 3.3 / 0.30)
+    seq = make_euroc_sequence(seed=seed, n_frames=n_frames, kf_every=1, n_points=n_points, max_kp=max_kp, track_p=0.35, stereo_only=True)
+    rng = np.random.default_rng(seed + 7)
+    sw, ids = new_window(seq), {}
+    opt = options or default_options()
+    out = []
+    for k in range(n_frames):
+        add_frame(sw, seq, k, ids, rng)
+        if k >= warm:
+            w, _ = sw.flatten()
+            nf = len(sw.frames)
+            sig_t, sig_r = pose_noise[0], np.deg2rad(pose_noise[1])
+            if sig_t > 0 or sig_r > 0:
+                for f in range(nf):
+                    d = np.concatenate([rng.normal(0, sig_t, 3), rng.normal(0, sig_r, 3)])
+                    w.pose_blocks[f] = pose_oplus(w.pose_blocks[f], d)
+            if landmark_noise > 0:
+                w.landmarks[:, :3] += rng.normal(0, landmark_noise, w.landmarks[:, :3].shape)
+            out.append(w.finalize())
+        sw.optimize(backend, opt)
+        sw.apply_marginalization_strategy(backend, num_keyframes, num_imu_frames)
+    return out
