@@ -1828,7 +1828,7 @@ int svin_ba_marginalize(svin_ba_ctx* c, int32_t wi, const SvinMargSpec* spec, Sv
   const size_t nd = (size_t)n * n + n                 // H, b
                     + 2 * nmax * nmax + nmax          // A, U, ev
                     + (size_t)nm * nm + 2 * (size_t)nk * nm + 2 * nmax + 4  // Vp, Wm, WV (also (c,s) scratch)
-                    + n                               // pvec
+                    + n + 8                           // pvec (+ the cluster Jacobi convergence slots)
                     + (size_t)pd * pd + pd            // prior
                     + 2 * (size_t)nk * nk + 2 * nk;   // Hk, J, bk, e0
   const size_t ni = (size_t)nk + nm + pd + nmax + 2;
@@ -1845,7 +1845,7 @@ int svin_ba_marginalize(svin_ba_ctx* c, int32_t wi, const SvinMargSpec* spec, Sv
   m.Vp = p; p += (size_t)nm * nm;
   m.Wm = p; p += (size_t)nk * nm;
   m.WV = p; p += (size_t)nk * nm + 2 * nmax + 4;
-  m.pvec = p; p += n;
+  m.pvec = p; p += n + 8;
   double* d_prior_H = p; p += (size_t)pd * pd;
   double* d_prior_b = p; p += pd;
   m.Hk = p; p += (size_t)nk * nk;

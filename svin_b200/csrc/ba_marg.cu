@@ -5,6 +5,7 @@
 //                       okvis_ceres/include/okvis/ceres/implementation/MarginalizationError.hpp:193-220)
 //   k_marg_dense     : one CTA — existing prior + dense terms (MarginalizationError.cpp:333-383), dense Schur with a
 //                      pseudo-inverse from a Jacobi eigen-decomposition (:621-667), updateErrorComputation (:725-758)
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -142,26 +143,34 @@ __global__ void __launch_bounds__(128) k_marg_landmarks(Batch b, MargArgs m) {
   }
 }
 
-// ---- CTA-wide symmetric eigen-decomposition: one-sided (Hestenes) Jacobi, one warp per column pair ------------------
+// ---- symmetric eigen-decomposition on a thread-block CLUSTER: one-sided (Hestenes) Jacobi, one warp per column pair ----
 // A (n x n, symmetric; row-major == column-major) is overwritten by G = A V with mutually orthogonal columns, V (the
 // eigenvectors, column k contiguous) is accumulated in U and transposed at the end into the layout the callers use
 // (U[i * n + k] = component i of eigenvector k); ev[k] = v_k . g_k = v_k^T A v_k keeps the sign of tiny negative
-// eigenvalues.  A rotation touches two contiguous columns only (three warp-reduced dot products, then 2 x 2n updates),
-// the n/2 pairs of a round-robin round are independent and go to the CTA's warps, one barrier per round - against the
-// two-sided variant this replaces (rows AND columns of a matrix in global memory, three barriers and a serial
-// reshuffle per round, 256 threads) the B9 call of bench.py's 10-KF window went from 135 ms to a few ms.
-__device__ void jacobi_eigh_cta(double* A, int n, double* U, double* ev, int* /*unused*/, double* /*unused*/) {
-  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+// eigenvalues.  A rotation touches two contiguous columns only (three warp-reduced dot products, then 2 x 2n updates); the
+// n/2 pairs of a round-robin round are independent and go to the 4 x 32 warps of a 4-CTA cluster (n ~ 180: one pair per
+// warp), one cluster barrier per round; the columns live in global memory (L2), read and written with .cg so that no SM's
+// L1 holds a stale copy.  History of the B9 call of bench.py's 10-KF window (195-dim): two-sided Jacobi, one 256-thread
+// CTA, matrices in global memory, three barriers + a serial reshuffle per round 135 ms (r1) -> one-sided, one 1024-thread
+// CTA 8.0 ms (r2p) -> this kernel.
+constexpr int kJacobiCluster = 4;
+__global__ void __cluster_dims__(kJacobiCluster, 1, 1) __launch_bounds__(1024) k_jacobi_cluster(double* A, int n, double* U,
+                                                                                                double* ev, double* conv) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int T = kJacobiCluster * 1024, gtid = crank * 1024 + tid;
+  const int gw = crank * 32 + wid, nw = kJacobiCluster * 32;
   const int mm_ = n + (n & 1);   // players (one dummy when n is odd)
   const int half = mm_ / 2;
   __shared__ double worst_s[32];
-  __shared__ int done_s;
-  for (int e = tid; e < n * n; e += T) U[e] = (e / n == e % n) ? 1.0 : 0.0;
-  __syncthreads();
+  for (int e = gtid; e < n * n; e += T) __stcg(&U[e], (e / n == e % n) ? 1.0 : 0.0);
+  cluster.sync();
   for (int sweep = 0; sweep < 40; ++sweep) {
     double worst = 0.0;   // largest |cos angle| between two columns seen by this warp in the sweep
     for (int round = 0; round < mm_ - 1; ++round) {
-      for (int k = wid; k < half; k += nw) {
+      for (int k = gw; k < half; k += nw) {
         // circle method: player mm_-1 stays, the others rotate
         int p = (k == 0) ? mm_ - 1 : (round + k) % (mm_ - 1);
         int q = (round + mm_ - 1 - k) % (mm_ - 1);
@@ -171,7 +180,7 @@ __device__ void jacobi_eigh_cta(double* A, int n, double* U, double* ev, int* /*
         double* gq = A + (size_t)q * n;
         double al = 0.0, be = 0.0, ga = 0.0;
         for (int i = lane; i < n; i += 32) {
-          const double x = gp[i], y = gq[i];
+          const double x = __ldcg(&gp[i]), y = __ldcg(&gq[i]);
           al += x * x;
           be += y * y;
           ga += x * y;
@@ -189,46 +198,51 @@ __device__ void jacobi_eigh_cta(double* A, int n, double* U, double* ev, int* /*
         double* vp = U + (size_t)p * n;
         double* vq = U + (size_t)q * n;
         for (int i = lane; i < n; i += 32) {
-          const double x = gp[i], y = gq[i];
-          gp[i] = c * x - sn * y;
-          gq[i] = sn * x + c * y;
-          const double u = vp[i], v = vq[i];
-          vp[i] = c * u - sn * v;
-          vq[i] = sn * u + c * v;
+          const double x = __ldcg(&gp[i]), y = __ldcg(&gq[i]);
+          __stcg(&gp[i], c * x - sn * y);
+          __stcg(&gq[i], sn * x + c * y);
+          const double u = __ldcg(&vp[i]), v = __ldcg(&vq[i]);
+          __stcg(&vp[i], c * u - sn * v);
+          __stcg(&vq[i], sn * u + c * v);
         }
       }
-      __syncthreads();
+      cluster.sync();
     }
     if (lane == 0) worst_s[wid] = worst;
     __syncthreads();
     if (tid == 0) {
       double w = 0.0;
-      for (int i = 0; i < nw; ++i) w = fmax(w, worst_s[i]);
-      done_s = w < 1.0e-14;
+      for (int i = 0; i < 32; ++i) w = fmax(w, worst_s[i]);
+      __stcg(&conv[crank], w);
     }
-    __syncthreads();
-    if (done_s) break;
+    cluster.sync();
+    double w = 0.0;
+    for (int r = 0; r < kJacobiCluster; ++r) w = fmax(w, __ldcg(&conv[r]));
+    cluster.sync();   // everyone has read conv before the next sweep may overwrite it
+    if (w < 1.0e-14) break;
   }
-  for (int k = wid; k < n; k += nw) {
+  for (int k = gw; k < n; k += nw) {
     double sdot = 0.0;
-    for (int i = lane; i < n; i += 32) sdot += U[(size_t)k * n + i] * A[(size_t)k * n + i];
+    for (int i = lane; i < n; i += 32) sdot += __ldcg(&U[(size_t)k * n + i]) * __ldcg(&A[(size_t)k * n + i]);
     sdot = warp_sum(sdot);
     if (lane == 0) ev[k] = sdot;
   }
-  __syncthreads();
+  cluster.sync();
   // V columns -> U[i][k]
-  for (int e = tid; e < n * n; e += T) {
+  for (int e = gtid; e < n * n; e += T) {
     const int i = e / n, k = e % n;
     if (i < k) {
-      const double x = U[(size_t)i * n + k], y = U[(size_t)k * n + i];
-      U[(size_t)i * n + k] = y;
-      U[(size_t)k * n + i] = x;
+      const double x = __ldcg(&U[(size_t)i * n + k]), y = __ldcg(&U[(size_t)k * n + i]);
+      __stcg(&U[(size_t)i * n + k], y);
+      __stcg(&U[(size_t)k * n + i], x);
     }
   }
-  __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024) k_marg_dense(Batch b, MargArgs m) {
+// stage 0: H += prior + Jd^T Jd, b likewise; scaled marginalised block -> A.   [k_jacobi_cluster on nm]
+// stage 1: pseudo-inverse, dense Schur complement -> Hk, bk; scaled Hk -> A.    [k_jacobi_cluster on nk]
+// stage 2: J = (p o U) S^1/2, e0 (MarginalizationError.cpp:725-758)
+__global__ void __launch_bounds__(1024) k_marg_dense(Batch b, MargArgs m, int stage) {
   const WinDesc& wd = b.win[m.w];
   const int buf = b.ws[m.w].cur;
   const int tid = threadIdx.x, T = blockDim.x;
@@ -236,89 +250,93 @@ __global__ void __launch_bounds__(1024) k_marg_dense(Batch b, MargArgs m) {
   const double* Jd = b.Jd[buf] + wd.Jd_off;
   const double* rd = b.rd[buf] + wd.rd_off;
   __shared__ double lmax_s;
-  // 1. H += prior + Jd^T Jd ; b += prior_b - Jd^T rd
-  for (int e = tid; e < n * n; e += T) {
-    const int i = e / n, j = e % n;
-    double s = m.H[e];
-    for (int r = 0; r < M; ++r) s += Jd[(size_t)r * n + i] * Jd[(size_t)r * n + j];
-    m.H[e] = s;
+  if (stage == 0) {
+    // 1. H += prior + Jd^T Jd ; b += prior_b - Jd^T rd
+    for (int e = tid; e < n * n; e += T) {
+      const int i = e / n, j = e % n;
+      double s = m.H[e];
+      for (int r = 0; r < M; ++r) s += Jd[(size_t)r * n + i] * Jd[(size_t)r * n + j];
+      m.H[e] = s;
+    }
+    for (int i = tid; i < n; i += T) {
+      double s = m.b[i];
+      for (int r = 0; r < M; ++r) s -= Jd[(size_t)r * n + i] * rd[r];
+      m.b[i] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < m.prior_dim * m.prior_dim; e += T) {
+      const int i = e / m.prior_dim, j = e % m.prior_dim;
+      m.H[(size_t)m.prior_map[i] * n + m.prior_map[j]] += m.prior_H[e];  // distinct (i,j) -> distinct entries
+    }
+    for (int i = tid; i < m.prior_dim; i += T) m.b[m.prior_map[i]] += m.prior_b[i];
+    __syncthreads();
+    if (nm > 0) {
+      for (int i = tid; i < n; i += T) m.pvec[i] = m.H[(size_t)i * n + i] > 1.0e-9 ? sqrt(m.H[(size_t)i * n + i]) : 1.0e-3;
+      __syncthreads();
+      for (int e = tid; e < nm * nm; e += T) {
+        const int i = e / nm, j = e % nm;
+        const int gi = m.marg_idx[i], gj = m.marg_idx[j];
+        m.A[e] = 0.5 * (m.H[(size_t)gi * n + gj] + m.H[(size_t)gj * n + gi]) / (m.pvec[gi] * m.pvec[gj]);
+      }
+    }
+    return;
   }
-  for (int i = tid; i < n; i += T) {
-    double s = m.b[i];
-    for (int r = 0; r < M; ++r) s -= Jd[(size_t)r * n + i] * rd[r];
-    m.b[i] = s;
-  }
-  __syncthreads();
-  for (int e = tid; e < m.prior_dim * m.prior_dim; e += T) {
-    const int i = e / m.prior_dim, j = e % m.prior_dim;
-    m.H[(size_t)m.prior_map[i] * n + m.prior_map[j]] += m.prior_H[e];  // distinct (i,j) -> distinct entries
-  }
-  for (int i = tid; i < m.prior_dim; i += T) m.b[m.prior_map[i]] += m.prior_b[i];
-  __syncthreads();
-  // 2. dense Schur
-  if (nm > 0) {
-    for (int i = tid; i < n; i += T) m.pvec[i] = m.H[(size_t)i * n + i] > 1.0e-9 ? sqrt(m.H[(size_t)i * n + i]) : 1.0e-3;
-    __syncthreads();
-    for (int e = tid; e < nm * nm; e += T) {
-      const int i = e / nm, j = e % nm;
-      const int gi = m.marg_idx[i], gj = m.marg_idx[j];
-      m.A[e] = 0.5 * (m.H[(size_t)gi * n + gj] + m.H[(size_t)gj * n + gi]) / (m.pvec[gi] * m.pvec[gj]);
+  if (stage == 1) {
+    // 2. dense Schur
+    if (nm > 0) {
+      if (tid == 0) {
+        double lm = -1e300;
+        for (int i = 0; i < nm; ++i) lm = fmax(lm, m.ev[i]);
+        lmax_s = lm;
+      }
+      __syncthreads();
+      const double tol = 2.220446049250313e-16 * nm * lmax_s;
+      for (int e = tid; e < nm * nm; e += T) {
+        const int i = e / nm, j = e % nm;
+        double s = 0;
+        for (int k = 0; k < nm; ++k)
+          if (m.ev[k] > tol) s += m.U[(size_t)i * nm + k] * (1.0 / m.ev[k]) * m.U[(size_t)j * nm + k];
+        m.Vp[e] = s;
+      }
+      for (int e = tid; e < nk * nm; e += T) {
+        const int i = e / nm, j = e % nm;
+        m.Wm[e] = m.H[(size_t)m.keep_idx[i] * n + m.marg_idx[j]] / (m.pvec[m.keep_idx[i]] * m.pvec[m.marg_idx[j]]);
+      }
+      __syncthreads();
+      for (int e = tid; e < nk * nm; e += T) {
+        const int i = e / nm, j = e % nm;
+        double s = 0;
+        for (int k = 0; k < nm; ++k) s += m.Wm[(size_t)i * nm + k] * m.Vp[(size_t)k * nm + j];
+        m.WV[e] = s;
+      }
+      __syncthreads();
+      for (int i = tid; i < nk; i += T) {
+        const int gi = m.keep_idx[i];
+        double s = m.b[gi] / m.pvec[gi];
+        for (int j = 0; j < nm; ++j) s -= m.WV[(size_t)i * nm + j] * (m.b[m.marg_idx[j]] / m.pvec[m.marg_idx[j]]);
+        m.bk[i] = s * m.pvec[gi];
+      }
+      for (int e = tid; e < nk * nk; e += T) {
+        const int i = e / nk, j = e % nk;
+        const int gi = m.keep_idx[i], gj = m.keep_idx[j];
+        double h = m.H[(size_t)gi * n + gj] / (m.pvec[gi] * m.pvec[gj]);
+        for (int k = 0; k < nm; ++k) h -= m.WV[(size_t)i * nm + k] * m.Wm[(size_t)j * nm + k];
+        m.Hk[e] = h * m.pvec[gi] * m.pvec[gj];
+      }
+    } else {
+      for (int i = tid; i < nk; i += T) m.bk[i] = m.b[m.keep_idx[i]];
+      for (int e = tid; e < nk * nk; e += T) m.Hk[e] = m.H[(size_t)m.keep_idx[e / nk] * n + m.keep_idx[e % nk]];
     }
     __syncthreads();
-    jacobi_eigh_cta(m.A, nm, m.U, m.ev, m.players, m.WV /* scratch for (c,s) */);
-    if (tid == 0) {
-      double lm = -1e300;
-      for (int i = 0; i < nm; ++i) lm = fmax(lm, m.ev[i]);
-      lmax_s = lm;
-    }
+    // 3. updateErrorComputation: scaled Hk -> A
+    for (int i = tid; i < nk; i += T) m.pvec[i] = m.Hk[(size_t)i * nk + i] > 1.0e-9 ? sqrt(m.Hk[(size_t)i * nk + i]) : 1.0e-3;
     __syncthreads();
-    const double tol = 2.220446049250313e-16 * nm * lmax_s;
-    for (int e = tid; e < nm * nm; e += T) {
-      const int i = e / nm, j = e % nm;
-      double s = 0;
-      for (int k = 0; k < nm; ++k)
-        if (m.ev[k] > tol) s += m.U[(size_t)i * nm + k] * (1.0 / m.ev[k]) * m.U[(size_t)j * nm + k];
-      m.Vp[e] = s;
-    }
-    for (int e = tid; e < nk * nm; e += T) {
-      const int i = e / nm, j = e % nm;
-      m.Wm[e] = m.H[(size_t)m.keep_idx[i] * n + m.marg_idx[j]] / (m.pvec[m.keep_idx[i]] * m.pvec[m.marg_idx[j]]);
-    }
-    __syncthreads();
-    for (int e = tid; e < nk * nm; e += T) {
-      const int i = e / nm, j = e % nm;
-      double s = 0;
-      for (int k = 0; k < nm; ++k) s += m.Wm[(size_t)i * nm + k] * m.Vp[(size_t)k * nm + j];
-      m.WV[e] = s;
-    }
-    __syncthreads();
-    for (int i = tid; i < nk; i += T) {
-      const int gi = m.keep_idx[i];
-      double s = m.b[gi] / m.pvec[gi];
-      for (int j = 0; j < nm; ++j) s -= m.WV[(size_t)i * nm + j] * (m.b[m.marg_idx[j]] / m.pvec[m.marg_idx[j]]);
-      m.bk[i] = s * m.pvec[gi];
-    }
     for (int e = tid; e < nk * nk; e += T) {
       const int i = e / nk, j = e % nk;
-      const int gi = m.keep_idx[i], gj = m.keep_idx[j];
-      double h = m.H[(size_t)gi * n + gj] / (m.pvec[gi] * m.pvec[gj]);
-      for (int k = 0; k < nm; ++k) h -= m.WV[(size_t)i * nm + k] * m.Wm[(size_t)j * nm + k];
-      m.Hk[e] = h * m.pvec[gi] * m.pvec[gj];
+      m.A[e] = 0.5 * (m.Hk[(size_t)i * nk + j] + m.Hk[(size_t)j * nk + i]) / (m.pvec[i] * m.pvec[j]);
     }
-  } else {
-    for (int i = tid; i < nk; i += T) m.bk[i] = m.b[m.keep_idx[i]];
-    for (int e = tid; e < nk * nk; e += T) m.Hk[e] = m.H[(size_t)m.keep_idx[e / nk] * n + m.keep_idx[e % nk]];
+    return;
   }
-  __syncthreads();
-  // 3. updateErrorComputation
-  for (int i = tid; i < nk; i += T) m.pvec[i] = m.Hk[(size_t)i * nk + i] > 1.0e-9 ? sqrt(m.Hk[(size_t)i * nk + i]) : 1.0e-3;
-  __syncthreads();
-  for (int e = tid; e < nk * nk; e += T) {
-    const int i = e / nk, j = e % nk;
-    m.A[e] = 0.5 * (m.Hk[(size_t)i * nk + j] + m.Hk[(size_t)j * nk + i]) / (m.pvec[i] * m.pvec[j]);
-  }
-  __syncthreads();
-  jacobi_eigh_cta(m.A, nk, m.U, m.ev, m.players, m.WV);
   if (tid == 0) {
     double lm = -1e300;
     for (int i = 0; i < nk; ++i) lm = fmax(lm, m.ev[i]);
@@ -348,7 +366,12 @@ void launch_marg(const Batch& b, const MargArgs& m, int num_landmarks, cudaStrea
     else
       k_marg_landmarks<false><<<grid, 128, 0, st>>>(b, m);
   }
-  k_marg_dense<<<1, 1024, 0, st>>>(b, m);
+  double* conv = m.pvec + m.n;   // kJacobiCluster doubles of scratch behind pvec (see the arena in svin_ba_marginalize)
+  k_marg_dense<<<1, 1024, 0, st>>>(b, m, 0);
+  if (m.nm > 0) k_jacobi_cluster<<<kJacobiCluster, 1024, 0, st>>>(m.A, m.nm, m.U, m.ev, conv);
+  k_marg_dense<<<1, 1024, 0, st>>>(b, m, 1);
+  k_jacobi_cluster<<<kJacobiCluster, 1024, 0, st>>>(m.A, m.nk, m.U, m.ev, conv);
+  k_marg_dense<<<1, 1024, 0, st>>>(b, m, 2);
 }
 
 }  // namespace svin

@@ -137,3 +137,20 @@ def make_chain_windows(backend, seed=20260925, n_windows=8, num_keyframes=10, nu
         sw.optimize(backend, opt)
         sw.apply_marginalization_strategy(backend, num_keyframes, num_imu_frames)
     return out
+
+
+def run_chain(backend, seed=20260925, n_frames=20, num_keyframes=10, num_imu_frames=2, max_kp=400, options=None):
+    """Drive a closed-loop chain of the make_chain_windows shape for n_frames and return the SlidingWindow (its
+    `last_marg` holds the window + spec of the last applyMarginalizationStrategy call - the steady-state B9 workload)."""
+    from .window import default_options
+    n_points = int(max_kp * (n_frames + 12) / 3.3 / 0.30)
+    seq = make_euroc_sequence(seed=seed, n_frames=n_frames, kf_every=1, n_points=n_points, max_kp=max_kp, track_p=0.35,
+                              stereo_only=True)
+    rng = np.random.default_rng(seed + 7)
+    sw, ids = new_window(seq), {}
+    opt = options or default_options()
+    for k in range(n_frames):
+        add_frame(sw, seq, k, ids, rng)
+        sw.optimize(backend, opt)
+        sw.apply_marginalization_strategy(backend, num_keyframes, num_imu_frames)
+    return sw

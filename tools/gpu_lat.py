@@ -10,4 +10,4 @@ eng.close()
 for k, v in out["latency"].items():
     if isinstance(v, dict):
         print(k, "e2e p50 %.3f ms  device %.3f  upload %.3f  cpu %.1f" % (v["e2e_ms"]["p50"], v["device_solve_ms_p50"], v["host_upload_ms_p50"], v["cpu_1thread_ms_p50"]))
-print("marg", out["marg"])
+print("marg", json.dumps(out["marg"], indent=1))
