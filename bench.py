@@ -538,6 +538,40 @@ def marginalization_section(eng):
     return out
 
 
+def cpu_baseline_timed(batch, seconds: float):
+    """Single-thread oracle (CPU restatement, not Ceres) over the batch's windows until `seconds` have passed."""
+    orc = oracle_solver()
+    opt = default_options()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        w = batch[n % len(batch)].copy()
+        w.c_struct()
+        orc.solve(w, opt, quality=True)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            return n / dt, dt, n
+
+
+def cpu_baseline(sample, threads: int):
+    """Oracle (CPU restatement, not Ceres) on `sample` windows using `threads` host threads -> windows/s."""
+    from concurrent.futures import ThreadPoolExecutor
+    orc = oracle_solver()
+    opt = default_options()
+    work = [w.copy() for w in sample]
+    for w in work:
+        w.c_struct()
+    t0 = time.perf_counter()
+    if threads == 1:
+        for w in work:
+            orc.solve(w, opt, quality=True)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(lambda w: orc.solve(w, opt, quality=True), work))
+    dt = time.perf_counter() - t0
+    return len(work) / dt, dt
+
+
 def run_reference(args):
     world, rank, local, dist = dist_setup(args.gpus)
     if rank != 0:

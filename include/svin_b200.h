@@ -499,6 +499,46 @@ int svin_ransac_relative(svin_ransac_ctx* ctx, int32_t num_problems, const SvinR
 int svin_ransac_timings(svin_ransac_ctx* ctx, double* device_ms, int64_t* kernel_launches);
 
 /* =====================================================================
+ *  (L) loop-closure QUERY path of pose_graph  (BASELINE configs[4]) - partial row:
+ *  the data-parallel part of LoopClosure / PoseGraph::detectLoop, i.e. DBoW2's vocabulary transform, the inverted-file L1
+ *  query and the BRIEF-256 candidate search.  FAST + BRIEF extraction, PnPRANSAC and the pose-graph optimisation are
+ *  NOT here.  Replaces
+ *    voc->transform(brief_descriptors, bowVec)     pose_graph/src/pose_graph/PoseGraph.cpp:176,
+ *                                                   pose_graph/ThirdParty/DBoW/TemplatedVocabulary.h:981-1028,1114-1153
+ *    db.add(brief_descriptors)                      PoseGraph.cpp:197
+ *    db.query(bowVec, ret, 4, frame_index - 50)     PoseGraph.cpp:196, ThirdParty/DBoW/TemplatedDatabase.h:587-646
+ *    Keyframe::searchByBRIEFDes                     pose_graph/src/pose_graph/Keyframe.cpp:262-306
+ *  Scoring: TF-IDF weights, L1 norm, L1 score (the defaults of TemplatedVocabulary.h:48).  Equal scores are returned in
+ *  ascending entry id (std::sort leaves that unspecified in the reference).
+ *  The vocabulary is the flattened DBoW2 tree: node 0 is the root, the children of a node are contiguous.
+ *  Sharding over ranks: entry e lives on rank e % world_size; every rank adds the same image sequence and keeps its own
+ *  entries; svin_loop_query returns the rank's best results with GLOBAL entry ids, the caller merges 4 x world_size pairs.
+ * ===================================================================== */
+typedef struct svin_loop_ctx svin_loop_ctx;
+typedef struct SvinVocabulary {
+  int32_t num_nodes;
+  const int32_t* first_child;   /* [num_nodes] index of the first child (> node) */
+  const int32_t* num_children;  /* [num_nodes] 0 = leaf (word) */
+  const uint8_t* descriptor;    /* [num_nodes][32] BRIEF-256 */
+  const double* weight;         /* [num_nodes] idf weight of a word (leaves) */
+  const int32_t* word_id;       /* [num_nodes] word id of a leaf, -1 otherwise */
+} SvinVocabulary;
+int svin_loop_create(int device, const SvinVocabulary* vocabulary, int32_t rank, int32_t world_size, svin_loop_ctx** out);
+void svin_loop_destroy(svin_loop_ctx* ctx);
+/* descriptors: the images' BRIEF descriptors back to back ([sum counts][32]); word_ids / values: capacity sum counts,
+ * image i's sparse vector starts at offset sum(counts[0..i)) and has num_words[i] entries (ids ascending). */
+int svin_loop_transform(svin_loop_ctx* ctx, int32_t num_images, const uint8_t* descriptors, const int32_t* counts,
+                        int32_t* word_ids, double* values, int32_t* num_words);
+int svin_loop_add(svin_loop_ctx* ctx, int32_t num_images, const uint8_t* descriptors, const int32_t* counts);
+/* max_id = -1: all entries, else only entries with id < max_id (PoseGraph.cpp:196: frame_index - 50). */
+int svin_loop_query(svin_loop_ctx* ctx, const uint8_t* descriptors, int32_t count, int32_t max_results, int32_t max_id,
+                    int32_t* entry_ids, double* scores, int32_t* num_results);
+int svin_loop_brief_search(svin_loop_ctx* ctx, const uint8_t* window_descriptors, int32_t num_window,
+                           const uint8_t* old_descriptors, int32_t num_old, int32_t* best_index, int32_t* best_distance,
+                           uint8_t* status);
+int svin_loop_stats(svin_loop_ctx* ctx, int32_t* entries_total, int32_t* entries_local, double* last_device_ms);
+
+/* =====================================================================
  *  (A0) image pre-processing in front of the detector  
  *  Replaces the OpenCV chain of Subscriber::imageCallback (okvis_ros/src/Subscriber.cpp:123-147):
  *    cv::resize(raw, Size(), resizeFactor, resizeFactor)  [INTER_LINEAR; an exact 2x decimation takes OpenCV's

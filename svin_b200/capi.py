@@ -183,6 +183,11 @@ class SvinRansacResult(C.Structure):
                 ("hypothesis_valid", c_uint8_p)]
 
 
+class SvinVocabulary(C.Structure):
+    _fields_ = [("num_nodes", C.c_int32), ("first_child", c_int32_p), ("num_children", c_int32_p),
+                ("descriptor", c_uint8_p), ("weight", c_double_p), ("word_id", c_int32_p)]
+
+
 class SvinError(RuntimeError):
     pass
 
@@ -201,6 +206,8 @@ EXPORTED_SYMBOLS = [
     "svin_pre_create", "svin_pre_destroy", "svin_pre_output_size", "svin_pre_process", "svin_pre_upload",
     "svin_pre_run", "svin_pre_download", "svin_pre_device_output", "svin_pre_timings",
     "svin_ransac_create", "svin_ransac_destroy", "svin_ransac_absolute", "svin_ransac_relative", "svin_ransac_timings",
+    "svin_loop_create", "svin_loop_destroy", "svin_loop_transform", "svin_loop_add", "svin_loop_query",
+    "svin_loop_brief_search", "svin_loop_stats",
 ]
 
 
@@ -272,6 +279,15 @@ def load(path: str | None = None) -> C.CDLL:
     lib.svin_ransac_relative.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SvinRansacRelProblem),
                                          C.POINTER(SvinRansacResult), C.POINTER(SvinRansacResult)]
     lib.svin_ransac_timings.argtypes = [C.c_void_p, c_double_p, C.POINTER(C.c_int64)]
+    lib.svin_loop_create.argtypes = [C.c_int, C.POINTER(SvinVocabulary), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.svin_loop_destroy.argtypes = [C.c_void_p]
+    lib.svin_loop_destroy.restype = None
+    lib.svin_loop_transform.argtypes = [C.c_void_p, C.c_int32, c_uint8_p, c_int32_p, c_int32_p, c_double_p, c_int32_p]
+    lib.svin_loop_add.argtypes = [C.c_void_p, C.c_int32, c_uint8_p, c_int32_p]
+    lib.svin_loop_query.argtypes = [C.c_void_p, c_uint8_p, C.c_int32, C.c_int32, C.c_int32, c_int32_p, c_double_p, c_int32_p]
+    lib.svin_loop_brief_search.argtypes = [C.c_void_p, c_uint8_p, C.c_int32, c_uint8_p, C.c_int32, c_int32_p, c_int32_p,
+                                           c_uint8_p]
+    lib.svin_loop_stats.argtypes = [C.c_void_p, c_int32_p, c_int32_p, c_double_p]
     if path is None:
         _lib = lib
     return lib
