@@ -773,6 +773,12 @@ def run_gpu(args):
 
     frontend = run_frontend(args, local, rank, world, dist, barrier) if args.frames > 0 else None
     sharded = sharded_section(args, local, rank, world, dist)
+    loop = None
+    if not args.skip_e2e:
+        try:
+            loop = loop_closure_section(args, local, rank, world, dist)
+        except Exception as exc:  # noqa: BLE001 - side section
+            loop = {"error": f"{type(exc).__name__}: {exc}"}
     if rank == 0:
         cpu_val, cpu_dt, cpu_n = cpu_baseline_timed(batch, args.cpu_seconds) if world == 1 else (None, None, 0)
         cpu_threads = None
@@ -837,11 +843,74 @@ def run_gpu(args):
             line["marginalization"] = marg
         if sharded is not None:
             line["sharded"] = sharded
+        if loop is not None:
+            line["loop_closure"] = loop
         emit(line)
     eng.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def loop_closure_section(args, local, rank, world, dist):
+    """BASELINE configs[4] (query part): a 5k-keyframe DBoW2 database (k = 10, L = 6 vocabulary of the shape of
+    brief_k10L6.bin, 500 BRIEF-256 descriptors per keyframe), db.query(bowVec, ret, 4, frame_index - 50) per new keyframe.
+    Entries are sharded id % N over the ranks; the per-rank top-4 are exchanged with ONE all_gather of 4 (id, score) pairs
+    per rank and merged.  The PGO half of configs[4] is not built."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from scene_loop import make_keyframes
+    from oracle import loop_oracle as lo      # vocabulary generator + CPU leg only
+    from svin_b200.loop import LoopEngine, merge_shards
+    n = 5000
+    voc = lo.Vocabulary.random(10, 6, seed=1)
+    frames, _ = make_keyframes(n, 1200, per_image=500, seed=21, revisit_after=1700)
+    eng = LoopEngine(voc.first_child, voc.num_children, voc.descriptor, voc.weight, voc.word_id, device=local, rank=rank,
+                     world=world)
+    t0 = time.perf_counter()
+    for s_ in range(0, n, 500):
+        eng.add(frames[s_:s_ + 500])
+    t_add = time.perf_counter() - t0
+    qs = list(range(n - 1, n - 201, -1))
+    for q in qs[:5]:
+        eng.query(frames[q], 4, q - 50)
+    dev, merged = [], []
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for q in qs:
+        r = eng.query(frames[q], 4, q - 50)
+        dev.append(eng.stats()["last_device_ms"])
+        if dist is not None:
+            mine = torch.full((4, 2), -1.0, dtype=torch.float64, device=f"cuda:{local}")
+            for k, (e, sc) in enumerate(r):
+                mine[k, 0], mine[k, 1] = e, sc
+            allr = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            r = merge_shards([[(int(e), float(sc)) for e, sc in t.cpu().tolist() if e >= 0] for t in allr], 4)
+        merged.append(r)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    dt = max_over_ranks(dist, dt, local)
+    out = {"database_keyframes": n, "descriptors_per_keyframe": 500, "vocabulary": "k=10 L=6 synthetic (1,111,111 nodes)",
+           "entries_this_rank": eng.stats()["entries_local"], "add_keyframes_per_s": n / t_add,
+           "query_ms_e2e_mean": 1e3 * dt / len(qs), "query_device_ms_p50": float(np.median(dev)),
+           "queries": len(qs), "exchange": None if dist is None else "one all_gather of 4 (id, score) pairs per rank per query",
+           "note": "e2e = host descriptors in, merged top-4 out; device = inverted-file scoring + top-k kernels only"}
+    eng.close()
+    if rank == 0 and world == 1:
+        db = lo.Database(voc, fast=True)
+        m = 1000
+        for f in frames[:m]:
+            db.add(f)
+        t0 = time.perf_counter()
+        for q in range(m - 1, m - 6, -1):
+            exp = db.query(frames[q], 4, q - 50)
+        out["cpu_port"] = {"query_ms": 1e3 * (time.perf_counter() - t0) / 5, "database_keyframes": m, "cores": 1,
+                           "kind": "port", "note": "numpy/python restatement on a 1000-keyframe database (building 5k "
+                                                   "entries takes 30 s of CPU); an interpreter loop, NOT representative "
+                                                   "of C++ DBoW2 - reported for completeness only"}
+    return out
 
 
 def sharded_section(args, local, rank, world, dist):

@@ -21,5 +21,6 @@ print("sharded", d.get("sharded"))
 print("cpu", d.get("cpu_baseline"))
 fe=d.get("frontend",{})
 print("fe", fe.get("value"), fe.get("e2e",{}).get("value"), fe.get("kernels_ms_per_step"), fe.get("cpu_baseline"))
+print("loop", d.get("loop_closure"))
 print("pre", {k:v for k,v in d.get("preprocess",{}).items() if k in ("value","e2e")})
 PY

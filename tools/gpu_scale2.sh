@@ -9,6 +9,7 @@ python - <<'PY'
 import json,os
 d=json.load(open("gpurun_out/%s_bench_%sgpu.json"%(os.environ["TAG"], os.environ.get("N","2"))))
 print("value", d["value"], "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], "dev ms", d["device_ms_per_step"])
+print("loop", d.get("loop_closure"))
 print("sharded", json.dumps(d.get("sharded"), indent=1))
 PY
 
