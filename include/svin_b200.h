@@ -347,6 +347,18 @@ int svin_ba_comm_init_local(svin_ba_ctx* const* ctxs, int32_t world_size);
 int svin_ba_plan(const SvinBaWindow* window, int32_t* landmark_order, int32_t capacity, int32_t* chunk_kind,
                  int32_t* chunk_landmarks, int32_t* chunk_runs, int32_t* num_chunks);
 
+/* The same planner's observation order: internal position -> caller observation (window-local), [num_obs]. */
+int svin_ba_plan_observations(const SvinBaWindow* window, int32_t* observation_order);
+/* What svin_ba_upload actually put on the device for window `window_index` (read back from HBM), in the format of
+ * svin_ba_plan + svin_ba_plan_observations.  *planned_on_device = 1 when the device planner (csrc/ba_plan.cu) produced it:
+ * svin_ba_upload orders the landmarks, cuts the chunks and builds the observation order ON THE GPU when every window of
+ * the batch has its observations sorted by (landmark, pose, camera), fixed extrinsics, <= 64 pose blocks and <= 8192
+ * landmarks, and on the host threads otherwise (SVIN_BA_DEVICE_PLAN=0 forces the host).  Both must agree entry by entry:
+ * tests/test_plan_gpu.py. */
+int svin_ba_uploaded_plan(svin_ba_ctx* ctx, int32_t window_index, int32_t* landmark_order, int32_t capacity,
+                          int32_t* chunk_kind, int32_t* chunk_landmarks, int32_t* chunk_runs, int32_t* num_chunks,
+                          int32_t* observation_order, int32_t* planned_on_device);
+
 int svin_ba_set_profiling(svin_ba_ctx* ctx, int enable);
 int svin_ba_kernel_times(svin_ba_ctx* ctx, SvinBaKernelTimes* out);
 

@@ -200,7 +200,7 @@ EXPORTED_SYMBOLS = [
     "svin_ba_upload", "svin_ba_evaluate", "svin_ba_solve", "svin_ba_download", "svin_ba_download_all", "svin_ba_reset", "svin_ba_optimize",
     "svin_ba_timings", "svin_ba_set_profiling", "svin_ba_kernel_times", "svin_nccl_unique_id", "svin_ba_comm_init",
     "svin_ba_comm_init_local",
-    "svin_ba_marginalize", "svin_ba_plan",
+    "svin_ba_marginalize", "svin_ba_plan", "svin_ba_plan_observations", "svin_ba_uploaded_plan",
     "svin_fe_default_options", "svin_fe_create", "svin_fe_destroy", "svin_fe_detect_describe", "svin_fe_upload",
     "svin_fe_run", "svin_fe_download", "svin_fe_scores", "svin_match", "svin_fe_timings", "svin_fe_upload_device",
     "svin_pre_create", "svin_pre_destroy", "svin_pre_output_size", "svin_pre_process", "svin_pre_upload",
@@ -245,6 +245,9 @@ def load(path: str | None = None) -> C.CDLL:
     lib.svin_ba_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.svin_ba_kernel_times.argtypes = [C.c_void_p, C.POINTER(SvinBaKernelTimes)]
     lib.svin_ba_plan.argtypes = [C.POINTER(SvinBaWindow), c_int32_p, C.c_int32, c_int32_p, c_int32_p, c_int32_p, c_int32_p]
+    lib.svin_ba_plan_observations.argtypes = [C.POINTER(SvinBaWindow), c_int32_p]
+    lib.svin_ba_uploaded_plan.argtypes = [C.c_void_p, C.c_int32, c_int32_p, C.c_int32, c_int32_p, c_int32_p, c_int32_p,
+                                          c_int32_p, c_int32_p, c_int32_p]
     lib.svin_fe_default_options.argtypes = [C.POINTER(SvinFeOptions)]
     lib.svin_fe_default_options.restype = None
     lib.svin_fe_create.argtypes = [C.c_int, C.POINTER(SvinFeOptions), C.POINTER(C.c_void_p)]

@@ -24,6 +24,7 @@
 #include <dlfcn.h>
 
 #include "ba_kernels.cuh"
+#include "ba_plan.cuh"
 #include "common.hpp"
 #include "host_pool.hpp"
 
@@ -81,7 +82,6 @@ struct WindowOrder {
   std::vector<int> run_pose, run_k0m;             // window-local pose block, (first obs k << 8) | obs count
 };
 
-constexpr int kSchurLrBelow = 16;  // fewer landmarks of one pattern than this -> run-parallel chunks
 
 void order_window(const SvinBaWindow& w, bool group, WindowOrder& out) {
   const int N = w.num_obs, L = w.num_landmarks;
@@ -191,7 +191,7 @@ void order_window(const SvinBaWindow& w, bool group, WindowOrder& out) {
   if (group) {
     // A/B knob: SVIN_SCHUR_LR=0 keeps the lane = landmark mappings for every chunk, 1 adds k_schur_lr only
     // 2 adds k_schur_wr, 3 (default) also the 2- and 4-warp k_schur_lr
-    static const int use_lr = std::getenv("SVIN_SCHUR_LR") ? std::atoi(std::getenv("SVIN_SCHUR_LR")) : 3;
+    const int use_lr = schur_use_lr();
     int k = 0;
     while (k < L) {
       // pose runs of this pattern (shared by all of its chunks)
@@ -214,33 +214,10 @@ void order_window(const SvinBaWindow& w, bool group, WindowOrder& out) {
       // The pattern's landmarks go to lane = landmark chunks (bounded by the operand tiles of k_schur_mma) while at
       // least kSchurLrBelow of them are left (one warp per run for 2..4 runs, k_schur_wr), the rest to run-parallel
       // chunks of <= 32 / runs landmarks (k_schur_lr); patterns neither kernel takes keep the lane = landmark mappings.
-      const int cap = std::max(1, std::min(32, schur_mma_max_chunk(std::max(runs, 1))));
-      const int lr1 = use_lr ? schur_lr_max_chunk(runs, 1) : 0;
-      const int lr2 = use_lr >= 3 ? schur_lr_max_chunk(runs, 2) : 0;
-      const int lr4 = use_lr >= 3 ? schur_lr_max_chunk(runs, 4) : 0;
+      const ChunkCaps cc = chunk_caps_for(runs);
       while (k < e_all) {
-        const int rem = e_all - k;
         int c, kind;
-        if (use_lr >= 2 && runs >= 2 && runs <= 4 && rem >= kSchurLrBelow) {
-          c = std::min(32, rem);
-          kind = 2 + runs;  // warp per run (k_schur_wr<runs>)
-        } else if (lr1 >= 1 && (use_lr >= 2 || rem < kSchurLrBelow || cap < kSchurLrBelow)) {
-          // run-parallel: the narrowest CTA that takes what is left, else equal parts of the widest
-          if (rem <= lr1 || lr2 < 1) {
-            c = std::min(lr1, rem);
-            kind = 3;
-          } else if (rem <= lr2) {
-            c = rem;
-            kind = 7;
-          } else {
-            const int parts = (rem + lr4 - 1) / lr4;
-            c = (rem + parts - 1) / parts;
-            kind = c <= lr1 ? 3 : (c <= lr2 ? 7 : 8);
-          }
-        } else {
-          c = std::min(cap, rem);
-          kind = schur_chunk_class(c);
-        }
+        plan_next_chunk(e_all - k, runs, cc, use_lr, c, kind);   // shared with the device planner (ba_plan.cuh)
         out.chunk_run_first.push_back(run_first);
         out.chunk_nruns.push_back(runs);
         out.chunk_begin.push_back(k);
@@ -389,6 +366,14 @@ struct svin_ba_ctx {
   std::vector<WinDesc> h_win;
   std::vector<int> obs_perm;  // sorted obs position -> caller's obs index (window-local)
   std::vector<int> lm_perm;   // internal landmark position (global) -> caller's landmark index (window-local)
+  // device planner: the landmark permutation is read back into pinned memory (after 16 ints of class totals), the
+  // observation permutation only when svin_ba_evaluate asks for it
+  bool device_plan = false, obs_perm_valid = true;
+  int* h_lm_perm = nullptr;
+  size_t h_lm_perm_cap = 0;
+  const int* lm_perm_p = nullptr;
+  const int* d_rord = nullptr;
+  size_t n_obs_total = 0, n_sw_cap = 0;
   int n_max = 0, smem_bytes = 0;
   int* d_active = nullptr;
   int* h_active = nullptr;
@@ -447,7 +432,8 @@ int ensure(void** p, size_t* cap, size_t need, bool pinned) {
   return SVIN_OK;
 }
 
-int validate(const SvinBaWindow& w, int idx) {
+// flags (optional): bit 0 = observations not in (landmark, pose, camera) order, bit 1 = an observation's extrinsics block is free
+int validate(const SvinBaWindow& w, int idx, int* flags = nullptr) {
   auto bad = [&](const char* what) {
     set_error("window " + std::to_string(idx) + ": " + what);
     return SVIN_ERR_INVALID_ARGUMENT;
@@ -484,11 +470,30 @@ int validate(const SvinBaWindow& w, int idx) {
   if (w.num_obs && (!w.obs_pose || !w.obs_landmark || !w.obs_extrinsics || !w.obs_camera || !w.obs_measurement ||
                     !w.obs_information || !w.intrinsics))
     return bad("observation arrays / intrinsics are NULL");
-  for (int i = 0; i < w.num_obs; ++i) {
-    if (w.obs_pose[i] < 0 || w.obs_pose[i] >= w.num_pose_blocks) return bad("obs_pose out of range");
-    if (w.obs_extrinsics[i] < 0 || w.obs_extrinsics[i] >= w.num_pose_blocks) return bad("obs_extrinsics out of range");
-    if (w.obs_landmark[i] < 0 || w.obs_landmark[i] >= w.num_landmarks) return bad("obs_landmark out of range");
-    if (w.obs_camera[i] < 0 || w.obs_camera[i] >= w.num_cameras) return bad("obs_camera out of range");
+  {
+    // one pass: ranges (any failure is diagnosed by the slow loop below), sortedness, free extrinsics
+    const unsigned np = (unsigned)w.num_pose_blocks, nl = (unsigned)w.num_landmarks, nc = (unsigned)w.num_cameras;
+    unsigned oob = 0, unsorted = 0, ext_free = 0;
+    uint64_t prev = 0;
+    for (int i = 0; i < w.num_obs; ++i) {
+      const unsigned p = (unsigned)w.obs_pose[i], e = (unsigned)w.obs_extrinsics[i], l = (unsigned)w.obs_landmark[i],
+                     c = (unsigned)w.obs_camera[i];
+      const unsigned bad_i = (unsigned)(p >= np) | (unsigned)(e >= np) | (unsigned)(l >= nl) | (unsigned)(c >= nc);
+      oob |= bad_i;
+      const uint64_t k = ((uint64_t)l << 32) | ((uint64_t)(p & 0xffffffu) << 8) | (uint64_t)(c & 255u);
+      unsorted |= (unsigned)(k < prev);
+      prev = k;
+      if (!bad_i) ext_free |= (unsigned)(w.pose_fixed[e] == 0);
+    }
+    if (oob)
+      for (int i = 0; i < w.num_obs; ++i) {
+        if (w.obs_pose[i] < 0 || w.obs_pose[i] >= w.num_pose_blocks) return bad("obs_pose out of range");
+        if (w.obs_extrinsics[i] < 0 || w.obs_extrinsics[i] >= w.num_pose_blocks) return bad("obs_extrinsics out of range");
+        if (w.obs_landmark[i] < 0 || w.obs_landmark[i] >= w.num_landmarks) return bad("obs_landmark out of range");
+        if (w.obs_camera[i] < 0 || w.obs_camera[i] >= w.num_cameras) return bad("obs_camera out of range");
+      }
+    if (flags)
+      *flags = ((unsorted || w.num_cameras > 256 || w.num_pose_blocks >= (1 << 24)) ? 1 : 0) | (ext_free ? 2 : 0);
   }
   for (int i = 0; i < w.num_imu; ++i) {
     if (w.imu_pose0[i] < 0 || w.imu_pose0[i] >= w.num_pose_blocks || w.imu_pose1[i] < 0 ||
@@ -622,6 +627,7 @@ void svin_ba_destroy(svin_ba_ctx* c) {
   cudaFree(c->d_out);
   cudaFreeHost(c->h_in);
   cudaFreeHost(c->h_out);
+  cudaFreeHost(c->h_lm_perm);
   cudaFree(c->d_active);
   cudaFreeHost(c->h_active);
   for (auto& ev : c->ev)
@@ -657,12 +663,14 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   }
   SVIN_CUDA(cudaSetDevice(c->device));
   const double t_begin = wall_ms();
+  std::vector<int> vflags;
   {
     // per window on the pool; the message of the first failing window is re-raised on the calling thread
     std::vector<int> vrc(B, SVIN_OK);
     std::vector<std::string> vmsg(B);
+    vflags.assign(B, 0);
     c->pool->run(B, [&](int i) {
-      vrc[i] = validate(wins[i], i);
+      vrc[i] = validate(wins[i], i, &vflags[i]);
       if (vrc[i] != SVIN_OK) vmsg[i] = svin_last_error();
     });
     for (int i = 0; i < B; ++i)
@@ -680,30 +688,33 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   c->h_win.assign(B, WinDesc{});
   c->n_max = 0;
   int has_ext = 0;
-  {
-    std::atomic<int> any{0};
-    c->pool->run(B, [&](int i) {
-      if (any.load(std::memory_order_relaxed)) return;
-      for (int o = 0; o < wins[i].num_obs; ++o)
-        if (!wins[i].pose_fixed[wins[i].obs_extrinsics[o]]) {
-          any.store(1);
-          return;
-        }
-    });
-    has_ext = any.load();
-  }
+  for (int i = 0; i < B; ++i) has_ext |= (vflags[i] >> 1) & 1;
   // pattern grouping (k_schur_mma) needs fixed extrinsics and at most 64 pose runs per landmark
   bool group = !has_ext;
   for (int i = 0; i < B; ++i)
     if (wins[i].num_pose_blocks > 64) group = false;
+  // Device planner (ba_plan.cu): pattern grouping, chunking and the observation order are computed on the GPU from the raw
+  // arrays when every window qualifies (observations sorted by (landmark, pose, camera) - what the adapter's Map walk
+  // delivers - and <= kPlanMaxLandmarks landmarks); otherwise the host threads do it (order_window).  SVIN_BA_DEVICE_PLAN=0
+  // forces the host planner (A/B, and the tests of that path).
+  static const bool dev_plan_wanted = !(std::getenv("SVIN_BA_DEVICE_PLAN") && std::atoi(std::getenv("SVIN_BA_DEVICE_PLAN")) == 0);
+  bool device_plan = group && dev_plan_wanted;
+  int max_landmarks = 0;
+  for (int i = 0; i < B; ++i) {
+    device_plan = device_plan && !(vflags[i] & 1) && wins[i].num_landmarks <= kPlanMaxLandmarks;
+    max_landmarks = std::max(max_landmarks, wins[i].num_landmarks);
+  }
+  c->device_plan = device_plan;
   std::vector<WindowOrder> orders(B);
   long long NSW = 0;
   // independent per window: spread over the context's host threads (this is on the end-to-end path)
-  c->pool->run(B, [&](int i) { order_window(wins[i], group, orders[i]); });
+  if (!device_plan) c->pool->run(B, [&](int i) { order_window(wins[i], group, orders[i]); });
   const double t_ordered = wall_ms();
   long long NRUN = 0;
   for (int i = 0; i < B; ++i) NSW += (long long)orders[i].chunk_begin.size();
   for (int i = 0; i < B; ++i) NRUN += (long long)orders[i].run_pose.size();
+  bool any_lmfix = false;
+  for (int i = 0; i < B; ++i) any_lmfix = any_lmfix || wins[i].landmark_fixed != nullptr;
   for (int i = 0; i < B; ++i) {
     const SvinBaWindow& w = wins[i];
     WinDesc& d = c->h_win[i];
@@ -753,7 +764,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   Region in;
   const size_t o_win = in.add(sizeof(WinDesc) * B), o_ws = in.add(sizeof(WinState) * B);
   const size_t o_pose = in.add(8 * 7 * NPB), o_sb = in.add(8 * 9 * NSB), o_lm = in.add(8 * 4 * NL);
-  const size_t o_poff = in.add(4 * NPB), o_sboff = in.add(4 * NSB), o_lmfix = in.add(NL), o_lmwin = in.add(4 * NL);
+  const size_t o_poff = in.add(4 * NPB), o_sboff = in.add(4 * NSB), o_lmfix = in.add(NL);
   const size_t o_pwin = in.add(4 * NPB), o_sbwin = in.add(4 * NSB);
   const size_t o_intr = in.add(8 * 8 * NC);
   const size_t o_opose = in.add(4 * NOBS), o_olm = in.add(4 * NOBS), o_oext = in.add(4 * NOBS), o_ocam = in.add(4 * NOBS);
@@ -768,20 +779,44 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   bool packed_idx = true;
   for (int i = 0; i < B; ++i) packed_idx = packed_idx && wins[i].num_pose_blocks <= 1024 && wins[i].num_cameras <= 1024;
   const size_t o_rpec = in.add(4 * NOBS);
+  // the planner's tables: filled by the host threads and copied (host planner), or written by ba_plan.cu on the device,
+  // where chunk ids are lm_begin + local chunk and run ids obs_begin + local run (capacities NL / NOBS, nothing travels)
+  if (device_plan) {
+    NSW = NL;
+    NRUN = NOBS;
+  }
+  const size_t o_plan = in.bytes;
+  const size_t o_lmwin = in.add(4 * NL);
   const size_t o_lmof = in.add(4 * NL), o_lmos = in.add(4 * NL), o_lmoc = in.add(4 * NL), o_linv = in.add(4 * NL);
-  const size_t o_otw = in.add(4 * (size_t)n_obs_tiles), o_otb = in.add(4 * (size_t)n_obs_tiles);
-  const size_t o_ltw = in.add(4 * (size_t)n_lm_tiles), o_ltb = in.add(4 * (size_t)n_lm_tiles);
   const size_t o_sww = in.add(4 * (size_t)NSW), o_swb = in.add(4 * (size_t)NSW), o_swc = in.add(4 * (size_t)NSW);
   const size_t o_swnr = in.add(4 * (size_t)NSW), o_swrf = in.add(4 * (size_t)NSW), o_swlist = in.add(4 * (size_t)NSW);
   const size_t o_runoff = in.add(4 * (size_t)NRUN), o_runkm = in.add(4 * (size_t)NRUN);
+  const size_t o_tail = in.bytes;
+  const size_t o_otw = in.add(4 * (size_t)n_obs_tiles), o_otb = in.add(4 * (size_t)n_obs_tiles);
+  const size_t o_ltw = in.add(4 * (size_t)n_lm_tiles), o_ltb = in.add(4 * (size_t)n_lm_tiles);
   const size_t o_imu = in.add(sizeof(ImuTerm) * NIMU), o_imuc = in.add(sizeof(ImuCache) * NIMU);
   const size_t o_mt = in.add(8 * NMEAS), o_mg = in.add(24 * NMEAS), o_ma = in.add(24 * NMEAS);
   const size_t o_pp = in.add(sizeof(PosePrior) * NPP), o_sp = in.add(sizeof(SbPrior) * NSP);
   const size_t o_rp = in.add(sizeof(RelPose) * NRP), o_so = in.add(sizeof(SonarTerm) * NSO);
   const size_t o_de = in.add(sizeof(DepthTerm) * NDE), o_mb = in.add(sizeof(MargBlock) * NMB);
   const size_t o_mJ = in.add(8 * NMJ), o_me = in.add(8 * NME), o_ml = in.add(8 * NMLIN);
+  // device only (device planner): permuted landmark state, landmark permutation for the download, chunk kinds, class
+  // counts and scratch.  With the device planner o_lm / o_lmfix hold the caller-order arrays.
+  const size_t host_bytes = in.bytes;
+  size_t o_lmi = 0, o_lmfixi = 0, o_lmperm = 0, o_swkind = 0, o_wcc = 0, o_wcb = 0, o_wnc = 0, o_ctot = 0, o_scr[5] = {};
+  if (device_plan) {
+    o_lmi = in.add(32 * NL);
+    o_lmfixi = in.add(NL);
+    o_lmperm = in.add(4 * NL);
+    o_swkind = in.add(4 * NL);
+    o_wcc = in.add(4 * (size_t)kSchurClasses * B);
+    o_wcb = in.add(4 * (size_t)kSchurClasses * B);
+    o_wnc = in.add(4 * (size_t)B);
+    o_ctot = in.add(4 * (kSchurClasses + 1));
+    for (int k = 0; k < 5; ++k) o_scr[k] = in.add(4 * ((size_t)NL + 2 * (size_t)B + 8));
+  }
   int rc;
-  if ((rc = ensure(&c->h_in, &c->h_in_cap, in.bytes, true)) != SVIN_OK) return rc;
+  if ((rc = ensure(&c->h_in, &c->h_in_cap, host_bytes, true)) != SVIN_OK) return rc;
   if ((rc = ensure(&c->d_in, &c->d_in_cap, in.bytes, false)) != SVIN_OK) return rc;
   char* H = (char*)c->h_in;
   auto hp = [&](size_t off) { return H + off; };
@@ -813,8 +848,15 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   MargBlock* h_mb = (MargBlock*)hp(o_mb);
   double *h_mJ = (double*)hp(o_mJ), *h_me = (double*)hp(o_me), *h_ml = (double*)hp(o_ml);
 
-  c->obs_perm.resize((size_t)NOBS);
-  c->lm_perm.resize((size_t)NL);
+  c->obs_perm_valid = !device_plan;
+  if (!device_plan) {
+    c->obs_perm.resize((size_t)NOBS);
+    c->lm_perm.resize((size_t)NL);
+    c->lm_perm_p = c->lm_perm.data();
+  } else {
+    if ((rc = ensure((void**)&c->h_lm_perm, &c->h_lm_perm_cap, 4 * (size_t)NL + 64, true)) != SVIN_OK) return rc;
+    c->lm_perm_p = c->h_lm_perm + 16;   // [0..15]: class totals read back from the planner
+  }
   // per-window bases of the running counters, so that windows can be packed by independent host threads
   std::vector<int> cam_base_v(B), ot_v(B), lt_v(B), sw_v(B), run_v(B);
   std::vector<long long> meas_base_v(B);
@@ -856,14 +898,25 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     }
     const WindowOrder& wo = orders[i];
     std::vector<int>& inv = cnt;  // caller landmark -> internal landmark (reuses the scratch vector)
-    inv.assign(w.num_landmarks, 0);
-    for (int k = 0; k < w.num_landmarks; ++k) {
-      const int lc = wo.lm_perm[k];
-      inv[lc] = k;
-      c->lm_perm[(size_t)d.lm_begin + k] = lc;
-      std::memcpy(h_lm + 4 * ((size_t)d.lm_begin + k), w.landmarks + 4 * (size_t)lc, 32);
-      h_lmfix[d.lm_begin + k] = (w.landmark_fixed && w.landmark_fixed[lc]) ? 1 : 0;
-      h_lmwin[d.lm_begin + k] = i;
+    if (device_plan) {
+      // caller order; the planner permutes on the device
+      if (w.num_landmarks) std::memcpy(h_lm + 4 * (size_t)d.lm_begin, w.landmarks, 32 * (size_t)w.num_landmarks);
+      if (any_lmfix) {
+        if (w.landmark_fixed)
+          for (int k = 0; k < w.num_landmarks; ++k) h_lmfix[d.lm_begin + k] = w.landmark_fixed[k] ? 1 : 0;
+        else
+          std::memset(h_lmfix + d.lm_begin, 0, (size_t)w.num_landmarks);
+      }
+    } else {
+      inv.assign(w.num_landmarks, 0);
+      for (int k = 0; k < w.num_landmarks; ++k) {
+        const int lc = wo.lm_perm[k];
+        inv[lc] = k;
+        c->lm_perm[(size_t)d.lm_begin + k] = lc;
+        std::memcpy(h_lm + 4 * ((size_t)d.lm_begin + k), w.landmarks + 4 * (size_t)lc, 32);
+        h_lmfix[d.lm_begin + k] = (w.landmark_fixed && w.landmark_fixed[lc]) ? 1 : 0;
+        h_lmwin[d.lm_begin + k] = i;
+      }
     }
     std::memcpy(h_intr + 8 * (size_t)cam_base, w.intrinsics, 64 * (size_t)w.num_cameras);
     // observations: the caller's arrays as they are + the internal order; the gather into the internal
@@ -902,26 +955,28 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
         t[2] = a[3];
       }
     }
-    std::memcpy(h_rord + g0, wo.obs_order.data(), 4 * (size_t)N);
-    std::memcpy(c->obs_perm.data() + g0, wo.obs_order.data(), 4 * (size_t)N);
-    std::memcpy(h_linv + d.lm_begin, inv.data(), 4 * (size_t)w.num_landmarks);
     d.cam_begin = cam_base;
-    for (int k = 0; k < w.num_landmarks; ++k) {
-      h_lmof[d.lm_begin + k] = d.obs_begin + wo.lm_first[k];
-      h_lmos[d.lm_begin + k] = wo.lm_stride[k];
-      h_lmoc[d.lm_begin + k] = wo.lm_count[k];
-    }
-    for (size_t k = 0; k < wo.chunk_begin.size(); ++k) {
-      h_sww[sw] = i;
-      h_swb[sw] = d.lm_begin + wo.chunk_begin[k];
-      h_swc[sw] = wo.chunk_count[k];
-      h_swnr[sw] = wo.chunk_nruns[k];
-      h_swrf[sw] = run_v[i] + wo.chunk_run_first[k];
-      ++sw;
-    }
-    for (size_t k = 0; k < wo.run_pose.size(); ++k) {
-      h_runoff[run_v[i] + k] = h_poff[d.pose_begin + wo.run_pose[k]];
-      h_runkm[run_v[i] + k] = wo.run_k0m[k];
+    if (!device_plan) {
+      std::memcpy(h_rord + g0, wo.obs_order.data(), 4 * (size_t)N);
+      std::memcpy(c->obs_perm.data() + g0, wo.obs_order.data(), 4 * (size_t)N);
+      std::memcpy(h_linv + d.lm_begin, inv.data(), 4 * (size_t)w.num_landmarks);
+      for (int k = 0; k < w.num_landmarks; ++k) {
+        h_lmof[d.lm_begin + k] = d.obs_begin + wo.lm_first[k];
+        h_lmos[d.lm_begin + k] = wo.lm_stride[k];
+        h_lmoc[d.lm_begin + k] = wo.lm_count[k];
+      }
+      for (size_t k = 0; k < wo.chunk_begin.size(); ++k) {
+        h_sww[sw] = i;
+        h_swb[sw] = d.lm_begin + wo.chunk_begin[k];
+        h_swc[sw] = wo.chunk_count[k];
+        h_swnr[sw] = wo.chunk_nruns[k];
+        h_swrf[sw] = run_v[i] + wo.chunk_run_first[k];
+        ++sw;
+      }
+      for (size_t k = 0; k < wo.run_pose.size(); ++k) {
+        h_runoff[run_v[i] + k] = h_poff[d.pose_begin + wo.run_pose[k]];
+        h_runkm[run_v[i] + k] = wo.run_k0m[k];
+      }
     }
     for (int t0 = 0; t0 < N; t0 += kObsTile) {
       h_otw[ot] = i;
@@ -1043,11 +1098,11 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   int sw_class_count[kSchurClasses] = {};
   {
     int* h_swlist = (int*)hp(o_swlist);
-    for (int i = 0; i < B; ++i)
+    for (int i = 0; i < B && !device_plan; ++i)
       for (int kind : orders[i].chunk_kind) sw_class_count[kind]++;
     int pos[kSchurClasses] = {};
     for (int k = 1; k < kSchurClasses; ++k) pos[k] = pos[k - 1] + sw_class_count[k - 1];
-    for (int i = 0; i < B; ++i)
+    for (int i = 0; i < B && !device_plan; ++i)
       for (size_t k = 0; k < orders[i].chunk_count.size(); ++k)
         h_swlist[pos[orders[i].chunk_kind[k]]++] = sw_v[i] + (int)k;
   }
@@ -1127,7 +1182,8 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   b.ws = (WinState*)(Wk + o_wsw);
   b.pose_init = (double*)(D + o_pose); b.sb_init = (double*)(D + o_sb); b.lm_init = (double*)(D + o_lm);
   b.pose_off = (int*)(D + o_poff); b.sb_off = (int*)(D + o_sboff);
-  b.lm_fixed = (uint8_t*)(D + o_lmfix); b.lm_win = (int*)(D + o_lmwin);
+  b.lm_fixed = (uint8_t*)(D + (device_plan ? o_lmfixi : o_lmfix)); b.lm_win = (int*)(D + o_lmwin);
+  if (device_plan) b.lm_init = (double*)(D + o_lmi);
   c->d_pose_win = (int*)(D + o_pwin); c->d_sb_win = (int*)(D + o_sbwin);
   b.intr = (double*)(D + o_intr);
   b.obs_pose = (int*)(D + o_opose); b.obs_lm = (int*)(D + o_olm); b.obs_ext = (int*)(D + o_oext);
@@ -1201,7 +1257,8 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
         const size_t e0 = (size_t)c->h_win[w0].obs_begin, e1 = (size_t)c->h_win[w1 - 1].obs_end;
         for (int a = 0; a < 8 && e1 > e0; ++a) {
           const bool skip = (packed_idx && (a == 0 || a == 2 || a == 3)) || (!packed_idx && a == 7) ||
-                            (a == 5 && group_info[g].load(std::memory_order_acquire) == 0);
+                            (a == 5 && group_info[g].load(std::memory_order_acquire) == 0) ||
+                            (a == 6 && device_plan);   // the observation order is computed on the device
           if (skip) {
             h2d_skipped += obs_elt[a] * (e1 - e0);
             continue;
@@ -1213,10 +1270,12 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
       w0 = w1;
     }
     c->pool->wait();
-    // everything else: the regions before and after the observation arrays
-    const size_t obs_lo = o_opose, obs_hi = o_lmof;
+    // everything else: the regions before and after the observation arrays (the planner's tables only when the host
+    // filled them)
+    const size_t obs_lo = o_opose, obs_hi = device_plan ? o_tail : o_plan;
     SVIN_CUDA(cudaMemcpyAsync(D, H, obs_lo, cudaMemcpyHostToDevice, c->stream));
-    SVIN_CUDA(cudaMemcpyAsync(D + obs_hi, H + obs_hi, in.bytes - obs_hi, cudaMemcpyHostToDevice, c->stream));
+    SVIN_CUDA(cudaMemcpyAsync(D + obs_hi, H + obs_hi, host_bytes - obs_hi, cudaMemcpyHostToDevice, c->stream));
+    h2d_skipped += obs_hi - o_plan;
   }
   const double t_filled = wall_ms();
   SVIN_CUDA(cudaEventRecord(c->ev[1], c->stream));
@@ -1224,6 +1283,34 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   // Jd must be zero outside the blocks the terms write (structure is static)
   for (int k = 0; k < 2; ++k) SVIN_CUDA(cudaMemsetAsync(b.Jd[k], 0, 8 * (size_t)NJD + 8, c->stream));
   SVIN_CUDA(cudaMemsetAsync(b.lm_quality, 0, 8 * (size_t)NL + 8, c->stream));
+  if (device_plan) {
+    PlanArgs pa{};
+    pa.B = B;
+    pa.packed = packed_idx ? 1 : 0;
+    pa.win = b.win;
+    pa.rlm = (const int*)(D + o_rlm); pa.rpec = (const int*)(D + o_rpec);
+    pa.rpose = (const int*)(D + o_rpose); pa.rcam = (const int*)(D + o_rcam);
+    pa.lm_raw = (const double*)(D + o_lm); pa.lmfix_raw = (const unsigned char*)(D + o_lmfix);
+    pa.poff = b.pose_off;
+    pa.lm_init = b.lm_init; pa.lm_fixed = b.lm_fixed; pa.lm_win = b.lm_win;
+    pa.linv = (int*)(D + o_linv); pa.lm_perm = (int*)(D + o_lmperm);
+    pa.lmof = b.lm_obs_first; pa.lmos = b.lm_obs_stride; pa.lmoc = b.lm_obs_cnt; pa.rord = (int*)(D + o_rord);
+    pa.sw_win = b.sw_win; pa.sw_lm_begin = b.sw_lm_begin; pa.sw_count = b.sw_count; pa.sw_nruns = b.sw_nruns;
+    pa.sw_run_first = b.sw_run_first; pa.sw_kind = (int*)(D + o_swkind);
+    pa.run_off = b.run_off; pa.run_k0m = b.run_k0m; pa.sw_list = b.sw_list;
+    pa.win_class_count = (int*)(D + o_wcc); pa.win_class_base = (int*)(D + o_wcb); pa.win_nchunks = (int*)(D + o_wnc);
+    pa.class_total = (int*)(D + o_ctot);
+    for (int k = 0; k < 5; ++k) pa.scratch[k] = (int*)(D + o_scr[k]);
+    pa.caps = plan_caps_table();
+    if (!any_lmfix) SVIN_CUDA(cudaMemsetAsync(D + o_lmfix, 0, (size_t)NL + 1, c->stream));
+    SVIN_CUDA(launch_plan(pa, max_landmarks, c->stream));
+    SVIN_CUDA(cudaMemcpyAsync(c->h_lm_perm, D + o_ctot, 4 * (kSchurClasses + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (NL)
+      SVIN_CUDA(cudaMemcpyAsync(c->h_lm_perm + 16, D + o_lmperm, 4 * (size_t)NL, cudaMemcpyDeviceToHost, c->stream));
+  }
+  c->d_rord = (const int*)(D + o_rord);
+  c->n_obs_total = (size_t)NOBS;
+  c->n_sw_cap = (size_t)NSW;
   launch_reset_state(b, c->stream);
   {
     RawObs raw{packed_idx ? (const int*)(D + o_rpec) : nullptr,
@@ -1249,12 +1336,17 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     SVIN_CUDA(configure_schur());
   }
   SVIN_CUDA(cudaStreamSynchronize(c->stream));
+  if (device_plan) {
+    // the chunk counts size the Schur launches
+    for (int k = 0; k < kSchurClasses; ++k) b.sw_class_count[k] = c->h_lm_perm[k];
+    b.n_schur_warps = c->h_lm_perm[kSchurClasses];
+  }
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
   c->tm = SvinBaTimings{};
   c->tm.h2d_ms = ms;
   // the SoA observation planes are produced on the device; packed indices / uniform information skip their slices
-  c->tm.h2d_bytes = (int64_t)(in.bytes - (o_rpose - o_opose)) - (int64_t)h2d_skipped;
+  c->tm.h2d_bytes = (int64_t)(host_bytes - (o_rpose - o_opose)) - (int64_t)h2d_skipped;
   c->tm.host_order_ms = t_ordered - t_begin;
   c->tm.host_fill_ms = t_filled - t_ordered;
   c->tm.host_upload_ms = wall_ms() - t_begin;
@@ -1295,6 +1387,69 @@ int svin_ba_plan(const SvinBaWindow* w, int32_t* lm_order, int32_t cap, int32_t*
     if (kind) kind[k] = wo.chunk_kind[k];
     if (count) count[k] = wo.chunk_count[k];
     if (runs) runs[k] = wo.chunk_nruns[k];
+  }
+  return SVIN_OK;
+}
+
+int svin_ba_plan_observations(const SvinBaWindow* w, int32_t* observation_order) {
+  if (!w || !observation_order) {
+    set_error("svin_ba_plan_observations: invalid arguments");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  const int rc = validate(*w, 0);
+  if (rc != SVIN_OK) return rc;
+  bool group = w->num_pose_blocks <= 64;
+  for (int o = 0; o < w->num_obs && group; ++o)
+    if (!w->pose_fixed[w->obs_extrinsics[o]]) group = false;
+  WindowOrder wo;
+  order_window(*w, group, wo);
+  for (int o = 0; o < w->num_obs; ++o) observation_order[o] = wo.obs_order[o];
+  return SVIN_OK;
+}
+
+int svin_ba_uploaded_plan(svin_ba_ctx* c, int32_t wi, int32_t* lm_order, int32_t cap, int32_t* kind, int32_t* count,
+                          int32_t* runs, int32_t* num_chunks, int32_t* observation_order, int32_t* planned_on_device) {
+  if (!c || !c->uploaded || wi < 0 || wi >= c->b.B || !num_chunks) {
+    set_error("svin_ba_uploaded_plan: nothing uploaded / window index out of range");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  SVIN_CUDA(cudaSetDevice(c->device));
+  const Batch& b = c->b;
+  const WinDesc& d = c->h_win[wi];
+  const int L = d.lm_end - d.lm_begin, N = d.obs_end - d.obs_begin;
+  if (planned_on_device) *planned_on_device = c->device_plan ? 1 : 0;
+  if (lm_order)
+    for (int k = 0; k < L; ++k) lm_order[k] = c->lm_perm_p[d.lm_begin + k];
+  if (observation_order && N)
+    SVIN_CUDA(cudaMemcpy(observation_order, c->d_rord + d.obs_begin, 4 * (size_t)N, cudaMemcpyDeviceToHost));
+  int total = 0;
+  for (int k = 0; k < kSchurClasses; ++k) total += b.sw_class_count[k];
+  std::vector<int> list(total > 0 ? total : 1), win(c->n_sw_cap + 1), beg(c->n_sw_cap + 1), cnt(c->n_sw_cap + 1),
+      nr(c->n_sw_cap + 1);
+  if (total) SVIN_CUDA(cudaMemcpy(list.data(), b.sw_list, 4 * (size_t)total, cudaMemcpyDeviceToHost));
+  if (c->n_sw_cap) {
+    SVIN_CUDA(cudaMemcpy(win.data(), b.sw_win, 4 * c->n_sw_cap, cudaMemcpyDeviceToHost));
+    SVIN_CUDA(cudaMemcpy(beg.data(), b.sw_lm_begin, 4 * c->n_sw_cap, cudaMemcpyDeviceToHost));
+    SVIN_CUDA(cudaMemcpy(cnt.data(), b.sw_count, 4 * c->n_sw_cap, cudaMemcpyDeviceToHost));
+    SVIN_CUDA(cudaMemcpy(nr.data(), b.sw_nruns, 4 * c->n_sw_cap, cudaMemcpyDeviceToHost));
+  }
+  // this window's chunks in internal landmark order, their class from the position in the class-sorted list
+  std::vector<std::pair<int, int>> mine;   // (first landmark, list position)
+  for (int p = 0; p < total; ++p)
+    if (list[p] >= 0 && (size_t)list[p] < c->n_sw_cap && win[list[p]] == wi) mine.push_back({beg[list[p]], p});
+  std::sort(mine.begin(), mine.end());
+  *num_chunks = (int)mine.size();
+  if ((int)mine.size() > cap) {
+    set_error("svin_ba_uploaded_plan: capacity too small");
+    return SVIN_ERR_INVALID_ARGUMENT;
+  }
+  for (size_t k = 0; k < mine.size(); ++k) {
+    const int p = mine[k].second, id = list[p];
+    int cls = 0, acc = 0;
+    while (cls < kSchurClasses && p >= acc + b.sw_class_count[cls]) acc += b.sw_class_count[cls++];
+    if (kind) kind[k] = cls;
+    if (count) count[k] = cnt[id];
+    if (runs) runs[k] = nr[id];
   }
   return SVIN_OK;
 }
@@ -1634,7 +1789,7 @@ static void scatter_window(svin_ba_ctx* c, int i, SvinBaWindow* w, double* quali
               72 * (size_t)(d.sb_end - d.sb_begin));
   const double* lm_out = (const double*)(Hh + c->out_off_lm) + 4 * (size_t)d.lm_begin;
   const double* q_out = (const double*)(Hh + c->out_off_q) + d.lm_begin;
-  const int* perm = c->lm_perm.data() + d.lm_begin;
+  const int* perm = c->lm_perm_p + d.lm_begin;
   for (int k = 0; k < d.lm_end - d.lm_begin; ++k) {
     std::memcpy(w->landmarks + 4 * (size_t)perm[k], lm_out + 4 * (size_t)k, 32);
     // without compute_landmark_quality the device buffer holds an earlier batch's values (or nothing): report "unknown"
@@ -1700,6 +1855,12 @@ int svin_ba_evaluate(svin_ba_ctx* c, int32_t wi, SvinBaEvaluation* out) {
   Batch& b = c->b;
   const WinDesc& d = c->h_win[wi];
   const int N = d.obs_end - d.obs_begin, NI = d.imu_end - d.imu_begin;
+  if (!c->obs_perm_valid) {   // device planner: the observation order lives on the device until someone asks
+    c->obs_perm.resize(c->n_obs_total);
+    if (c->n_obs_total)
+      SVIN_CUDA(cudaMemcpy(c->obs_perm.data(), c->d_rord, 4 * c->n_obs_total, cudaMemcpyDeviceToHost));
+    c->obs_perm_valid = true;
+  }
   // total cost at the current estimate: regular evaluation, then restore the state
   int rc = svin_ba_reset(c);
   if (rc != SVIN_OK) return rc;

@@ -190,6 +190,10 @@ class SlidingWindow:
         w.landmarks = np.array([self.landmarks[l] for l in lm_ids]).reshape(-1, 4)
         w.intrinsics = self.intrinsics
         if obs:
+            # the walk order of the C++ adapter (adapters/EstimatorB200.cpp: landmarksMap_, then each landmark's
+            # observations map keyed by (frame, camera, keypoint)) = sorted by (landmark, pose, camera); svin_ba_upload
+            # plans such windows on the device (csrc/ba_plan.cu)
+            obs = sorted(obs, key=lambda o: (li[o[0]], pi[fr[o[1]].pose_id], o[2]))
             w.obs_pose = [pi[fr[o[1]].pose_id] for o in obs]
             w.obs_landmark = [li[o[0]] for o in obs]
             w.obs_extrinsics = [pi[fr[o[1]].ext_ids[o[2]]] for o in obs]

@@ -1,0 +1,110 @@
+"""GPU: the device planner of the upload path (svin_b200/csrc/ba_plan.cu) against the host planner (svin_ba_plan /
+svin_ba_plan_observations, the CPU checker): landmark order, chunk kinds / sizes / run counts and the observation order
+read back from HBM must equal the host's entry by entry, and a solve through either planner gives the same solution."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from svin_b200 import capi
+from svin_b200.engine import BaEngine
+from svin_b200.synthetic import make_window
+from svin_b200.window import default_options
+
+pytestmark = pytest.mark.gpu
+
+
+def host_plan(w):
+    lib = capi.load()
+    s = w.c_struct()
+    L, N = w.num_landmarks, w.num_obs
+    order, obs = np.zeros(max(L, 1), np.int32), np.zeros(max(N, 1), np.int32)
+    kind, cnt, runs = (np.zeros(max(L, 1), np.int32) for _ in range(3))
+    n = C.c_int32()
+    p = lambda a: a.ctypes.data_as(capi.c_int32_p)  # noqa: E731
+    capi.check(lib.svin_ba_plan(C.byref(s), p(order), max(L, 1), p(kind), p(cnt), p(runs), C.byref(n)), lib)
+    capi.check(lib.svin_ba_plan_observations(C.byref(s), p(obs)), lib)
+    return order[:L], kind[:n.value], cnt[:n.value], runs[:n.value], obs[:N]
+
+
+def uploaded_plan(eng, i, w):
+    lib = capi.load()
+    L, N = w.num_landmarks, w.num_obs
+    order, obs = np.zeros(max(L, 1), np.int32), np.zeros(max(N, 1), np.int32)
+    kind, cnt, runs = (np.zeros(max(L, 1), np.int32) for _ in range(3))
+    n, dev = C.c_int32(), C.c_int32()
+    p = lambda a: a.ctypes.data_as(capi.c_int32_p)  # noqa: E731
+    capi.check(lib.svin_ba_uploaded_plan(eng._ctx, i, p(order), max(L, 1), p(kind), p(cnt), p(runs), C.byref(n), p(obs),
+                                         C.byref(dev)), lib)
+    return (order[:L], kind[:n.value], cnt[:n.value], runs[:n.value], obs[:N]), dev.value
+
+
+def assert_same_plan(eng, windows, expect_device):
+    eng.upload(windows)
+    for i, w in enumerate(windows):
+        got, dev = uploaded_plan(eng, i, w)
+        assert dev == expect_device
+        exp = host_plan(w)
+        for name, g, e in zip(("landmark order", "chunk kind", "chunk landmarks", "chunk runs", "observation order"),
+                              got, exp):
+            assert g.tolist() == e.tolist(), f"window {i}: {name} differs"
+
+
+def variants():
+    ws = []
+    for k, (kf, lm, mode) in enumerate([(10, 2000, "steady"), (5, 800, "initial"), (20, 8000, "steady"), (3, 40, "initial"),
+                                        (10, 1, "steady"), (7, 333, "steady")]):
+        w, _ = make_window(seed=900 + k, num_keyframes=kf, num_imu_frames=3, num_landmarks=lm, mode=mode)
+        ws.append(w)
+    # fixed landmarks split patterns; landmarks without observations; holes in the tracks (order kept)
+    w, _ = make_window(seed=950, num_keyframes=8, num_imu_frames=3, num_landmarks=600, mode="steady")
+    rng = np.random.default_rng(3)
+    w.landmark_fixed = (rng.random(w.num_landmarks) < 0.15).astype(np.uint8)
+    keep = rng.random(w.num_obs) > 0.3
+    keep &= ~np.isin(w.obs_landmark, rng.choice(w.num_landmarks, 40, replace=False))
+    for name in ("obs_pose", "obs_landmark", "obs_extrinsics", "obs_camera", "obs_measurement", "obs_information"):
+        setattr(w, name, getattr(w, name)[keep].copy())
+    w._struct = None
+    w.finalize()
+    ws.append(w)
+    return ws
+
+
+def test_device_plan_equals_host_plan():
+    with BaEngine() as eng:
+        ws = variants()
+        assert_same_plan(eng, ws, expect_device=1)
+        assert_same_plan(eng, ws[:1] * 5 + ws[3:5], expect_device=1)       # repeated windows, other batch offsets
+
+
+def test_unsorted_observations_take_the_host_planner():
+    ws = variants()[:2]
+    rng = np.random.default_rng(1)
+    w = ws[1]
+    perm = rng.permutation(w.num_obs)
+    for name in ("obs_pose", "obs_landmark", "obs_extrinsics", "obs_camera", "obs_measurement", "obs_information"):
+        setattr(w, name, getattr(w, name)[perm].copy())
+    w._struct = None
+    w.finalize()
+    with BaEngine() as eng:
+        assert_same_plan(eng, ws, expect_device=0)
+
+
+def test_solution_does_not_depend_on_the_planner():
+    """Same window, observations in sorted order (device planner) and shuffled (host planner): the two plans are the same
+    up to the caller's observation numbering, so the solutions agree to rounding of the fp64 atomics."""
+    w, _ = make_window(seed=20260925, num_keyframes=10, num_imu_frames=3, num_landmarks=2000, mode="steady")
+    w2 = w.copy()
+    perm = np.random.default_rng(5).permutation(w2.num_obs)
+    for name in ("obs_pose", "obs_landmark", "obs_extrinsics", "obs_camera", "obs_measurement", "obs_information"):
+        setattr(w2, name, getattr(w2, name)[perm].copy())
+    w2._struct = None
+    w2.finalize()
+    opt = default_options()
+    with BaEngine() as eng:
+        (sa,), _ = eng.optimize([w], opt)
+        (sb,), _ = eng.optimize([w2], opt)
+    assert sa["iterations"] == sb["iterations"]
+    np.testing.assert_allclose(w.pose_blocks, w2.pose_blocks, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(w.landmarks, w2.landmarks, rtol=0, atol=1e-7)
+    assert abs(sa["final_cost"] - sb["final_cost"]) <= 1e-9 * abs(sa["final_cost"])

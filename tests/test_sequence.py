@@ -123,13 +123,14 @@ class _CheckedCuda:
         if os.environ.get("SVIN_SEQ_REPORT"):
             return out
         # The windows being linearised hold IMU terms, whose 15x15 square-root information agrees to ~1e-8 relative
-        # only (condition ~1e8, tests/test_ba_gpu.py); H inherits that: 1e-6 here (1e-9 in tests/test_marg_gpu.py on
-        # windows without that amplification)
+        # only (condition ~1e8, tests/test_ba_gpu.py); H inherits that (1e-9 in tests/test_marg_gpu.py on windows without
+        # that amplification).  Measured on the last EuRoC-shape frame: 0.7e-6 .. 1.6e-6 from run to run (the inputs carry the
+        # rounding noise of the solve before, profiles/r2af_*, gpurun r2bc) - 1e-5 here, the tolerance b0 already has.
         sH, sb = np.abs(ref["H"]).max(), max(1.0, np.abs(ref["b0"]).max())
-        assert np.abs(out["H"] - ref["H"]).max() < 1e-6 * sH
+        assert np.abs(out["H"] - ref["H"]).max() < 1e-5 * sH
         assert np.abs(out["b0"] - ref["b0"]).max() < 1e-5 * sb
         # J_, e0_ through what they are used for (the eigenbasis of a degenerate eigenvalue is not unique)
-        assert np.abs(out["J"].T @ out["J"] - ref["J"].T @ ref["J"]).max() < 1e-6 * sH
+        assert np.abs(out["J"].T @ out["J"] - ref["J"].T @ ref["J"]).max() < 1e-5 * sH
         assert np.abs(out["J"].T @ out["e0"] - ref["J"].T @ ref["e0"]).max() < 1e-5 * sb
         return out
 
