@@ -340,6 +340,7 @@ struct svin_ba_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;  // dense-term evaluation runs here, concurrently with k_linearize
+  cudaStream_t up = nullptr;    // svin_ba_upload's copies and kernels (high priority)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_gram = nullptr;
   SchurStreams schur_par{};               // concurrent Schur chunk kernels (SVIN_SCHUR_STREAMS=0 disables)
   cudaGraphExec_t graph_exec = nullptr;  // first solve pass of the current upload (SVIN_BA_GRAPH)
@@ -593,6 +594,7 @@ int svin_ba_create(int device, svin_ba_ctx** out) {
     int lo = 0, hi = 0;
     SVIN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     SVIN_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));
+    SVIN_CUDA(cudaStreamCreateWithPriority(&c->up, cudaStreamNonBlocking, hi));
   }
   SVIN_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   SVIN_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -648,6 +650,7 @@ void svin_ba_destroy(svin_ba_ctx* c) {
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->up) cudaStreamDestroy(c->up);
   delete c->pool;
   delete c;
 }
@@ -1241,7 +1244,11 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   c->in_bytes = in.bytes;
 
   // ---------------- copy + initialise
-  SVIN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  // The upload's copies and its small kernels (planner, pack) go to a high-priority stream: in a pipeline another
+  // context's solve is usually running, and on an equal-priority stream these grids would only be dispatched in the
+  // tails of its kernels - the upload would take as long as that solve.
+  cudaStream_t up = c->up;
+  SVIN_CUDA(cudaEventRecord(c->ev[0], up));
   size_t h2d_skipped = 0;   // slices of the observation arrays that did not have to travel
   if (c->pool->workers() == 0) c->pool->help();
   {
@@ -1264,7 +1271,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
             continue;
           }
           SVIN_CUDA(cudaMemcpyAsync(D + obs_arr[a] + obs_elt[a] * e0, H + obs_arr[a] + obs_elt[a] * e0,
-                                    obs_elt[a] * (e1 - e0), cudaMemcpyHostToDevice, c->stream));
+                                    obs_elt[a] * (e1 - e0), cudaMemcpyHostToDevice, up));
         }
       }
       w0 = w1;
@@ -1273,16 +1280,16 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     // everything else: the regions before and after the observation arrays (the planner's tables only when the host
     // filled them)
     const size_t obs_lo = o_opose, obs_hi = device_plan ? o_tail : o_plan;
-    SVIN_CUDA(cudaMemcpyAsync(D, H, obs_lo, cudaMemcpyHostToDevice, c->stream));
-    SVIN_CUDA(cudaMemcpyAsync(D + obs_hi, H + obs_hi, host_bytes - obs_hi, cudaMemcpyHostToDevice, c->stream));
+    SVIN_CUDA(cudaMemcpyAsync(D, H, obs_lo, cudaMemcpyHostToDevice, up));
+    SVIN_CUDA(cudaMemcpyAsync(D + obs_hi, H + obs_hi, host_bytes - obs_hi, cudaMemcpyHostToDevice, up));
     h2d_skipped += obs_hi - o_plan;
   }
   const double t_filled = wall_ms();
-  SVIN_CUDA(cudaEventRecord(c->ev[1], c->stream));
-  SVIN_CUDA(cudaMemsetAsync(Wk + o_sacc, 0, 8 * kShardAcc * (size_t)B, c->stream));
+  SVIN_CUDA(cudaEventRecord(c->ev[1], up));
+  SVIN_CUDA(cudaMemsetAsync(Wk + o_sacc, 0, 8 * kShardAcc * (size_t)B, up));
   // Jd must be zero outside the blocks the terms write (structure is static)
-  for (int k = 0; k < 2; ++k) SVIN_CUDA(cudaMemsetAsync(b.Jd[k], 0, 8 * (size_t)NJD + 8, c->stream));
-  SVIN_CUDA(cudaMemsetAsync(b.lm_quality, 0, 8 * (size_t)NL + 8, c->stream));
+  for (int k = 0; k < 2; ++k) SVIN_CUDA(cudaMemsetAsync(b.Jd[k], 0, 8 * (size_t)NJD + 8, up));
+  SVIN_CUDA(cudaMemsetAsync(b.lm_quality, 0, 8 * (size_t)NL + 8, up));
   if (device_plan) {
     PlanArgs pa{};
     pa.B = B;
@@ -1302,28 +1309,28 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     pa.class_total = (int*)(D + o_ctot);
     for (int k = 0; k < 5; ++k) pa.scratch[k] = (int*)(D + o_scr[k]);
     pa.caps = plan_caps_table();
-    if (!any_lmfix) SVIN_CUDA(cudaMemsetAsync(D + o_lmfix, 0, (size_t)NL + 1, c->stream));
-    SVIN_CUDA(launch_plan(pa, max_landmarks, c->stream));
-    SVIN_CUDA(cudaMemcpyAsync(c->h_lm_perm, D + o_ctot, 4 * (kSchurClasses + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (!any_lmfix) SVIN_CUDA(cudaMemsetAsync(D + o_lmfix, 0, (size_t)NL + 1, up));
+    SVIN_CUDA(launch_plan(pa, max_landmarks, up));
+    SVIN_CUDA(cudaMemcpyAsync(c->h_lm_perm, D + o_ctot, 4 * (kSchurClasses + 1), cudaMemcpyDeviceToHost, up));
     if (NL)
-      SVIN_CUDA(cudaMemcpyAsync(c->h_lm_perm + 16, D + o_lmperm, 4 * (size_t)NL, cudaMemcpyDeviceToHost, c->stream));
+      SVIN_CUDA(cudaMemcpyAsync(c->h_lm_perm + 16, D + o_lmperm, 4 * (size_t)NL, cudaMemcpyDeviceToHost, up));
   }
   c->d_rord = (const int*)(D + o_rord);
   c->n_obs_total = (size_t)NOBS;
   c->n_sw_cap = (size_t)NSW;
-  launch_reset_state(b, c->stream);
+  launch_reset_state(b, up);
   {
     RawObs raw{packed_idx ? (const int*)(D + o_rpec) : nullptr,
                (const int*)(D + o_rpose), (const int*)(D + o_rlm), (const int*)(D + o_rext), (const int*)(D + o_rcam),
                (const double*)(D + o_rmeas), (const double*)(D + o_rinfo), (const int*)(D + o_rord),
                (const int*)(D + o_linv)};
-    launch_pack_obs(b, raw, c->stream);
+    launch_pack_obs(b, raw, up);
   }
-  launch_obs_poff(b, c->stream);
-  SVIN_CUDA(cudaMemcpyAsync(b.ws, c->d_ws_init, sizeof(WinState) * B, cudaMemcpyDeviceToDevice, c->stream));
+  launch_obs_poff(b, up);
+  SVIN_CUDA(cudaMemcpyAsync(b.ws, c->d_ws_init, sizeof(WinState) * B, cudaMemcpyDeviceToDevice, up));
   if (NIMU)
     SVIN_CUDA(cudaMemcpyAsync(b.imu_cache, c->d_imu_cache_init, sizeof(ImuCache) * NIMU, cudaMemcpyDeviceToDevice,
-                              c->stream));
+                              up));
   SVIN_CUDA(cudaGetLastError());
   // the reduced system lives in shared memory when it fits
   {
@@ -1335,7 +1342,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     }
     SVIN_CUDA(configure_schur());
   }
-  SVIN_CUDA(cudaStreamSynchronize(c->stream));
+  SVIN_CUDA(cudaStreamSynchronize(up));
   if (device_plan) {
     // the chunk counts size the Schur launches
     for (int k = 0; k < kSchurClasses; ++k) b.sw_class_count[k] = c->h_lm_perm[k];
