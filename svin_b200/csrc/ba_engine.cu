@@ -433,7 +433,8 @@ int ensure(void** p, size_t* cap, size_t need, bool pinned) {
   return SVIN_OK;
 }
 
-// flags (optional): bit 0 = observations not in (landmark, pose, camera) order, bit 1 = an observation's extrinsics block is free
+// flags (optional): bit 0 = observations not in (landmark, pose, camera) order, bit 1 = an observation's extrinsics block is
+// free, bit 2 = a measurement coordinate is not exactly a float
 int validate(const SvinBaWindow& w, int idx, int* flags = nullptr) {
   auto bad = [&](const char* what) {
     set_error("window " + std::to_string(idx) + ": " + what);
@@ -474,7 +475,7 @@ int validate(const SvinBaWindow& w, int idx, int* flags = nullptr) {
   {
     // one pass: ranges (any failure is diagnosed by the slow loop below), sortedness, free extrinsics
     const unsigned np = (unsigned)w.num_pose_blocks, nl = (unsigned)w.num_landmarks, nc = (unsigned)w.num_cameras;
-    unsigned oob = 0, unsorted = 0, ext_free = 0;
+    unsigned oob = 0, unsorted = 0, ext_free = 0, inexact = 0;
     uint64_t prev = 0;
     for (int i = 0; i < w.num_obs; ++i) {
       const unsigned p = (unsigned)w.obs_pose[i], e = (unsigned)w.obs_extrinsics[i], l = (unsigned)w.obs_landmark[i],
@@ -485,6 +486,8 @@ int validate(const SvinBaWindow& w, int idx, int* flags = nullptr) {
       unsorted |= (unsigned)(k < prev);
       prev = k;
       if (!bad_i) ext_free |= (unsigned)(w.pose_fixed[e] == 0);
+      const double zx = w.obs_measurement[2 * (size_t)i], zy = w.obs_measurement[2 * (size_t)i + 1];
+      inexact |= (unsigned)((double)(float)zx != zx) | (unsigned)((double)(float)zy != zy);
     }
     if (oob)
       for (int i = 0; i < w.num_obs; ++i) {
@@ -494,7 +497,8 @@ int validate(const SvinBaWindow& w, int idx, int* flags = nullptr) {
         if (w.obs_camera[i] < 0 || w.obs_camera[i] >= w.num_cameras) return bad("obs_camera out of range");
       }
     if (flags)
-      *flags = ((unsorted || w.num_cameras > 256 || w.num_pose_blocks >= (1 << 24)) ? 1 : 0) | (ext_free ? 2 : 0);
+      *flags = ((unsorted || w.num_cameras > 256 || w.num_pose_blocks >= (1 << 24)) ? 1 : 0) | (ext_free ? 2 : 0) |
+               (inexact ? 4 : 0);
   }
   for (int i = 0; i < w.num_imu; ++i) {
     if (w.imu_pose0[i] < 0 || w.imu_pose0[i] >= w.num_pose_blocks || w.imu_pose1[i] < 0 ||
@@ -700,7 +704,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   // arrays when every window qualifies (observations sorted by (landmark, pose, camera) - what the adapter's Map walk
   // delivers - and <= kPlanMaxLandmarks landmarks); otherwise the host threads do it (order_window).  SVIN_BA_DEVICE_PLAN=0
   // forces the host planner (A/B, and the tests of that path).
-  static const bool dev_plan_wanted = !(std::getenv("SVIN_BA_DEVICE_PLAN") && std::atoi(std::getenv("SVIN_BA_DEVICE_PLAN")) == 0);
+  const bool dev_plan_wanted = !(std::getenv("SVIN_BA_DEVICE_PLAN") && std::atoi(std::getenv("SVIN_BA_DEVICE_PLAN")) == 0);
   bool device_plan = group && dev_plan_wanted;
   int max_landmarks = 0;
   for (int i = 0; i < B; ++i) {
@@ -782,6 +786,16 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   bool packed_idx = true;
   for (int i = 0; i < B; ++i) packed_idx = packed_idx && wins[i].num_pose_blocks <= 1024 && wins[i].num_cameras <= 1024;
   const size_t o_rpec = in.add(4 * NOBS);
+  // more compact still (SVIN_BA_COMPACT_OBS=0 turns both off): landmark | pose << 18 | ext << 24 | cam << 30 in ONE word
+  // when every window has <= 64 pose blocks, <= 4 cameras and < 2^18 landmarks (the landmark array then stays home), and
+  // float measurements when every coordinate is float-exact - BRISK keypoints are (cv::KeyPoint::pt is float, the
+  // reference widens it in Frame::getKeypoint), so nothing is rounded.  12 B instead of 24 B per observation.
+  const bool compact_wanted = !(std::getenv("SVIN_BA_COMPACT_OBS") && std::atoi(std::getenv("SVIN_BA_COMPACT_OBS")) == 0);
+  bool one_word = packed_idx && compact_wanted, meas_f32 = compact_wanted;
+  for (int i = 0; i < B; ++i) {
+    one_word = one_word && wins[i].num_pose_blocks <= 64 && wins[i].num_cameras <= 4 && wins[i].num_landmarks < (1 << 18);
+    meas_f32 = meas_f32 && !(vflags[i] & 4);
+  }
   // the planner's tables: filled by the host threads and copied (host planner), or written by ba_plan.cu on the device,
   // where chunk ids are lm_begin + local chunk and run ids obs_begin + local run (capacities NL / NOBS, nothing travels)
   if (device_plan) {
@@ -926,15 +940,25 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     // (landmark-major, pattern-major inside a chunk) SoA planes and U = chol(information)^T run on the device
     const int N = w.num_obs;
     const size_t g0 = (size_t)d.obs_begin;
-    std::memcpy(h_rlm + g0, w.obs_landmark, 4 * (size_t)N);
-    if (packed_idx) {
+    if (one_word) {
+      for (int o = 0; o < N; ++o)
+        h_rpec[g0 + o] = (int)((unsigned)w.obs_landmark[o] | ((unsigned)w.obs_pose[o] << 18) |
+                               ((unsigned)w.obs_extrinsics[o] << 24) | ((unsigned)w.obs_camera[o] << 30));
+    } else if (packed_idx) {
+      std::memcpy(h_rlm + g0, w.obs_landmark, 4 * (size_t)N);
       for (int o = 0; o < N; ++o) h_rpec[g0 + o] = w.obs_pose[o] | (w.obs_extrinsics[o] << 10) | (w.obs_camera[o] << 20);
     } else {
+      std::memcpy(h_rlm + g0, w.obs_landmark, 4 * (size_t)N);
       std::memcpy(h_rpose + g0, w.obs_pose, 4 * (size_t)N);
       std::memcpy(h_rext + g0, w.obs_extrinsics, 4 * (size_t)N);
       std::memcpy(h_rcam + g0, w.obs_camera, 4 * (size_t)N);
     }
-    std::memcpy(h_rmeas + 2 * g0, w.obs_measurement, 16 * (size_t)N);
+    if (meas_f32) {
+      float* zf = reinterpret_cast<float*>(h_rmeas) + 2 * g0;
+      for (int o = 0; o < 2 * N; ++o) zf[o] = (float)w.obs_measurement[o];
+    } else {
+      std::memcpy(h_rmeas + 2 * g0, w.obs_measurement, 16 * (size_t)N);
+    }
     // information: the three entries the Cholesky factor reads (row-major 2x2: a00, a10, a11); one copy per window when
     // they are all equal (OKVIS: 64 / size^2 * I with one keypoint size, Estimator.hpp impl:64-67)
     bool uniform = N > 0;
@@ -1255,6 +1279,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     // the seven raw per-observation arrays, sliced by window group
     const size_t obs_arr[9] = {o_rpose, o_rlm, o_rext, o_rcam, o_rmeas, o_rinfo, o_rord, o_rpec, 0};
     const size_t obs_elt[9] = {4, 4, 4, 4, 16, 24, 4, 4, 0};
+    const size_t meas_elt = meas_f32 ? 8 : 16;
     int w0 = 0;
     for (int g = 0; g < G; ++g) {
       int w1 = w0;
@@ -1265,13 +1290,16 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
         for (int a = 0; a < 8 && e1 > e0; ++a) {
           const bool skip = (packed_idx && (a == 0 || a == 2 || a == 3)) || (!packed_idx && a == 7) ||
                             (a == 5 && group_info[g].load(std::memory_order_acquire) == 0) ||
-                            (a == 6 && device_plan);   // the observation order is computed on the device
+                            (a == 6 && device_plan) ||   // the observation order is computed on the device
+                            (a == 1 && one_word);
           if (skip) {
             h2d_skipped += obs_elt[a] * (e1 - e0);
             continue;
           }
-          SVIN_CUDA(cudaMemcpyAsync(D + obs_arr[a] + obs_elt[a] * e0, H + obs_arr[a] + obs_elt[a] * e0,
-                                    obs_elt[a] * (e1 - e0), cudaMemcpyHostToDevice, up));
+          const size_t elt = a == 4 ? meas_elt : obs_elt[a];
+          h2d_skipped += (obs_elt[a] - elt) * (e1 - e0);
+          SVIN_CUDA(cudaMemcpyAsync(D + obs_arr[a] + elt * e0, H + obs_arr[a] + elt * e0, elt * (e1 - e0),
+                                    cudaMemcpyHostToDevice, up));
         }
       }
       w0 = w1;
@@ -1293,7 +1321,7 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   if (device_plan) {
     PlanArgs pa{};
     pa.B = B;
-    pa.packed = packed_idx ? 1 : 0;
+    pa.packed = one_word ? 2 : (packed_idx ? 1 : 0);
     pa.win = b.win;
     pa.rlm = (const int*)(D + o_rlm); pa.rpec = (const int*)(D + o_rpec);
     pa.rpose = (const int*)(D + o_rpose); pa.rcam = (const int*)(D + o_rcam);
@@ -1320,10 +1348,10 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   c->n_sw_cap = (size_t)NSW;
   launch_reset_state(b, up);
   {
-    RawObs raw{packed_idx ? (const int*)(D + o_rpec) : nullptr,
+    RawObs raw{packed_idx ? (const int*)(D + o_rpec) : nullptr, one_word ? 1 : 0,
                (const int*)(D + o_rpose), (const int*)(D + o_rlm), (const int*)(D + o_rext), (const int*)(D + o_rcam),
-               (const double*)(D + o_rmeas), (const double*)(D + o_rinfo), (const int*)(D + o_rord),
-               (const int*)(D + o_linv)};
+               (const double*)(D + o_rmeas), meas_f32 ? (const float*)(D + o_rmeas) : nullptr,
+               (const double*)(D + o_rinfo), (const int*)(D + o_rord), (const int*)(D + o_linv)};
     launch_pack_obs(b, raw, up);
   }
   launch_obs_poff(b, up);

@@ -2801,23 +2801,37 @@ __global__ void __launch_bounds__(kObsTile) k_pack_obs(Batch b, RawObs raw) {
   const WinDesc& wd = b.win[w];
   if (g >= wd.obs_end) return;
   const int src = wd.obs_begin + raw.order[g];
-  int ip, ie, ic;
-  if (raw.pec) {   // one word per observation: pose | ext << 10 | cam << 20
+  int ip, ie, ic, il;
+  if (raw.one_word) {   // landmark | pose << 18 | ext << 24 | cam << 30
+    const unsigned v = (unsigned)raw.pec[src];
+    il = (int)(v & 0x3ffffu);
+    ip = (int)((v >> 18) & 63u);
+    ie = (int)((v >> 24) & 63u);
+    ic = (int)(v >> 30);
+  } else if (raw.pec) {   // one word per observation: pose | ext << 10 | cam << 20
     const int v = raw.pec[src];
     ip = v & 1023;
     ie = (v >> 10) & 1023;
     ic = (v >> 20) & 1023;
+    il = raw.lm[src];
   } else {
     ip = raw.pose[src];
     ie = raw.ext[src];
     ic = raw.cam[src];
+    il = raw.lm[src];
   }
   b.obs_pose[g] = wd.pose_begin + ip;
-  b.obs_lm[g] = wd.lm_begin + raw.lm_inv[wd.lm_begin + raw.lm[src]];
+  b.obs_lm[g] = wd.lm_begin + raw.lm_inv[wd.lm_begin + il];
   b.obs_ext[g] = wd.pose_begin + ie;
   b.obs_cam[g] = wd.cam_begin + ic;
-  b.obs_zx[g] = raw.meas[2 * (size_t)src];
-  b.obs_zy[g] = raw.meas[2 * (size_t)src + 1];
+  if (raw.meas32) {
+    const float2 z = reinterpret_cast<const float2*>(raw.meas32)[src];
+    b.obs_zx[g] = (double)z.x;
+    b.obs_zy[g] = (double)z.y;
+  } else {
+    b.obs_zx[g] = raw.meas[2 * (size_t)src];
+    b.obs_zy[g] = raw.meas[2 * (size_t)src + 1];
+  }
   double a0, a2, a3;
   if (wd.info_uniform) {   // one information matrix for the whole window (single-scale detector: one keypoint size)
     a0 = wd.info3[0];

@@ -74,9 +74,15 @@ __device__ int block_excl_scan(int* a, int n, int* part) {
   return total;
 }
 
-__device__ __forceinline__ int obs_pose_of(const PlanArgs& a, int g) { return a.packed ? (a.rpec[g] & 1023) : a.rpose[g]; }
+// packed: 0 = separate arrays, 1 = pose | ext << 10 | cam << 20 (+ rlm), 2 = landmark | pose << 18 | ext << 24 | cam << 30
+__device__ __forceinline__ int obs_pose_of(const PlanArgs& a, int g) {
+  return a.packed == 2 ? (int)(((unsigned)a.rpec[g] >> 18) & 63u) : (a.packed ? (a.rpec[g] & 1023) : a.rpose[g]);
+}
 __device__ __forceinline__ int obs_cam_of(const PlanArgs& a, int g) {
-  return a.packed ? ((a.rpec[g] >> 20) & 1023) : a.rcam[g];
+  return a.packed == 2 ? (int)((unsigned)a.rpec[g] >> 30) : (a.packed ? ((a.rpec[g] >> 20) & 1023) : a.rcam[g]);
+}
+__device__ __forceinline__ int obs_lm_of(const PlanArgs& a, int g) {
+  return a.packed == 2 ? (int)((unsigned)a.rpec[g] & 0x3ffffu) : a.rlm[g];
 }
 
 __global__ void __launch_bounds__(kPlanThreads) k_plan_window(PlanArgs a) {
@@ -96,11 +102,10 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan_window(PlanArgs a) {
   int* seg_begin = a.scratch[2] + sb;    // [segments + 1] internal landmark position
   int* seg_chunks = a.scratch[3] + sb;   // chunks of a segment -> first chunk
   int* seg_runs = a.scratch[4] + sb;     // pose runs of a segment -> first run
-  const int* rlm = a.rlm + ob0;
   if (tid < kSchurClasses) cls[tid] = 0;
   for (int l = tid; l <= L; l += T) start[l] = 0;
   __syncthreads();
-  for (int o = tid; o < N; o += T) atomicAdd(&start[rlm[o]], 1);
+  for (int o = tid; o < N; o += T) atomicAdd(&start[obs_lm_of(a, ob0 + o)], 1);
   __syncthreads();
   block_excl_scan(start, L + 1, part);
 

@@ -55,7 +55,7 @@ const PlanCapsTable& plan_caps_table();  // the same for runs 0..64, passed to t
 // chunks and writes every table order_window + fill_window used to produce on the host.
 struct PlanArgs {
   int B;
-  int packed;  // rpec valid, else rpose / rcam
+  int packed;  // 0: rpose / rcam / rlm, 1: rpec (pose | ext << 10 | cam << 20) + rlm, 2: rpec = landmark | pose << 18 | ext << 24 | cam << 30
   const WinDesc* win;
   const int *rlm, *rpec, *rpose, *rcam;  // caller's observation arrays (window by window), already on the device
   const double* lm_raw;                  // [NL][4] landmarks in caller order

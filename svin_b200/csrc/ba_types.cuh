@@ -194,8 +194,10 @@ struct Batch {
 // The caller's observation arrays (window by window, caller order) as uploaded; k_pack_obs gathers them.
 struct RawObs {
   const int* pec;                    // packed pose | ext << 10 | cam << 20 (window-local), or nullptr -> the three arrays below
+  int one_word;                      // pec holds landmark | pose << 18 | ext << 24 | cam << 30 instead, `lm` is not uploaded
   const int *pose, *lm, *ext, *cam;  // window-local indices
   const double* meas;                // [2] per observation
+  const float* meas32;               // the same as float when every coordinate is float-exact (BRISK keypoints are), else nullptr
   const double* info3;               // a00, a10, a11 of the 2x2 information
   const int* order;                  // internal observation -> caller observation (window-local)
   const int* lm_inv;                 // [NL] caller landmark -> internal landmark (window-local)

@@ -64,7 +64,9 @@ def make_euroc_sequence(seed=20260925, n_frames=30, frame_dt=0.05, kf_every=3, n
         for c in range(2):
             vis = np.nonzero(oks[c])[0][:max_kp]                  # lowest ids first: persistent tracks
             for j in vis:
-                obs.append((int(j), c, ips[c][j] + rng.normal(0, pixel_noise, 2)))
+                # keypoint coordinates are floats in the reference (cv::KeyPoint::pt, widened by Frame::getKeypoint)
+                z = (ips[c][j] + rng.normal(0, pixel_noise, 2)).astype(np.float32).astype(np.float64)
+                obs.append((int(j), c, z))
         frames.append(dict(t_ns=ms * 1000000, keyframe=(k % kf_every == 0), pose=np.concatenate([traj["r"][ms], traj["q"][ms]]),
                            vel=traj["v"][ms].copy(), obs=obs))
     return dict(points=points, frames=frames, imu=(traj["t_imu"], gyro, accel), bias=(bg, ba), intrinsics=intr,

@@ -108,3 +108,41 @@ def test_solution_does_not_depend_on_the_planner():
     np.testing.assert_allclose(w.pose_blocks, w2.pose_blocks, rtol=0, atol=1e-9)
     np.testing.assert_allclose(w.landmarks, w2.landmarks, rtol=0, atol=1e-7)
     assert abs(sa["final_cost"] - sb["final_cost"]) <= 1e-9 * abs(sa["final_cost"])
+
+
+def _solve_copy(w, opt):
+    v = w.copy()
+    with BaEngine() as eng:
+        (s,), _ = eng.optimize([v], opt)
+    return v, s
+
+
+def test_upload_formats_give_the_same_solution(monkeypatch):
+    """The compact upload (one index word + float measurements, 12 B / observation) against the plain one (index word +
+    landmark array + double measurements, 24 B) and against the host planner: same data on the device, same solution up to
+    the order of the fp64 atomics."""
+    w, _ = make_window(seed=77, num_keyframes=10, num_imu_frames=3, num_landmarks=1500, mode="steady")
+    w.obs_measurement = w.obs_measurement.astype(np.float32).astype(np.float64)      # float-exact, as BRISK keypoints are
+    w._struct = None
+    w.finalize()
+    opt = default_options()
+    a, sa = _solve_copy(w, opt)
+    monkeypatch.setenv("SVIN_BA_COMPACT_OBS", "0")
+    b, sb = _solve_copy(w, opt)
+    monkeypatch.setenv("SVIN_BA_DEVICE_PLAN", "0")
+    c, sc = _solve_copy(w, opt)
+    for x, sx in ((b, sb), (c, sc)):
+        assert sx["iterations"] == sa["iterations"]
+        np.testing.assert_allclose(x.pose_blocks, a.pose_blocks, rtol=0, atol=1e-9)
+        # distant landmarks' depth is weakly determined: the rounding noise of the atomics shows amplified there
+        np.testing.assert_allclose(x.landmarks, a.landmarks, rtol=1e-7, atol=1e-6)
+        assert abs(sx["final_cost"] - sa["final_cost"]) <= 1e-10 * abs(sa["final_cost"])
+    # measurements that are NOT float-exact travel as doubles: nothing is rounded
+    w2, _ = make_window(seed=77, num_keyframes=10, num_imu_frames=3, num_landmarks=1500, mode="steady")
+    monkeypatch.delenv("SVIN_BA_COMPACT_OBS")
+    monkeypatch.delenv("SVIN_BA_DEVICE_PLAN")
+    d, sd = _solve_copy(w2, opt)
+    monkeypatch.setenv("SVIN_BA_COMPACT_OBS", "0")
+    e, se = _solve_copy(w2, opt)
+    np.testing.assert_allclose(d.pose_blocks, e.pose_blocks, rtol=0, atol=1e-9)
+    assert abs(sd["final_cost"] - se["final_cost"]) <= 1e-10 * abs(sd["final_cost"])
