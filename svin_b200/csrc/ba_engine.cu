@@ -372,6 +372,8 @@ struct svin_ba_ctx {
   bool device_plan = false, obs_perm_valid = true;
   int* h_lm_perm = nullptr;
   size_t h_lm_perm_cap = 0;
+  char* h_obs = nullptr;       // pinned: compact observation records written by the validation pass
+  size_t h_obs_cap = 0;
   const int* lm_perm_p = nullptr;
   const int* d_rord = nullptr;
   size_t n_obs_total = 0, n_sw_cap = 0;
@@ -435,7 +437,13 @@ int ensure(void** p, size_t* cap, size_t need, bool pinned) {
 
 // flags (optional): bit 0 = observations not in (landmark, pose, camera) order, bit 1 = an observation's extrinsics block is
 // free, bit 2 = a measurement coordinate is not exactly a float
-int validate(const SvinBaWindow& w, int idx, int* flags = nullptr) {
+// sink (optional): the same pass writes the compact upload records - one index word and two floats per observation - so
+// that the caller's index and measurement arrays are read once, not once to validate and once to pack
+struct ObsSink {
+  int* word = nullptr;   // landmark | pose << 18 | ext << 24 | cam << 30
+  float* z = nullptr;    // [2] per observation
+};
+int validate(const SvinBaWindow& w, int idx, int* flags = nullptr, const ObsSink* sink = nullptr) {
   auto bad = [&](const char* what) {
     set_error("window " + std::to_string(idx) + ": " + what);
     return SVIN_ERR_INVALID_ARGUMENT;
@@ -477,6 +485,8 @@ int validate(const SvinBaWindow& w, int idx, int* flags = nullptr) {
     const unsigned np = (unsigned)w.num_pose_blocks, nl = (unsigned)w.num_landmarks, nc = (unsigned)w.num_cameras;
     unsigned oob = 0, unsorted = 0, ext_free = 0, inexact = 0;
     uint64_t prev = 0;
+    int* const sw = sink ? sink->word : nullptr;
+    float* const sz = sink ? sink->z : nullptr;
     for (int i = 0; i < w.num_obs; ++i) {
       const unsigned p = (unsigned)w.obs_pose[i], e = (unsigned)w.obs_extrinsics[i], l = (unsigned)w.obs_landmark[i],
                      c = (unsigned)w.obs_camera[i];
@@ -488,6 +498,11 @@ int validate(const SvinBaWindow& w, int idx, int* flags = nullptr) {
       if (!bad_i) ext_free |= (unsigned)(w.pose_fixed[e] == 0);
       const double zx = w.obs_measurement[2 * (size_t)i], zy = w.obs_measurement[2 * (size_t)i + 1];
       inexact |= (unsigned)((double)(float)zx != zx) | (unsigned)((double)(float)zy != zy);
+      if (sw) sw[i] = (int)(l | (p << 18) | (e << 24) | (c << 30));
+      if (sz) {
+        sz[2 * (size_t)i] = (float)zx;
+        sz[2 * (size_t)i + 1] = (float)zy;
+      }
     }
     if (oob)
       for (int i = 0; i < w.num_obs; ++i) {
@@ -634,6 +649,7 @@ void svin_ba_destroy(svin_ba_ctx* c) {
   cudaFreeHost(c->h_in);
   cudaFreeHost(c->h_out);
   cudaFreeHost(c->h_lm_perm);
+  cudaFreeHost(c->h_obs);
   cudaFree(c->d_active);
   cudaFreeHost(c->h_active);
   for (auto& ev : c->ev)
@@ -671,13 +687,29 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
   SVIN_CUDA(cudaSetDevice(c->device));
   const double t_begin = wall_ms();
   std::vector<int> vflags;
+  bool prepacked = false;
   {
     // per window on the pool; the message of the first failing window is re-raised on the calling thread
     std::vector<int> vrc(B, SVIN_OK);
     std::vector<std::string> vmsg(B);
     vflags.assign(B, 0);
+    // the compact records are written by the validation pass itself when the batch's COUNTS allow the one-word format
+    // (whether the measurements are float-exact is only known afterwards: if not, the doubles are copied by the fill pass)
+    const bool compact_wanted = !(std::getenv("SVIN_BA_COMPACT_OBS") && std::atoi(std::getenv("SVIN_BA_COMPACT_OBS")) == 0);
+    std::vector<size_t> obs0(B + 1, 0);
+    prepacked = compact_wanted;
+    for (int i = 0; i < B; ++i) {
+      obs0[i + 1] = obs0[i] + (size_t)std::max(0, wins[i].num_obs);
+      prepacked = prepacked && wins[i].num_pose_blocks <= 64 && wins[i].num_cameras <= 4 && wins[i].num_landmarks < (1 << 18);
+    }
+    if (prepacked && ensure((void**)&c->h_obs, &c->h_obs_cap, 12 * obs0[B] + 64, true) != SVIN_OK) prepacked = false;
     c->pool->run(B, [&](int i) {
-      vrc[i] = validate(wins[i], i, &vflags[i]);
+      ObsSink sink;
+      if (prepacked) {
+        sink.word = reinterpret_cast<int*>(c->h_obs) + obs0[i];
+        sink.z = reinterpret_cast<float*>(c->h_obs + 4 * obs0[B]) + 2 * obs0[i];
+      }
+      vrc[i] = validate(wins[i], i, &vflags[i], prepacked ? &sink : nullptr);
       if (vrc[i] != SVIN_OK) vmsg[i] = svin_last_error();
     });
     for (int i = 0; i < B; ++i)
@@ -941,9 +973,10 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
     const int N = w.num_obs;
     const size_t g0 = (size_t)d.obs_begin;
     if (one_word) {
-      for (int o = 0; o < N; ++o)
-        h_rpec[g0 + o] = (int)((unsigned)w.obs_landmark[o] | ((unsigned)w.obs_pose[o] << 18) |
-                               ((unsigned)w.obs_extrinsics[o] << 24) | ((unsigned)w.obs_camera[o] << 30));
+      if (!prepacked)
+        for (int o = 0; o < N; ++o)
+          h_rpec[g0 + o] = (int)((unsigned)w.obs_landmark[o] | ((unsigned)w.obs_pose[o] << 18) |
+                                 ((unsigned)w.obs_extrinsics[o] << 24) | ((unsigned)w.obs_camera[o] << 30));
     } else if (packed_idx) {
       std::memcpy(h_rlm + g0, w.obs_landmark, 4 * (size_t)N);
       for (int o = 0; o < N; ++o) h_rpec[g0 + o] = w.obs_pose[o] | (w.obs_extrinsics[o] << 10) | (w.obs_camera[o] << 20);
@@ -954,8 +987,10 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
       std::memcpy(h_rcam + g0, w.obs_camera, 4 * (size_t)N);
     }
     if (meas_f32) {
-      float* zf = reinterpret_cast<float*>(h_rmeas) + 2 * g0;
-      for (int o = 0; o < 2 * N; ++o) zf[o] = (float)w.obs_measurement[o];
+      if (!prepacked) {
+        float* zf = reinterpret_cast<float*>(h_rmeas) + 2 * g0;
+        for (int o = 0; o < 2 * N; ++o) zf[o] = (float)w.obs_measurement[o];
+      }
     } else {
       std::memcpy(h_rmeas + 2 * g0, w.obs_measurement, 16 * (size_t)N);
     }
@@ -1298,8 +1333,11 @@ int svin_ba_upload(svin_ba_ctx* c, const SvinBaWindow* wins, int32_t B) {
           }
           const size_t elt = a == 4 ? meas_elt : obs_elt[a];
           h2d_skipped += (obs_elt[a] - elt) * (e1 - e0);
-          SVIN_CUDA(cudaMemcpyAsync(D + obs_arr[a] + elt * e0, H + obs_arr[a] + elt * e0, elt * (e1 - e0),
-                                    cudaMemcpyHostToDevice, up));
+          // the records the validation pass wrote live in their own staging buffer (words, then floats)
+          const char* src = H + obs_arr[a] + elt * e0;
+          if (prepacked && a == 7 && one_word) src = c->h_obs + 4 * e0;
+          if (prepacked && a == 4 && meas_f32) src = c->h_obs + 4 * (size_t)NOBS + 8 * e0;
+          SVIN_CUDA(cudaMemcpyAsync(D + obs_arr[a] + elt * e0, src, elt * (e1 - e0), cudaMemcpyHostToDevice, up));
         }
       }
       w0 = w1;
