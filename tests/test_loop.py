@@ -1,6 +1,7 @@
 """Loop-closure query slice (BASELINE configs[4]): the CPU oracle against hand-computed vectors
 of DBoW2's formulas, and (gpu) svin_loop_* against the oracle - words, bag-of-words vectors, L1 scores, the top-4 and the
 BRIEF candidate search bit-exact at small sizes, and at the 5k-keyframe size of configs[4]."""
+import os
 import sys
 from pathlib import Path
 
@@ -120,6 +121,69 @@ def test_search_by_brief_thresholds():
     far = old[2:3].copy()          # distance 4 * 31 = 124 < 128 but >= 80: found, not accepted
     idx, dist, st = lo.search_by_brief(near, far)
     assert idx[0] == 0 and dist[0] == 124 and st[0] == 0
+
+
+# ---------------------------------------------------------------- N > 1: entries sharded by id, one all_gather per query (gloo)
+def _shard_query(voc, frames, q, max_id, rank, world):
+    """What rank `rank` returns: its entries (global id % world == rank) scored, best four with GLOBAL ids - the contract of
+    svin_loop_query on a context created with (rank, world)."""
+    db = lo.Database(voc)
+    gids = []
+    for g, f in enumerate(frames):
+        if g % world == rank:
+            db.add(f)
+            gids.append(g)
+    local_max = -1 if max_id < 0 else sum(1 for g in gids if g < max_id)   # entries are added in id order
+    return [(gids[e], s) for e, s in db.query(frames[q], 4, local_max)]
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from svin_b200.loop import merge_shards
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    voc = lo.Vocabulary.random(4, 3, seed=3)
+    frames, _ = make_keyframes(30, 6, per_image=60, seed=5)
+    res = []
+    for q, max_id in ((29, -1), (29, 20), (14, 9)):
+        mine = torch.full((4, 2), -1.0, dtype=torch.float64)
+        for k, (e, s) in enumerate(_shard_query(voc, frames, q, max_id, rank, world)):
+            mine[k, 0], mine[k, 1] = e, s
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)               # the exchange step of the sharded query
+        res.append(merge_shards([[(int(e), float(s)) for e, s in t.tolist() if e >= 0] for t in allr], 4))
+    if rank == 0:
+        out.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_query_merges_to_the_single_database_gloo():
+    import multiprocessing as mp
+    import socket
+    voc = lo.Vocabulary.random(4, 3, seed=3)
+    frames, _ = make_keyframes(30, 6, per_image=60, seed=5)
+    db = lo.Database(voc)
+    for f in frames:
+        db.add(f)
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for got, (qq, max_id) in zip(res, ((29, -1), (29, 20), (14, 9))):
+        exp = db.query(frames[qq], 4, max_id)
+        assert [e for e, _ in got] == [e for e, _ in exp]
+        assert [s for _, s in got] == [float(s) for _, s in exp]
 
 
 # ---------------------------------------------------------------- CUDA path against the oracle
