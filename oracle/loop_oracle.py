@@ -2,8 +2,12 @@
 (BASELINE configs[4]).  Only tests/, smoke() and bench.py's CPU legs may import this file; the
 product path is svin_b200/csrc/loop_engine.cu behind svin_loop_* (include/svin_b200.h).
 
-Restated from the VENDORED sources under /root/reference/pose_graph (DBoW2 needs OpenCV + boost to compile, which this
-image lacks, so it cannot be built into oracle/_ref; the arithmetic below follows it line by line):
+Restated from the VENDORED sources under /root/reference/pose_graph.  PINNED against the reference's own code where that
+compiles here: BowVector.cpp + ScoringObject.cpp -> oracle/_ref/libref_dbow.so (oracle/Makefile) - bag-of-words accumulation,
+L1 normalisation and the L1 score are bit-identical to it on the committed golden vectors (tests/golden/dbow_golden.npz,
+made by tests/golden/make_dbow_golden.py) and, when _ref is present, on fresh random vectors.  The vocabulary tree and the
+database (TemplatedVocabulary.h / TemplatedDatabase.h) are templates over OpenCV + boost types, unbuildable in this image:
+those parts follow the sources line by line and are pinned to hand-computed vectors only (tests/test_loop.py):
   * BRIEF-256 distance           FBrief::distance = popcount(a ^ b)            ThirdParty/DBoW/FBrief.cpp:44
   * word lookup                  TemplatedVocabulary::transform(feature, id, weight): from the root, at every level the
                                  child with the smallest distance, first one on ties (`d < best_d`)
@@ -106,22 +110,31 @@ class Vocabulary:
 
     def transform(self, features, fast=False):
         """-> (word ids ascending, L1-normalised values)."""
-        acc = {}
         if fast:
-            pairs = zip(*[x.tolist() for x in self.words(features)]) if len(features) else []
+            w, v = (x.tolist() for x in self.words(features)) if len(features) else ([], [])
         else:
-            pairs = (self.transform_feature(f) for f in features)
-        for w, v in pairs:
-            if v > 0:
-                acc[w] = acc.get(w, 0.0) + v       # BowVector::addWeight, feature order
-        ids = sorted(acc)
-        vals = np.array([acc[i] for i in ids], dtype=np.float64)
+            pairs = [self.transform_feature(f) for f in features]
+            w, v = [p[0] for p in pairs], [p[1] for p in pairs]
+        return bow_from_words(w, v)
+
+
+def bow_from_words(words, weights, normalise=True):
+    """TemplatedVocabulary::transform's accumulation: words with weight > 0 are added in FEATURE order
+    (BowVector::addWeight, BowVector.cpp:30-38), then BowVector::normalize(L1) sums |v| in ascending word order and divides
+    (BowVector.cpp:52-66).  Pinned against the reference's own BowVector (oracle/_ref/libref_dbow.so, tests/golden/dbow_golden.npz)."""
+    acc = {}
+    for w, v in zip(words, weights):
+        if v > 0:
+            acc[w] = acc.get(w, 0.0) + v
+    ids = sorted(acc)
+    vals = np.array([acc[i] for i in ids], dtype=np.float64)
+    if normalise:
         norm = 0.0
-        for x in vals:                              # BowVector::normalize(L1): ascending id order
+        for x in vals:
             norm += abs(x)
         if norm > 0.0:
             vals = vals / norm
-        return np.array(ids, dtype=np.int32), vals
+    return np.array(ids, dtype=np.int32), vals
 
 
 def l1_score(ids_a, val_a, ids_b, val_b):

@@ -123,6 +123,51 @@ def test_search_by_brief_thresholds():
     assert idx[0] == 0 and dist[0] == 124 and st[0] == 0
 
 
+# ---------------------------------------------------------------- oracle pinned to the REFERENCE's own DBoW2 code
+GOLDEN = ROOT / "tests" / "golden" / "dbow_golden.npz"
+
+
+def test_bow_and_l1_score_equal_the_reference_dbow_goldens():
+    """tests/golden/dbow_golden.npz comes from the reference's BowVector.cpp + ScoringObject.cpp compiled as they are
+    (oracle/_ref/libref_dbow.so, tests/golden/make_dbow_golden.py): accumulation, normalisation and score bit for bit."""
+    g = np.load(GOLDEN)
+    n = int(g["n_seq"])
+    bows = []
+    for k in range(n):
+        ids, vals = lo.bow_from_words(g[f"words_{k}"].tolist(), g[f"weights_{k}"].tolist())
+        assert ids.tolist() == g[f"ids_{k}"].tolist()
+        assert (vals == g[f"vals_{k}"]).all()
+        bows.append((ids, vals))
+    assert len(bows[0][0]) == 0                                    # the empty image
+    for a in range(n):
+        for b in range(n):
+            assert lo.l1_score(*bows[a], *bows[b]) == g["scores"][a, b]
+    assert all(g["scores"][k, k] == 1.0 or abs(g["scores"][k, k] - 1.0) < 1e-15 for k in range(1, n))
+
+
+def test_database_query_scores_equal_reference_l1scoring_when_ref_is_built():
+    """The database's inverted-file sum (TemplatedDatabase.h:587-646, restated) against L1Scoring::score of the reference
+    on the same pair of vectors: the same terms in the same order."""
+    so = ROOT / "oracle" / "_ref" / "libref_dbow.so"
+    if not so.exists():
+        pytest.skip("oracle/_ref/libref_dbow.so not built (no reference tree here); the golden test above covers it")
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    import make_dbow_golden as mg
+    lib = mg.load_ref()
+    v = lo.Vocabulary.random(4, 3, seed=3)
+    frames, _ = make_keyframes(24, 6, per_image=60, seed=5)
+    db = lo.Database(v)
+    for f in frames:
+        db.add(f)
+    for q in (23, 11):
+        qv = v.transform(frames[q])
+        w, wt = zip(*[v.transform_feature(f) for f in frames[q]])
+        rid, rval = mg.ref_bow(lib, w, wt)
+        assert rid.tolist() == qv[0].tolist() and (rval == qv[1]).all()
+        for e, s in db.query(frames[q], 0, -1):
+            assert s == mg.ref_score(lib, qv, db.entries[e])
+
+
 # ---------------------------------------------------------------- N > 1: entries sharded by id, one all_gather per query (gloo)
 def _shard_query(voc, frames, q, max_id, rank, world):
     """What rank `rank` returns: its entries (global id % world == rank) scored, best four with GLOBAL ids - the contract of
