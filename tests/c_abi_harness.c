@@ -232,6 +232,13 @@ static void layout(void) {
   FIELD(SvinRansacResult, inliers);
   FIELD(SvinRansacResult, hypothesis_inliers);
   FIELD(SvinRansacResult, hypothesis_valid);
+  SIZE(SvinVocabulary);
+  FIELD(SvinVocabulary, num_nodes);
+  FIELD(SvinVocabulary, first_child);
+  FIELD(SvinVocabulary, num_children);
+  FIELD(SvinVocabulary, descriptor);
+  FIELD(SvinVocabulary, weight);
+  FIELD(SvinVocabulary, word_id);
   SIZE(SvinPreOptions);
   FIELD(SvinPreOptions, src_width);
   FIELD(SvinPreOptions, src_height);
