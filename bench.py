@@ -148,15 +148,22 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons)}
 
 
-def ncu_traffic(kernel: str, windows: int):
+def ncu_traffic(kernel: str, windows: int, obs_per_window: float):
     """DRAM bytes per launch of a kernel family from the committed `ncu --set full` capture (profiles/), scaled to
-    this run's batch; (None, None) when no capture is committed.  Not measured in this run: ncu replays kernels."""
+    this run's batch and observation count (the per-observation kernels' traffic is proportional to both);
+    (None, None) when no capture is committed.  Not measured in this run: ncu replays kernels."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(path) as f:
             t = json.load(f)
         k = t["kernels"][kernel]
-        return k["dram_bytes_per_launch"] * windows / t["windows"], t.get("source")
+        scale = windows / t["windows"]
+        src = t.get("source")
+        if t.get("observations_per_window"):
+            scale *= obs_per_window / t["observations_per_window"]
+            src = "%s (captured at %d windows x %.0f observations, scaled to this run's %d x %.0f)" % (
+                src, t["windows"], t["observations_per_window"], windows, obs_per_window)
+        return k["dram_bytes_per_launch"] * scale, src
     except (OSError, KeyError, ValueError):
         return None, None
 
@@ -769,7 +776,7 @@ def run_gpu(args):
         if k not in kern:
             kern[k] = {"ms_total": kt[k]["ms"], "launches": kt[k]["launches"], "share": kt[k]["ms"] / total_ms}
     achieved = kern[dominant]["gbs"]
-    traffic, traffic_src = ncu_traffic(dominant, B)
+    traffic, traffic_src = ncu_traffic(dominant, B, float(obs.mean()))
 
     frontend = run_frontend(args, local, rank, world, dist, barrier) if args.frames > 0 else None
     sharded = sharded_section(args, local, rank, world, dist)
