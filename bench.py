@@ -865,15 +865,13 @@ def loop_closure_section(args, local, rank, world, dist):
     Entries are sharded id % N over the ranks; the per-rank top-4 are exchanged with ONE all_gather of 4 (id, score) pairs
     per rank and merged.  The PGO half of configs[4] is not built."""
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from scene_loop import make_keyframes
-    from oracle import loop_oracle as lo      # vocabulary generator + CPU leg only
     from svin_b200.loop import LoopEngine, merge_shards
+    from svin_b200.synthetic_loop import make_keyframes, random_vocabulary
     n = 5000
-    voc = lo.Vocabulary.random(10, 6, seed=1)
+    voc = random_vocabulary(10, 6, seed=1)
     frames, _ = make_keyframes(n, 1200, per_image=500, seed=21, revisit_after=1700)
-    eng = LoopEngine(voc.first_child, voc.num_children, voc.descriptor, voc.weight, voc.word_id, device=local, rank=rank,
-                     world=world)
+    eng = LoopEngine(voc["first_child"], voc["num_children"], voc["descriptor"], voc["weight"], voc["word_id"], device=local,
+                     rank=rank, world=world)
     t0 = time.perf_counter()
     for s_ in range(0, n, 500):
         eng.add(frames[s_:s_ + 500])
@@ -906,7 +904,9 @@ def loop_closure_section(args, local, rank, world, dist):
            "note": "e2e = host descriptors in, merged top-4 out; device = inverted-file scoring + top-k kernels only"}
     eng.close()
     if rank == 0 and world == 1:
-        db = lo.Database(voc, fast=True)
+        from oracle import loop_oracle as lo      # CPU leg only
+        db = lo.Database(lo.Vocabulary(voc["first_child"], voc["num_children"], voc["descriptor"], voc["weight"],
+                                       voc["word_id"]), fast=True)
         m = 1000
         for f in frames[:m]:
             db.add(f)

@@ -50,32 +50,12 @@ class Vocabulary:
         self.word_id = np.asarray(word_id, np.int32)
 
     @staticmethod
-    def random(k, L, seed=0, leaf_fraction=1.0):
-        """Synthetic k-ary tree of depth L (the shipped vocabulary brief_k10L6.bin is k = 10, L = 6) with random BRIEF
-        node descriptors and idf-like weights ln(N / Ni)."""
-        rng = np.random.default_rng(seed)
-        first, num, word = [0], [0], [-1]
-        level = [0]
-        for depth in range(L):
-            nxt = []
-            for node in level:
-                first[node] = len(first)
-                num[node] = k
-                for _ in range(k):
-                    nxt.append(len(first))
-                    first.append(0)
-                    num.append(0)
-                    word.append(-1)
-            level = nxt
-        n = len(first)
-        wid = 0
-        for node in range(n):
-            if num[node] == 0:
-                word[node] = wid
-                wid += 1
-        desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
-        weight = np.where(np.array(num) == 0, np.log(rng.uniform(2.0, 2000.0, n)), 0.0)
-        return Vocabulary(first, num, desc, weight, word)
+    def random(k, L, seed=0):
+        """Synthetic k-ary tree of depth L (svin_b200.synthetic_loop.random_vocabulary: the inputs' generator is shared with
+        the bench, the arithmetic below is not)."""
+        from svin_b200.synthetic_loop import random_vocabulary
+        v = random_vocabulary(k, L, seed)
+        return Vocabulary(v["first_child"], v["num_children"], v["descriptor"], v["weight"], v["word_id"])
 
     def transform_feature(self, f):
         node = 0
