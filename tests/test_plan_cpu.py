@@ -87,3 +87,13 @@ def test_plan_rejects_malformed_window():
     w.obs_pose[0] = 99
     with pytest.raises(capi.SvinError, match="obs_pose"):
         plan(w)
+
+
+@pytest.mark.parametrize("field,value,msg", [("obs_landmark", -1, "obs_landmark"), ("obs_extrinsics", 1000, "obs_extrinsics"),
+                                             ("obs_camera", -3, "obs_camera"), ("obs_pose", -2147483648, "obs_pose")])
+def test_plan_rejects_out_of_range_indices_of_either_sign(field, value, msg):
+    # validate() checks the four index arrays in one branch-free pass (unsigned compare) and names the culprit in a second
+    w, _ = make_window(seed=6, num_keyframes=3, num_imu_frames=3, num_landmarks=40, mode="initial")
+    getattr(w, field)[w.num_obs // 2] = value
+    with pytest.raises(capi.SvinError, match=msg):
+        plan(w)
