@@ -207,6 +207,36 @@ void Estimator::optimize(size_t numIter, size_t /*numThreads*/, bool verbose) {
       OKVIS_THROW(Exception, "svin_b200: unsupported error term " << e->typeInfo());
     }
   }
+  // The residual map is unordered: put the observations in (landmark, pose block, camera) order.  svin_ba_upload accepts
+  // any order, but for this one it plans the window on the device (grouping, chunking, observation order:
+  // csrc/ba_plan.cu) instead of on the host threads.
+  {
+    const size_t n = obsPose.size();
+    std::vector<size_t> ord(n);
+    for (size_t i = 0; i < n; ++i) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
+      if (obsLm[a] != obsLm[b]) return obsLm[a] < obsLm[b];
+      if (obsPose[a] != obsPose[b]) return obsPose[a] < obsPose[b];
+      return obsCam[a] < obsCam[b];
+    });
+    std::vector<int32_t> p2(n), l2(n), e2(n), c2(n);
+    std::vector<double> z2(2 * n), i2(4 * n);
+    for (size_t k = 0; k < n; ++k) {
+      const size_t s = ord[k];
+      p2[k] = obsPose[s];
+      l2[k] = obsLm[s];
+      e2[k] = obsExt[s];
+      c2[k] = obsCam[s];
+      for (int j = 0; j < 2; ++j) z2[2 * k + j] = obsZ[2 * s + j];
+      for (int j = 0; j < 4; ++j) i2[4 * k + j] = obsInfo[4 * s + j];
+    }
+    obsPose.swap(p2);
+    obsLm.swap(l2);
+    obsExt.swap(e2);
+    obsCam.swap(c2);
+    obsZ.swap(z2);
+    obsInfo.swap(i2);
+  }
   // intrinsics of every camera that carries observations: [fu fv cu cv k1 k2 p1 p2]
   std::vector<double> intrinsics;
   if (!obsCam.empty()) {

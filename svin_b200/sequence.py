@@ -190,8 +190,7 @@ class SlidingWindow:
         w.landmarks = np.array([self.landmarks[l] for l in lm_ids]).reshape(-1, 4)
         w.intrinsics = self.intrinsics
         if obs:
-            # the walk order of the C++ adapter (adapters/EstimatorB200.cpp: landmarksMap_, then each landmark's
-            # observations map keyed by (frame, camera, keypoint)) = sorted by (landmark, pose, camera); svin_ba_upload
+            # the order the C++ adapter emits (adapters/EstimatorB200.cpp sorts by (landmark, pose, camera)); svin_ba_upload
             # plans such windows on the device (csrc/ba_plan.cu)
             obs = sorted(obs, key=lambda o: (li[o[0]], pi[fr[o[1]].pose_id], o[2]))
             w.obs_pose = [pi[fr[o[1]].pose_id] for o in obs]
